@@ -1,0 +1,149 @@
+/* b200voc -- C ABI of the B200-native (sm_100a) vocoder7 waveform-synthesis hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point
+ * cites the reference interface it replaces (paths relative to the reference repository
+ * ChiefTriston/TTS-Core-Remastered-1).  The reference has no FFI of its own (it is pure Python
+ * calling PyTorch library ops), so the "binding a maintainer would add" is the ctypes stub in
+ * INTEGRATION.md / tts-core-remastered-1_b200/b200voc/_lib.py.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name says `host`;
+ *   - the library never allocates or frees caller-visible device memory in the forward calls:
+ *     outputs and workspaces are caller-allocated, sizes come from the *_workspace_bytes queries
+ *     (handles own their packed weights);
+ *   - every launch goes on the `stream` argument (a cudaStream_t passed as void*); calls are
+ *     CUDA-graph capturable; handles are immutable after finalize, so concurrent forwards on
+ *     different streams with different workspaces are safe;
+ *   - return value 0 = ok, negative = error, text via b200voc_last_error_string() (thread local);
+ *   - there is NO CPU fallback: without an sm_100 device the compute entry points fail.
+ */
+#ifndef B200VOC_H_
+#define B200VOC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VOC_OK 0
+#define B200VOC_ERR_BAD_ARG (-1)
+#define B200VOC_ERR_UNSUPPORTED (-2)
+#define B200VOC_ERR_CUDA (-3)
+#define B200VOC_ERR_STATE (-4)
+
+/* 16-bit tensor-core operand / activation storage formats (tcgen05 kind::f16 runs both at the
+ * same rate). */
+#define B200VOC_FMT_FP16 0
+#define B200VOC_FMT_BF16 1
+
+/* precision plans (DESIGN.md "Numerics plan"): per-stage operand format. */
+#define B200VOC_PLAN_FP16 0  /* fp16 operands everywhere: meets max-abs<=1e-3, SNR>=40 dB (default) */
+#define B200VOC_PLAN_BF16 1  /* bf16 operands everywhere: SNR gate only (max-abs ~5e-3)          */
+#define B200VOC_PLAN_MIXED 2 /* bf16 stage 0, fp16 stages 1..3                                   */
+
+int b200voc_version(void);
+const char* b200voc_last_error_string(void);
+/* 0 if device `dev` is sm_100 (B200), B200VOC_ERR_UNSUPPORTED otherwise. */
+int b200voc_device_supported(int dev);
+
+/* ----------------------------------------------------------------------------------------
+ * Generator (replaces vocoder7/generator.py:9-98 `class Generator`).
+ * -------------------------------------------------------------------------------------- */
+typedef struct {
+  /* vocoder7/config.py:11-20 */
+  int32_t channels;      /* 80  */
+  int32_t cond_dim;      /* 128 */
+  int32_t style_dim;     /* 128 */
+  int32_t num_bands;     /* 4   */
+  int32_t n_stages;      /* len(upsample_factors) = 4 */
+  int32_t upsample_factors[8];
+  int32_t n_dilations;   /* len(res_dilations) = 3 */
+  int32_t res_dilations[8];
+  /* repairs R1/R3 (the reference leaves them undefined) */
+  int32_t hidden_dim;    /* 512 */
+  int32_t use_attention; /* generator.py:43-44 */
+  int32_t attn_window;   /* 0 = global attention over all L positions, else block-local window */
+  /* B200 knobs */
+  int32_t precision_plan; /* B200VOC_PLAN_* */
+  int32_t reserved[7];
+} b200voc_gen_config;
+
+typedef struct b200voc_gen b200voc_gen;
+
+/* Generator.__init__ (generator.py:13-48): builds the layer plan, allocates packed-weight storage. */
+int b200voc_gen_create(const b200voc_gen_config* cfg, b200voc_gen** out);
+/* load_state_dict (train/blocks/vocoder.py:20-24 path): `name` is the reference state_dict key
+ * (e.g. "upsample_blocks.0.0.weight"), `w` an fp32 device tensor in the reference layout
+ * (Conv1d [out,in,k]; ConvTranspose1d [in,out,k]; Linear [out,in]).  Packs to the kernel layout. */
+int b200voc_gen_set_weight(b200voc_gen* g, const char* name, const float* w, int64_t numel, void* stream);
+/* number of state_dict entries the plan expects / i-th key (for host-side validation). */
+int b200voc_gen_num_weights(const b200voc_gen* g);
+const char* b200voc_gen_weight_name(const b200voc_gen* g, int i);
+int64_t b200voc_gen_weight_numel(const b200voc_gen* g, int i);
+/* fails with B200VOC_ERR_STATE if a key was never set. */
+int b200voc_gen_finalize(b200voc_gen* g);
+int64_t b200voc_gen_workspace_bytes(const b200voc_gen* g, int B, int T);
+/* Generator.forward (generator.py:50-98).
+ *   mel[B,channels,T] prosody[B,T,18] style[B,style_dim] emotion[B,6]  (fp32, contiguous)
+ *   wav_out[B,1,hop*T] fp32.
+ * tap_name/tap_out (both NULL normally): copy the named intermediate ("split","up0","res0.0",..,
+ * "attn", oracle tap names) as fp32 [num_bands*B? no: B*num_bands, C, L] into tap_out. */
+int b200voc_gen_forward(b200voc_gen* g, const float* mel, const float* prosody, const float* style,
+                        const float* emotion, int B, int T, int style_drop, int emo_drop, float w_style,
+                        float w_emo, float* wav_out, void* workspace, int64_t workspace_bytes,
+                        const char* tap_name, float* tap_out, void* stream);
+/* how many kernels one forward(B,T) launches (bench.py's gpu_launches). */
+int b200voc_gen_launch_count(const b200voc_gen* g);
+int b200voc_gen_destroy(b200voc_gen* g);
+
+/* ----------------------------------------------------------------------------------------
+ * Layer-level entry points (used by the Generator internally and by the layer-wise parity tests).
+ * Activations are channels-last 16-bit: x16[N, L, C].
+ * -------------------------------------------------------------------------------------- */
+/* nn.ConvTranspose1d(Cin, Cout, 2*s, stride=s, padding=s/2)  (generator.py:35-38,87).
+ * w_packed from b200voc_pack_convt_weight ([s*Cout rows][2*Cin] 16-bit).  out16[N, s*Lin, Cout];
+ * store_lrelu != 0 stores leaky_relu(y, 0.1) instead of y. */
+int64_t b200voc_convt_packed_elems(int Cin, int Cout, int s);
+int b200voc_pack_convt_weight(const float* w_ref, int Cin, int Cout, int s, int fmt, void* w_packed, void* stream);
+int b200voc_convt1d(const void* x16, const void* w_packed, const float* bias, int N, int Lin, int Cin, int Cout,
+                    int s, int fmt, int store_lrelu, void* out16, void* stream);
+
+/* ResidualBlock(C, dilation, cond_dim).forward(x, cond) (generator.py:40-41,89-90; body = repair
+ * R2).  a16 holds leaky_relu(x) (the form the producer stores); film[B,T,2C] fp32 holds
+ * (1+scale | shift) at frame rate; N = num_bands*B sequences, sequence n uses film row n/num_bands.
+ * w1_packed [2C rows (GLU-interleaved)][3C], w2_packed [C][C]. */
+int64_t b200voc_resblock_packed_elems(int C);   /* elements of w1_packed + w2_packed */
+int b200voc_pack_resblock_weights(const float* w_conv, const float* w_proj, int C, int fmt, void* w_packed,
+                                  void* stream);
+int b200voc_resblock(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
+                     const float* film, int N, int L, int C, int dilation, int T, int num_bands, int fmt,
+                     int store_lrelu, void* out16, void* stream);
+
+/* experiment: UMMA descriptors whose start address is offset by whole 128B rows. */
+int b200voc_exp_rowshift(const void* a16_144x64, const void* b16_64x64, float* out_2x16x128x64, void* stream);
+
+/* ----------------------------------------------------------------------------------------
+ * STFT family (replaces vocoder7/stft.py:9-54 and the torchaudio MelSpectrogram call sites
+ * reference_encoder/utils.py:31-36).  fp32 throughout.  frames = 1 + N / hop, bins = n_fft/2+1.
+ * -------------------------------------------------------------------------------------- */
+/* LearnableSTFT.forward (stft.py:22-34): out[B,bins,frames] = |STFT(wav[B,N])| * gain[bins]
+ * (gain may be NULL = ones). */
+int b200voc_stft_mag(const float* wav, int B, int N, int n_fft, int hop, const float* gain, float* out, void* stream);
+/* complex STFT, out_ri[B,bins,frames,2] (interleaved re,im = torch complex64 layout). */
+int b200voc_stft_complex(const float* wav, int B, int N, int n_fft, int hop, float* out_ri, void* stream);
+/* fused STFT -> |X|^2 -> 80-bin HTK mel -> log(clamp(.,1e-5)); out[B,n_mels,frames].
+ * log_compress=0 returns the linear power mel. */
+int b200voc_stft_logmel(const float* wav, int B, int N, int n_fft, int hop, int n_mels, int sample_rate,
+                        int log_compress, float* out, void* stream);
+/* torch.istft semantics (center, hann, length=N): spec_ri[B,bins,frames,2] -> wav[B,N]. */
+int b200voc_istft(const float* spec_ri, int B, int frames, int n_fft, int hop, int N, float* wav, void* stream);
+/* STFTLoss.forward (stft.py:48-54) partial sums: out_sum[0] += sum |mag(fake)-mag(real)|*|gain|
+ * for one resolution (host divides by numel and multiplies lambda). */
+int b200voc_stft_l1(const float* wav_fake, const float* wav_real, int B, int N, int n_fft, int hop,
+                    const float* gain, double* out_sum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VOC_H_ */

@@ -1,0 +1,8 @@
+"""b200voc -- B200-native (sm_100a) implementation of the vocoder7 waveform-synthesis hot path of
+ChiefTriston/TTS-Core-Remastered-1: Generator inference and the STFT / mel / iSTFT transforms,
+behind the reference's Python API.  See DESIGN.md."""
+from .config import GANConfig
+from .generator import Generator, ResidualBlock, SelfAttention
+from . import _lib
+
+__all__ = ["GANConfig", "Generator", "ResidualBlock", "SelfAttention"]

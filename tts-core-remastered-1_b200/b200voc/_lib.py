@@ -1,0 +1,105 @@
+"""ctypes binding of libb200voc.so (include/b200voc.h).  There is no CPU fallback: if the shared
+library is missing or the device is not sm_100, every compute entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb200voc.so")
+
+OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
+FMT_FP16, FMT_BF16 = 0, 1
+PLAN_FP16, PLAN_BF16, PLAN_MIXED = 0, 1, 2
+PLANS = {"fp16": PLAN_FP16, "bf16": PLAN_BF16, "mixed": PLAN_MIXED}
+
+
+class GenConfig(C.Structure):
+    _fields_ = [
+        ("channels", C.c_int32), ("cond_dim", C.c_int32), ("style_dim", C.c_int32), ("num_bands", C.c_int32),
+        ("n_stages", C.c_int32), ("upsample_factors", C.c_int32 * 8),
+        ("n_dilations", C.c_int32), ("res_dilations", C.c_int32 * 8),
+        ("hidden_dim", C.c_int32), ("use_attention", C.c_int32), ("attn_window", C.c_int32),
+        ("precision_plan", C.c_int32), ("reserved", C.c_int32 * 7),
+    ]
+
+
+_P, _I, _I64, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_SIGNATURES = {
+    "b200voc_version": (C.c_int, []),
+    "b200voc_last_error_string": (C.c_char_p, []),
+    "b200voc_device_supported": (C.c_int, [_I]),
+    "b200voc_gen_create": (C.c_int, [C.POINTER(GenConfig), C.POINTER(_P)]),
+    "b200voc_gen_set_weight": (C.c_int, [_P, C.c_char_p, _P, _I64, _P]),
+    "b200voc_gen_num_weights": (C.c_int, [_P]),
+    "b200voc_gen_weight_name": (C.c_char_p, [_P, _I]),
+    "b200voc_gen_weight_numel": (_I64, [_P, _I]),
+    "b200voc_gen_finalize": (C.c_int, [_P]),
+    "b200voc_gen_workspace_bytes": (_I64, [_P, _I, _I]),
+    "b200voc_gen_forward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _I64, C.c_char_p, _P, _P]),
+    "b200voc_gen_launch_count": (C.c_int, [_P]),
+    "b200voc_gen_destroy": (C.c_int, [_P]),
+    "b200voc_convt_packed_elems": (_I64, [_I, _I, _I]),
+    "b200voc_pack_convt_weight": (C.c_int, [_P, _I, _I, _I, _I, _P, _P]),
+    "b200voc_convt1d": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "b200voc_resblock_packed_elems": (_I64, [_I]),
+    "b200voc_pack_resblock_weights": (C.c_int, [_P, _P, _I, _I, _P, _P]),
+    "b200voc_resblock": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "b200voc_exp_rowshift": (C.c_int, [_P, _P, _P, _P]),
+    "b200voc_stft_mag": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "b200voc_stft_complex": (C.c_int, [_P, _I, _I, _I, _I, _P, _P]),
+    "b200voc_stft_logmel": (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "b200voc_istft": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "b200voc_stft_l1": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+_lib: Optional[C.CDLL] = None
+
+
+class B200VocError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library and bind every symbol the header declares."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200VocError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU / PyTorch fallback for the b200voc hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status == OK:
+        return
+    msg = load().b200voc_last_error_string().decode("utf-8", "replace")
+    text = f"b200voc {what} failed ({status}): {msg}"
+    if status in (ERR_BAD_ARG, ERR_UNSUPPORTED):
+        raise ValueError(text)
+    raise B200VocError(text)
+
+
+def ptr(t) -> int:
+    """device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise B200VocError("b200voc has no CPU path: tensors must live on a CUDA (sm_100) device")

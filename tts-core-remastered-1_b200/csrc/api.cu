@@ -1,0 +1,566 @@
+// C ABI (include/b200voc.h): error plumbing, TMA descriptor encoding, the Generator handle
+// (weight packing + layer plan + forward) and the layer-level entry points.
+#include <stdarg.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// ------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+static int encode(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return B200VOC_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("TMA base pointer %p is not 16-byte aligned", base);
+    return B200VOC_ERR_BAD_ARG;
+  }
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u sw %d)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1], swizzle_bytes);
+    return B200VOC_ERR_CUDA;
+  }
+  return B200VOC_OK;
+}
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t stride1_bytes, uint32_t box0,
+                 uint32_t box1, int swizzle_bytes) {
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {stride1_bytes};
+  cuuint32_t box[2] = {box0, box1};
+  return encode(out, base, 2, dims, strides, box, swizzle_bytes);
+}
+int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                 uint64_t stride2_bytes, uint32_t box0, uint32_t box1, int swizzle_bytes) {
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, 1};
+  return encode(out, base, 3, dims, strides, box, swizzle_bytes);
+}
+
+// ------------------------------------------------------------------ launchers defined elsewhere
+int convt1d_launch(const void*, const void*, const float*, int, int, int, int, int, int, int, void*, cudaStream_t);
+int linear_launch(const void*, const void*, const float*, int, int, int, int, int, int, void*, cudaStream_t);
+int pack_convt_launch(const float*, int, int, int, int, void*, cudaStream_t);
+int exp_rowshift_launch(const void*, const void*, float*, cudaStream_t);
+int pack_resblock_launch(const float*, const float*, int, int, void*, cudaStream_t);
+int resblock_launch(const void* a16, const void* w, const float* b_conv, const float* b_proj, const float* film,
+                    int film_stride, int N, int L, int C, int dilation, int T, int num_bands, int fmt, int store_lrelu,
+                    void* out16, cudaStream_t st);
+int style_emo_launch(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int,
+                     float, float, int, int, float*, float*, cudaStream_t);
+int cond_launch(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int,
+                int, float*, cudaStream_t);
+int film_launch(const float*, const float*, const float*, int, int, float*, cudaStream_t);
+int band_split_launch(const float*, const float*, const float*, int, int, int, int, int, int, void*, cudaStream_t);
+int pack_split_launch(const float*, int, int, float*, cudaStream_t);
+int band_merge_launch(const void*, const float*, const float*, int, int, int, int, int, float*, cudaStream_t);
+int tap_extract_launch(const void*, int, int, int, int, int, float*, cudaStream_t);
+int copy_f32_launch(const float*, float*, long long, float, cudaStream_t);
+int cvt16_launch(const float*, void*, long long, int, cudaStream_t);
+int attention_launch(const void* x16, const void* wqkv, const float* bqkv, const void* wo, const float* bo, int N,
+                     int L, int C, int window, int fmt, void* q16, void* k16, void* vt16, void* o16, void* out16,
+                     cudaStream_t st);
+long long attention_scratch_elems(int N, int L, int C);
+
+}  // namespace b200
+
+using namespace b200;
+
+// ==================================================================== Generator handle
+namespace {
+
+enum WKind {
+  W_SPLIT_W, W_SPLIT_B, W_CP0_W, W_CP0_B, W_CP2_W, W_CP2_B, W_STY_W, W_STY_B, W_EMO_W, W_EMO_B,
+  W_UP_W, W_UP_B, W_RB_CONV_W, W_RB_CONV_B, W_RB_FILM_W, W_RB_FILM_B, W_RB_PROJ_W, W_RB_PROJ_B,
+  W_ATT_W, W_ATT_B, W_MERGE_W, W_MERGE_B
+};
+
+struct WSlot {
+  std::string name;
+  long long numel;
+  WKind kind;
+  int a, b;      // stage / band index, block index (or q/k/v/out index)
+  bool set;
+};
+
+struct ResW {
+  int C, dilation;
+  uint16_t* w;          // packed w1 | w2
+  float* conv_w_stage;  // fp32 staging of conv weight until proj arrives (and vice versa)
+  float* proj_w_stage;
+  bool have_conv, have_proj;
+  float *b_conv, *b_proj;
+  int film_col;         // column offset in the concatenated FiLM matrix
+};
+
+struct StageW {
+  int Cin, Cout, s, fmt;
+  uint16_t* up_w;
+  float* up_b;
+  std::vector<ResW> res;
+};
+
+}  // namespace
+
+struct b200voc_gen {
+  b200voc_gen_config cfg;
+  int H, band_size, hop;
+  std::vector<WSlot> slots;
+  std::vector<StageW> stages;
+  // fp32 parameters
+  float *split_wt, *split_b;     // [nb][bs*7][H], [nb][H]
+  float *cp0_w, *cp0_b, *cp2_w, *cp2_b, *sty_w, *sty_b, *emo_w, *emo_b;
+  float *film_w, *film_b;        // [film_cols][cond_dim], [film_cols] (scale half has +1 folded in)
+  int film_cols;
+  float *merge_w, *merge_b;
+  // attention (stage n_stages/2)
+  int att_stage, att_C;
+  uint16_t *att_wqkv, *att_wo;   // [3C][C], [C][C]
+  float *att_bqkv, *att_bo;
+  float* att_stage_w;            // fp32 staging [4][C*C]
+  bool finalized;
+  int launches;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(b200voc_gen* g, T** p, long long n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, (size_t)(n * sizeof(T)));
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%lld bytes) failed: %s", n * (long long)sizeof(T), cudaGetErrorString(e));
+    return B200VOC_ERR_CUDA;
+  }
+  g->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return B200VOC_OK;
+}
+
+int stage_fmt(const b200voc_gen_config& c, int i) {
+  switch (c.precision_plan) {
+    case B200VOC_PLAN_BF16: return B200VOC_FMT_BF16;
+    case B200VOC_PLAN_MIXED: return i == 0 ? B200VOC_FMT_BF16 : B200VOC_FMT_FP16;
+    default: return B200VOC_FMT_FP16;
+  }
+}
+
+void add_slot(b200voc_gen* g, const std::string& name, long long numel, WKind kind, int a = 0, int b = 0) {
+  g->slots.push_back(WSlot{name, numel, kind, a, b, false});
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200voc_version(void) { return 100; }
+const char* b200voc_last_error_string(void) { return get_error(); }
+
+int b200voc_device_supported(int dev) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceProperties(%d): %s", dev, cudaGetErrorString(e));
+    return B200VOC_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; b200voc kernels are built for sm_100a only (no fallback)", dev, prop.major,
+              prop.minor);
+    return B200VOC_ERR_UNSUPPORTED;
+  }
+  return B200VOC_OK;
+}
+
+int b200voc_gen_create(const b200voc_gen_config* cfg, b200voc_gen** out) {
+  B200_CHECK_ARG(cfg && out, "gen_create: null argument");
+  B200_CHECK_ARG(cfg->num_bands > 0 && cfg->channels % cfg->num_bands == 0, "channels %% num_bands != 0");
+  B200_CHECK_ARG(cfg->n_stages >= 1 && cfg->n_stages <= 8 && cfg->n_dilations >= 1 && cfg->n_dilations <= 8,
+                 "bad n_stages / n_dilations");
+  B200_CHECK_ARG(cfg->cond_dim == 128, "cond_dim=%d unsupported (128)", cfg->cond_dim);
+  int H = cfg->hidden_dim;
+  B200_CHECK_ARG(H % 64 == 0 && H >= 128, "hidden_dim=%d unsupported", H);
+  {
+    int c = H;
+    for (int i = 0; i < cfg->n_stages; ++i) {
+      const int s = cfg->upsample_factors[i];
+      B200_CHECK_ARG(c % 64 == 0, "stage %d input channels %d must be a multiple of 64", i, c);
+      c /= 2;
+      B200_CHECK_ARG(c == 32 || c == 64 || c == 128 || c == 256, "stage %d channels %d unsupported", i, c);
+      B200_CHECK_ARG(s >= 2 && s % 2 == 0 && (s * c) % 64 == 0, "stage %d stride %d unsupported", i, s);
+    }
+    B200_CHECK_ARG(c == 32, "final per-band channels %d unsupported (32)", c);
+  }
+  b200voc_gen* g = new b200voc_gen();
+  g->cfg = *cfg;
+  g->H = H;
+  g->band_size = cfg->channels / cfg->num_bands;
+  g->finalized = false;
+  g->att_stage = cfg->n_stages / 2;
+  g->launches = 0;
+  const int nb = cfg->num_bands, bs = g->band_size, cd = cfg->cond_dim;
+  int st = B200VOC_OK;
+#define A(ptr, n) if (st == B200VOC_OK) st = dev_alloc(g, &(ptr), (n))
+  A(g->split_wt, (long long)nb * bs * 7 * H);
+  A(g->split_b, (long long)nb * H);
+  A(g->cp0_w, (cd / 2) * 18); A(g->cp0_b, cd / 2);
+  A(g->cp2_w, cd * (cd / 2)); A(g->cp2_b, cd);
+  A(g->sty_w, cd * cfg->style_dim); A(g->sty_b, cd);
+  A(g->emo_w, cd * 6); A(g->emo_b, cd);
+  for (int i = 0; i < nb; ++i) {
+    char nm[64];
+    snprintf(nm, sizeof nm, "band_split.%d.weight", i); add_slot(g, nm, (long long)H * bs * 7, W_SPLIT_W, i);
+    snprintf(nm, sizeof nm, "band_split.%d.bias", i); add_slot(g, nm, H, W_SPLIT_B, i);
+  }
+  add_slot(g, "cond_prosody.0.weight", (cd / 2) * 18, W_CP0_W); add_slot(g, "cond_prosody.0.bias", cd / 2, W_CP0_B);
+  add_slot(g, "cond_prosody.2.weight", cd * (cd / 2), W_CP2_W); add_slot(g, "cond_prosody.2.bias", cd, W_CP2_B);
+  add_slot(g, "style_proj.weight", cd * cfg->style_dim, W_STY_W); add_slot(g, "style_proj.bias", cd, W_STY_B);
+  add_slot(g, "emotion_proj.weight", cd * 6, W_EMO_W); add_slot(g, "emotion_proj.bias", cd, W_EMO_B);
+  int c = H, film_cols = 0;
+  g->hop = 1;
+  for (int i = 0; i < cfg->n_stages; ++i) {
+    StageW sw{};
+    sw.Cin = c; sw.Cout = c / 2; sw.s = cfg->upsample_factors[i]; sw.fmt = stage_fmt(*cfg, i);
+    g->hop *= sw.s;
+    A(sw.up_w, b200voc_convt_packed_elems(sw.Cin, sw.Cout, sw.s));
+    A(sw.up_b, sw.Cout);
+    char nm[96];
+    snprintf(nm, sizeof nm, "upsample_blocks.%d.0.weight", i); add_slot(g, nm, (long long)sw.Cin * sw.Cout * 2 * sw.s, W_UP_W, i);
+    snprintf(nm, sizeof nm, "upsample_blocks.%d.0.bias", i); add_slot(g, nm, sw.Cout, W_UP_B, i);
+    for (int j = 0; j < cfg->n_dilations; ++j) {
+      ResW r{};
+      r.C = sw.Cout; r.dilation = cfg->res_dilations[j]; r.film_col = film_cols;
+      film_cols += 2 * r.C;
+      A(r.w, b200voc_resblock_packed_elems(r.C));
+      A(r.conv_w_stage, 2ll * r.C * r.C * 3);
+      A(r.proj_w_stage, (long long)r.C * r.C);
+      A(r.b_conv, 2 * r.C); A(r.b_proj, r.C);
+      const long long C = r.C;
+      snprintf(nm, sizeof nm, "upsample_blocks.%d.%d.conv.weight", i, j + 1); add_slot(g, nm, 2 * C * C * 3, W_RB_CONV_W, i, j);
+      snprintf(nm, sizeof nm, "upsample_blocks.%d.%d.conv.bias", i, j + 1); add_slot(g, nm, 2 * C, W_RB_CONV_B, i, j);
+      snprintf(nm, sizeof nm, "upsample_blocks.%d.%d.film.weight", i, j + 1); add_slot(g, nm, 2 * C * cd, W_RB_FILM_W, i, j);
+      snprintf(nm, sizeof nm, "upsample_blocks.%d.%d.film.bias", i, j + 1); add_slot(g, nm, 2 * C, W_RB_FILM_B, i, j);
+      snprintf(nm, sizeof nm, "upsample_blocks.%d.%d.proj.weight", i, j + 1); add_slot(g, nm, C * C, W_RB_PROJ_W, i, j);
+      snprintf(nm, sizeof nm, "upsample_blocks.%d.%d.proj.bias", i, j + 1); add_slot(g, nm, C, W_RB_PROJ_B, i, j);
+      sw.res.push_back(r);
+    }
+    if (i == g->att_stage) {
+      // generator.py:43-44: the module (and its state_dict entries) exists whether or not it is evaluated
+      g->att_C = sw.Cout;
+      const long long C = sw.Cout;
+      A(g->att_wqkv, 3 * C * C); A(g->att_wo, C * C); A(g->att_bqkv, 3 * C); A(g->att_bo, C);
+      A(g->att_stage_w, 4 * C * C);
+      const char* nmq[4] = {"q", "k", "v", "out"};
+      for (int q = 0; q < 4; ++q) {
+        snprintf(nm, sizeof nm, "upsample_blocks.%d.%d.%s.weight", i, cfg->n_dilations + 1, nmq[q]); add_slot(g, nm, C * C, W_ATT_W, i, q);
+        snprintf(nm, sizeof nm, "upsample_blocks.%d.%d.%s.bias", i, cfg->n_dilations + 1, nmq[q]); add_slot(g, nm, C, W_ATT_B, i, q);
+      }
+    }
+    g->stages.push_back(sw);
+    c /= 2;
+  }
+  g->film_cols = film_cols;
+  A(g->film_w, (long long)film_cols * cd);
+  A(g->film_b, film_cols);
+  A(g->merge_w, (long long)c * nb * 7);
+  A(g->merge_b, 1);
+  add_slot(g, "band_merge.weight", (long long)c * nb * 7, W_MERGE_W);
+  add_slot(g, "band_merge.bias", 1, W_MERGE_B);
+#undef A
+  if (st != B200VOC_OK) {
+    b200voc_gen_destroy(g);
+    return st;
+  }
+  if (film_cols % 64 != 0) {
+    set_error("film column count %d not a multiple of 64", film_cols);
+    b200voc_gen_destroy(g);
+    return B200VOC_ERR_UNSUPPORTED;
+  }
+  *out = g;
+  return B200VOC_OK;
+}
+
+int b200voc_gen_num_weights(const b200voc_gen* g) { return g ? (int)g->slots.size() : 0; }
+const char* b200voc_gen_weight_name(const b200voc_gen* g, int i) {
+  return (g && i >= 0 && i < (int)g->slots.size()) ? g->slots[i].name.c_str() : nullptr;
+}
+int64_t b200voc_gen_weight_numel(const b200voc_gen* g, int i) {
+  return (g && i >= 0 && i < (int)g->slots.size()) ? g->slots[i].numel : -1;
+}
+
+int b200voc_gen_set_weight(b200voc_gen* g, const char* name, const float* w, int64_t numel, void* stream) {
+  B200_CHECK_ARG(g && name && w, "gen_set_weight: null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  WSlot* sl = nullptr;
+  for (auto& s : g->slots)
+    if (s.name == name) { sl = &s; break; }
+  B200_CHECK_ARG(sl, "gen_set_weight: unexpected key '%s'", name);
+  B200_CHECK_ARG(sl->numel == numel, "gen_set_weight: '%s' has %lld elements, expected %lld", name, (long long)numel,
+                 sl->numel);
+  const int cd = g->cfg.cond_dim, H = g->H, bs = g->band_size;
+  switch (sl->kind) {
+    case W_SPLIT_W: B200_TRY(pack_split_launch(w, bs, H, g->split_wt + (long long)sl->a * bs * 7 * H, st)); break;
+    case W_SPLIT_B: B200_TRY(copy_f32_launch(w, g->split_b + (long long)sl->a * H, H, 0.f, st)); break;
+    case W_CP0_W: B200_TRY(copy_f32_launch(w, g->cp0_w, numel, 0.f, st)); break;
+    case W_CP0_B: B200_TRY(copy_f32_launch(w, g->cp0_b, numel, 0.f, st)); break;
+    case W_CP2_W: B200_TRY(copy_f32_launch(w, g->cp2_w, numel, 0.f, st)); break;
+    case W_CP2_B: B200_TRY(copy_f32_launch(w, g->cp2_b, numel, 0.f, st)); break;
+    case W_STY_W: B200_TRY(copy_f32_launch(w, g->sty_w, numel, 0.f, st)); break;
+    case W_STY_B: B200_TRY(copy_f32_launch(w, g->sty_b, numel, 0.f, st)); break;
+    case W_EMO_W: B200_TRY(copy_f32_launch(w, g->emo_w, numel, 0.f, st)); break;
+    case W_EMO_B: B200_TRY(copy_f32_launch(w, g->emo_b, numel, 0.f, st)); break;
+    case W_UP_W: {
+      StageW& s = g->stages[sl->a];
+      B200_TRY(pack_convt_launch(w, s.Cin, s.Cout, s.s, s.fmt, s.up_w, st));
+    } break;
+    case W_UP_B: B200_TRY(copy_f32_launch(w, g->stages[sl->a].up_b, numel, 0.f, st)); break;
+    case W_RB_CONV_W:
+    case W_RB_PROJ_W: {
+      StageW& s = g->stages[sl->a];
+      ResW& r = s.res[sl->b];
+      if (sl->kind == W_RB_CONV_W) {
+        B200_TRY(copy_f32_launch(w, r.conv_w_stage, numel, 0.f, st));
+        r.have_conv = true;
+      } else {
+        B200_TRY(copy_f32_launch(w, r.proj_w_stage, numel, 0.f, st));
+        r.have_proj = true;
+      }
+      if (r.have_conv && r.have_proj) B200_TRY(pack_resblock_launch(r.conv_w_stage, r.proj_w_stage, r.C, s.fmt, r.w, st));
+    } break;
+    case W_RB_CONV_B: B200_TRY(copy_f32_launch(w, g->stages[sl->a].res[sl->b].b_conv, numel, 0.f, st)); break;
+    case W_RB_PROJ_B: B200_TRY(copy_f32_launch(w, g->stages[sl->a].res[sl->b].b_proj, numel, 0.f, st)); break;
+    case W_RB_FILM_W: {
+      ResW& r = g->stages[sl->a].res[sl->b];
+      B200_TRY(copy_f32_launch(w, g->film_w + (long long)r.film_col * cd, numel, 0.f, st));
+    } break;
+    case W_RB_FILM_B: {
+      ResW& r = g->stages[sl->a].res[sl->b];
+      // first C entries are `scale`: the kernels consume (1 + scale)
+      B200_TRY(copy_f32_launch(w, g->film_b + r.film_col, r.C, 1.0f, st));
+      B200_TRY(copy_f32_launch(w + r.C, g->film_b + r.film_col + r.C, r.C, 0.f, st));
+    } break;
+    case W_ATT_W: {
+      const long long C = g->att_C;
+      const int fmt = g->stages[g->att_stage].fmt;
+      if (sl->b < 3) B200_TRY(cvt16_launch(w, g->att_wqkv + sl->b * C * C, C * C, fmt, st));
+      else B200_TRY(cvt16_launch(w, g->att_wo, C * C, fmt, st));
+    } break;
+    case W_ATT_B: {
+      const long long C = g->att_C;
+      if (sl->b < 3) B200_TRY(copy_f32_launch(w, g->att_bqkv + sl->b * C, C, 0.f, st));
+      else B200_TRY(copy_f32_launch(w, g->att_bo, C, 0.f, st));
+    } break;
+    case W_MERGE_W: B200_TRY(copy_f32_launch(w, g->merge_w, numel, 0.f, st)); break;
+    case W_MERGE_B: B200_TRY(copy_f32_launch(w, g->merge_b, numel, 0.f, st)); break;
+  }
+  sl->set = true;
+  g->finalized = false;
+  return B200VOC_OK;
+}
+
+int b200voc_gen_finalize(b200voc_gen* g) {
+  B200_CHECK_ARG(g, "gen_finalize: null handle");
+  for (auto& s : g->slots)
+    if (!s.set) {
+      set_error("gen_finalize: state_dict key '%s' was never set", s.name.c_str());
+      return B200VOC_ERR_STATE;
+    }
+  g->finalized = true;
+  return B200VOC_OK;
+}
+
+namespace {
+struct WsLayout {
+  long long sty, emo, cond, film, act0, act1, att, total;
+};
+long long align_up(long long x) { return (x + 255) & ~255ll; }
+WsLayout ws_layout(const b200voc_gen* g, int B, int T) {
+  WsLayout w{};
+  const long long cd = g->cfg.cond_dim, N = (long long)B * g->cfg.num_bands;
+  long long off = 0;
+  w.sty = off; off = align_up(off + B * cd * 4);
+  w.emo = off; off = align_up(off + B * cd * 4);
+  w.cond = off; off = align_up(off + (long long)B * T * cd * 4);
+  w.film = off; off = align_up(off + (long long)B * T * g->film_cols * 4);
+  long long max_act = N * T * g->H;
+  long long P = 1, attn_elems = 0;
+  for (size_t i = 0; i < g->stages.size(); ++i) {
+    P *= g->stages[i].s;
+    const long long e = N * T * P * g->stages[i].Cout;
+    if (e > max_act) max_act = e;
+    if ((int)i == g->att_stage && g->cfg.use_attention) attn_elems = attention_scratch_elems((int)N, (int)(T * P), g->stages[i].Cout);
+  }
+  w.act0 = off; off = align_up(off + max_act * 2);
+  w.act1 = off; off = align_up(off + max_act * 2);
+  w.att = off; off = align_up(off + attn_elems * 2);
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+int64_t b200voc_gen_workspace_bytes(const b200voc_gen* g, int B, int T) {
+  if (!g || B <= 0 || T <= 0) return 0;
+  return ws_layout(g, B, T).total;
+}
+
+int b200voc_gen_launch_count(const b200voc_gen* g) { return g ? g->launches : 0; }
+
+int b200voc_gen_forward(b200voc_gen* g, const float* mel, const float* prosody, const float* style,
+                        const float* emotion, int B, int T, int style_drop, int emo_drop, float w_style,
+                        float w_emo, float* wav_out, void* workspace, int64_t workspace_bytes,
+                        const char* tap_name, float* tap_out, void* stream) {
+  B200_CHECK_ARG(g && mel && prosody && style && emotion && wav_out && workspace, "gen_forward: null argument");
+  B200_CHECK_ARG(B > 0 && T > 0, "gen_forward: empty batch (B=%d, T=%d)", B, T);
+  if (!g->finalized) {
+    set_error("gen_forward: weights not finalized (call b200voc_gen_finalize after load_state_dict)");
+    return B200VOC_ERR_STATE;
+  }
+  const WsLayout w = ws_layout(g, B, T);
+  B200_CHECK_ARG(workspace_bytes >= w.total, "gen_forward: workspace %lld < required %lld bytes",
+                 (long long)workspace_bytes, w.total);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "gen_forward: workspace must be 256B aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* sty = reinterpret_cast<float*>(ws + w.sty);
+  float* emo = reinterpret_cast<float*>(ws + w.emo);
+  float* cond = reinterpret_cast<float*>(ws + w.cond);
+  float* film = reinterpret_cast<float*>(ws + w.film);
+  void* act[2] = {ws + w.act0, ws + w.act1};
+  const int nb = g->cfg.num_bands, N = B * nb, cd = g->cfg.cond_dim;
+  const std::string tap = tap_name ? tap_name : "";
+  int launches = 0;
+
+  // conditioning (generator.py:65-73) and all FiLM projections (frame rate, fp32)
+  B200_TRY(style_emo_launch(style, emotion, g->sty_w, g->sty_b, g->emo_w, g->emo_b, B, g->cfg.style_dim, cd, w_style,
+                            w_emo, style_drop, emo_drop, sty, emo, st));
+  B200_TRY(cond_launch(prosody, g->cp0_w, g->cp0_b, g->cp2_w, g->cp2_b, sty, emo, B, T, cond, st));
+  B200_TRY(film_launch(cond, g->film_w, g->film_b, B * T, g->film_cols, film, st));
+  launches += 3;
+  if (tap == "cond" && tap_out) {  // [B, T, cd] -> [B, cd, T] happens on the host side; raw copy here
+    B200_CUDA(cudaMemcpyAsync(tap_out, cond, (size_t)B * T * cd * 4, cudaMemcpyDeviceToDevice, st));
+  }
+
+  // band split (generator.py:76-81): raw 16-bit, channels-last [N, T, H]
+  int cur = 0;
+  B200_TRY(band_split_launch(mel, g->split_wt, g->split_b, B, g->cfg.channels, g->band_size, T, g->H,
+                             g->stages[0].fmt, act[cur], st));
+  ++launches;
+  if (tap == "split" && tap_out) B200_TRY(tap_extract_launch(act[cur], N, T, g->H, g->stages[0].fmt, 0, tap_out, st));
+
+  int L = T;
+  for (size_t i = 0; i < g->stages.size(); ++i) {
+    const StageW& s = g->stages[i];
+    // the producer of this stage's input wrote it in this stage's format
+    B200_TRY(convt1d_launch(act[cur], s.up_w, s.up_b, N, L, s.Cin, s.Cout, s.s, s.fmt, 1, act[cur ^ 1], st));
+    ++launches;
+    cur ^= 1;
+    L *= s.s;
+    char nm[32];
+    snprintf(nm, sizeof nm, "up%d", (int)i);
+    if (tap == nm && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, s.Cout, s.fmt, 1, tap_out, st));
+    const bool att_here = (int)i == g->att_stage && g->cfg.use_attention;
+    for (size_t j = 0; j < s.res.size(); ++j) {
+      const ResW& r = s.res[j];
+      const bool last = j + 1 == s.res.size();
+      // last block of a stage stores raw x (for the next ConvT / attention / band_merge) in the
+      // consumer's format; inner blocks store leaky_relu(x).
+      const int store_lrelu = last ? 0 : 1;
+      B200_TRY(resblock_launch(act[cur], r.w, r.b_conv, r.b_proj, film + r.film_col, g->film_cols, N, L, r.C, r.dilation, T, nb,
+                               s.fmt, store_lrelu, act[cur ^ 1], st));
+      ++launches;
+      cur ^= 1;
+      snprintf(nm, sizeof nm, "res%d.%d", (int)i, (int)j);
+      if (tap == nm && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, r.C, s.fmt, store_lrelu, tap_out, st));
+    }
+    if (att_here) {
+      uint16_t* sc = reinterpret_cast<uint16_t*>(ws + w.att);
+      const long long e = (long long)N * L * s.Cout;
+      B200_TRY(attention_launch(act[cur], g->att_wqkv, g->att_bqkv, g->att_wo, g->att_bo, N, L, s.Cout,
+                                g->cfg.attn_window, s.fmt, sc, sc + e, sc + 2 * e, sc + 3 * e, act[cur ^ 1], st));
+      launches += 3;
+      cur ^= 1;
+      if (tap == "attn" && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, s.Cout, s.fmt, 0, tap_out, st));
+    }
+  }
+  const StageW& last = g->stages.back();
+  B200_TRY(band_merge_launch(act[cur], g->merge_w, g->merge_b, B, nb, L, last.Cout, last.fmt, wav_out, st));
+  ++launches;
+  g->launches = launches;
+  return B200VOC_OK;
+}
+
+int b200voc_gen_destroy(b200voc_gen* g) {
+  if (!g) return B200VOC_OK;
+  for (void* p : g->allocs) cudaFree(p);
+  delete g;
+  return B200VOC_OK;
+}
+
+// ==================================================================== layer-level entry points
+int64_t b200voc_convt_packed_elems(int Cin, int Cout, int s) { return (int64_t)s * Cout * 2 * Cin; }
+int b200voc_pack_convt_weight(const float* w_ref, int Cin, int Cout, int s, int fmt, void* w_packed, void* stream) {
+  B200_CHECK_ARG(w_ref && w_packed, "pack_convt_weight: null argument");
+  return pack_convt_launch(w_ref, Cin, Cout, s, fmt, w_packed, reinterpret_cast<cudaStream_t>(stream));
+}
+int b200voc_convt1d(const void* x16, const void* w_packed, const float* bias, int N, int Lin, int Cin, int Cout,
+                    int s, int fmt, int store_lrelu, void* out16, void* stream) {
+  B200_CHECK_ARG(x16 && w_packed && bias && out16, "convt1d: null argument");
+  return convt1d_launch(x16, w_packed, bias, N, Lin, Cin, Cout, s, fmt, store_lrelu, out16,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+int64_t b200voc_resblock_packed_elems(int C) { return 2ll * C * 3 * C + (int64_t)C * C; }
+int b200voc_pack_resblock_weights(const float* w_conv, const float* w_proj, int C, int fmt, void* w_packed,
+                                  void* stream) {
+  B200_CHECK_ARG(w_conv && w_proj && w_packed, "pack_resblock_weights: null argument");
+  return pack_resblock_launch(w_conv, w_proj, C, fmt, w_packed, reinterpret_cast<cudaStream_t>(stream));
+}
+int b200voc_resblock(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
+                     const float* film, int N, int L, int C, int dilation, int T, int num_bands, int fmt,
+                     int store_lrelu, void* out16, void* stream) {
+  B200_CHECK_ARG(a16 && w_packed && b_conv && b_proj && film && out16, "resblock: null argument");
+  return resblock_launch(a16, w_packed, b_conv, b_proj, film, 2 * C, N, L, C, dilation, T, num_bands, fmt, store_lrelu,
+                         out16, reinterpret_cast<cudaStream_t>(stream));
+}
+int b200voc_exp_rowshift(const void* a16, const void* b16, float* out, void* stream) {
+  B200_CHECK_ARG(a16 && b16 && out, "exp_rowshift: null argument");
+  return exp_rowshift_launch(a16, b16, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

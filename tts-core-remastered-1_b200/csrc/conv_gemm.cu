@@ -1,0 +1,318 @@
+// K1: multi-tap implicit GEMM on tcgen05/TMEM fed by TMA -- the transposed-convolution stages
+// (generator.py:35-38,87) and every plain [rows x Cin] x [Cin x Cout] projection.
+//
+// GEMM view (time on the M axis, channels-last activations x16[N, L, Cin]):
+//   D[m, c] = sum_tap sum_ci  X[n, m + shift_tap, ci] * W[c, tap*Cin + ci]
+// A tiles (128 rows x 64 ch) are TMA loads from a 3-D tensor map (ci, l, n): a tap is the same
+// tile with the l coordinate shifted, rows outside [0, L) are zero-filled by TMA, which is exactly
+// the convolution's zero padding.  B tiles (BN rows x 64) come from the packed weight matrix.
+// Accumulators live in TMEM; the epilogue reads them with tcgen05.ld, adds the bias, optionally
+// applies leaky-ReLU, rounds to the 16-bit storage format and writes channels-last.
+//
+// ConvTranspose1d(Cin, Cout, k=2s, stride=s, pad=s/2) is the polyphase GEMM
+//   y[m*s + r - p, co] = sum_ci x[m, ci] W[ci, co, r] + x[m-1, ci] W[ci, co, r+s],  m in [0, Lin]
+// i.e. 2 taps (shift 0, -1), GEMM column c = r*Cout + co, and because the output is channels-last
+// the GEMM output row m IS the contiguous run out[(m*s - p)*Cout ...] -- the pixel shuffle is free.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+struct GemmTapsParams {
+  int rows_per_seq;   // GEMM rows per sequence (Lin + 1 for ConvT)
+  int n_taps;
+  int tap_shift[4];
+  int k_per_tap;      // Cin (multiple of 64)
+  int n_total;        // GEMM columns (s * Cout)
+  int cout;           // bias period
+  long long out_seq_stride;  // elements between sequences in the output
+  long long out_valid;       // valid output elements per sequence (Lout * Cout)
+  int out_shift;      // p * Cout: GEMM (m, c) -> flat m*n_total + c - out_shift
+  int fmt;            // B200VOC_FMT_*
+  int store_lrelu;
+  const float* bias;
+  void* out;
+};
+
+constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 x 2B
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmTapsParams p) {
+  constexpr int B_TILE = BN * 128;
+  constexpr int STAGE_BYTES = kATileBytes + B_TILE;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN, seq = blockIdx.z;
+  const int kpt = p.k_per_tap >> 6;
+  const int num_k = p.n_taps * kpt;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        const int tap = kb / kpt, kk = kb - tap * kpt;
+        uint8_t* st = smem + s * STAGE_BYTES;
+        tma_load_3d(st, &tmA, &full[s], kk * 64, m0 + p.tap_shift[tap], seq);
+        tma_load_2d(st + kATileBytes, &tmB, &full[s], tap * p.k_per_tap + kk * 64, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(p.fmt, BN);
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t a_desc = make_kmajor_desc<128>(a_addr);
+        const uint64_t b_desc = make_kmajor_desc<128>(a_addr + kATileBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // UMMA_K = 16 elements = 32 bytes = +2 in the >>4 start field
+          umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum_full);
+    }
+  } else {
+    // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const long long m = (long long)m0 + row;
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    uint16_t* out = reinterpret_cast<uint16_t*>(p.out) + (long long)seq * p.out_seq_stride;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      const int col0 = n0 + c * 32;
+      const long long idx = m * p.n_total + col0 - p.out_shift;
+      const bool valid = (m < p.rows_per_seq) && idx >= 0 && idx < p.out_valid;
+      if (valid) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + (col0 % p.cout));
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bb = __ldg(b4 + i);
+          float y0 = __uint_as_float(v[4 * i + 0]) + bb.x, y1 = __uint_as_float(v[4 * i + 1]) + bb.y;
+          float y2 = __uint_as_float(v[4 * i + 2]) + bb.z, y3 = __uint_as_float(v[4 * i + 3]) + bb.w;
+          if (p.store_lrelu) { y0 = lrelu(y0); y1 = lrelu(y1); y2 = lrelu(y2); y3 = lrelu(y3); }
+          w[2 * i] = pack2(y0, y1, p.fmt);
+          w[2 * i + 1] = pack2(y2, y3, p.fmt);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + idx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int STAGES>
+static int launch_gemm_taps(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTapsParams& p, int n_seq,
+                            cudaStream_t stream) {
+  constexpr int SMEM = STAGES * (kATileBytes + BN * 128) + 256 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(gemm_taps_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  dim3 grid(ceil_div(p.rows_per_seq, 128), p.n_total / BN, n_seq);
+  gemm_taps_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(tmA, tmB, p);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
+// ---------------------------------------------------------------------------- ConvT packing
+// reference layout w[Cin][Cout][2s] (fp32) -> packed[(r*Cout + co)][tap*Cin + ci], tap 0 = k=r
+// (pairs with x[m]), tap 1 = k=r+s (pairs with x[m-1]).
+__global__ void pack_convt_kernel(const float* __restrict__ w, int Cin, int Cout, int s, int fmt,
+                                  uint16_t* __restrict__ out) {
+  const long long total = (long long)s * Cout * 2 * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kcol = (int)(i % (2 * Cin));
+    const int nrow = (int)(i / (2 * Cin));
+    const int tap = kcol / Cin, ci = kcol % Cin;
+    const int r = nrow / Cout, co = nrow % Cout;
+    const float v = w[((long long)ci * Cout + co) * (2 * s) + r + tap * s];
+    out[i] = fmt == 0 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  }
+}
+
+int convt1d_launch(const void* x16, const void* w_packed, const float* bias, int N, int Lin, int Cin, int Cout, int s,
+                   int fmt, int store_lrelu, void* out16, cudaStream_t stream) {
+  B200_CHECK_ARG(Cin % 64 == 0 && Cin >= 64, "convt1d: Cin=%d must be a multiple of 64", Cin);
+  B200_CHECK_ARG(Cout % 32 == 0, "convt1d: Cout=%d must be a multiple of 32", Cout);
+  B200_CHECK_ARG(s >= 2 && s % 2 == 0, "convt1d: stride %d must be even", s);
+  B200_CHECK_ARG(N > 0 && Lin > 0, "convt1d: empty input");
+  const int n_total = s * Cout;
+  CUtensorMap tmA, tmB;
+  B200_TRY(make_tmap_3d(&tmA, x16, Cin, Lin, N, (uint64_t)Cin * 2, (uint64_t)Lin * Cin * 2, 64, 128, 128));
+  GemmTapsParams p{};
+  p.rows_per_seq = Lin + 1;
+  p.n_taps = 2;
+  p.tap_shift[0] = 0;
+  p.tap_shift[1] = -1;
+  p.k_per_tap = Cin;
+  p.n_total = n_total;
+  p.cout = Cout;
+  p.out_seq_stride = (long long)s * Lin * Cout;
+  p.out_valid = (long long)s * Lin * Cout;
+  p.out_shift = (s / 2) * Cout;
+  p.fmt = fmt;
+  p.store_lrelu = store_lrelu;
+  p.bias = bias;
+  p.out = out16;
+  if (n_total % 256 == 0) {
+    B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 256, 128));
+    return launch_gemm_taps<256, 4>(tmA, tmB, p, N, stream);
+  } else if (n_total % 128 == 0) {
+    B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 128, 128));
+    return launch_gemm_taps<128, 4>(tmA, tmB, p, N, stream);
+  } else if (n_total % 64 == 0) {
+    B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 64, 128));
+    return launch_gemm_taps<64, 4>(tmA, tmB, p, N, stream);
+  }
+  set_error("convt1d: s*Cout=%d must be a multiple of 64", n_total);
+  return B200VOC_ERR_UNSUPPORTED;
+}
+
+// Plain projection y[n, l, :] = W x[n, l, :] + b on channels-last 16-bit (1x1 conv).
+int linear_launch(const void* x16, const void* w_packed /*[Cout][Cin]*/, const float* bias, int N, int L, int Cin,
+                  int Cout, int fmt, int store_lrelu, void* out16, cudaStream_t stream) {
+  B200_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0, "linear: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);
+  CUtensorMap tmA, tmB;
+  B200_TRY(make_tmap_3d(&tmA, x16, Cin, L, N, (uint64_t)Cin * 2, (uint64_t)L * Cin * 2, 64, 128, 128));
+  GemmTapsParams p{};
+  p.rows_per_seq = L;
+  p.n_taps = 1;
+  p.k_per_tap = Cin;
+  p.n_total = Cout;
+  p.cout = Cout;
+  p.out_seq_stride = (long long)L * Cout;
+  p.out_valid = (long long)L * Cout;
+  p.fmt = fmt;
+  p.store_lrelu = store_lrelu;
+  p.bias = bias;
+  p.out = out16;
+  if (Cout % 256 == 0) {
+    B200_TRY(make_tmap_2d(&tmB, w_packed, Cin, Cout, (uint64_t)Cin * 2, 64, 256, 128));
+    return launch_gemm_taps<256, 4>(tmA, tmB, p, N, stream);
+  } else if (Cout % 128 == 0) {
+    B200_TRY(make_tmap_2d(&tmB, w_packed, Cin, Cout, (uint64_t)Cin * 2, 64, 128, 128));
+    return launch_gemm_taps<128, 4>(tmA, tmB, p, N, stream);
+  }
+  B200_TRY(make_tmap_2d(&tmB, w_packed, Cin, Cout, (uint64_t)Cin * 2, 64, 64, 128));
+  return launch_gemm_taps<64, 4>(tmA, tmB, p, N, stream);
+}
+
+// ---------------------------------------------------------------------------- experiment
+// Can a K-major SWIZZLE_128B descriptor start at an arbitrary 128-byte row of a TMA-written tile?
+// variant 0: base_offset field = 0; variant 1: base_offset = (start >> 7) & 7.
+__global__ void __launch_bounds__(128, 1)
+exp_rowshift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                 // 144 rows x 128 B = 18432
+  uint8_t* sB = smem + 19 * 1024;     // 64 rows x 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 28 * 1024);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bars[0], 144 * 128 + 64 * 128);
+    tma_load_2d(sA, &tmA, &bars[0], 0, 0);
+    tma_load_2d(sB, &tmB, &bars[0], 0, 0);
+  }
+  mbar_wait(&bars[0], 0);
+  const uint32_t idesc = make_idesc_f16(0, 64);
+  uint32_t parity = 0;
+  for (int variant = 0; variant < 2; ++variant) {
+    for (int shift = 0; shift < 16; ++shift) {
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA) + shift * 128;
+        const uint64_t a_desc = make_kmajor_desc<128>(a_addr, variant ? ((a_addr >> 7) & 7) : 0);
+        const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sB));
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, k != 0);
+        umma_commit(&bars[1]);
+      }
+      mbar_wait(&bars[1], parity);
+      parity ^= 1;
+      tc_fence_after();
+      float* o = out + ((long long)(variant * 16 + shift) * 128 + warp * 32 + lane) * 64;
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+      __syncthreads();
+    }
+  }
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+int exp_rowshift_launch(const void* a16, const void* b16, float* out, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  B200_TRY(make_tmap_2d(&tmA, a16, 64, 144, 128, 64, 144, 128));
+  B200_TRY(make_tmap_2d(&tmB, b16, 64, 64, 128, 64, 64, 128));
+  const int SMEM = 30 * 1024;
+  exp_rowshift_kernel<<<1, 128, SMEM, stream>>>(tmA, tmB, out);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
+int pack_convt_launch(const float* w, int Cin, int Cout, int s, int fmt, void* out, cudaStream_t stream) {
+  const long long total = (long long)s * Cout * 2 * Cin;
+  pack_convt_kernel<<<(int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256), 256, 0, stream>>>(
+      w, Cin, Cout, s, fmt, reinterpret_cast<uint16_t*>(out));
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
+}  // namespace b200
