@@ -1,0 +1,312 @@
+"""bench.py -- vocoder7 Generator synthesis throughput (audio-seconds per second) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one Generator.forward over one batch of synthetic mels (BASELINE.json configs[1]:
+batch 16 x 10 s, T = 861 frames, default GANConfig, hidden_dim 512, random-init weights).
+For N > 1 the driver launches one rank per GPU with torch.distributed.run; every rank synthesises
+its own 16 x 10 s shard (independent utterances, no data-path collective -> "weak" scaling), time
+is the max over ranks, value is the whole-job audio-s/s.
+
+`--impl reference` times the reference path (the CPU oracle port of vocoder7/generator.py, see
+oracle/vocoder7_oracle.py) on the host cores with all threads, on a bounded sample of the same
+workload.  It is the only place besides cpu_baseline where oracle/ is executed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tts-core-remastered-1_b200"))
+
+METRIC = "vocoder7_audio_seconds_per_second"
+UNIT = "audio-s/s"
+B_PER_GPU, T_FRAMES, SR, HOP = 16, 861, 22050, 256
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt, self.proc = index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+                if self._stop_evt.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = max(smax, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_throughput(sample_B: int, sample_T: int, reps: int, threads: int):
+    """Reference path on the host cores: the oracle port of Generator.forward, fp32, all threads."""
+    import torch
+    from oracle import vocoder7_oracle as O
+    torch.set_num_threads(threads)
+    cfg = O.OracleConfig(use_attention=False)
+    gen = O.make_generator(cfg, seed=1234)
+    sd = gen.state_dict()
+    mel, pros, sty, emo = O.synthetic_inputs(sample_B, sample_T, seed=4321)
+    with torch.no_grad():
+        O.generator_forward(sd, cfg, mel, pros, sty, emo)          # warm-up
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.generator_forward(sd, cfg, mel, pros, sty, emo)
+            times.append(time.perf_counter() - t0)
+    audio_s = sample_B * HOP * sample_T / SR
+    return audio_s / min(times), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample of the configs[1] workload: 1 utterance x 10 s (T=861) per step
+    per_step = []
+    import torch
+    from oracle import vocoder7_oracle as O
+    torch.set_num_threads(cores)
+    cfg = O.OracleConfig(use_attention=False)
+    sd = O.make_generator(cfg, seed=1234).state_dict()
+    mel, pros, sty, emo = O.synthetic_inputs(1, T_FRAMES, seed=4321)
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    with torch.no_grad():
+        for _ in range(warm):
+            O.generator_forward(sd, cfg, mel, pros, sty, emo)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.generator_forward(sd, cfg, mel, pros, sty, emo)
+        dt = time.perf_counter() - t0
+    audio_s = 1 * HOP * T_FRAMES / SR
+    value = audio_s * steps / dt
+    sample = f"{steps} steps x (1 utterance x T={T_FRAMES}) of the B=16 workload, fp32, torch CPU, attention off"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, note="reference arm: CPU oracle port of vocoder7/generator.py"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, note=None):
+    c = {
+        "workload": f"vocoder7 Generator forward, default GANConfig + hidden_dim=512, B={B_PER_GPU} x T={T_FRAMES} "
+                    f"(10 s) per GPU, random-init weights (seed 1234), synthetic randn mels",
+        "batch_per_gpu": B_PER_GPU, "frames": T_FRAMES, "audio_seconds_per_step_per_gpu": B_PER_GPU * HOP * T_FRAMES / SR,
+        "precision_plan": "fp16 operands (tcgen05 kind::f16, same rate as bf16), fp32 accumulate",
+        "attention": "off (SelfAttention K6 kernel not built; reference class is undefined, see DESIGN.md D3)",
+        "l2": "per-layer activations (0.9 GB) exceed the 126 MB L2; no explicit flush",
+        "parallelism": f"dp{n_gpus} (independent utterance shards, no collective)",
+    }
+    if note:
+        c["note"] = note
+    return c
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from b200voc import GANConfig, Generator, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = GANConfig(use_attention=False)
+    torch.manual_seed(1234)
+    gen = Generator(cfg).eval().to(dev)
+    g = torch.Generator().manual_seed(4321 + rank)
+    B, T = B_PER_GPU, T_FRAMES
+    host = [torch.randn(B, 80, T, generator=g).pin_memory(), torch.randn(B, T, 18, generator=g).pin_memory(),
+            torch.randn(B, 128, generator=g).pin_memory(),
+            torch.softmax(torch.randn(B, 6, generator=g), -1).pin_memory()]
+    dev_in = [h.to(dev) for h in host]
+    out = torch.empty(B, 1, HOP * T, device=dev)
+    host_out = torch.empty(B, 1, HOP * T).pin_memory()
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            gen(*dev_in, out=out)
+        barrier()
+        # ---------------- kernel-resident timing (inputs already in HBM) ----------------
+        lib.b200voc_gen_profile_enable(gen._handle, 1)
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.3)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        per_layer = {}
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            gen(*dev_in, out=out)
+        ev1.record()
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        # per-launch events of the last timed step
+        n = lib.b200voc_gen_profile_count(gen._handle)
+        for i in range(n):
+            nm = lib.b200voc_gen_profile_name(gen._handle, i).decode()
+            per_layer[nm] = dict(ms=float(lib.b200voc_gen_profile_ms(gen._handle, i)),
+                                 flops=float(lib.b200voc_gen_profile_flops(gen._handle, i)),
+                                 bytes=float(lib.b200voc_gen_profile_bytes(gen._handle, i)))
+        lib.b200voc_gen_profile_enable(gen._handle, 0)
+        # ---------------- end-to-end: pinned host -> device -> forward -> host ----------------
+        for _ in range(2):
+            d = [h.to(dev, non_blocking=True) for h in host]
+            host_out.copy_(gen(*d, out=out), non_blocking=True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            d = [h.to(dev, non_blocking=True) for h in host]
+            host_out.copy_(gen(*d, out=out), non_blocking=True)
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        sampler.stop()
+
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    audio_s_step = world * B * HOP * T / SR
+    value = audio_s_step * args.steps / (ms_total / 1e3)
+    e2e_value = audio_s_step * args.steps / (ms_e2e / 1e3)
+    peaks = measured_peaks()
+    # dominant kernel: the fused residual-block kernel at C=128 (stage 1), 3 launches per step
+    dom = [v for k, v in per_layer.items() if k.startswith("res1.")]
+    dom_ms = sum(v["ms"] for v in dom) / max(len(dom), 1)
+    dom_flops = dom[0]["flops"] if dom else 0.0
+    achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    total_flops = sum(v["flops"] for v in per_layer.values())
+    conv_ms = sum(v["ms"] for v in per_layer.values())
+    traffic_path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    traffic = None
+    if os.path.exists(traffic_path):
+        try:
+            traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    cores = os.cpu_count() or 1
+    cpu_val, cpu_times = cpu_oracle_throughput(1, T_FRAMES, reps=3, threads=cores)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": workload_config(world),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "kernel": "resblock_kernel<128> (stage-1 fused residual block, 3 launches/step)",
+                     "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
+                     "flops_per_launch": dom_flops, "ms_per_launch": dom_ms},
+        "whole_step": {"algorithmic_tflop": total_flops / 1e12, "sum_kernel_ms": conv_ms,
+                       "tflops_over_step": total_flops / (ms_total / args.steps * 1e-3) / 1e12 * 1.0,
+                       "frac_of_tensor_peak": total_flops / (ms_total / args.steps * 1e-3) / 1e12 / peak},
+        "layers": {k: {"ms": round(v["ms"], 4),
+                       "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["ms"] > 0 else None,
+                       "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None}
+                   for k, v in per_layer.items()},
+        "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"best of 3 forwards of 1 utterance x T={T_FRAMES} (10 s) of the same workload, "
+                                   f"fp32 torch CPU oracle, attention off; {['%.2f' % t for t in cpu_times]} s"},
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host)),
+                "d2h_bytes_per_step": int(host_out.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": gen.launch_count() * args.steps,
+        "clocks": sampler.summary(),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

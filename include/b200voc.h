@@ -93,6 +93,15 @@ int b200voc_gen_forward(b200voc_gen* g, const float* mel, const float* prosody, 
                         const float* emotion, int B, int T, int style_drop, int emo_drop, float w_style,
                         float w_emo, float* wav_out, void* workspace, int64_t workspace_bytes,
                         const char* tap_name, float* tap_out, void* stream);
+/* Per-launch CUDA-event timing of the LAST forward (bench.py's roofline numbers).  Enable, run a
+ * forward, synchronise the stream, then read entry i: layer name (oracle tap names), elapsed ms,
+ * algorithmic FLOPs and algorithmic HBM bytes (DESIGN.md states the per-unit figures). */
+int b200voc_gen_profile_enable(b200voc_gen* g, int enable);
+int b200voc_gen_profile_count(const b200voc_gen* g);
+const char* b200voc_gen_profile_name(const b200voc_gen* g, int i);
+float b200voc_gen_profile_ms(const b200voc_gen* g, int i);
+double b200voc_gen_profile_flops(const b200voc_gen* g, int i);
+double b200voc_gen_profile_bytes(const b200voc_gen* g, int i);
 /* how many kernels one forward(B,T) launches (bench.py's gpu_launches). */
 int b200voc_gen_launch_count(const b200voc_gen* g);
 int b200voc_gen_destroy(b200voc_gen* g);

@@ -39,6 +39,12 @@ _SIGNATURES = {
     "b200voc_gen_workspace_bytes": (_I64, [_P, _I, _I]),
     "b200voc_gen_forward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _I64, C.c_char_p, _P, _P]),
     "b200voc_gen_launch_count": (C.c_int, [_P]),
+    "b200voc_gen_profile_enable": (C.c_int, [_P, _I]),
+    "b200voc_gen_profile_count": (C.c_int, [_P]),
+    "b200voc_gen_profile_name": (C.c_char_p, [_P, _I]),
+    "b200voc_gen_profile_ms": (C.c_float, [_P, _I]),
+    "b200voc_gen_profile_flops": (C.c_double, [_P, _I]),
+    "b200voc_gen_profile_bytes": (C.c_double, [_P, _I]),
     "b200voc_gen_destroy": (C.c_int, [_P]),
     "b200voc_convt_packed_elems": (_I64, [_I, _I, _I]),
     "b200voc_pack_convt_weight": (C.c_int, [_P, _I, _I, _I, _I, _P, _P]),

@@ -158,6 +158,11 @@ struct b200voc_gen {
   bool finalized;
   int launches;
   std::vector<void*> allocs;
+  // optional per-launch CUDA-event timing of the last forward
+  bool profile;
+  std::vector<cudaEvent_t> ev;
+  struct ProfEntry { std::string name; double flops; double bytes; };
+  std::vector<ProfEntry> prof;
 };
 
 namespace {
@@ -235,6 +240,7 @@ int b200voc_gen_create(const b200voc_gen_config* cfg, b200voc_gen** out) {
   g->finalized = false;
   g->att_stage = cfg->n_stages / 2;
   g->launches = 0;
+  g->profile = false;
   const int nb = cfg->num_bands, bs = g->band_size, cd = cfg->cond_dim;
   int st = B200VOC_OK;
 #define A(ptr, n) if (st == B200VOC_OK) st = dev_alloc(g, &(ptr), (n))
@@ -466,69 +472,129 @@ int b200voc_gen_forward(b200voc_gen* g, const float* mel, const float* prosody, 
   const int nb = g->cfg.num_bands, N = B * nb, cd = g->cfg.cond_dim;
   const std::string tap = tap_name ? tap_name : "";
   int launches = 0;
+  // every launch goes through `run` so that the optional event timing brackets exactly one kernel
+  g->prof.clear();
+  int status = B200VOC_OK;
+  auto run = [&](const char* name, double flops, double bytes, int rc) {
+    (void)name; (void)flops; (void)bytes;
+    if (status == B200VOC_OK) status = rc;
+  };
+  auto pre = [&](const char* name, double flops, double bytes) {
+    if (!g->profile) return;
+    const size_t i = g->prof.size();
+    while (g->ev.size() < 2 * (i + 1)) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      g->ev.push_back(e);
+    }
+    g->prof.push_back({name, flops, bytes});
+    cudaEventRecord(g->ev[2 * i], st);
+  };
+  auto post = [&]() {
+    if (!g->profile) return;
+    cudaEventRecord(g->ev[2 * (g->prof.size() - 1) + 1], st);
+  };
+#define RUN(name, flops, bytes, call)      \
+  do {                                     \
+    pre(name, flops, bytes);               \
+    run(name, flops, bytes, (call));       \
+    post();                                \
+    if (status != B200VOC_OK) return status; \
+    ++launches;                            \
+  } while (0)
 
+  const double dBT = (double)B * T;
   // conditioning (generator.py:65-73) and all FiLM projections (frame rate, fp32)
-  B200_TRY(style_emo_launch(style, emotion, g->sty_w, g->sty_b, g->emo_w, g->emo_b, B, g->cfg.style_dim, cd, w_style,
-                            w_emo, style_drop, emo_drop, sty, emo, st));
-  B200_TRY(cond_launch(prosody, g->cp0_w, g->cp0_b, g->cp2_w, g->cp2_b, sty, emo, B, T, cond, st));
-  B200_TRY(film_launch(cond, g->film_w, g->film_b, B * T, g->film_cols, film, st));
-  launches += 3;
-  if (tap == "cond" && tap_out) {  // [B, T, cd] -> [B, cd, T] happens on the host side; raw copy here
+  RUN("style_emo", 2.0 * B * cd * (g->cfg.style_dim + 6), 0,
+      style_emo_launch(style, emotion, g->sty_w, g->sty_b, g->emo_w, g->emo_b, B, g->cfg.style_dim, cd, w_style, w_emo,
+                       style_drop, emo_drop, sty, emo, st));
+  RUN("cond_mlp", 2.0 * dBT * (18 * (cd / 2) + (cd / 2) * cd), dBT * (18 + cd) * 4,
+      cond_launch(prosody, g->cp0_w, g->cp0_b, g->cp2_w, g->cp2_b, sty, emo, B, T, cond, st));
+  RUN("film", 2.0 * dBT * cd * g->film_cols, dBT * (cd + g->film_cols) * 4,
+      film_launch(cond, g->film_w, g->film_b, B * T, g->film_cols, film, st));
+  if (tap == "cond" && tap_out) {  // raw [B, T, cd]; the host transposes
     B200_CUDA(cudaMemcpyAsync(tap_out, cond, (size_t)B * T * cd * 4, cudaMemcpyDeviceToDevice, st));
   }
 
   // band split (generator.py:76-81): raw 16-bit, channels-last [N, T, H]
   int cur = 0;
-  B200_TRY(band_split_launch(mel, g->split_wt, g->split_b, B, g->cfg.channels, g->band_size, T, g->H,
-                             g->stages[0].fmt, act[cur], st));
-  ++launches;
+  RUN("band_split", 2.0 * dBT * nb * g->band_size * 7 * g->H, dBT * (g->cfg.channels * 4 + nb * g->H * 2.0),
+      band_split_launch(mel, g->split_wt, g->split_b, B, g->cfg.channels, g->band_size, T, g->H, g->stages[0].fmt,
+                        act[cur], st));
   if (tap == "split" && tap_out) B200_TRY(tap_extract_launch(act[cur], N, T, g->H, g->stages[0].fmt, 0, tap_out, st));
 
   int L = T;
   for (size_t i = 0; i < g->stages.size(); ++i) {
     const StageW& s = g->stages[i];
-    // the producer of this stage's input wrote it in this stage's format
-    B200_TRY(convt1d_launch(act[cur], s.up_w, s.up_b, N, L, s.Cin, s.Cout, s.s, s.fmt, 1, act[cur ^ 1], st));
-    ++launches;
-    cur ^= 1;
-    L *= s.s;
     char nm[32];
     snprintf(nm, sizeof nm, "up%d", (int)i);
+    // ConvT: 2 taps per output sample (generator.py:35-38,87); stores leaky_relu(y) for the res blocks
+    RUN(nm, 2.0 * N * (double)L * s.s * 2.0 * s.Cin * s.Cout, (double)N * L * (s.Cin + (double)s.s * s.Cout) * 2,
+        convt1d_launch(act[cur], s.up_w, s.up_b, N, L, s.Cin, s.Cout, s.s, s.fmt, 1, act[cur ^ 1], st));
+    cur ^= 1;
+    L *= s.s;
     if (tap == nm && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, s.Cout, s.fmt, 1, tap_out, st));
     const bool att_here = (int)i == g->att_stage && g->cfg.use_attention;
     for (size_t j = 0; j < s.res.size(); ++j) {
       const ResW& r = s.res[j];
       const bool last = j + 1 == s.res.size();
-      // last block of a stage stores raw x (for the next ConvT / attention / band_merge) in the
-      // consumer's format; inner blocks store leaky_relu(x).
+      // last block of a stage stores raw x (for the next ConvT / attention / band_merge);
+      // inner blocks store leaky_relu(x).
       const int store_lrelu = last ? 0 : 1;
-      B200_TRY(resblock_launch(act[cur], r.w, r.b_conv, r.b_proj, film + r.film_col, g->film_cols, N, L, r.C, r.dilation, T, nb,
-                               s.fmt, store_lrelu, act[cur ^ 1], st));
-      ++launches;
-      cur ^= 1;
       snprintf(nm, sizeof nm, "res%d.%d", (int)i, (int)j);
+      RUN(nm, 2.0 * N * (double)L * (6.0 * r.C * r.C + (double)r.C * r.C), (double)N * L * r.C * 2 * 2.0,
+          resblock_launch(act[cur], r.w, r.b_conv, r.b_proj, film + r.film_col, g->film_cols, N, L, r.C, r.dilation, T,
+                          nb, s.fmt, store_lrelu, act[cur ^ 1], st));
+      cur ^= 1;
       if (tap == nm && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, r.C, s.fmt, store_lrelu, tap_out, st));
     }
     if (att_here) {
       uint16_t* sc = reinterpret_cast<uint16_t*>(ws + w.att);
       const long long e = (long long)N * L * s.Cout;
-      B200_TRY(attention_launch(act[cur], g->att_wqkv, g->att_bqkv, g->att_wo, g->att_bo, N, L, s.Cout,
-                                g->cfg.attn_window, s.fmt, sc, sc + e, sc + 2 * e, sc + 3 * e, act[cur ^ 1], st));
-      launches += 3;
+      const double Lw = g->cfg.attn_window > 0 && g->cfg.attn_window < L ? g->cfg.attn_window : L;
+      RUN("attn", 2.0 * N * ((double)L * Lw * 2.0 * s.Cout + 4.0 * s.Cout * s.Cout * L), (double)e * 2 * 6,
+          attention_launch(act[cur], g->att_wqkv, g->att_bqkv, g->att_wo, g->att_bo, N, L, s.Cout, g->cfg.attn_window,
+                           s.fmt, sc, sc + e, sc + 2 * e, sc + 3 * e, act[cur ^ 1], st));
+      launches += 2;
       cur ^= 1;
       if (tap == "attn" && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, s.Cout, s.fmt, 0, tap_out, st));
     }
   }
   const StageW& last = g->stages.back();
-  B200_TRY(band_merge_launch(act[cur], g->merge_w, g->merge_b, B, nb, L, last.Cout, last.fmt, wav_out, st));
-  ++launches;
+  RUN("band_merge", 2.0 * B * (double)L * nb * last.Cout * 7, (double)N * L * last.Cout * 2 + (double)B * L * 4,
+      band_merge_launch(act[cur], g->merge_w, g->merge_b, B, nb, L, last.Cout, last.fmt, wav_out, st));
+#undef RUN
   g->launches = launches;
   return B200VOC_OK;
+}
+
+int b200voc_gen_profile_enable(b200voc_gen* g, int enable) {
+  B200_CHECK_ARG(g, "profile_enable: null handle");
+  g->profile = enable != 0;
+  return B200VOC_OK;
+}
+int b200voc_gen_profile_count(const b200voc_gen* g) { return g ? (int)g->prof.size() : 0; }
+const char* b200voc_gen_profile_name(const b200voc_gen* g, int i) {
+  return (g && i >= 0 && i < (int)g->prof.size()) ? g->prof[i].name.c_str() : nullptr;
+}
+double b200voc_gen_profile_flops(const b200voc_gen* g, int i) {
+  return (g && i >= 0 && i < (int)g->prof.size()) ? g->prof[i].flops : 0.0;
+}
+double b200voc_gen_profile_bytes(const b200voc_gen* g, int i) {
+  return (g && i >= 0 && i < (int)g->prof.size()) ? g->prof[i].bytes : 0.0;
+}
+/* elapsed ms of launch i of the last profiled forward (the stream must have been synchronised). */
+float b200voc_gen_profile_ms(const b200voc_gen* g, int i) {
+  if (!g || i < 0 || i >= (int)g->prof.size()) return -1.f;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, g->ev[2 * i], g->ev[2 * i + 1]) != cudaSuccess) return -1.f;
+  return ms;
 }
 
 int b200voc_gen_destroy(b200voc_gen* g) {
   if (!g) return B200VOC_OK;
   for (void* p : g->allocs) cudaFree(p);
+  for (cudaEvent_t e : g->ev) cudaEventDestroy(e);
   delete g;
   return B200VOC_OK;
 }
