@@ -81,8 +81,8 @@ int pack_convt_launch(const float*, int, int, int, int, void*, cudaStream_t);
 int exp_rowshift_launch(const void*, const void*, float*, cudaStream_t);
 int pack_resblock_launch(const float*, const float*, int, int, void*, cudaStream_t);
 int resblock_launch(const void* a16, const void* w, const float* b_conv, const float* b_proj, const float* film,
-                    int film_stride, int N, int L, int C, int dilation, int T, int num_bands, int fmt, int store_lrelu,
-                    void* out16, cudaStream_t st);
+                    int film_stride, int N, int L, int C, int dilation, int T, int num_bands, int fmt, int out_fmt,
+                    int store_lrelu, void* out16, cudaStream_t st);
 int style_emo_launch(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int,
                      float, float, int, int, float*, float*, cudaStream_t);
 int cond_launch(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int,
@@ -541,12 +541,13 @@ int b200voc_gen_forward(b200voc_gen* g, const float* mel, const float* prosody, 
       // last block of a stage stores raw x (for the next ConvT / attention / band_merge);
       // inner blocks store leaky_relu(x).
       const int store_lrelu = last ? 0 : 1;
+      const int out_fmt = (last && i + 1 < g->stages.size()) ? g->stages[i + 1].fmt : s.fmt;
       snprintf(nm, sizeof nm, "res%d.%d", (int)i, (int)j);
       RUN(nm, 2.0 * N * (double)L * (6.0 * r.C * r.C + (double)r.C * r.C), (double)N * L * r.C * 2 * 2.0,
           resblock_launch(act[cur], r.w, r.b_conv, r.b_proj, film + r.film_col, g->film_cols, N, L, r.C, r.dilation, T,
-                          nb, s.fmt, store_lrelu, act[cur ^ 1], st));
+                          nb, s.fmt, out_fmt, store_lrelu, act[cur ^ 1], st));
       cur ^= 1;
-      if (tap == nm && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, r.C, s.fmt, store_lrelu, tap_out, st));
+      if (tap == nm && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, r.C, out_fmt, store_lrelu, tap_out, st));
     }
     if (att_here) {
       uint16_t* sc = reinterpret_cast<uint16_t*>(ws + w.att);
@@ -621,7 +622,7 @@ int b200voc_resblock(const void* a16, const void* w_packed, const float* b_conv,
                      const float* film, int N, int L, int C, int dilation, int T, int num_bands, int fmt,
                      int store_lrelu, void* out16, void* stream) {
   B200_CHECK_ARG(a16 && w_packed && b_conv && b_proj && film && out16, "resblock: null argument");
-  return resblock_launch(a16, w_packed, b_conv, b_proj, film, 2 * C, N, L, C, dilation, T, num_bands, fmt, store_lrelu,
+  return resblock_launch(a16, w_packed, b_conv, b_proj, film, 2 * C, N, L, C, dilation, T, num_bands, fmt, fmt, store_lrelu,
                          out16, reinterpret_cast<cudaStream_t>(stream));
 }
 int b200voc_exp_rowshift(const void* a16, const void* b16, float* out, void* stream) {

@@ -145,10 +145,12 @@ template <int BN, int STAGES>
 static int launch_gemm_taps(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTapsParams& p, int n_seq,
                             cudaStream_t stream) {
   constexpr int SMEM = STAGES * (kATileBytes + BN * 128) + 256 + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[16] = {};
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 15]) {
     B200_CUDA(cudaFuncSetAttribute(gemm_taps_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
+    configured[dev & 15] = true;
   }
   dim3 grid(ceil_div(p.rows_per_seq, 128), p.n_total / BN, n_seq);
   gemm_taps_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(tmA, tmB, p);
@@ -199,13 +201,13 @@ int convt1d_launch(const void* x16, const void* w_packed, const float* bias, int
   p.out = out16;
   if (n_total % 256 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 256, 128));
-    return launch_gemm_taps<256, 4>(tmA, tmB, p, N, stream);
+    return launch_gemm_taps<256, 2>(tmA, tmB, p, N, stream);
   } else if (n_total % 128 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 128, 128));
-    return launch_gemm_taps<128, 4>(tmA, tmB, p, N, stream);
+    return launch_gemm_taps<128, 3>(tmA, tmB, p, N, stream);
   } else if (n_total % 64 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 64, 128));
-    return launch_gemm_taps<64, 4>(tmA, tmB, p, N, stream);
+    return launch_gemm_taps<64, 2>(tmA, tmB, p, N, stream);
   }
   set_error("convt1d: s*Cout=%d must be a multiple of 64", n_total);
   return B200VOC_ERR_UNSUPPORTED;
@@ -231,13 +233,13 @@ int linear_launch(const void* x16, const void* w_packed /*[Cout][Cin]*/, const f
   p.out = out16;
   if (Cout % 256 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, Cin, Cout, (uint64_t)Cin * 2, 64, 256, 128));
-    return launch_gemm_taps<256, 4>(tmA, tmB, p, N, stream);
+    return launch_gemm_taps<256, 2>(tmA, tmB, p, N, stream);
   } else if (Cout % 128 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, Cin, Cout, (uint64_t)Cin * 2, 64, 128, 128));
-    return launch_gemm_taps<128, 4>(tmA, tmB, p, N, stream);
+    return launch_gemm_taps<128, 3>(tmA, tmB, p, N, stream);
   }
   B200_TRY(make_tmap_2d(&tmB, w_packed, Cin, Cout, (uint64_t)Cin * 2, 64, 64, 128));
-  return launch_gemm_taps<64, 4>(tmA, tmB, p, N, stream);
+  return launch_gemm_taps<64, 2>(tmA, tmB, p, N, stream);
 }
 
 // ---------------------------------------------------------------------------- experiment

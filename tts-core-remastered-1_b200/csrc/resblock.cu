@@ -23,6 +23,7 @@ struct ResblockParams {
   int P;            // L / T
   int num_bands;
   int fmt;
+  int out_fmt;      // storage format of the output (the consumer's operand format)
   int store_lrelu;
   const uint16_t* a16;   // [N, L, C] leaky_relu(x), 16-bit
   const float* b_conv;   // [2C] reference order (value half | gate half)
@@ -253,7 +254,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             float y0 = lrelu_inv(xs.x) + __uint_as_float(vd[i8 * 8 + e2 * 2]) + bv[e2 * 2];
             float y1 = lrelu_inv(xs.y) + __uint_as_float(vd[i8 * 8 + e2 * 2 + 1]) + bv[e2 * 2 + 1];
             if (p.store_lrelu) { y0 = lrelu(y0); y1 = lrelu(y1); }
-            ow[e2] = pack2(y0, y1, fmt);
+            ow[e2] = pack2(y0, y1, p.out_fmt);
           }
           dst[cc * 4 + i8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
@@ -299,7 +300,7 @@ int pack_resblock_launch(const float* w_conv, const float* w_proj, int C, int fm
 template <int C>
 static int launch_resblock(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
                            const float* film, int film_stride, int N, int L, int dilation, int T, int num_bands,
-                           int fmt, int store_lrelu, void* out16, cudaStream_t stream) {
+                           int fmt, int out_fmt, int store_lrelu, void* out16, cudaStream_t stream) {
   using K = RbCfg<C>;
   CUtensorMap tmX, tmW1, tmW2;
   B200_TRY(make_tmap_3d(&tmX, a16, C, L, N, (uint64_t)C * 2, (uint64_t)L * C * 2, K::KB, 128, K::ROWB));
@@ -314,6 +315,7 @@ static int launch_resblock(const void* a16, const void* w_packed, const float* b
   p.P = L / T;
   p.num_bands = num_bands;
   p.fmt = fmt;
+  p.out_fmt = out_fmt;
   p.store_lrelu = store_lrelu;
   p.a16 = reinterpret_cast<const uint16_t*>(a16);
   p.b_conv = b_conv;
@@ -334,17 +336,27 @@ static int launch_resblock(const void* a16, const void* w_packed, const float* b
   return B200VOC_OK;
 }
 
+int resblock2_launch(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
+                     const float* film, int film_stride, int N, int L, int C, int dilation, int T, int num_bands,
+                     int fmt, int out_fmt, int store_lrelu, void* out16, cudaStream_t stream);
+
 int resblock_launch(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
                     const float* film, int film_stride, int N, int L, int C, int dilation, int T, int num_bands,
-                    int fmt, int store_lrelu, void* out16, cudaStream_t stream) {
+                    int fmt, int out_fmt, int store_lrelu, void* out16, cudaStream_t stream) {
   B200_CHECK_ARG(N > 0 && L > 0 && T > 0 && L % T == 0, "resblock: L=%d must be a multiple of T=%d", L, T);
   B200_CHECK_ARG(N % num_bands == 0, "resblock: N=%d not a multiple of num_bands=%d", N, num_bands);
   B200_CHECK_ARG(a16 != out16, "resblock: in-place is not supported (neighbour tiles read the halo)");
   switch (C) {
-    case 32: return launch_resblock<32>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, store_lrelu, out16, stream);
-    case 64: return launch_resblock<64>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, store_lrelu, out16, stream);
-    case 128: return launch_resblock<128>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, store_lrelu, out16, stream);
-    case 256: return launch_resblock<256>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, store_lrelu, out16, stream);
+    case 32:
+    case 64:
+      if (dilation <= 8)
+        return resblock2_launch(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, C, dilation, T, num_bands, fmt,
+                                out_fmt, store_lrelu, out16, stream);
+      if (C == 32)
+        return launch_resblock<32>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, out_fmt, store_lrelu, out16, stream);
+      return launch_resblock<64>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, out_fmt, store_lrelu, out16, stream);
+    case 128: return launch_resblock<128>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, out_fmt, store_lrelu, out16, stream);
+    case 256: return launch_resblock<256>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, out_fmt, store_lrelu, out16, stream);
   }
   set_error("resblock: C=%d unsupported (32/64/128/256)", C);
   return B200VOC_ERR_UNSUPPORTED;

@@ -1,0 +1,322 @@
+// K2b: persistent fused residual block for the narrow stages (C = 32, 64).
+//
+// Same math as resblock.cu (generator.py:40-41,89-90 / repair R2), different schedule.  The late
+// stages are bandwidth/epilogue bound (224 -> 112 flop/B), so this kernel is organised to stream:
+//   * one persistent CTA per SM loops over (sequence, 128-row) tiles;
+//   * W1 (3 taps) and W2 stay resident in shared memory for the whole kernel (<= 56 KB);
+//   * ONE TMA load per tile brings 144 rows (128 + 8-row halo each side) of leaky_relu(x); the
+//     three dilated taps are the same tile addressed through UMMA descriptors whose start address
+//     is shifted by (8 +- d) rows -- legal because the 128B/64B swizzle is a function of the
+//     absolute shared-memory address (tests/test_gpu_generator.py::test_rowshifted_umma_descriptors);
+//   * the residual x is recovered from the same shared-memory tile (no second global read);
+//   * A tiles, the h operand and both TMEM accumulators are double buffered, and the work is
+//     split over specialised warps: TMA producer | MMA issuer | 4 warps GLU+FiLM epilogue |
+//     4 warps residual+store epilogue, so tile i+1's GEMM1 and GLU overlap tile i's GEMM2/store.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+struct Resblock2Params {
+  int L, dilation, T, P, num_bands, fmt, out_fmt, store_lrelu;
+  int tiles_per_seq, total_tiles;
+  const float* b_conv;   // [2C]
+  const float* b_proj;   // [C]
+  const float* film;     // [B, T, film_stride]
+  int film_stride;
+  uint16_t* out;         // [N, L, C]
+};
+
+template <int C>
+struct Rb2Cfg {
+  static constexpr int KB = C;                      // C in {32, 64}: one k-block per tap
+  static constexpr int ROWB = KB * 2;               // 64 or 128 bytes per row = swizzle span
+  static constexpr int N1 = 2 * C;
+  static constexpr int HALO = 8;
+  static constexpr int A_ROWS = 128 + 2 * HALO;
+  static constexpr int A_BYTES = A_ROWS * ROWB;
+  static constexpr int A_SLOT = (A_BYTES + 1023) & ~1023;
+  static constexpr int W1_TILE = N1 * ROWB;
+  static constexpr int W2_BYTES = C * ROWB;
+  static constexpr int H_BYTES = 128 * ROWB;
+  static constexpr int OFF_W1 = 0;
+  static constexpr int OFF_W2 = 3 * W1_TILE;
+  static constexpr int OFF_A = (OFF_W2 + W2_BYTES + 1023) & ~1023;
+  static constexpr int OFF_H = OFF_A + 2 * A_SLOT;
+  static constexpr int OFF_BAR = OFF_H + 2 * H_BYTES;
+  static constexpr int SMEM = OFF_BAR + 256 + 1024;
+  static constexpr int D2_COL = 2 * N1;
+  static constexpr int TMEM_NEED = 2 * N1 + 2 * C;
+  static constexpr uint32_t TMEM_COLS = TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+};
+
+template <int C>
+__global__ void __launch_bounds__(320, 1)
+resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const Resblock2Params p) {
+  using K = Rb2Cfg<C>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW1 = smem + K::OFF_W1;
+  uint8_t* sW2 = smem + K::OFF_W2;
+  uint8_t* sA = smem + K::OFF_A;
+  uint8_t* sH = smem + K::OFF_H;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_BAR);
+  uint64_t* w_full = bars;            // [1]
+  uint64_t* a_full = bars + 1;        // [2]
+  uint64_t* a_empty = bars + 3;       // [2]
+  uint64_t* d1_full = bars + 5;       // [2]
+  uint64_t* d1_empty = bars + 7;      // [2]
+  uint64_t* h_full = bars + 9;        // [2]
+  uint64_t* h_empty = bars + 11;      // [2]
+  uint64_t* d2_full = bars + 13;      // [2]
+  uint64_t* d2_empty = bars + 15;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    mbar_init(w_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&a_full[b], 1);
+      mbar_init(&a_empty[b], 128);
+      mbar_init(&d1_full[b], 1);
+      mbar_init(&d1_empty[b], 128);
+      mbar_init(&h_full[b], 128);
+      mbar_init(&h_empty[b], 1);
+      mbar_init(&d2_full[b], 1);
+      mbar_init(&d2_empty[b], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, K::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(w_full, 3 * K::W1_TILE + K::W2_BYTES);
+      for (int tap = 0; tap < 3; ++tap) tma_load_2d(sW1 + tap * K::W1_TILE, &tmW1, w_full, tap * C, 0);
+      tma_load_2d(sW2, &tmW2, w_full, 0, 0);
+      int i = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
+        const int b = i & 1;
+        const int seq = tile / p.tiles_per_seq, l0 = (tile - seq * p.tiles_per_seq) * 128;
+        mbar_wait(&a_empty[b], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&a_full[b], K::A_BYTES);
+        tma_load_3d(sA + b * K::A_SLOT, &tmX, &a_full[b], 0, l0 - K::HALO, seq);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc_f16(p.fmt, K::N1);
+      const uint32_t idesc2 = make_idesc_f16(p.fmt, C);
+      mbar_wait(w_full, 0);
+      auto issue_g2 = [&](int i) {
+        const int b = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait(&h_full[b], ph);
+        mbar_wait(&d2_empty[b], ph ^ 1);
+        tc_fence_after();
+        const uint64_t a_desc = make_kmajor_desc<K::ROWB>(smem_u32(sH + b * K::H_BYTES));
+        const uint64_t b_desc = make_kmajor_desc<K::ROWB>(smem_u32(sW2));
+#pragma unroll
+        for (int k = 0; k < K::KB / 16; ++k)
+          umma_f16(tmem_base + K::D2_COL + b * C, a_desc + 2 * k, b_desc + 2 * k, idesc2, k != 0);
+        umma_commit(&d2_full[b]);
+        umma_commit(&h_empty[b]);
+      };
+      int i = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
+        const int b = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait(&a_full[b], ph);
+        mbar_wait(&d1_empty[b], ph ^ 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + b * K::A_SLOT);
+#pragma unroll
+        for (int tap = 0; tap < 3; ++tap) {
+          const uint64_t a_desc = make_kmajor_desc<K::ROWB>(a_base + (K::HALO + (tap - 1) * p.dilation) * K::ROWB);
+          const uint64_t b_desc = make_kmajor_desc<K::ROWB>(smem_u32(sW1 + tap * K::W1_TILE));
+#pragma unroll
+          for (int k = 0; k < K::KB / 16; ++k)
+            umma_f16(tmem_base + b * K::N1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (tap | k) != 0);
+        }
+        umma_commit(&d1_full[b]);
+        if (i >= 1) issue_g2(i - 1);
+      }
+      if (i >= 1) issue_g2(i - 1);
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------ epilogue 1 (warps 2..5): GLU + FiLM -> h
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int fmt = p.fmt;
+    constexpr float kLog2e = 1.4426950408889634f;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
+      const int b = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      const int seq = tile / p.tiles_per_seq, l = (tile - seq * p.tiles_per_seq) * 128 + row;
+      int t = l / p.P;
+      if (t > p.T - 1) t = p.T - 1;
+      const float* film = p.film + ((long long)(seq / p.num_bands) * p.T + t) * p.film_stride;
+      mbar_wait(&d1_full[b], ph);
+      mbar_wait(&h_empty[b], ph ^ 1);
+      tc_fence_after();
+      uint8_t* hrow = sH + b * K::H_BYTES + row * K::ROWB;
+#pragma unroll 1
+      for (int cc = 0; cc < C / 32; ++cc) {
+        uint32_t va[32], vg[32];
+        tmem_ld32(lane_addr + b * K::N1 + cc * 32, va);
+        tmem_ld32(lane_addr + b * K::N1 + C + cc * 32, vg);
+        tmem_ld_wait();
+        const int ch0 = cc * 32;
+        const float4* ba = reinterpret_cast<const float4*>(p.b_conv + ch0);
+        const float4* bg = reinterpret_cast<const float4*>(p.b_conv + C + ch0);
+        const float4* fs = reinterpret_cast<const float4*>(film + ch0);
+        const float4* fh = reinterpret_cast<const float4*>(film + C + ch0);
+#pragma unroll
+        for (int i8 = 0; i8 < 4; ++i8) {
+          float hv[8];
+#pragma unroll
+          for (int h4 = 0; h4 < 2; ++h4) {
+            const int i4 = i8 * 2 + h4;
+            const float4 A = __ldg(ba + i4), G = __ldg(bg + i4), S = __ldg(fs + i4), H = __ldg(fh + i4);
+            const float av[4] = {A.x, A.y, A.z, A.w}, gv[4] = {G.x, G.y, G.z, G.w};
+            const float sv[4] = {S.x, S.y, S.z, S.w}, tv[4] = {H.x, H.y, H.z, H.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = __uint_as_float(va[i4 * 4 + e]) + av[e];
+              const float g = __uint_as_float(vg[i4 * 4 + e]) + gv[e];
+              const float sg = __fdividef(1.0f, 1.0f + exp2f(-kLog2e * g));
+              hv[h4 * 4 + e] = fmaf(a * sg, sv[e], tv[e]);
+            }
+          }
+          const int chunk = cc * 4 + i8;
+          const int phys = K::ROWB == 128 ? (chunk ^ (row & 7)) : (chunk ^ ((row >> 1) & 3));
+          *reinterpret_cast<uint4*>(hrow + phys * 16) =
+              make_uint4(pack2(hv[0], hv[1], fmt), pack2(hv[2], hv[3], fmt), pack2(hv[4], hv[5], fmt),
+                         pack2(hv[6], hv[7], fmt));
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&h_full[b]);
+      mbar_arrive(&d1_empty[b]);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue 2 (warps 6..9): residual + store
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int fmt = p.fmt, ofmt = p.out_fmt;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
+      const int b = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      const int seq = tile / p.tiles_per_seq, l = (tile - seq * p.tiles_per_seq) * 128 + row;
+      const bool valid = l < p.L;
+      mbar_wait(&a_full[b], ph);      // visibility of the TMA-written tile to this thread
+      mbar_wait(&d2_full[b], ph);
+      tc_fence_after();
+      const uint8_t* xrow = sA + b * K::A_SLOT + (row + K::HALO) * K::ROWB;
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)seq * p.L + (valid ? l : 0)) * C);
+#pragma unroll 1
+      for (int cc = 0; cc < C / 32; ++cc) {
+        uint32_t vd[32];
+        tmem_ld32(lane_addr + K::D2_COL + b * C + cc * 32, vd);
+        tmem_ld_wait();
+        const float4* b2 = reinterpret_cast<const float4*>(p.b_proj + cc * 32);
+#pragma unroll
+        for (int i8 = 0; i8 < 4; ++i8) {
+          const int chunk = cc * 4 + i8;
+          const int phys = K::ROWB == 128 ? (chunk ^ (row & 7)) : (chunk ^ ((row >> 1) & 3));
+          const uint4 xa = *reinterpret_cast<const uint4*>(xrow + phys * 16);
+          const uint32_t xw[4] = {xa.x, xa.y, xa.z, xa.w};
+          const float4 B0 = __ldg(b2 + i8 * 2), B1 = __ldg(b2 + i8 * 2 + 1);
+          const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const float2 xs = unpack2(xw[e2], fmt);
+            float y0 = lrelu_inv(xs.x) + __uint_as_float(vd[i8 * 8 + e2 * 2]) + bv[e2 * 2];
+            float y1 = lrelu_inv(xs.y) + __uint_as_float(vd[i8 * 8 + e2 * 2 + 1]) + bv[e2 * 2 + 1];
+            if (p.store_lrelu) { y0 = lrelu(y0); y1 = lrelu(y1); }
+            ow[e2] = pack2(y0, y1, ofmt);
+          }
+          if (valid) dst[chunk] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&d2_empty[b]);
+      mbar_arrive(&a_empty[b]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, K::TMEM_COLS);
+}
+
+static int num_sms() {
+  static int n[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!n[dev & 15]) cudaDeviceGetAttribute(&n[dev & 15], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev & 15];
+}
+
+template <int C>
+static int launch_resblock2(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
+                            const float* film, int film_stride, int N, int L, int dilation, int T, int num_bands,
+                            int fmt, int out_fmt, int store_lrelu, void* out16, cudaStream_t stream) {
+  using K = Rb2Cfg<C>;
+  CUtensorMap tmX, tmW1, tmW2;
+  B200_TRY(make_tmap_3d(&tmX, a16, C, L, N, (uint64_t)C * 2, (uint64_t)L * C * 2, K::KB, K::A_ROWS, K::ROWB));
+  const uint16_t* w1 = reinterpret_cast<const uint16_t*>(w_packed);
+  const uint16_t* w2 = w1 + 2ll * C * 3 * C;
+  B200_TRY(make_tmap_2d(&tmW1, w1, 3 * C, 2 * C, (uint64_t)3 * C * 2, K::KB, K::N1, K::ROWB));
+  B200_TRY(make_tmap_2d(&tmW2, w2, C, C, (uint64_t)C * 2, K::KB, C, K::ROWB));
+  Resblock2Params p{};
+  p.L = L; p.dilation = dilation; p.T = T; p.P = L / T; p.num_bands = num_bands;
+  p.fmt = fmt; p.out_fmt = out_fmt; p.store_lrelu = store_lrelu;
+  p.tiles_per_seq = ceil_div(L, 128);
+  p.total_tiles = p.tiles_per_seq * N;
+  p.b_conv = b_conv; p.b_proj = b_proj; p.film = film; p.film_stride = film_stride;
+  p.out = reinterpret_cast<uint16_t*>(out16);
+  static bool configured[16] = {};
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 15]) {
+    B200_CUDA(cudaFuncSetAttribute(resblock2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+    configured[dev & 15] = true;
+  }
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  resblock2_kernel<C><<<grid, 320, K::SMEM, stream>>>(tmX, tmW1, tmW2, p);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
+int resblock2_launch(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
+                     const float* film, int film_stride, int N, int L, int C, int dilation, int T, int num_bands,
+                     int fmt, int out_fmt, int store_lrelu, void* out16, cudaStream_t stream) {
+  B200_CHECK_ARG(dilation >= 1 && dilation <= 8, "resblock2: dilation %d exceeds the 8-row halo", dilation);
+  if (C == 32)
+    return launch_resblock2<32>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt,
+                                out_fmt, store_lrelu, out16, stream);
+  if (C == 64)
+    return launch_resblock2<64>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt,
+                                out_fmt, store_lrelu, out16, stream);
+  set_error("resblock2: C=%d unsupported (32/64)", C);
+  return B200VOC_ERR_UNSUPPORTED;
+}
+
+}  // namespace b200
