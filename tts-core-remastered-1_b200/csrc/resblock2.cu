@@ -42,11 +42,13 @@ struct Rb2Cfg {
   static constexpr int OFF_W1 = 0;
   static constexpr int OFF_W2 = 3 * W1_TILE;
   static constexpr int OFF_A = (OFF_W2 + W2_BYTES + 1023) & ~1023;
-  static constexpr int OFF_H = OFF_A + 2 * A_SLOT;
-  static constexpr int OFF_BAR = OFF_H + 2 * H_BYTES;
-  static constexpr int SMEM = OFF_BAR + 256 + 1024;
-  static constexpr int D2_COL = 2 * N1;
-  static constexpr int TMEM_NEED = 2 * N1 + 2 * C;
+  static constexpr int ND = C == 32 ? 4 : 2;         // ring depth of the TMEM accumulators and of h
+  static constexpr int NA = ND + 2;                 // ring depth of the input tiles (TMA prefetch distance)
+  static constexpr int OFF_H = OFF_A + NA * A_SLOT;
+  static constexpr int OFF_BAR = OFF_H + ND * H_BYTES;
+  static constexpr int SMEM = OFF_BAR + 512 + 1024;
+  static constexpr int D2_COL = ND * N1;
+  static constexpr int TMEM_NEED = ND * N1 + ND * C;
   static constexpr uint32_t TMEM_COLS = TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
 };
 
@@ -62,16 +64,17 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* sA = smem + K::OFF_A;
   uint8_t* sH = smem + K::OFF_H;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_BAR);
-  uint64_t* w_full = bars;            // [1]
-  uint64_t* a_full = bars + 1;        // [2]
-  uint64_t* a_empty = bars + 3;       // [2]
-  uint64_t* d1_full = bars + 5;       // [2]
-  uint64_t* d1_empty = bars + 7;      // [2]
-  uint64_t* h_full = bars + 9;        // [2]
-  uint64_t* h_empty = bars + 11;      // [2]
-  uint64_t* d2_full = bars + 13;      // [2]
-  uint64_t* d2_empty = bars + 15;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  constexpr int ND = K::ND, NA = K::NA;
+  uint64_t* w_full = bars;                 // [1]
+  uint64_t* a_full = bars + 1;             // [NA]
+  uint64_t* a_empty = a_full + NA;         // [NA]
+  uint64_t* d1_full = a_empty + NA;        // [ND]
+  uint64_t* d1_empty = d1_full + ND;       // [ND]
+  uint64_t* h_full = d1_empty + ND;        // [ND]
+  uint64_t* h_empty = h_full + ND;         // [ND]
+  uint64_t* d2_full = h_empty + ND;        // [ND]
+  uint64_t* d2_empty = d2_full + ND;       // [ND]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + ND);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -80,9 +83,11 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     mbar_init(w_full, 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NA; ++b) {
       mbar_init(&a_full[b], 1);
       mbar_init(&a_empty[b], 128);
+    }
+    for (int b = 0; b < ND; ++b) {
       mbar_init(&d1_full[b], 1);
       mbar_init(&d1_empty[b], 128);
       mbar_init(&h_full[b], 128);
@@ -106,11 +111,11 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tma_load_2d(sW2, &tmW2, w_full, 0, 0);
       int i = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
-        const int b = i & 1;
+        const int ab = i % NA;
         const int seq = tile / p.tiles_per_seq, l0 = (tile - seq * p.tiles_per_seq) * 128;
-        mbar_wait(&a_empty[b], ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&a_full[b], K::A_BYTES);
-        tma_load_3d(sA + b * K::A_SLOT, &tmX, &a_full[b], 0, l0 - K::HALO, seq);
+        mbar_wait(&a_empty[ab], ((i / NA) & 1) ^ 1);
+        mbar_expect_tx(&a_full[ab], K::A_BYTES);
+        tma_load_3d(sA + ab * K::A_SLOT, &tmX, &a_full[ab], 0, l0 - K::HALO, seq);
       }
     }
   } else if (warp == 1) {
@@ -120,8 +125,8 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const uint32_t idesc2 = make_idesc_f16(p.fmt, C);
       mbar_wait(w_full, 0);
       auto issue_g2 = [&](int i) {
-        const int b = i & 1;
-        const uint32_t ph = (i >> 1) & 1;
+        const int b = i % ND;
+        const uint32_t ph = (i / ND) & 1;
         mbar_wait(&h_full[b], ph);
         mbar_wait(&d2_empty[b], ph ^ 1);
         tc_fence_after();
@@ -135,12 +140,12 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       };
       int i = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
-        const int b = i & 1;
-        const uint32_t ph = (i >> 1) & 1;
-        mbar_wait(&a_full[b], ph);
+        const int b = i % ND, ab = i % NA;
+        const uint32_t ph = (i / ND) & 1;
+        mbar_wait(&a_full[ab], (i / NA) & 1);
         mbar_wait(&d1_empty[b], ph ^ 1);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(sA + b * K::A_SLOT);
+        const uint32_t a_base = smem_u32(sA + ab * K::A_SLOT);
 #pragma unroll
         for (int tap = 0; tap < 3; ++tap) {
           const uint64_t a_desc = make_kmajor_desc<K::ROWB>(a_base + (K::HALO + (tap - 1) * p.dilation) * K::ROWB);
@@ -150,9 +155,9 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             umma_f16(tmem_base + b * K::N1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (tap | k) != 0);
         }
         umma_commit(&d1_full[b]);
-        if (i >= 1) issue_g2(i - 1);
+        if (i >= ND - 1) issue_g2(i - (ND - 1));     // GEMM2 trails GEMM1 by ND-1 tiles
       }
-      if (i >= 1) issue_g2(i - 1);
+      for (int j = (i >= ND - 1 ? i - (ND - 1) : 0); j < i; ++j) issue_g2(j);
     }
   } else if (warp < 6) {
     // ------------------------------------------------------------ epilogue 1 (warps 2..5): GLU + FiLM -> h
@@ -163,8 +168,8 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     constexpr float kLog2e = 1.4426950408889634f;
     int i = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
-      const int b = i & 1;
-      const uint32_t ph = (i >> 1) & 1;
+      const int b = i % ND;
+      const uint32_t ph = (i / ND) & 1;
       const int seq = tile / p.tiles_per_seq, l = (tile - seq * p.tiles_per_seq) * 128 + row;
       int t = l / p.P;
       if (t > p.T - 1) t = p.T - 1;
@@ -221,14 +226,14 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int fmt = p.fmt, ofmt = p.out_fmt;
     int i = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
-      const int b = i & 1;
-      const uint32_t ph = (i >> 1) & 1;
+      const int b = i % ND, ab = i % NA;
+      const uint32_t ph = (i / ND) & 1;
       const int seq = tile / p.tiles_per_seq, l = (tile - seq * p.tiles_per_seq) * 128 + row;
       const bool valid = l < p.L;
-      mbar_wait(&a_full[b], ph);      // visibility of the TMA-written tile to this thread
+      mbar_wait(&a_full[ab], (i / NA) & 1);   // visibility of the TMA-written tile to this thread
       mbar_wait(&d2_full[b], ph);
       tc_fence_after();
-      const uint8_t* xrow = sA + b * K::A_SLOT + (row + K::HALO) * K::ROWB;
+      const uint8_t* xrow = sA + ab * K::A_SLOT + (row + K::HALO) * K::ROWB;
       uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)seq * p.L + (valid ? l : 0)) * C);
 #pragma unroll 1
       for (int cc = 0; cc < C / 32; ++cc) {
@@ -258,7 +263,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(&d2_empty[b]);
-      mbar_arrive(&a_empty[b]);
+      mbar_arrive(&a_empty[ab]);
     }
   }
   tc_fence_before();

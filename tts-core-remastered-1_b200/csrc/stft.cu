@@ -1,11 +1,412 @@
-// K7/K8/K9: STFT family -- placeholder entry points (fail loudly) until the kernels land.
+// K7/K8/K9: STFT family in fp32 (replaces vocoder7/stft.py:9-54 and the torchaudio
+// MelSpectrogram call sites).  Shared-memory Stockham FFTs (fft_core.cuh): N/8 threads per frame,
+// 8 frames per CTA, every input sample is read from HBM once per CTA (frames overlap 50-87 %),
+// the complex spectrogram is never materialised when the consumer is |X|*gain, mel or log-mel.
+//
+//   stft:  frame = reflect-padded wav[f*hop - n/2 ...] * periodic Hann  ->  rFFT (packed complex
+//          FFT of n/2 points + split)  ->  |X|*gain  |  re,im  |  |X|^2 -> sparse HTK mel -> log
+//   istft: spectrum block -> inverse packed FFT -> * window, gather overlap-add, / sum w^2
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+#include <cmath>
+
 #include "common.cuh"
-using namespace b200;
-extern "C" {
-#define NOT_YET(name) set_error(name ": kernel not built yet"); return B200VOC_ERR_UNSUPPORTED
-int b200voc_stft_mag(const float*, int, int, int, int, const float*, float*, void*) { NOT_YET("stft_mag"); }
-int b200voc_stft_complex(const float*, int, int, int, int, float*, void*) { NOT_YET("stft_complex"); }
-int b200voc_stft_logmel(const float*, int, int, int, int, int, int, int, float*, void*) { NOT_YET("stft_logmel"); }
-int b200voc_istft(const float*, int, int, int, int, int, float*, void*) { NOT_YET("istft"); }
-int b200voc_stft_l1(const float*, const float*, int, int, int, int, const float*, double*, void*) { NOT_YET("stft_l1"); }
+#include "fft_core.cuh"
+
+namespace b200 {
+
+using namespace fft;
+
+constexpr int kFPB = 8;   // frames (thread groups) per CTA per round
+
+enum StftMode { MODE_MAG = 0, MODE_COMPLEX = 1, MODE_MEL = 2, MODE_L1 = 3 };
+
+struct MelTable {      // CSR by mel bin over frequency bins
+  const int* lo;       // [n_mels] first bin with non-zero weight
+  const int* cnt;      // [n_mels]
+  const int* off;      // [n_mels] offset into w
+  const float* w;
+  int n_mels;
+};
+
+struct StftParams {
+  const float* wav;    // [B, Nsamp]
+  const float* wav2;   // MODE_L1: second waveform
+  int B, Nsamp, hop, frames;
+  const float* gain;   // [bins] or null
+  float* out;
+  double* out_sum;     // MODE_L1
+  MelTable mel;
+  int log_compress;
+};
+
+__device__ __forceinline__ int reflect(int s, int n) {
+  if (s < 0) s = -s;
+  if (s >= n) s = 2 * (n - 1) - s;
+  return s;
 }
+
+template <int NFFT, int MODE>
+__global__ void __launch_bounds__(kFPB * (NFFT / 16))
+stft_kernel(const StftParams p) {
+  constexpr int N = NFFT / 2, T = N / 8, BINS = N + 1, NPAD = N + N / 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int span_len = (kFPB - 1) * p.hop + NFFT;
+  float* span = reinterpret_cast<float*>(smem_raw);
+  float* win = span + ((span_len + 3) & ~3);
+  float2* tw = reinterpret_cast<float2*>(win + NFFT);
+  float2* tw2 = tw + N;
+  float2* buf = tw2 + (N + 2);
+  float* stage = reinterpret_cast<float*>(buf + kFPB * NPAD);   // [BINS][kFPB+1] (float2 for MODE_COMPLEX)
+
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  const int b = blockIdx.y, f0 = blockIdx.x * kFPB;
+  float2* mybuf = buf + g * NPAD;
+
+  for (int i = threadIdx.x; i < NFFT; i += blockDim.x) win[i] = 0.5f - 0.5f * cospif(2.0f * i / NFFT);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float s, c;
+    sincospif(-2.0f * i / N, &s, &c);
+    tw[i] = make_float2(c, s);
+  }
+  for (int i = threadIdx.x; i <= N; i += blockDim.x) {
+    float s, c;
+    sincospif(-(float)i / N, &s, &c);
+    tw2[i] = make_float2(c, s);
+  }
+  float l1_acc = 0.f;
+  constexpr int NPASS = MODE == MODE_L1 ? 2 : 1;
+#pragma unroll 1
+  for (int pass = 0; pass < NPASS; ++pass) {
+    const float* w = (pass == 0 ? p.wav : p.wav2) + (long long)b * p.Nsamp;
+    __syncthreads();
+    for (int i = threadIdx.x; i < span_len; i += blockDim.x)
+      span[i] = __ldg(w + reflect(f0 * p.hop - N + i, p.Nsamp));
+    __syncthreads();
+    const float* fr = span + g * p.hop;
+    auto load0 = [&](int m) { return make_float2(fr[2 * m] * win[2 * m], fr[2 * m + 1] * win[2 * m + 1]); };
+    transform<N, false>(t, load0, mybuf, tw, [] { __syncthreads(); });
+    // split -> bins k = t, t+T, ... and k = N
+    for (int k = t; k <= N; k += T) {
+      const float2 X = rfft_bin(mybuf, tw2, N, k);
+      if (MODE == MODE_COMPLEX) {
+        reinterpret_cast<float2*>(stage)[k * (kFPB + 1) + g] = X;
+      } else if (MODE == MODE_MEL) {
+        stage[k * (kFPB + 1) + g] = X.x * X.x + X.y * X.y;
+      } else {
+        float mag = sqrtf(X.x * X.x + X.y * X.y);
+        if (p.gain) mag *= __ldg(p.gain + k);
+        if (MODE == MODE_L1) {
+          if (pass == 0) stage[k * (kFPB + 1) + g] = mag;
+          else if (f0 + g < p.frames) l1_acc += fabsf(stage[k * (kFPB + 1) + g] - mag);
+        } else {
+          stage[k * (kFPB + 1) + g] = mag;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (MODE == MODE_MAG) {
+    float* o = p.out + (long long)b * BINS * p.frames;
+    for (int i = threadIdx.x; i < BINS * kFPB; i += blockDim.x) {
+      const int k = i / kFPB, f = i % kFPB;
+      if (f0 + f < p.frames) o[(long long)k * p.frames + f0 + f] = stage[k * (kFPB + 1) + f];
+    }
+  } else if (MODE == MODE_COMPLEX) {
+    float2* o = reinterpret_cast<float2*>(p.out) + (long long)b * BINS * p.frames;
+    for (int i = threadIdx.x; i < BINS * kFPB; i += blockDim.x) {
+      const int k = i / kFPB, f = i % kFPB;
+      if (f0 + f < p.frames) o[(long long)k * p.frames + f0 + f] = reinterpret_cast<float2*>(stage)[k * (kFPB + 1) + f];
+    }
+  } else if (MODE == MODE_MEL) {
+    float* o = p.out + (long long)b * p.mel.n_mels * p.frames;
+    for (int i = threadIdx.x; i < p.mel.n_mels * kFPB; i += blockDim.x) {
+      const int m = i / kFPB, f = i % kFPB;
+      const int lo = __ldg(p.mel.lo + m), cnt = __ldg(p.mel.cnt + m);
+      const float* wv = p.mel.w + __ldg(p.mel.off + m);
+      float acc = 0.f;
+      for (int k = 0; k < cnt; ++k) acc = fmaf(__ldg(wv + k), stage[(lo + k) * (kFPB + 1) + f], acc);
+      if (p.log_compress) acc = logf(fmaxf(acc, 1e-5f));
+      if (f0 + f < p.frames) o[(long long)m * p.frames + f0 + f] = acc;
+    }
+  } else {
+    // block reduction of the L1 partial sum -> one double atomic per CTA
+    __shared__ float red[32];
+    for (int o = 16; o > 0; o >>= 1) l1_acc += __shfl_xor_sync(0xffffffffu, l1_acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l1_acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (threadIdx.x == 0) atomicAdd(p.out_sum, (double)v);
+    }
+  }
+}
+
+template <int NFFT>
+static size_t stft_smem(int hop, int mode) {
+  constexpr int N = NFFT / 2, NPAD = N + N / 8, BINS = N + 1;
+  const int span_len = (kFPB - 1) * hop + NFFT;
+  size_t s = (size_t)((span_len + 3) & ~3) * 4 + NFFT * 4 + (size_t)N * 8 + (size_t)(N + 2) * 8 + (size_t)kFPB * NPAD * 8;
+  s += (size_t)BINS * (kFPB + 1) * (mode == MODE_COMPLEX ? 8 : 4);
+  return s + 64;
+}
+
+template <int NFFT, int MODE>
+static int launch_stft(const StftParams& p, cudaStream_t st) {
+  const size_t smem = stft_smem<NFFT>(p.hop, MODE);
+  B200_CHECK_ARG(smem <= 227 * 1024, "stft: hop %d needs %zu bytes of shared memory", p.hop, smem);
+  B200_CUDA(cudaFuncSetAttribute(stft_kernel<NFFT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(p.frames, kFPB), p.B);
+  stft_kernel<NFFT, MODE><<<grid, kFPB * (NFFT / 16), smem, st>>>(p);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
+template <int MODE>
+static int dispatch_stft(int n_fft, const StftParams& p, cudaStream_t st) {
+  switch (n_fft) {
+    case 512: return launch_stft<512, MODE>(p, st);
+    case 1024: return launch_stft<1024, MODE>(p, st);
+    case 2048: return launch_stft<2048, MODE>(p, st);
+  }
+  set_error("stft: n_fft=%d unsupported (512/1024/2048, vocoder7/config.py:39 stft_sizes)", n_fft);
+  return B200VOC_ERR_UNSUPPORTED;
+}
+
+static int check_stft_args(const float* wav, int B, int N, int n_fft, int hop) {
+  B200_CHECK_ARG(wav != nullptr, "stft: null waveform");
+  B200_CHECK_ARG(B > 0 && N > 0, "stft: empty input (B=%d, N=%d)", B, N);
+  B200_CHECK_ARG(hop > 0 && hop <= n_fft, "stft: hop %d out of range", hop);
+  B200_CHECK_ARG(N > n_fft / 2, "stft: reflect padding needs N=%d > n_fft/2=%d (same as torch.stft)", N, n_fft / 2);
+  return B200VOC_OK;
+}
+
+// ------------------------------------------------------------------ mel filterbank (host, cached)
+// HTK mel scale, triangular, no area normalisation: the matrix torchaudio's MelSpectrogram builds
+// (reference_encoder/utils.py:31-36 call site).  Stored sparse by mel bin.
+struct MelDev {
+  int *lo, *cnt, *off;
+  float* w;
+};
+static std::mutex g_mel_mu;
+static std::map<std::tuple<int, int, int, int>, MelDev> g_mel_cache;
+
+static int get_mel_table(int n_fft, int n_mels, int sr, MelTable* out) {
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_mel_mu);
+  auto key = std::make_tuple(dev, n_fft, n_mels, sr);
+  auto it = g_mel_cache.find(key);
+  if (it == g_mel_cache.end()) {
+    const int bins = n_fft / 2 + 1;
+    const double f_max = (double)(sr / 2);
+    auto hz2mel = [](double f) { return 2595.0 * std::log10(1.0 + f / 700.0); };
+    auto mel2hz = [](double m) { return 700.0 * (std::pow(10.0, m / 2595.0) - 1.0); };
+    std::vector<double> fpts(n_mels + 2);
+    const double m_lo = hz2mel(0.0), m_hi = hz2mel(f_max);
+    for (int i = 0; i < n_mels + 2; ++i) fpts[i] = mel2hz(m_lo + (m_hi - m_lo) * i / (n_mels + 1));
+    std::vector<int> lo(n_mels), cnt(n_mels), off(n_mels);
+    std::vector<float> w;
+    for (int m = 0; m < n_mels; ++m) {
+      int first = -1, last = -1;
+      std::vector<float> col(bins);
+      for (int k = 0; k < bins; ++k) {
+        const double f = (double)(sr / 2) * k / (bins - 1);
+        const double down = (f - fpts[m]) / (fpts[m + 1] - fpts[m]);
+        const double up = (fpts[m + 2] - f) / (fpts[m + 2] - fpts[m + 1]);
+        const double v = std::fmax(0.0, std::fmin(down, up));
+        col[k] = (float)v;
+        if (v > 0.0) {
+          if (first < 0) first = k;
+          last = k;
+        }
+      }
+      lo[m] = first < 0 ? 0 : first;
+      cnt[m] = first < 0 ? 0 : last - first + 1;
+      off[m] = (int)w.size();
+      for (int k = 0; k < cnt[m]; ++k) w.push_back(col[lo[m] + k]);
+    }
+    if (w.empty()) w.push_back(0.f);
+    MelDev d{};
+    B200_CUDA(cudaMalloc(&d.lo, n_mels * sizeof(int)));
+    B200_CUDA(cudaMalloc(&d.cnt, n_mels * sizeof(int)));
+    B200_CUDA(cudaMalloc(&d.off, n_mels * sizeof(int)));
+    B200_CUDA(cudaMalloc(&d.w, w.size() * sizeof(float)));
+    B200_CUDA(cudaMemcpy(d.lo, lo.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(d.cnt, cnt.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(d.off, off.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(d.w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    it = g_mel_cache.emplace(key, d).first;
+  }
+  out->lo = it->second.lo;
+  out->cnt = it->second.cnt;
+  out->off = it->second.off;
+  out->w = it->second.w;
+  out->n_mels = n_mels;
+  return B200VOC_OK;
+}
+
+// ------------------------------------------------------------------ K9: iSTFT
+// One CTA produces OPB = (2*kFPB - n/hop + 1) * hop output samples from the 2*kFPB frames that
+// touch them: the spectrum block is loaded coalesced (frames are the contiguous axis), each frame
+// group runs the inverse packed FFT, and every output sample gathers its n/hop windowed
+// contributions and the window-envelope (sum w^2) -- deterministic, no atomics.
+struct IstftParams {
+  const float2* spec;   // [B, bins, frames]
+  float* wav;           // [B, Nout]
+  int B, frames, hop, Nout;
+};
+
+template <int NFFT>
+__global__ void __launch_bounds__(kFPB * (NFFT / 16))
+istft_kernel(const IstftParams p) {
+  constexpr int N = NFFT / 2, T = N / 8, NPAD = N + N / 8, SLOTS = 2 * kFPB;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* win = reinterpret_cast<float*>(smem_raw);
+  float2* tw = reinterpret_cast<float2*>(win + NFFT);
+  float2* tw2 = tw + N;
+  float2* xN = tw2 + (N + 2);               // [SLOTS] Nyquist bins
+  float2* buf = xN + SLOTS;                 // [SLOTS][NPAD]
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  const int b = blockIdx.y;
+  const int ratio = NFFT / p.hop;
+  const int opb = (SLOTS - ratio + 1) * p.hop;
+  const int n0 = blockIdx.x * opb;                       // first output sample of this CTA
+  const int f_lo = (n0 - N) / p.hop + 1;                 // may be negative (n0 - N is a multiple of hop)
+  const int bins = N + 1;
+
+  for (int i = threadIdx.x; i < NFFT; i += blockDim.x) win[i] = 0.5f - 0.5f * cospif(2.0f * i / NFFT);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float s, c;
+    sincospif(-2.0f * i / N, &s, &c);
+    tw[i] = make_float2(c, s);
+  }
+  for (int i = threadIdx.x; i <= N; i += blockDim.x) {
+    float s, c;
+    sincospif(-(float)i / N, &s, &c);
+    tw2[i] = make_float2(c, s);
+  }
+  // coalesced load of the spectrum block: consecutive threads -> consecutive frames of one bin
+  const float2* sp = p.spec + (long long)b * bins * p.frames;
+  for (int i = threadIdx.x; i < bins * SLOTS; i += blockDim.x) {
+    const int k = i / SLOTS, s = i % SLOTS;
+    const int f = f_lo + s;
+    float2 v = make_float2(0.f, 0.f);
+    if (f >= 0 && f < p.frames) v = __ldg(sp + (long long)k * p.frames + f);
+    if (k == 0 || k == N) v.y = 0.f;                     // c2r ignores the imaginary part of DC / Nyquist
+    if (k < N) buf[s * NPAD + pad(k)] = v;
+    else xN[s] = v;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int r = 0; r < 2; ++r) {
+    const int slot = r * kFPB + g;
+    float2* mybuf = buf + slot * NPAD;
+    const float2 xn = xN[slot];
+    auto load0 = [&](int k) {
+      const float2 xk = mybuf[pad(k)];
+      const float2 xnk = k == 0 ? xn : mybuf[pad(N - k)];
+      return irfft_pack(xk, cconj(xnk), tw2[k]);
+    };
+    transform<N, true>(t, load0, mybuf, tw, [] { __syncthreads(); });
+  }
+  // gather overlap-add
+  const float inv_n = 1.0f / N;
+  float* o = p.wav + (long long)b * p.Nout;
+  for (int i = threadIdx.x; i < opb; i += blockDim.x) {
+    const int n = n0 + i;
+    if (n >= p.Nout) break;
+    const int j = n + N;                                 // padded-signal coordinate
+    const int f_hi = j / p.hop;
+    float acc = 0.f, env = 0.f;
+    for (int q = 0; q < ratio; ++q) {
+      const int f = f_hi - q;
+      const int idx = j - f * p.hop;                     // position inside frame f
+      if (f < 0 || f >= p.frames || idx >= NFFT) continue;
+      const float w = win[idx];
+      const float2 z = buf[(f - f_lo) * NPAD + pad(idx >> 1)];
+      acc = fmaf((idx & 1) ? z.y : z.x, w * inv_n, acc);
+      env = fmaf(w, w, env);
+    }
+    o[n] = env > 1e-11f ? acc / env : 0.f;
+  }
+}
+
+template <int NFFT>
+static int launch_istft(const IstftParams& p, cudaStream_t st) {
+  constexpr int N = NFFT / 2, NPAD = N + N / 8, SLOTS = 2 * kFPB;
+  const size_t smem = (size_t)NFFT * 4 + (size_t)N * 8 + (size_t)(N + 2) * 8 + SLOTS * 8 + (size_t)SLOTS * NPAD * 8 + 64;
+  B200_CUDA(cudaFuncSetAttribute(istft_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int ratio = NFFT / p.hop;
+  const int opb = (SLOTS - ratio + 1) * p.hop;
+  dim3 grid(ceil_div(p.Nout, opb), p.B);
+  istft_kernel<NFFT><<<grid, kFPB * (NFFT / 16), smem, st>>>(p);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200voc_stft_mag(const float* wav, int B, int N, int n_fft, int hop, const float* gain, float* out, void* stream) {
+  B200_TRY(check_stft_args(wav, B, N, n_fft, hop));
+  B200_CHECK_ARG(out != nullptr, "stft_mag: null output");
+  StftParams p{};
+  p.wav = wav; p.B = B; p.Nsamp = N; p.hop = hop; p.frames = 1 + N / hop; p.gain = gain; p.out = out;
+  return dispatch_stft<MODE_MAG>(n_fft, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200voc_stft_complex(const float* wav, int B, int N, int n_fft, int hop, float* out_ri, void* stream) {
+  B200_TRY(check_stft_args(wav, B, N, n_fft, hop));
+  B200_CHECK_ARG(out_ri != nullptr, "stft_complex: null output");
+  StftParams p{};
+  p.wav = wav; p.B = B; p.Nsamp = N; p.hop = hop; p.frames = 1 + N / hop; p.out = out_ri;
+  return dispatch_stft<MODE_COMPLEX>(n_fft, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200voc_stft_logmel(const float* wav, int B, int N, int n_fft, int hop, int n_mels, int sample_rate,
+                        int log_compress, float* out, void* stream) {
+  B200_TRY(check_stft_args(wav, B, N, n_fft, hop));
+  B200_CHECK_ARG(out != nullptr && n_mels > 0 && n_mels <= 512 && sample_rate > 0, "stft_logmel: bad arguments");
+  StftParams p{};
+  p.wav = wav; p.B = B; p.Nsamp = N; p.hop = hop; p.frames = 1 + N / hop; p.out = out; p.log_compress = log_compress;
+  B200_TRY(get_mel_table(n_fft, n_mels, sample_rate, &p.mel));
+  return dispatch_stft<MODE_MEL>(n_fft, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200voc_stft_l1(const float* wav_fake, const float* wav_real, int B, int N, int n_fft, int hop,
+                    const float* gain, double* out_sum, void* stream) {
+  B200_TRY(check_stft_args(wav_fake, B, N, n_fft, hop));
+  B200_CHECK_ARG(wav_real != nullptr && out_sum != nullptr, "stft_l1: null argument");
+  StftParams p{};
+  p.wav = wav_fake; p.wav2 = wav_real; p.B = B; p.Nsamp = N; p.hop = hop; p.frames = 1 + N / hop; p.gain = gain;
+  p.out_sum = out_sum;
+  return dispatch_stft<MODE_L1>(n_fft, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200voc_istft(const float* spec_ri, int B, int frames, int n_fft, int hop, int N, float* wav, void* stream) {
+  B200_CHECK_ARG(spec_ri && wav, "istft: null argument");
+  B200_CHECK_ARG(B > 0 && frames > 0 && N > 0, "istft: empty input");
+  B200_CHECK_ARG(hop > 0 && (n_fft / 2) % hop == 0, "istft: hop %d must divide n_fft/2 = %d", hop, n_fft / 2);
+  B200_CHECK_ARG(n_fft / hop <= 2 * kFPB, "istft: n_fft/hop = %d too large", n_fft / hop);
+  B200_CHECK_ARG((long long)N <= (long long)hop * (frames - 1) + n_fft / 2 + n_fft / 2,
+                 "istft: length %d exceeds the signal the %d frames cover", N, frames);
+  IstftParams p{};
+  p.spec = reinterpret_cast<const float2*>(spec_ri); p.wav = wav; p.B = B; p.frames = frames; p.hop = hop; p.Nout = N;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (n_fft) {
+    case 512: return launch_istft<512>(p, st);
+    case 1024: return launch_istft<1024>(p, st);
+    case 2048: return launch_istft<2048>(p, st);
+  }
+  set_error("istft: n_fft=%d unsupported (512/1024/2048)", n_fft);
+  return B200VOC_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"
