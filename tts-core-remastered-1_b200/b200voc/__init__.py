@@ -3,6 +3,8 @@ ChiefTriston/TTS-Core-Remastered-1: Generator inference and the STFT / mel / iST
 behind the reference's Python API.  See DESIGN.md."""
 from .config import GANConfig
 from .generator import Generator, ResidualBlock, SelfAttention
+from .stft import LearnableSTFT, STFTLoss, stft, istft, mel_spectrogram, log_mel, stft_magnitude
 from . import _lib
 
-__all__ = ["GANConfig", "Generator", "ResidualBlock", "SelfAttention"]
+__all__ = ["GANConfig", "Generator", "ResidualBlock", "SelfAttention", "LearnableSTFT", "STFTLoss", "stft", "istft",
+           "mel_spectrogram", "log_mel", "stft_magnitude"]

@@ -1,0 +1,127 @@
+"""STFT family: drop-ins for ``vocoder7.stft.LearnableSTFT`` / ``STFTLoss`` (vocoder7/stft.py:9-54)
+and the functional transforms north_star names (stft, istft, mel_spectrogram, log_mel), all running
+the hand-written sm_100a kernels of csrc/stft.cu through the C ABI.  fp32 throughout; inference
+only (no autograd); no CPU fallback.
+
+Semantics (identical to what the reference calls, see oracle/vocoder7_oracle.py):
+  STFT  = torch.stft(center=True, pad_mode="reflect", win_length=n_fft, periodic Hann, onesided,
+          unnormalised) -- i.e. torchaudio ``Spectrogram(power=None)``;
+  mel   = HTK filterbank, f_min 0, f_max sr/2, norm None, power 2 (torchaudio ``MelSpectrogram``
+          defaults, reference_encoder/utils.py:31-36);  log_mel = log(clamp(mel, 1e-5));
+  iSTFT = torch.istft(center=True, same window, length=N).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .config import GANConfig
+
+
+def _prep(wav: torch.Tensor) -> torch.Tensor:
+    _lib.require_cuda(wav)
+    if wav.dim() == 3 and wav.shape[1] == 1:
+        wav = wav.squeeze(1)
+    if wav.dim() != 2:
+        raise ValueError(f"waveform must be [B,N] or [B,1,N], got {tuple(wav.shape)}")
+    return wav.detach().to(torch.float32).contiguous()
+
+
+def stft_magnitude(wav: torch.Tensor, n_fft: int, hop_length: int, gain: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """|STFT(wav)| * gain[:, None] -> [B, n_fft/2+1, 1+N//hop]."""
+    w = _prep(wav)
+    B, N = w.shape
+    out = torch.empty(B, n_fft // 2 + 1, 1 + N // hop_length, device=w.device, dtype=torch.float32)
+    g = None if gain is None else gain.detach().to(torch.float32).contiguous()
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().b200voc_stft_mag(_lib.ptr(w), B, N, n_fft, hop_length, _lib.ptr(g), _lib.ptr(out),
+                                                _lib.current_stream()), "stft_mag")
+    return out
+
+
+def stft(wav: torch.Tensor, n_fft: int, hop_length: int) -> torch.Tensor:
+    """complex64 [B, n_fft/2+1, 1+N//hop]."""
+    w = _prep(wav)
+    B, N = w.shape
+    out = torch.empty(B, n_fft // 2 + 1, 1 + N // hop_length, 2, device=w.device, dtype=torch.float32)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().b200voc_stft_complex(_lib.ptr(w), B, N, n_fft, hop_length, _lib.ptr(out),
+                                                    _lib.current_stream()), "stft_complex")
+    return torch.view_as_complex(out)
+
+
+def mel_spectrogram(wav: torch.Tensor, n_fft: int = 1024, hop_length: int = 256, n_mels: int = 80,
+                    sample_rate: int = 22050, log: bool = False) -> torch.Tensor:
+    """power mel [B, n_mels, frames] (log=True: log(clamp(mel, 1e-5))), fused STFT -> |X|^2 -> mel."""
+    w = _prep(wav)
+    B, N = w.shape
+    out = torch.empty(B, n_mels, 1 + N // hop_length, device=w.device, dtype=torch.float32)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().b200voc_stft_logmel(_lib.ptr(w), B, N, n_fft, hop_length, n_mels, sample_rate, int(log),
+                                                   _lib.ptr(out), _lib.current_stream()), "stft_logmel")
+    return out
+
+
+def log_mel(wav: torch.Tensor, n_fft: int = 1024, hop_length: int = 256, n_mels: int = 80,
+            sample_rate: int = 22050) -> torch.Tensor:
+    return mel_spectrogram(wav, n_fft, hop_length, n_mels, sample_rate, log=True)
+
+
+def istft(spec: torch.Tensor, n_fft: int, hop_length: int, length: int) -> torch.Tensor:
+    """complex [B, n_fft/2+1, frames] -> wav [B, length] (torch.istft semantics, Hann, center)."""
+    _lib.require_cuda(spec)
+    if not spec.is_complex() or spec.dim() != 3 or spec.shape[1] != n_fft // 2 + 1:
+        raise ValueError(f"spec must be complex [B,{n_fft // 2 + 1},frames], got {tuple(spec.shape)} {spec.dtype}")
+    ri = torch.view_as_real(spec.detach().to(torch.complex64).contiguous())
+    B, _, frames = spec.shape
+    out = torch.empty(B, length, device=spec.device, dtype=torch.float32)
+    with torch.cuda.device(spec.device):
+        _lib.check(_lib.load().b200voc_istft(_lib.ptr(ri), B, frames, n_fft, hop_length, length, _lib.ptr(out),
+                                             _lib.current_stream()), "istft")
+    return out
+
+
+class LearnableSTFT(nn.Module):
+    """``LearnableSTFT(n_fft, hop_length)(wav[B,1,T]) -> [B, n_fft/2+1, frames]`` (stft.py:9-34):
+    Hann STFT magnitude times a learnable per-bin gain (``filterbank`` ~ randn, same names/shapes
+    so a reference state_dict loads unchanged)."""
+
+    def __init__(self, n_fft: int, hop_length: int):
+        super().__init__()
+        self.n_fft = n_fft
+        self.hop_length = hop_length
+        self.register_buffer("window", torch.hann_window(n_fft))
+        self.filterbank = nn.Parameter(torch.randn(n_fft // 2 + 1))
+
+    def forward(self, wav: torch.Tensor) -> torch.Tensor:
+        return stft_magnitude(wav, self.n_fft, self.hop_length, self.filterbank)
+
+
+class STFTLoss(nn.Module):
+    """Multi-resolution STFT L1 loss (stft.py:36-54), forward value only."""
+
+    def __init__(self, cfg: GANConfig):
+        super().__init__()
+        self.stfts = nn.ModuleList([LearnableSTFT(n_fft, cfg.hop_length) for n_fft in cfg.stft_sizes])
+        self.lambda_stft = cfg.lambda_stft
+
+    def forward(self, wav_fake: torch.Tensor, wav_real: torch.Tensor) -> torch.Tensor:
+        f, r = _prep(wav_fake), _prep(wav_real)
+        if f.shape != r.shape:
+            raise ValueError(f"shape mismatch {tuple(f.shape)} vs {tuple(r.shape)}")
+        B, N = f.shape
+        lib = _lib.load()
+        sums = torch.zeros(len(self.stfts), device=f.device, dtype=torch.float64)
+        loss = torch.zeros((), device=f.device, dtype=torch.float32)
+        with torch.cuda.device(f.device):
+            for i, m in enumerate(self.stfts):
+                # L1(|X_f| g, |X_r| g) = mean(|g| * | |X_f| - |X_r| |): the kernel is given |g|
+                g = m.filterbank.detach().abs().to(torch.float32).contiguous()
+                _lib.check(lib.b200voc_stft_l1(_lib.ptr(f), _lib.ptr(r), B, N, m.n_fft, m.hop_length, _lib.ptr(g),
+                                               sums[i:i + 1].data_ptr(), _lib.current_stream()), "stft_l1")
+                numel = B * (m.n_fft // 2 + 1) * (1 + N // m.hop_length)
+                loss = loss + (sums[i] / numel).to(torch.float32)
+        return loss * self.lambda_stft
