@@ -39,15 +39,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Spin with a watchdog: a mis-programmed pipeline must fault (trap -> launch failure the host
-// reports) instead of hanging the GPU.  ~2^31 cycles is about a second at B200 clocks.
+// reports) instead of hanging the GPU.  The hot loop is try_wait + branch only; the clock is
+// consulted once every 64K failed probes (~2^31 cycles is about a second at B200 clocks).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 31)) {
-      printf("b200voc: mbarrier watchdog (block %d,%d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, parity);
-      __trap();
+    if ((++spins & 0xFFFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > (1ll << 31)) {
+        printf("b200voc: mbarrier watchdog (block %d,%d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
+               blockIdx.z, threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }
@@ -104,6 +110,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ UMMA
@@ -158,7 +171,38 @@ __device__ __forceinline__ float2 unpack2(uint32_t w, int fmt) {
   return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w));
 }
 
+// compile-time-format variants (no per-element branch)
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2t(float a, float b) {
+  if constexpr (FMT == 0) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+template <int FMT>
+__device__ __forceinline__ float2 unpack2t(uint32_t w) {
+  if constexpr (FMT == 0) return __half22float2(*reinterpret_cast<__half2*>(&w));
+  else return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid(g) with g already scaled: pass t = -log2(e) * g
+__device__ __forceinline__ float sigmoid_from_neg_log2e_g(float t) { return rcp_approx(1.0f + ex2_approx(t)); }
+
 constexpr float kLreluSlope = 0.1f;
+__device__ __forceinline__ float lrelu_fast(float x) { return fmaxf(x, kLreluSlope * x); }
+__device__ __forceinline__ float lrelu_inv_fast(float a) { return fminf(a, a * 10.0f); }
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : kLreluSlope * x; }
 // inverse of lrelu for values stored as lrelu(x)
 __device__ __forceinline__ float lrelu_inv(float a) { return a >= 0.f ? a : a * 10.0f; }

@@ -9,9 +9,11 @@
 //     is shifted by (8 +- d) rows -- legal because the 128B/64B swizzle is a function of the
 //     absolute shared-memory address (tests/test_gpu_generator.py::test_rowshifted_umma_descriptors);
 //   * the residual x is recovered from the same shared-memory tile (no second global read);
-//   * A tiles, the h operand and both TMEM accumulators are double buffered, and the work is
-//     split over specialised warps: TMA producer | MMA issuer | 4 warps GLU+FiLM epilogue |
-//     4 warps residual+store epilogue, so tile i+1's GEMM1 and GLU overlap tile i's GEMM2/store.
+//   * A tiles, the h operand and both TMEM accumulators are ring buffered, and the work is
+//     split over specialised warps: TMA producer | MMA issuer | 8 warps GLU+FiLM epilogue |
+//     8 warps residual+store epilogue, so tile i+1's GEMM1 and GLU overlap tile i's GEMM2/store;
+//     operand format / output format / stored activation are template parameters (no per-element
+//     branches in the epilogues, which are the instruction-issue bottleneck of these stages).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -46,14 +48,15 @@ struct Rb2Cfg {
   static constexpr int NA = ND + 2;                 // ring depth of the input tiles (TMA prefetch distance)
   static constexpr int OFF_H = OFF_A + NA * A_SLOT;
   static constexpr int OFF_BAR = OFF_H + ND * H_BYTES;
-  static constexpr int SMEM = OFF_BAR + 512 + 1024;
+  static constexpr int OFF_PAR = OFF_BAR + 512;
+  static constexpr int SMEM = OFF_PAR + 3 * C * 4 + 1024;
   static constexpr int D2_COL = ND * N1;
   static constexpr int TMEM_NEED = ND * N1 + ND * C;
   static constexpr uint32_t TMEM_COLS = TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
 };
 
-template <int C>
-__global__ void __launch_bounds__(320, 1)
+template <int C, int FMT, int OFMT, bool LRELU>
+__global__ void __launch_bounds__(576, 1)
 resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const Resblock2Params p) {
   using K = Rb2Cfg<C>;
@@ -75,9 +78,17 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* d2_full = h_empty + ND;        // [ND]
   uint64_t* d2_empty = d2_full + ND;       // [ND]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + ND);
+  float* sPar = reinterpret_cast<float*>(smem + K::OFF_PAR);   // [ba | -log2e*bg | b2], C floats each
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr float kNegLog2e = -1.4426950408889634f;
+  constexpr int kEpiThreads = 256;          // 8 warps per epilogue role (2 per TMEM lane quadrant)
 
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    sPar[i] = p.b_conv[i];
+    sPar[C + i] = kNegLog2e * p.b_conv[C + i];
+    sPar[2 * C + i] = p.b_proj[i];
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW1);
@@ -85,15 +96,15 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     mbar_init(w_full, 1);
     for (int b = 0; b < NA; ++b) {
       mbar_init(&a_full[b], 1);
-      mbar_init(&a_empty[b], 128);
+      mbar_init(&a_empty[b], kEpiThreads);
     }
     for (int b = 0; b < ND; ++b) {
       mbar_init(&d1_full[b], 1);
-      mbar_init(&d1_empty[b], 128);
-      mbar_init(&h_full[b], 128);
+      mbar_init(&d1_empty[b], kEpiThreads);
+      mbar_init(&h_full[b], kEpiThreads);
       mbar_init(&h_empty[b], 1);
       mbar_init(&d2_full[b], 1);
-      mbar_init(&d2_empty[b], 128);
+      mbar_init(&d2_empty[b], kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -121,8 +132,8 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc1 = make_idesc_f16(p.fmt, K::N1);
-      const uint32_t idesc2 = make_idesc_f16(p.fmt, C);
+      const uint32_t idesc1 = make_idesc_f16(FMT, K::N1);
+      const uint32_t idesc2 = make_idesc_f16(FMT, C);
       mbar_wait(w_full, 0);
       auto issue_g2 = [&](int i) {
         const int b = i % ND;
@@ -159,13 +170,16 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       for (int j = (i >= ND - 1 ? i - (ND - 1) : 0); j < i; ++j) issue_g2(j);
     }
-  } else if (warp < 6) {
-    // ------------------------------------------------------------ epilogue 1 (warps 2..5): GLU + FiLM -> h
-    const int q = warp & 3;
+  } else if (warp < 10) {
+    // ------------------------------------------------------------ epilogue 1 (warps 2..9): GLU + FiLM -> h
+    // two warps per TMEM lane quadrant; each owns half of the channels of its 32 rows
+    const int q = warp & 3, hsel = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    constexpr int CW = C / 2;
+    const int cbase = hsel * CW;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int fmt = p.fmt;
-    constexpr float kLog2e = 1.4426950408889634f;
+    const float4* sBA = reinterpret_cast<const float4*>(sPar);
+    const float4* sNB = reinterpret_cast<const float4*>(sPar + C);
     int i = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
       const int b = i % ND;
@@ -178,52 +192,53 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_wait(&h_empty[b], ph ^ 1);
       tc_fence_after();
       uint8_t* hrow = sH + b * K::H_BYTES + row * K::ROWB;
-#pragma unroll 1
-      for (int cc = 0; cc < C / 32; ++cc) {
-        uint32_t va[32], vg[32];
-        tmem_ld32(lane_addr + b * K::N1 + cc * 32, va);
-        tmem_ld32(lane_addr + b * K::N1 + C + cc * 32, vg);
-        tmem_ld_wait();
-        const int ch0 = cc * 32;
-        const float4* ba = reinterpret_cast<const float4*>(p.b_conv + ch0);
-        const float4* bg = reinterpret_cast<const float4*>(p.b_conv + C + ch0);
-        const float4* fs = reinterpret_cast<const float4*>(film + ch0);
-        const float4* fh = reinterpret_cast<const float4*>(film + C + ch0);
 #pragma unroll
-        for (int i8 = 0; i8 < 4; ++i8) {
+      for (int c0 = cbase; c0 < cbase + CW; c0 += 16) {
+        uint32_t va[16], vg[16];
+        tmem_ld16(lane_addr + b * K::N1 + c0, va);
+        tmem_ld16(lane_addr + b * K::N1 + C + c0, vg);
+        const float4* fs = reinterpret_cast<const float4*>(film + c0);
+        const float4* fh = reinterpret_cast<const float4*>(film + C + c0);
+        float4 S[4], H[4];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) { S[i4] = __ldg(fs + i4); H[i4] = __ldg(fh + i4); }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i8 = 0; i8 < 2; ++i8) {
           float hv[8];
 #pragma unroll
           for (int h4 = 0; h4 < 2; ++h4) {
             const int i4 = i8 * 2 + h4;
-            const float4 A = __ldg(ba + i4), G = __ldg(bg + i4), S = __ldg(fs + i4), H = __ldg(fh + i4);
+            const float4 A = sBA[(c0 >> 2) + i4], G = sNB[(c0 >> 2) + i4];
             const float av[4] = {A.x, A.y, A.z, A.w}, gv[4] = {G.x, G.y, G.z, G.w};
-            const float sv[4] = {S.x, S.y, S.z, S.w}, tv[4] = {H.x, H.y, H.z, H.w};
+            const float sv[4] = {S[i4].x, S[i4].y, S[i4].z, S[i4].w}, tv[4] = {H[i4].x, H[i4].y, H[i4].z, H[i4].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float a = __uint_as_float(va[i4 * 4 + e]) + av[e];
-              const float g = __uint_as_float(vg[i4 * 4 + e]) + gv[e];
-              const float sg = __fdividef(1.0f, 1.0f + exp2f(-kLog2e * g));
+              const float sg = sigmoid_from_neg_log2e_g(fmaf(__uint_as_float(vg[i4 * 4 + e]), kNegLog2e, gv[e]));
               hv[h4 * 4 + e] = fmaf(a * sg, sv[e], tv[e]);
             }
           }
-          const int chunk = cc * 4 + i8;
+          const int chunk = (c0 >> 3) + i8;
           const int phys = K::ROWB == 128 ? (chunk ^ (row & 7)) : (chunk ^ ((row >> 1) & 3));
           *reinterpret_cast<uint4*>(hrow + phys * 16) =
-              make_uint4(pack2(hv[0], hv[1], fmt), pack2(hv[2], hv[3], fmt), pack2(hv[4], hv[5], fmt),
-                         pack2(hv[6], hv[7], fmt));
+              make_uint4(pack2t<FMT>(hv[0], hv[1]), pack2t<FMT>(hv[2], hv[3]), pack2t<FMT>(hv[4], hv[5]),
+                         pack2t<FMT>(hv[6], hv[7]));
         }
       }
       tc_fence_before();
-      fence_proxy_async_smem();
+      fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the UMMA (async proxy)
       mbar_arrive(&h_full[b]);
       mbar_arrive(&d1_empty[b]);
     }
   } else {
-    // ------------------------------------------------------------ epilogue 2 (warps 6..9): residual + store
-    const int q = warp & 3;
+    // ------------------------------------------------------------ epilogue 2 (warps 10..17): residual + store
+    const int q = warp & 3, hsel = (warp - 10) >> 2;
     const int row = q * 32 + lane;
+    constexpr int CW = C / 2;
+    const int cbase = hsel * CW;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int fmt = p.fmt, ofmt = p.out_fmt;
+    const float4* sB2 = reinterpret_cast<const float4*>(sPar + 2 * C);
     int i = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
       const int b = i % ND, ab = i % NA;
@@ -235,30 +250,33 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tc_fence_after();
       const uint8_t* xrow = sA + ab * K::A_SLOT + (row + K::HALO) * K::ROWB;
       uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)seq * p.L + (valid ? l : 0)) * C);
-#pragma unroll 1
-      for (int cc = 0; cc < C / 32; ++cc) {
-        uint32_t vd[32];
-        tmem_ld32(lane_addr + K::D2_COL + b * C + cc * 32, vd);
-        tmem_ld_wait();
-        const float4* b2 = reinterpret_cast<const float4*>(p.b_proj + cc * 32);
 #pragma unroll
-        for (int i8 = 0; i8 < 4; ++i8) {
-          const int chunk = cc * 4 + i8;
+      for (int c0 = cbase; c0 < cbase + CW; c0 += 16) {
+        uint32_t vd[16];
+        tmem_ld16(lane_addr + K::D2_COL + b * C + c0, vd);
+        uint4 xa[2];
+#pragma unroll
+        for (int i8 = 0; i8 < 2; ++i8) {
+          const int chunk = (c0 >> 3) + i8;
           const int phys = K::ROWB == 128 ? (chunk ^ (row & 7)) : (chunk ^ ((row >> 1) & 3));
-          const uint4 xa = *reinterpret_cast<const uint4*>(xrow + phys * 16);
-          const uint32_t xw[4] = {xa.x, xa.y, xa.z, xa.w};
-          const float4 B0 = __ldg(b2 + i8 * 2), B1 = __ldg(b2 + i8 * 2 + 1);
+          xa[i8] = *reinterpret_cast<const uint4*>(xrow + phys * 16);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i8 = 0; i8 < 2; ++i8) {
+          const uint32_t xw[4] = {xa[i8].x, xa[i8].y, xa[i8].z, xa[i8].w};
+          const float4 B0 = sB2[(c0 >> 2) + i8 * 2], B1 = sB2[(c0 >> 2) + i8 * 2 + 1];
           const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
           uint32_t ow[4];
 #pragma unroll
           for (int e2 = 0; e2 < 4; ++e2) {
-            const float2 xs = unpack2(xw[e2], fmt);
-            float y0 = lrelu_inv(xs.x) + __uint_as_float(vd[i8 * 8 + e2 * 2]) + bv[e2 * 2];
-            float y1 = lrelu_inv(xs.y) + __uint_as_float(vd[i8 * 8 + e2 * 2 + 1]) + bv[e2 * 2 + 1];
-            if (p.store_lrelu) { y0 = lrelu(y0); y1 = lrelu(y1); }
-            ow[e2] = pack2(y0, y1, ofmt);
+            const float2 xs = unpack2t<FMT>(xw[e2]);
+            float y0 = (lrelu_inv_fast(xs.x) + bv[e2 * 2]) + __uint_as_float(vd[i8 * 8 + e2 * 2]);
+            float y1 = (lrelu_inv_fast(xs.y) + bv[e2 * 2 + 1]) + __uint_as_float(vd[i8 * 8 + e2 * 2 + 1]);
+            if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
+            ow[e2] = pack2t<OFMT>(y0, y1);
           }
-          if (valid) dst[chunk] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          if (valid) dst[(c0 >> 3) + i8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
       }
       tc_fence_before();
@@ -279,10 +297,10 @@ static int num_sms() {
   return n[dev & 15];
 }
 
-template <int C>
+template <int C, int FMT, int OFMT, bool LRELU>
 static int launch_resblock2(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
                             const float* film, int film_stride, int N, int L, int dilation, int T, int num_bands,
-                            int fmt, int out_fmt, int store_lrelu, void* out16, cudaStream_t stream) {
+                            void* out16, cudaStream_t stream) {
   using K = Rb2Cfg<C>;
   CUtensorMap tmX, tmW1, tmW2;
   B200_TRY(make_tmap_3d(&tmX, a16, C, L, N, (uint64_t)C * 2, (uint64_t)L * C * 2, K::KB, K::A_ROWS, K::ROWB));
@@ -292,7 +310,7 @@ static int launch_resblock2(const void* a16, const void* w_packed, const float* 
   B200_TRY(make_tmap_2d(&tmW2, w2, C, C, (uint64_t)C * 2, K::KB, C, K::ROWB));
   Resblock2Params p{};
   p.L = L; p.dilation = dilation; p.T = T; p.P = L / T; p.num_bands = num_bands;
-  p.fmt = fmt; p.out_fmt = out_fmt; p.store_lrelu = store_lrelu;
+  p.fmt = FMT; p.out_fmt = OFMT; p.store_lrelu = LRELU;
   p.tiles_per_seq = ceil_div(L, 128);
   p.total_tiles = p.tiles_per_seq * N;
   p.b_conv = b_conv; p.b_proj = b_proj; p.film = film; p.film_stride = film_stride;
@@ -301,25 +319,42 @@ static int launch_resblock2(const void* a16, const void* w_packed, const float* 
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 15]) {
-    B200_CUDA(cudaFuncSetAttribute(resblock2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+    B200_CUDA(cudaFuncSetAttribute(resblock2_kernel<C, FMT, OFMT, LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   K::SMEM));
     configured[dev & 15] = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  resblock2_kernel<C><<<grid, 320, K::SMEM, stream>>>(tmX, tmW1, tmW2, p);
+  resblock2_kernel<C, FMT, OFMT, LRELU><<<grid, 576, K::SMEM, stream>>>(tmX, tmW1, tmW2, p);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
+}
+
+template <int C>
+static int dispatch_resblock2(const void* a16, const void* w, const float* bc, const float* bp, const float* film,
+                              int fs, int N, int L, int d, int T, int nb, int fmt, int ofmt, int lrelu, void* out,
+                              cudaStream_t st) {
+#define RB2(F, O, R) return launch_resblock2<C, F, O, R>(a16, w, bc, bp, film, fs, N, L, d, T, nb, out, st)
+  if (fmt == 0) {
+    if (ofmt == 0) { if (lrelu) RB2(0, 0, true); else RB2(0, 0, false); }
+    else { if (lrelu) RB2(0, 1, true); else RB2(0, 1, false); }
+  } else {
+    if (ofmt == 0) { if (lrelu) RB2(1, 0, true); else RB2(1, 0, false); }
+    else { if (lrelu) RB2(1, 1, true); else RB2(1, 1, false); }
+  }
+#undef RB2
 }
 
 int resblock2_launch(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
                      const float* film, int film_stride, int N, int L, int C, int dilation, int T, int num_bands,
                      int fmt, int out_fmt, int store_lrelu, void* out16, cudaStream_t stream) {
   B200_CHECK_ARG(dilation >= 1 && dilation <= 8, "resblock2: dilation %d exceeds the 8-row halo", dilation);
+  B200_CHECK_ARG((fmt == 0 || fmt == 1) && (out_fmt == 0 || out_fmt == 1), "resblock2: bad format");
   if (C == 32)
-    return launch_resblock2<32>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt,
-                                out_fmt, store_lrelu, out16, stream);
+    return dispatch_resblock2<32>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt,
+                                  out_fmt, store_lrelu, out16, stream);
   if (C == 64)
-    return launch_resblock2<64>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt,
-                                out_fmt, store_lrelu, out16, stream);
+    return dispatch_resblock2<64>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt,
+                                  out_fmt, store_lrelu, out16, stream);
   set_error("resblock2: C=%d unsupported (32/64)", C);
   return B200VOC_ERR_UNSUPPORTED;
 }

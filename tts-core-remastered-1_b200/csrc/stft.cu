@@ -45,7 +45,7 @@ struct StftParams {
 __device__ __forceinline__ int reflect(int s, int n) {
   if (s < 0) s = -s;
   if (s >= n) s = 2 * (n - 1) - s;
-  return s;
+  return min(max(s, 0), n - 1);   // frames past the end of the signal (tail CTA) read clamped garbage, never stored
 }
 
 template <int NFFT, int MODE>
