@@ -11,6 +11,8 @@
 // chunk's GLU/FiLM epilogue writes 64 channels of h as a K-major swizzled SMEM tile, which is
 // k-block j of GEMM2 -- h never touches HBM.  Chunk j+1's MMAs overlap chunk j's epilogue
 // (two TMEM accumulator buffers), GEMM2 k-block j is issued as soon as h chunk j is ready.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -340,6 +342,20 @@ int resblock2_launch(const void* a16, const void* w_packed, const float* b_conv,
                      const float* film, int film_stride, int N, int L, int C, int dilation, int T, int num_bands,
                      int fmt, int out_fmt, int store_lrelu, void* out16, cudaStream_t stream);
 
+int resblock3_launch(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
+                     const float* film, int film_stride, int N, int L, int C, int dilation, int T, int num_bands,
+                     int fmt, int out_fmt, int store_lrelu, void* out16, cudaStream_t stream);
+
+// B200VOC_RESBLOCK_V1=1 forces the first-generation one-tile-per-CTA kernel (A/B measurements).
+static bool force_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200VOC_RESBLOCK_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int resblock_launch(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
                     const float* film, int film_stride, int N, int L, int C, int dilation, int T, int num_bands,
                     int fmt, int out_fmt, int store_lrelu, void* out16, cudaStream_t stream) {
@@ -349,14 +365,20 @@ int resblock_launch(const void* a16, const void* w_packed, const float* b_conv, 
   switch (C) {
     case 32:
     case 64:
-      if (dilation <= 8)
+      if (dilation <= 8 && !force_v1())
         return resblock2_launch(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, C, dilation, T, num_bands, fmt,
                                 out_fmt, store_lrelu, out16, stream);
       if (C == 32)
         return launch_resblock<32>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, out_fmt, store_lrelu, out16, stream);
       return launch_resblock<64>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, out_fmt, store_lrelu, out16, stream);
-    case 128: return launch_resblock<128>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, out_fmt, store_lrelu, out16, stream);
-    case 256: return launch_resblock<256>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, out_fmt, store_lrelu, out16, stream);
+    case 128:
+    case 256:
+      if (dilation <= 8 && !force_v1())
+        return resblock3_launch(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, C, dilation, T, num_bands, fmt,
+                                out_fmt, store_lrelu, out16, stream);
+      if (C == 256)
+        return launch_resblock<256>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, out_fmt, store_lrelu, out16, stream);
+      return launch_resblock<128>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, out_fmt, store_lrelu, out16, stream);
   }
   set_error("resblock: C=%d unsupported (32/64/128/256)", C);
   return B200VOC_ERR_UNSUPPORTED;

@@ -1,0 +1,389 @@
+// K2c: persistent fused residual block for the wide stages (C = 128, 256) -- the tensor-bound
+// part of the network (81 % of all FLOPs live in residual blocks, stages 0-1 hold two thirds).
+//
+// Same math as resblock.cu (generator.py:40-41,89-90 / repair R2).  Schedule:
+//   * one persistent CTA per SM loops over (sequence, 128-row) tiles;
+//   * the leaky_relu(x) tile (128 rows + 8-row halo each side, all channels) is loaded ONCE per
+//     tile; the three dilated taps are row-shifted UMMA descriptors over that tile;
+//   * weights do not fit in shared memory (W1 is 192/768 KB), so they stream through a TMA ring of
+//     16 KB tiles (L2-resident: every CTA walks the same 224/896 KB sequence);
+//   * GEMM1 runs in chunks of 64 value + 64 gate channels into two alternating TMEM accumulators;
+//     the GLU/FiLM epilogue of chunk j (8 warps) overlaps the MMAs of chunk j+1; it writes h as
+//     k-block j of GEMM2's A operand; GEMM2's k-block j is issued one chunk later, the last
+//     one after the first chunk of the NEXT tile, so the tensor pipe never waits for an epilogue;
+//   * the residual/store epilogue (8 more warps) drains D2 while the next tile's GEMM1 runs.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+struct Resblock3Params {
+  int L, dilation, T, P, num_bands;
+  int tiles_per_seq, total_tiles;
+  const uint16_t* a16;   // [N, L, C] leaky_relu(x)
+  const float* b_conv;   // [2C]
+  const float* b_proj;   // [C]
+  const float* film;     // [B, T, film_stride]
+  int film_stride;
+  uint16_t* out;         // [N, L, C]
+};
+
+template <int C>
+struct Rb3Cfg {
+  static constexpr int KPT = C / 64;                 // k-blocks per tap = GEMM1 chunks = GEMM2 k-blocks
+  static constexpr int NCH = KPT;
+  static constexpr int NH = C / 128;                 // GEMM2 output halves of 128 columns
+  static constexpr int HALO = 8;
+  static constexpr int A_ROWS = 128 + 2 * HALO;
+  static constexpr int A_KB_BYTES = A_ROWS * 128;    // 18 KB per k-block
+  static constexpr int A_BYTES = KPT * A_KB_BYTES;
+  static constexpr int NA = C == 128 ? 2 : 1;
+  static constexpr int H_KB_BYTES = 128 * 128;       // 16 KB per k-block
+  static constexpr int W_TILE = 128 * 128;           // 16 KB ring slot: [128 rows x 64 k]
+  static constexpr int NW = C == 128 ? 6 : 4;
+  static constexpr int ND2 = C == 128 ? 2 : 1;
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_H = OFF_A + NA * A_BYTES;
+  static constexpr int OFF_W = OFF_H + KPT * H_KB_BYTES;
+  static constexpr int OFF_BAR = OFF_W + NW * W_TILE;
+  static constexpr int OFF_PAR = OFF_BAR + 512;
+  static constexpr int SMEM = OFF_PAR + 3 * C * 4 + 1024;
+  static constexpr int D2_COL = 256;
+  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr int A_PREFETCH_AFTER_CHUNK = NA == 2 ? 0 : NCH - 1;
+  static_assert(OFF_H % 1024 == 0 && OFF_W % 1024 == 0 && A_KB_BYTES % 1024 == 0, "1024B alignment for SWIZZLE_128B");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+template <int C, int FMT, int OFMT, bool LRELU>
+__global__ void __launch_bounds__(576, 1)
+resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const Resblock3Params p) {
+  using K = Rb3Cfg<C>;
+  constexpr int KPT = K::KPT, NCH = K::NCH, NH = K::NH, NA = K::NA, NW = K::NW, ND2 = K::ND2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem + K::OFF_A;
+  uint8_t* sH = smem + K::OFF_H;
+  uint8_t* sW = smem + K::OFF_W;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_BAR);
+  uint64_t* a_full = bars;                  // [NA]
+  uint64_t* a_empty = a_full + NA;          // [NA]
+  uint64_t* w_full = a_empty + NA;          // [NW]
+  uint64_t* w_empty = w_full + NW;          // [NW]
+  uint64_t* d1_full = w_empty + NW;         // [2]
+  uint64_t* d1_empty = d1_full + 2;         // [2]
+  uint64_t* h_full = d1_empty + 2;          // [KPT]
+  uint64_t* h_empty = h_full + KPT;         // [KPT]
+  uint64_t* d2_full = h_empty + KPT;        // [ND2]
+  uint64_t* d2_empty = d2_full + ND2;       // [ND2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + ND2);
+  float* sPar = reinterpret_cast<float*>(smem + K::OFF_PAR);   // [ba | -log2e*bg | b2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr float kNegLog2e = -1.4426950408889634f;
+  constexpr int kEpiThreads = 256;
+
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    sPar[i] = p.b_conv[i];
+    sPar[C + i] = kNegLog2e * p.b_conv[C + i];
+    sPar[2 * C + i] = p.b_proj[i];
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    for (int b = 0; b < NA; ++b) { mbar_init(&a_full[b], 1); mbar_init(&a_empty[b], 1); }
+    for (int b = 0; b < NW; ++b) { mbar_init(&w_full[b], 1); mbar_init(&w_empty[b], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&d1_full[b], 1); mbar_init(&d1_empty[b], kEpiThreads); }
+    for (int b = 0; b < KPT; ++b) { mbar_init(&h_full[b], kEpiThreads); mbar_init(&h_empty[b], 1); }
+    for (int b = 0; b < ND2; ++b) { mbar_init(&d2_full[b], 1); mbar_init(&d2_empty[b], kEpiThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, K::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (A tiles + weight ring)
+    if (lane == 0) {
+      int wi = 0;
+      auto w_slot = [&]() -> uint8_t* {
+        const int s = wi % NW;
+        mbar_wait(&w_empty[s], ((wi / NW) & 1) ^ 1);
+        mbar_expect_tx(&w_full[s], K::W_TILE);
+        return sW + s * K::W_TILE;
+      };
+      auto load_a = [&](int it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int seq = tile / p.tiles_per_seq, l0 = (tile - seq * p.tiles_per_seq) * 128;
+        const int ab = it % NA;
+        mbar_wait(&a_empty[ab], ((it / NA) & 1) ^ 1);
+        mbar_expect_tx(&a_full[ab], K::A_BYTES);
+        for (int kb = 0; kb < KPT; ++kb)
+          tma_load_3d(sA + ab * K::A_BYTES + kb * K::A_KB_BYTES, &tmX, &a_full[ab], kb * 64, l0 - K::HALO, seq);
+      };
+      auto load_w2 = [&](int kb) {
+        for (int half = 0; half < NH; ++half) {
+          uint8_t* dst = w_slot();
+          tma_load_2d(dst, &tmW2, &w_full[wi % NW], kb * 64, half * 128);
+          ++wi;
+        }
+      };
+      if (n_my_tiles > 0) load_a(0);
+      int gc = 0;
+      for (int it = 0; it < n_my_tiles; ++it) {
+        for (int j = 0; j < NCH; ++j, ++gc) {
+          for (int tap = 0; tap < 3; ++tap)
+            for (int kb = 0; kb < KPT; ++kb) {
+              uint8_t* dst = w_slot();
+              tma_load_2d(dst, &tmW1, &w_full[wi % NW], tap * C + kb * 64, j * 128);
+              ++wi;
+            }
+          if (j == K::A_PREFETCH_AFTER_CHUNK && it + 1 < n_my_tiles) load_a(it + 1);
+          if (gc >= 1) load_w2((gc - 1) % NCH);
+        }
+      }
+      if (gc >= 1) load_w2((gc - 1) % NCH);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(FMT, 128);
+      int wi = 0;
+      auto g2 = [&](int it2, int kb) {
+        const int db = it2 % ND2;
+        mbar_wait(&h_full[kb], it2 & 1);
+        if (kb == 0) mbar_wait(&d2_empty[db], ((it2 / ND2) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sH + kb * K::H_KB_BYTES));
+        for (int half = 0; half < NH; ++half) {
+          const int s = wi % NW;
+          mbar_wait(&w_full[s], (wi / NW) & 1);
+          tc_fence_after();
+          const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + s * K::W_TILE));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + K::D2_COL + db * C + half * 128, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                     (kb | k) != 0);
+          umma_commit(&w_empty[s]);
+          ++wi;
+        }
+        umma_commit(&h_empty[kb]);
+        if (kb == NCH - 1) umma_commit(&d2_full[db]);
+      };
+      int gc = 0;
+      for (int it = 0; it < n_my_tiles; ++it) {
+        const int ab = it % NA;
+        for (int j = 0; j < NCH; ++j, ++gc) {
+          const int b = gc & 1;
+          if (j == 0) mbar_wait(&a_full[ab], (it / NA) & 1);
+          mbar_wait(&d1_empty[b], ((gc >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int tap = 0; tap < 3; ++tap)
+            for (int kb = 0; kb < KPT; ++kb) {
+              const int s = wi % NW;
+              mbar_wait(&w_full[s], (wi / NW) & 1);
+              tc_fence_after();
+              const uint32_t a_addr = smem_u32(sA + ab * K::A_BYTES + kb * K::A_KB_BYTES) +
+                                      (K::HALO + (tap - 1) * p.dilation) * 128;
+              const uint64_t a_desc = make_kmajor_desc<128>(a_addr);
+              const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + s * K::W_TILE));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem_base + b * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, (tap | kb | k) != 0);
+              umma_commit(&w_empty[s]);
+              ++wi;
+            }
+          umma_commit(&d1_full[b]);
+          if (j == NCH - 1) umma_commit(&a_empty[ab]);
+          if (gc >= 1) g2((gc - 1) / NCH, (gc - 1) % NCH);
+        }
+      }
+      if (gc >= 1) g2((gc - 1) / NCH, (gc - 1) % NCH);
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------ epilogue 1 (warps 2..9): GLU + FiLM -> h
+    const int q = warp & 3, hsel = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float4* sBA = reinterpret_cast<const float4*>(sPar);
+    const float4* sNB = reinterpret_cast<const float4*>(sPar + C);
+    int gc = 0;
+    for (int it = 0; it < n_my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int seq = tile / p.tiles_per_seq, l = (tile - seq * p.tiles_per_seq) * 128 + row;
+      int t = l / p.P;
+      if (t > p.T - 1) t = p.T - 1;
+      const float* film = p.film + ((long long)(seq / p.num_bands) * p.T + t) * p.film_stride;
+      for (int j = 0; j < NCH; ++j, ++gc) {
+        const int b = gc & 1;
+        mbar_wait(&d1_full[b], (gc >> 1) & 1);
+        mbar_wait(&h_empty[j], (it & 1) ^ 1);
+        tc_fence_after();
+        uint8_t* hrow = sH + j * K::H_KB_BYTES + row * 128;
+#pragma unroll
+        for (int cl = hsel * 32; cl < hsel * 32 + 32; cl += 16) {   // column inside the chunk's 64 value channels
+          uint32_t va[16], vg[16];
+          tmem_ld16(lane_addr + b * 128 + cl, va);
+          tmem_ld16(lane_addr + b * 128 + 64 + cl, vg);
+          const int ch = j * 64 + cl;
+          const float4* fs = reinterpret_cast<const float4*>(film + ch);
+          const float4* fh = reinterpret_cast<const float4*>(film + C + ch);
+          float4 S[4], H[4];
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) { S[i4] = __ldg(fs + i4); H[i4] = __ldg(fh + i4); }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i8 = 0; i8 < 2; ++i8) {
+            float hv[8];
+#pragma unroll
+            for (int h4 = 0; h4 < 2; ++h4) {
+              const int i4 = i8 * 2 + h4;
+              const float4 A = sBA[(ch >> 2) + i4], G = sNB[(ch >> 2) + i4];
+              const float av[4] = {A.x, A.y, A.z, A.w}, gv[4] = {G.x, G.y, G.z, G.w};
+              const float sv[4] = {S[i4].x, S[i4].y, S[i4].z, S[i4].w}, tv[4] = {H[i4].x, H[i4].y, H[i4].z, H[i4].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = __uint_as_float(va[i4 * 4 + e]) + av[e];
+                const float sg = sigmoid_from_neg_log2e_g(fmaf(__uint_as_float(vg[i4 * 4 + e]), kNegLog2e, gv[e]));
+                hv[h4 * 4 + e] = fmaf(a * sg, sv[e], tv[e]);
+              }
+            }
+            const int chunk = (cl >> 3) + i8;
+            *reinterpret_cast<uint4*>(hrow + ((chunk ^ (row & 7)) << 4)) =
+                make_uint4(pack2t<FMT>(hv[0], hv[1]), pack2t<FMT>(hv[2], hv[3]), pack2t<FMT>(hv[4], hv[5]),
+                           pack2t<FMT>(hv[6], hv[7]));
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(&h_full[j]);
+        mbar_arrive(&d1_empty[b]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue 2 (warps 10..17): residual + store
+    const int q = warp & 3, hsel = (warp - 10) >> 2;
+    const int row = q * 32 + lane;
+    constexpr int CW = C / 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float4* sB2 = reinterpret_cast<const float4*>(sPar + 2 * C);
+    for (int it = 0; it < n_my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int seq = tile / p.tiles_per_seq, l = (tile - seq * p.tiles_per_seq) * 128 + row;
+      const bool valid = l < p.L;
+      const int db = it % ND2;
+      const long long roff = ((long long)seq * p.L + (valid ? l : 0)) * C;
+      const uint4* xin = reinterpret_cast<const uint4*>(p.a16 + roff);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + roff);
+      mbar_wait(&d2_full[db], (it / ND2) & 1);
+      tc_fence_after();
+#pragma unroll 2
+      for (int c0 = hsel * CW; c0 < hsel * CW + CW; c0 += 16) {
+        uint32_t vd[16];
+        tmem_ld16(lane_addr + K::D2_COL + db * C + c0, vd);
+        uint4 xa[2];
+        xa[0] = __ldg(xin + (c0 >> 3));
+        xa[1] = __ldg(xin + (c0 >> 3) + 1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i8 = 0; i8 < 2; ++i8) {
+          const uint32_t xw[4] = {xa[i8].x, xa[i8].y, xa[i8].z, xa[i8].w};
+          const float4 B0 = sB2[(c0 >> 2) + i8 * 2], B1 = sB2[(c0 >> 2) + i8 * 2 + 1];
+          const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const float2 xs = unpack2t<FMT>(xw[e2]);
+            float y0 = (lrelu_inv_fast(xs.x) + bv[e2 * 2]) + __uint_as_float(vd[i8 * 8 + e2 * 2]);
+            float y1 = (lrelu_inv_fast(xs.y) + bv[e2 * 2 + 1]) + __uint_as_float(vd[i8 * 8 + e2 * 2 + 1]);
+            if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
+            ow[e2] = pack2t<OFMT>(y0, y1);
+          }
+          if (valid) dst[(c0 >> 3) + i8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&d2_empty[db]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, K::TMEM_COLS);
+}
+
+static int num_sms3() {
+  static int n[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!n[dev & 15]) cudaDeviceGetAttribute(&n[dev & 15], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev & 15];
+}
+
+template <int C, int FMT, int OFMT, bool LRELU>
+static int launch_resblock3(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
+                            const float* film, int film_stride, int N, int L, int dilation, int T, int num_bands,
+                            void* out16, cudaStream_t stream) {
+  using K = Rb3Cfg<C>;
+  CUtensorMap tmX, tmW1, tmW2;
+  B200_TRY(make_tmap_3d(&tmX, a16, C, L, N, (uint64_t)C * 2, (uint64_t)L * C * 2, 64, K::A_ROWS, 128));
+  const uint16_t* w1 = reinterpret_cast<const uint16_t*>(w_packed);
+  const uint16_t* w2 = w1 + 2ll * C * 3 * C;
+  B200_TRY(make_tmap_2d(&tmW1, w1, 3 * C, 2 * C, (uint64_t)3 * C * 2, 64, 128, 128));
+  B200_TRY(make_tmap_2d(&tmW2, w2, C, C, (uint64_t)C * 2, 64, 128, 128));
+  Resblock3Params p{};
+  p.L = L; p.dilation = dilation; p.T = T; p.P = L / T; p.num_bands = num_bands;
+  p.tiles_per_seq = ceil_div(L, 128);
+  p.total_tiles = p.tiles_per_seq * N;
+  p.a16 = reinterpret_cast<const uint16_t*>(a16);
+  p.b_conv = b_conv; p.b_proj = b_proj; p.film = film; p.film_stride = film_stride;
+  p.out = reinterpret_cast<uint16_t*>(out16);
+  static bool configured[16] = {};
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 15]) {
+    B200_CUDA(cudaFuncSetAttribute(resblock3_kernel<C, FMT, OFMT, LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   K::SMEM));
+    configured[dev & 15] = true;
+  }
+  const int grid = p.total_tiles < num_sms3() ? p.total_tiles : num_sms3();
+  resblock3_kernel<C, FMT, OFMT, LRELU><<<grid, 576, K::SMEM, stream>>>(tmX, tmW1, tmW2, p);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
+template <int C>
+static int dispatch_resblock3(const void* a16, const void* w, const float* bc, const float* bp, const float* film,
+                              int fs, int N, int L, int d, int T, int nb, int fmt, int ofmt, int lrelu, void* out,
+                              cudaStream_t st) {
+#define RB3(F, O, R) return launch_resblock3<C, F, O, R>(a16, w, bc, bp, film, fs, N, L, d, T, nb, out, st)
+  if (fmt == 0) {
+    if (ofmt == 0) { if (lrelu) RB3(0, 0, true); else RB3(0, 0, false); }
+    else { if (lrelu) RB3(0, 1, true); else RB3(0, 1, false); }
+  } else {
+    if (ofmt == 0) { if (lrelu) RB3(1, 0, true); else RB3(1, 0, false); }
+    else { if (lrelu) RB3(1, 1, true); else RB3(1, 1, false); }
+  }
+#undef RB3
+}
+
+int resblock3_launch(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
+                     const float* film, int film_stride, int N, int L, int C, int dilation, int T, int num_bands,
+                     int fmt, int out_fmt, int store_lrelu, void* out16, cudaStream_t stream) {
+  B200_CHECK_ARG(dilation >= 1 && dilation <= 8, "resblock3: dilation %d exceeds the 8-row halo", dilation);
+  B200_CHECK_ARG((fmt == 0 || fmt == 1) && (out_fmt == 0 || out_fmt == 1), "resblock3: bad format");
+  if (C == 128)
+    return dispatch_resblock3<128>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt,
+                                   out_fmt, store_lrelu, out16, stream);
+  if (C == 256)
+    return dispatch_resblock3<256>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt,
+                                   out_fmt, store_lrelu, out16, stream);
+  set_error("resblock3: C=%d unsupported (128/256)", C);
+  return B200VOC_ERR_UNSUPPORTED;
+}
+
+}  // namespace b200
