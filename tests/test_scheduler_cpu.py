@@ -1,0 +1,106 @@
+"""CPU: host-side scheduler logic, including the N>1 path on gloo (world_size 2) with the CPU
+oracle standing in for the CUDA Generator (same call signature)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from b200voc import scheduler as S
+from oracle import vocoder7_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_plan_shards_balanced_and_complete():
+    lengths = [861, 120, 500, 500, 30, 861, 77, 400, 860, 1]
+    for world in (1, 2, 4, 8):
+        shards = S.plan_shards(lengths, world)
+        assert sorted(i for s in shards for i in s) == list(range(len(lengths)))
+        loads = [sum(lengths[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(lengths)
+    assert S.plan_shards([], 4) == [[], [], [], []]
+    with pytest.raises(ValueError):
+        S.plan_shards([1], 0)
+
+
+def test_group_by_length_exact_and_bounded():
+    lengths = [10, 12, 10, 10, 12, 7]
+    batches = S.group_by_length(lengths, max_batch=2)
+    assert sorted(i for b in batches for i in b) == list(range(6))
+    for b in batches:
+        assert len(b) <= 2 and len({lengths[i] for i in b}) == 1
+
+
+def test_chunk_plan_tiles_the_utterance():
+    for T, chunk, halo in [(5167, 512, 8), (100, 512, 8), (513, 512, 6), (1024, 256, 0)]:
+        plan = S.chunk_plan(T, chunk, halo)
+        assert plan[0][2] == 0 and plan[-1][3] == T
+        for (a, b, ks, ke), nxt in zip(plan, plan[1:] + [None]):
+            assert 0 <= a <= ks < ke <= b <= T
+            assert ks - a <= halo and b - ke <= halo
+            if nxt is not None:
+                assert ke == nxt[2]
+
+
+def _oracle_synth():
+    cfg = O.OracleConfig(use_attention=False)
+    sd = {k: v.double() for k, v in O.make_generator(cfg, seed=1234).state_dict().items()}
+
+    def synth(mel, pros, sty, emo, **kw):
+        with torch.no_grad():
+            return O.generator_forward(sd, cfg, mel.double(), pros.double(), sty.double(), emo.double(), **kw).float()
+    return synth
+
+
+def test_synthesize_long_equals_full_on_oracle():
+    synth = _oracle_synth()
+    mel, pros, sty, emo = O.synthetic_inputs(1, 70, seed=11)
+    full = synth(mel, pros, sty, emo)
+    got = S.synthesize_long(synth, mel, pros, sty, emo, chunk_frames=24, halo=6, max_batch=4)
+    assert got.shape == full.shape
+    assert float((got - full).abs().max()) <= 1e-6
+    short = S.synthesize_long(synth, mel, pros, sty, emo, chunk_frames=24, halo=2)
+    assert float((short - full).abs().max()) > 1e-5      # a halo below the receptive field is NOT exact
+
+
+def test_synthesize_batch_ragged_matches_individual():
+    synth = _oracle_synth()
+    items = [O.synthetic_inputs(1, T, seed=T) for T in (9, 14, 9, 5)]
+    outs = S.synthesize_batch(synth, [m[0] for m, _, _, _ in items], [p[0] for _, p, _, _ in items],
+                              [s[0] for _, _, s, _ in items], [e[0] for _, _, _, e in items], max_batch=2)
+    for (m, p, s, e), w in zip(items, outs):
+        ref = synth(m, p, s, e)[0]
+        assert w.shape == ref.shape and float((w - ref).abs().max()) <= 1e-6
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tts-core-remastered-1_b200"))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    synth = _oracle_synth()
+    items = [O.synthetic_inputs(1, T, seed=100 + k) for k, T in enumerate((6, 11, 6, 8, 11))]
+    args = ([m[0] for m, _, _, _ in items], [p[0] for _, p, _, _ in items], [s[0] for _, _, s, _ in items],
+            [e[0] for _, _, _, e in items])
+    got = S.sharded_synthesize(synth, *args, max_batch=2, gather_to=0)
+    if rank == 0:
+        ok = sorted(got) == list(range(5))
+        for i, (m, p, s, e) in enumerate(items):
+            ok = ok and bool(torch.equal(got[i], synth(m, p, s, e)[0]))     # sharded == unsharded, bit for bit
+        ret[0] = ok
+    else:
+        ret[rank] = set(got) == set(S.plan_shards([6, 11, 6, 8, 11], world)[rank])
+    dist.destroy_process_group()
+
+
+def test_sharded_synthesis_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert ret[0] is True and ret[1] is True

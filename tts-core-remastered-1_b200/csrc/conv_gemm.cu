@@ -44,7 +44,7 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int STAGE_BYTES = kATileBytes + B_TILE;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* accum_full = empty + STAGES;
@@ -248,7 +248,7 @@ int linear_launch(const void* x16, const void* w_packed /*[Cout][Cin]*/, const f
 __global__ void __launch_bounds__(128, 1)
 exp_rowshift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sA = smem;                 // 144 rows x 128 B = 18432
   uint8_t* sB = smem + 19 * 1024;     // 64 rows x 128 B
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 28 * 1024);

@@ -64,7 +64,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmW2, const ResblockParams p) {
   using K = RbCfg<C>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* stages = smem;
   uint8_t* h_smem = smem + K::STAGES * K::STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(h_smem + K::H_BYTES);

@@ -61,7 +61,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmW2, const Resblock2Params p) {
   using K = Rb2Cfg<C>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sW1 = smem + K::OFF_W1;
   uint8_t* sW2 = smem + K::OFF_W2;
   uint8_t* sA = smem + K::OFF_A;
@@ -188,6 +188,8 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       int t = l / p.P;
       if (t > p.T - 1) t = p.T - 1;
       const float* film = p.film + ((long long)(seq / p.num_bands) * p.T + t) * p.film_stride;
+#pragma unroll
+      for (int k = 0; k < (2 * C) / 32; ++k) prefetch_l1(film + k * 32);     // this row's FiLM line(s) -> L1
       mbar_wait(&d1_full[b], ph);
       mbar_wait(&h_empty[b], ph ^ 1);
       tc_fence_after();

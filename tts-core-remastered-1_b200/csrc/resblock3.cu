@@ -62,7 +62,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   using K = Rb3Cfg<C>;
   constexpr int KPT = K::KPT, NCH = K::NCH, NH = K::NH, NA = K::NA, NW = K::NW, ND2 = K::ND2;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sA = smem + K::OFF_A;
   uint8_t* sH = smem + K::OFF_H;
   uint8_t* sW = smem + K::OFF_W;
@@ -219,6 +219,8 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       int t = l / p.P;
       if (t > p.T - 1) t = p.T - 1;
       const float* film = p.film + ((long long)(seq / p.num_bands) * p.T + t) * p.film_stride;
+#pragma unroll
+      for (int k = 0; k < (2 * C) / 32; ++k) prefetch_l1(film + k * 32);     // this row's FiLM line(s) -> L1
       for (int j = 0; j < NCH; ++j, ++gc) {
         const int b = gc & 1;
         mbar_wait(&d1_full[b], (gc >> 1) & 1);
@@ -280,31 +282,40 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const long long roff = ((long long)seq * p.L + (valid ? l : 0)) * C;
       const uint4* xin = reinterpret_cast<const uint4*>(p.a16 + roff);
       uint4* dst = reinterpret_cast<uint4*>(p.out + roff);
-      mbar_wait(&d2_full[db], (it / ND2) & 1);
-      tc_fence_after();
-#pragma unroll 2
-      for (int c0 = hsel * CW; c0 < hsel * CW + CW; c0 += 16) {
-        uint32_t vd[16];
-        tmem_ld16(lane_addr + K::D2_COL + db * C + c0, vd);
-        uint4 xa[2];
-        xa[0] = __ldg(xin + (c0 >> 3));
-        xa[1] = __ldg(xin + (c0 >> 3) + 1);
-        tmem_ld_wait();
+      // the residual operand comes from global (L2): issue the loads BEFORE waiting for the accumulator
+      constexpr int XV = CW / 8 < 8 ? CW / 8 : 8;       // uint4 vectors prefetched per pass (<= 32 registers)
+#pragma unroll 1
+      for (int pass = 0; pass < CW / (XV * 8); ++pass) {
+        const int cp = hsel * CW + pass * XV * 8;
+        uint4 xa[XV];
 #pragma unroll
-        for (int i8 = 0; i8 < 2; ++i8) {
-          const uint32_t xw[4] = {xa[i8].x, xa[i8].y, xa[i8].z, xa[i8].w};
-          const float4 B0 = sB2[(c0 >> 2) + i8 * 2], B1 = sB2[(c0 >> 2) + i8 * 2 + 1];
-          const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
-          uint32_t ow[4];
+        for (int v = 0; v < XV; ++v) xa[v] = __ldg(xin + (cp >> 3) + v);
+        if (pass == 0) {
+          mbar_wait(&d2_full[db], (it / ND2) & 1);
+          tc_fence_after();
+        }
 #pragma unroll
-          for (int e2 = 0; e2 < 4; ++e2) {
-            const float2 xs = unpack2t<FMT>(xw[e2]);
-            float y0 = (lrelu_inv_fast(xs.x) + bv[e2 * 2]) + __uint_as_float(vd[i8 * 8 + e2 * 2]);
-            float y1 = (lrelu_inv_fast(xs.y) + bv[e2 * 2 + 1]) + __uint_as_float(vd[i8 * 8 + e2 * 2 + 1]);
-            if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
-            ow[e2] = pack2t<OFMT>(y0, y1);
+        for (int c0 = cp; c0 < cp + XV * 8; c0 += 16) {
+          uint32_t vd[16];
+          tmem_ld16(lane_addr + K::D2_COL + db * C + c0, vd);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i8 = 0; i8 < 2; ++i8) {
+            const uint4 xv = xa[((c0 - cp) >> 3) + i8];
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float4 B0 = sB2[(c0 >> 2) + i8 * 2], B1 = sB2[(c0 >> 2) + i8 * 2 + 1];
+            const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+              const float2 xs = unpack2t<FMT>(xw[e2]);
+              float y0 = (lrelu_inv_fast(xs.x) + bv[e2 * 2]) + __uint_as_float(vd[i8 * 8 + e2 * 2]);
+              float y1 = (lrelu_inv_fast(xs.y) + bv[e2 * 2 + 1]) + __uint_as_float(vd[i8 * 8 + e2 * 2 + 1]);
+              if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
+              ow[e2] = pack2t<OFMT>(y0, y1);
+            }
+            if (valid) dst[(c0 >> 3) + i8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
           }
-          if (valid) dst[(c0 >> 3) + i8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
       }
       tc_fence_before();
