@@ -131,6 +131,8 @@ int b200voc_resblock(const void* a16, const void* w_packed, const float* b_conv,
 
 /* experiment: UMMA descriptors whose start address is offset by whole 128B rows. */
 int b200voc_exp_rowshift(const void* a16_144x64, const void* b16_64x64, float* out_2x16x128x64, void* stream);
+/* experiment: cycles for iters x 4 tcgen05.mma (M=128, N=n, K=16, operands in shared memory). */
+int b200voc_exp_mma_rate(int n, int iters, int blocks, int64_t* out_cycles, void* stream);
 
 /* ----------------------------------------------------------------------------------------
  * STFT family (replaces vocoder7/stft.py:9-54 and the torchaudio MelSpectrogram call sites

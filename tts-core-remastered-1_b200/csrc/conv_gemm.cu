@@ -309,6 +309,59 @@ int exp_rowshift_launch(const void* a16, const void* b16, float* out, cudaStream
   return B200VOC_OK;
 }
 
+// ---------------------------------------------------------------------------- experiment
+// Raw tcgen05.mma issue rate from shared-memory operands (SS mode), M = 128, K = 16 per MMA, for a
+// given N: one thread per CTA issues `iters` x 4 MMAs on a fixed (uninitialised) operand tile and
+// times them with clock64.  out[blockIdx.x] = cycles.  DESIGN.md uses the result to pick N.
+__global__ void __launch_bounds__(128, 1) exp_mma_rate_kernel(int n, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;               // 128 rows x 128 B
+  uint8_t* sB = smem + 16384;       // 256 rows x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 49152);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 49152 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_f16(0, n);
+    const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sA));
+    const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sB));
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, 1);
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    out[blockIdx.x] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+int exp_mma_rate_launch(int n, int iters, int blocks, long long* out, cudaStream_t stream) {
+  B200_CHECK_ARG(n % 16 == 0 && n >= 16 && n <= 256, "exp_mma_rate: N=%d", n);
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(exp_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024));
+    configured = true;
+  }
+  exp_mma_rate_kernel<<<blocks, 128, 52 * 1024, stream>>>(n, iters, out);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
 int pack_convt_launch(const float* w, int Cin, int Cout, int s, int fmt, void* out, cudaStream_t stream) {
   const long long total = (long long)s * Cout * 2 * Cin;
   pack_convt_kernel<<<(int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256), 256, 0, stream>>>(
