@@ -221,3 +221,41 @@ def test_rowshifted_umma_descriptors():
     for s in range(16):
         ref = a[s:s + 128].float() @ b.float().t()
         assert float((out[0, s] - ref).abs().max()) <= 1e-3
+
+
+# ------------------------------------------------------------------ SelfAttention (K6)
+def _attn_models(window=None):
+    from b200voc import GANConfig, Generator
+    ocfg = O.OracleConfig(use_attention=True, attn_window=window)
+    ora = O.make_generator(ocfg, seed=1234)
+    gen = Generator(GANConfig(use_attention=True, attn_window=window)).eval()
+    gen.load_state_dict(ora.state_dict())
+    return ocfg, ora, gen.cuda()
+
+
+@pytest.mark.parametrize("name,window", [("gen_b1_t12_attn", None), ("gen_b1_t16_attnwin", 512)])
+def test_generator_with_attention_matches_golden(golden_dir, name, window):
+    """generator.py:43-44,91-92: SelfAttention after the residual blocks of stage 2 (global, and
+    block-local with a 512-position window)."""
+    _, _, gen = _attn_models(window)
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    t = lambda k: torch.from_numpy(gold[k]).cuda()
+    with torch.no_grad():
+        wav, tap = gen(t("mel"), t("prosody"), t("style"), t("emotion"), _tap="attn")
+    ref = torch.from_numpy(gold["wav"])
+    assert float((wav.cpu() - ref).abs().max()) <= 1e-3
+    assert O.snr_db(ref, wav.cpu()) >= 40.0
+    want = torch.from_numpy(gold["tap_attn"])                  # band 0, batch 0, 8 channels, 64 steps
+    got = tap.view(-1, 64, wav.shape[-1] // 2).cpu()[0, :8, :64]
+    assert float((got - want).abs().max()) <= 4e-3 * max(1.0, float(want.abs().max()))
+    assert gen.launch_count() == 24
+
+
+def test_generator_with_attention_matches_oracle_batch():
+    ocfg, ora, gen = _attn_models(None)
+    mel, pros, sty, emo = O.synthetic_inputs(2, 21, seed=31)
+    with torch.no_grad():
+        ref = O.generator_forward(ora.state_dict(), ocfg, mel, pros, sty, emo)
+        wav = gen(mel.cuda(), pros.cuda(), sty.cuda(), emo.cuda()).cpu()
+    assert float((wav - ref).abs().max()) <= 1e-3
+    assert O.snr_db(ref, wav) >= 40.0

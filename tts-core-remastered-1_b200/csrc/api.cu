@@ -1,5 +1,6 @@
 // C ABI (include/b200voc.h): error plumbing, TMA descriptor encoding, the Generator handle
 // (weight packing + layer plan + forward) and the layer-level entry points.
+#include <math.h>
 #include <stdarg.h>
 
 #include <string>
@@ -93,11 +94,10 @@ int band_split_launch(const float*, const float*, const float*, int, int, int, i
 int pack_split_launch(const float*, int, int, float*, cudaStream_t);
 int band_merge_launch(const void*, const float*, const float*, int, int, int, int, int, float*, cudaStream_t);
 int tap_extract_launch(const void*, int, int, int, int, int, float*, cudaStream_t);
-int copy_f32_launch(const float*, float*, long long, float, cudaStream_t);
-int cvt16_launch(const float*, void*, long long, int, cudaStream_t);
+int copy_f32_launch(const float*, float*, long long, float add, cudaStream_t, float mul = 1.0f);
+int cvt16_launch(const float*, void*, long long, int, cudaStream_t, float mul = 1.0f);
 int attention_launch(const void* x16, const void* wqkv, const float* bqkv, const void* wo, const float* bo, int N,
-                     int L, int C, int window, int fmt, void* q16, void* k16, void* vt16, void* o16, void* out16,
-                     cudaStream_t st);
+                     int L, int C, int window, int fmt, void* scratch, void* out16, cudaStream_t st);
 long long attention_scratch_elems(int N, int L, int C);
 
 }  // namespace b200
@@ -386,12 +386,15 @@ int b200voc_gen_set_weight(b200voc_gen* g, const char* name, const float* w, int
     case W_ATT_W: {
       const long long C = g->att_C;
       const int fmt = g->stages[g->att_stage].fmt;
-      if (sl->b < 3) B200_TRY(cvt16_launch(w, g->att_wqkv + sl->b * C * C, C * C, fmt, st));
+      // q carries log2(e)/sqrt(C) so the kernel's softmax runs on exp2 of raw S = q k^T
+      const float qs = sl->b == 0 ? 1.4426950408889634f / sqrtf((float)C) : 1.0f;
+      if (sl->b < 3) B200_TRY(cvt16_launch(w, g->att_wqkv + sl->b * C * C, C * C, fmt, st, qs));
       else B200_TRY(cvt16_launch(w, g->att_wo, C * C, fmt, st));
     } break;
     case W_ATT_B: {
       const long long C = g->att_C;
-      if (sl->b < 3) B200_TRY(copy_f32_launch(w, g->att_bqkv + sl->b * C, C, 0.f, st));
+      const float qs = sl->b == 0 ? 1.4426950408889634f / sqrtf((float)C) : 1.0f;
+      if (sl->b < 3) B200_TRY(copy_f32_launch(w, g->att_bqkv + sl->b * C, C, 0.f, st, qs));
       else B200_TRY(copy_f32_launch(w, g->att_bo, C, 0.f, st));
     } break;
     case W_MERGE_W: B200_TRY(copy_f32_launch(w, g->merge_w, numel, 0.f, st)); break;
@@ -556,7 +559,7 @@ int b200voc_gen_forward(b200voc_gen* g, const float* mel, const float* prosody, 
       const double Lw = g->cfg.attn_window > 0 && g->cfg.attn_window < L ? g->cfg.attn_window : L;
       RUN("attn", 2.0 * N * ((double)L * Lw * 2.0 * s.Cout + 4.0 * s.Cout * s.Cout * L), (double)e * 2 * 6,
           attention_launch(act[cur], g->att_wqkv, g->att_bqkv, g->att_wo, g->att_bo, N, L, s.Cout, g->cfg.attn_window,
-                           s.fmt, sc, sc + e, sc + 2 * e, sc + 3 * e, act[cur ^ 1], st));
+                           s.fmt, sc, act[cur ^ 1], st));
       launches += 2;
       cur ^= 1;
       if (tap == "attn" && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, s.Cout, s.fmt, 0, tap_out, st));

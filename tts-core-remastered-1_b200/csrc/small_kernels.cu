@@ -227,13 +227,15 @@ __global__ void tap_extract_kernel(const uint16_t* __restrict__ x, int N, int L,
   }
 }
 
-__global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, float add) {
+__global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, float add,
+                                float mul) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    dst[i] = src[i] + add;
+    dst[i] = src[i] * mul + add;
 }
-__global__ void cvt16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n, int fmt) {
+__global__ void cvt16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n, int fmt,
+                             float mul) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    dst[i] = to16(src[i], fmt);
+    dst[i] = to16(src[i] * mul, fmt);
 }
 
 // ------------------------------------------------------------------ launchers
@@ -295,13 +297,13 @@ int tap_extract_launch(const void* x16, int N, int L, int C, int fmt, int stored
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
-int copy_f32_launch(const float* src, float* dst, long long n, float add, cudaStream_t st) {
-  copy_f32_kernel<<<grid_for(n), 256, 0, st>>>(src, dst, n, add);
+int copy_f32_launch(const float* src, float* dst, long long n, float add, cudaStream_t st, float mul) {
+  copy_f32_kernel<<<grid_for(n), 256, 0, st>>>(src, dst, n, add, mul);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
-int cvt16_launch(const float* src, void* dst, long long n, int fmt, cudaStream_t st) {
-  cvt16_kernel<<<grid_for(n), 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(dst), n, fmt);
+int cvt16_launch(const float* src, void* dst, long long n, int fmt, cudaStream_t st, float mul) {
+  cvt16_kernel<<<grid_for(n), 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(dst), n, fmt, mul);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
