@@ -162,6 +162,78 @@ def workload_config(n_gpus, note=None):
     return c
 
 
+def secondary_measurements(dev, dev_in, B, T):
+    """Not the headline: (a) the same workload with the SelfAttention layer evaluated (global
+    attention); (b) BASELINE configs[2], the STFT family on 1024 x 4 s waveforms."""
+    import torch
+    import b200voc
+    from b200voc import GANConfig, Generator, _lib
+    lib = _lib.load()
+    peaks = measured_peaks()
+    out = {}
+    try:
+        torch.manual_seed(1234)
+        gen_a = Generator(GANConfig(use_attention=True)).eval().to(dev)
+        with torch.no_grad():
+            gen_a(*dev_in)
+            torch.cuda.synchronize()
+            lib.b200voc_gen_profile_enable(gen_a._handle, 1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gen_a(*dev_in)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        att = None
+        for i in range(lib.b200voc_gen_profile_count(gen_a._handle)):
+            if lib.b200voc_gen_profile_name(gen_a._handle, i).decode() == "attn":
+                att = dict(ms=float(lib.b200voc_gen_profile_ms(gen_a._handle, i)),
+                           flops=float(lib.b200voc_gen_profile_flops(gen_a._handle, i)))
+        out["with_attention"] = {
+            "value": B * HOP * T / SR / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": 1,
+            "note": "global single-head attention over L=128*T=110208 positions (97 % of all FLOPs)",
+            "attn_kernels_ms": att["ms"] if att else None,
+            "attn_tflops": att["flops"] / (att["ms"] * 1e-3) / 1e12 if att else None}
+        del gen_a
+    except Exception as e:  # keep the headline line even if the secondary run fails
+        out["with_attention"] = {"error": str(e)[:200]}
+    try:
+        Bw, Nw = 1024, 88200
+        x = torch.rand(Bw, Nw, device=dev) * 2 - 1
+        res = {}
+
+        def timeit(fn, reps=5):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                r = fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps, r
+        frames = 1 + Nw // 256
+        ms, lm = timeit(lambda: b200voc.log_mel(x))
+        by = Bw * Nw * 4 + Bw * 80 * frames * 4
+        res["stft_logmel"] = {"ms": ms, "algorithmic_gb": by / 1e9, "gbs": by / ms / 1e6, "frac_of_hbm": by / ms / 1e6 / peaks["hbm_gbs"]}
+        ms, mg = timeit(lambda: b200voc.stft_magnitude(x, 1024, 256))
+        by = Bw * Nw * 4 + Bw * 513 * frames * 4
+        res["stft_mag"] = {"ms": ms, "algorithmic_gb": by / 1e9, "gbs": by / ms / 1e6, "frac_of_hbm": by / ms / 1e6 / peaks["hbm_gbs"]}
+        del mg
+        ms, sp = timeit(lambda: b200voc.stft(x, 1024, 256))
+        by = Bw * Nw * 4 + Bw * 513 * frames * 8
+        res["stft_complex"] = {"ms": ms, "algorithmic_gb": by / 1e9, "gbs": by / ms / 1e6, "frac_of_hbm": by / ms / 1e6 / peaks["hbm_gbs"]}
+        ms, y = timeit(lambda: b200voc.istft(sp, 1024, 256, Nw))
+        res["istft"] = {"ms": ms, "algorithmic_gb": by / 1e9, "gbs": by / ms / 1e6, "frac_of_hbm": by / ms / 1e6 / peaks["hbm_gbs"],
+                        "roundtrip_maxabs": float((y - x).abs().max())}
+        res["audio_seconds"] = Bw * Nw / SR
+        res["workload"] = "BASELINE configs[2]: 1024 x 4 s uniform(-1,1) waveforms, n_fft 1024, hop 256, 80 HTK mels"
+        out["stft"] = res
+    except Exception as e:
+        out["stft"] = {"error": str(e)[:200]}
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -233,6 +305,9 @@ def run_b200(args):
         barrier()
         ms_e2e = e0.elapsed_time(e1)
         sampler.stop()
+        extra = {}
+        if rank == 0:
+            extra = secondary_measurements(dev, dev_in, B, T)
 
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
@@ -289,6 +364,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": int(host_out.numel() * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": gen.launch_count() * args.steps,
         "clocks": sampler.summary(),
+        **extra,
     }
     print(json.dumps(line))
     if world > 1:
