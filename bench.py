@@ -153,7 +153,7 @@ def workload_config(n_gpus, note=None):
                     f"(10 s) per GPU, random-init weights (seed 1234), synthetic randn mels",
         "batch_per_gpu": B_PER_GPU, "frames": T_FRAMES, "audio_seconds_per_step_per_gpu": B_PER_GPU * HOP * T_FRAMES / SR,
         "precision_plan": "fp16 operands (tcgen05 kind::f16, same rate as bf16), fp32 accumulate",
-        "attention": "off (SelfAttention K6 kernel not built; reference class is undefined, see DESIGN.md D3)",
+        "attention": "off for the headline value (the conv hot path north_star names); the same step with the SelfAttention layer on (global, builder-defined D3) is reported under with_attention",
         "l2": "per-layer activations (0.9 GB) exceed the 126 MB L2; no explicit flush",
         "parallelism": f"dp{n_gpus} (independent utterance shards, no collective)",
     }
