@@ -82,7 +82,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr float kNegLog2e = -1.4426950408889634f;
-  constexpr int kEpiThreads = 256;          // 8 warps per epilogue role (2 per TMEM lane quadrant)
+  constexpr int kEpiThreads = 128;          // per tile: the 4 warps (one per TMEM lane quadrant) of one parity set
 
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     sPar[i] = p.b_conv[i];
@@ -172,16 +172,18 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   } else if (warp < 10) {
     // ------------------------------------------------------------ epilogue 1 (warps 2..9): GLU + FiLM -> h
-    // two warps per TMEM lane quadrant; each owns half of the channels of its 32 rows
-    const int q = warp & 3, hsel = (warp - 2) >> 2;
+    // two warps per TMEM lane quadrant; warp set `par` owns the tiles with i % 2 == par, so two
+    // tiles' GLU epilogues are in flight per quadrant and their latencies overlap
+    const int q = warp & 3, par = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    constexpr int CW = C / 2;
-    const int cbase = hsel * CW;
+    constexpr int CW = C;
+    const int cbase = 0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float4* sBA = reinterpret_cast<const float4*>(sPar);
     const float4* sNB = reinterpret_cast<const float4*>(sPar + C);
     int i = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
+      if ((i & 1) != par) continue;
       const int b = i % ND;
       const uint32_t ph = (i / ND) & 1;
       const int seq = tile / p.tiles_per_seq, l = (tile - seq * p.tiles_per_seq) * 128 + row;
@@ -235,14 +237,15 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------ epilogue 2 (warps 10..17): residual + store
-    const int q = warp & 3, hsel = (warp - 10) >> 2;
+    const int q = warp & 3, par = (warp - 10) >> 2;
     const int row = q * 32 + lane;
-    constexpr int CW = C / 2;
-    const int cbase = hsel * CW;
+    constexpr int CW = C;
+    const int cbase = 0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float4* sB2 = reinterpret_cast<const float4*>(sPar + 2 * C);
     int i = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
+      if ((i & 1) != par) continue;
       const int b = i % ND, ab = i % NA;
       const uint32_t ph = (i / ND) & 1;
       const int seq = tile / p.tiles_per_seq, l = (tile - seq * p.tiles_per_seq) * 128 + row;

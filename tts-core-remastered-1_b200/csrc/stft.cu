@@ -31,7 +31,21 @@ struct MelTable {      // CSR by mel bin over frequency bins
   int n_mels;
 };
 
+struct FftTables {     // per (device, n_fft), built once on the host in double precision
+  const float* win;    // [n_fft] periodic Hann
+  const float2* tw;    // [n_fft/2]   exp(-2 pi i m / (n_fft/2))
+  const float2* tw2;   // [n_fft/2+1] exp(-pi i k / (n_fft/2))
+};
+
+static int get_fft_tables(int n_fft, FftTables* out);
+
+__device__ __forceinline__ void group_sync(int g, int threads) {
+  if (threads == 32) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(threads) : "memory");
+}
+
 struct StftParams {
+  FftTables tab;
   const float* wav;    // [B, Nsamp]
   const float* wav2;   // MODE_L1: second waveform
   int B, Nsamp, hop, frames;
@@ -65,17 +79,9 @@ stft_kernel(const StftParams p) {
   const int b = blockIdx.y, f0 = blockIdx.x * kFPB;
   float2* mybuf = buf + g * NPAD;
 
-  for (int i = threadIdx.x; i < NFFT; i += blockDim.x) win[i] = 0.5f - 0.5f * cospif(2.0f * i / NFFT);
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    float s, c;
-    sincospif(-2.0f * i / N, &s, &c);
-    tw[i] = make_float2(c, s);
-  }
-  for (int i = threadIdx.x; i <= N; i += blockDim.x) {
-    float s, c;
-    sincospif(-(float)i / N, &s, &c);
-    tw2[i] = make_float2(c, s);
-  }
+  for (int i = threadIdx.x; i < NFFT; i += blockDim.x) win[i] = __ldg(p.tab.win + i);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = __ldg(p.tab.tw + i);
+  for (int i = threadIdx.x; i <= N; i += blockDim.x) tw2[i] = __ldg(p.tab.tw2 + i);
   float l1_acc = 0.f;
   constexpr int NPASS = MODE == MODE_L1 ? 2 : 1;
 #pragma unroll 1
@@ -87,7 +93,7 @@ stft_kernel(const StftParams p) {
     __syncthreads();
     const float* fr = span + g * p.hop;
     auto load0 = [&](int m) { return make_float2(fr[2 * m] * win[2 * m], fr[2 * m + 1] * win[2 * m + 1]); };
-    transform<N, false>(t, load0, mybuf, tw, [] { __syncthreads(); });
+    transform<N, false>(t, load0, mybuf, tw, [g] { group_sync(g, T); });
     // split -> bins k = t, t+T, ... and k = N
     for (int k = t; k <= N; k += T) {
       const float2 X = rfft_bin(mybuf, tw2, N, k);
@@ -166,7 +172,12 @@ static int launch_stft(const StftParams& p, cudaStream_t st) {
 }
 
 template <int MODE>
-static int dispatch_stft(int n_fft, const StftParams& p, cudaStream_t st) {
+static int dispatch_stft(int n_fft, StftParams p, cudaStream_t st) {
+  if (n_fft != 512 && n_fft != 1024 && n_fft != 2048) {
+    set_error("stft: n_fft=%d unsupported (512/1024/2048, vocoder7/config.py:39 stft_sizes)", n_fft);
+    return B200VOC_ERR_UNSUPPORTED;
+  }
+  B200_TRY(get_fft_tables(n_fft, &p.tab));
   switch (n_fft) {
     case 512: return launch_stft<512, MODE>(p, st);
     case 1024: return launch_stft<1024, MODE>(p, st);
@@ -181,6 +192,39 @@ static int check_stft_args(const float* wav, int B, int N, int n_fft, int hop) {
   B200_CHECK_ARG(B > 0 && N > 0, "stft: empty input (B=%d, N=%d)", B, N);
   B200_CHECK_ARG(hop > 0 && hop <= n_fft, "stft: hop %d out of range", hop);
   B200_CHECK_ARG(N > n_fft / 2, "stft: reflect padding needs N=%d > n_fft/2=%d (same as torch.stft)", N, n_fft / 2);
+  return B200VOC_OK;
+}
+
+// ------------------------------------------------------------------ FFT tables (host, cached)
+static std::mutex g_tab_mu;
+static std::map<std::pair<int, int>, FftTables> g_tab_cache;
+
+static int get_fft_tables(int n_fft, FftTables* out) {
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  auto key = std::make_pair(dev, n_fft);
+  auto it = g_tab_cache.find(key);
+  if (it == g_tab_cache.end()) {
+    const int N = n_fft / 2;
+    std::vector<float> win(n_fft);
+    std::vector<float2> tw(N), tw2(N + 1);
+    for (int i = 0; i < n_fft; ++i) win[i] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * i / n_fft));
+    for (int i = 0; i < N; ++i) tw[i] = make_float2((float)std::cos(-2.0 * M_PI * i / N), (float)std::sin(-2.0 * M_PI * i / N));
+    for (int i = 0; i <= N; ++i) tw2[i] = make_float2((float)std::cos(-M_PI * i / N), (float)std::sin(-M_PI * i / N));
+    float* dwin;
+    float2 *dtw, *dtw2;
+    B200_CUDA(cudaMalloc(&dwin, n_fft * sizeof(float)));
+    B200_CUDA(cudaMalloc(&dtw, N * sizeof(float2)));
+    B200_CUDA(cudaMalloc(&dtw2, (N + 1) * sizeof(float2)));
+    B200_CUDA(cudaMemcpy(dwin, win.data(), n_fft * sizeof(float), cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(dtw, tw.data(), N * sizeof(float2), cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(dtw2, tw2.data(), (N + 1) * sizeof(float2), cudaMemcpyHostToDevice));
+    FftTables t{};
+    t.win = dwin; t.tw = dtw; t.tw2 = dtw2;
+    it = g_tab_cache.emplace(key, t).first;
+  }
+  *out = it->second;
   return B200VOC_OK;
 }
 
@@ -255,6 +299,7 @@ static int get_mel_table(int n_fft, int n_mels, int sr, MelTable* out) {
 // group runs the inverse packed FFT, and every output sample gathers its n/hop windowed
 // contributions and the window-envelope (sum w^2) -- deterministic, no atomics.
 struct IstftParams {
+  FftTables tab;
   const float2* spec;   // [B, bins, frames]
   float* wav;           // [B, Nout]
   int B, frames, hop, Nout;
@@ -278,17 +323,9 @@ istft_kernel(const IstftParams p) {
   const int f_lo = (n0 - N) / p.hop + 1;                 // may be negative (n0 - N is a multiple of hop)
   const int bins = N + 1;
 
-  for (int i = threadIdx.x; i < NFFT; i += blockDim.x) win[i] = 0.5f - 0.5f * cospif(2.0f * i / NFFT);
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    float s, c;
-    sincospif(-2.0f * i / N, &s, &c);
-    tw[i] = make_float2(c, s);
-  }
-  for (int i = threadIdx.x; i <= N; i += blockDim.x) {
-    float s, c;
-    sincospif(-(float)i / N, &s, &c);
-    tw2[i] = make_float2(c, s);
-  }
+  for (int i = threadIdx.x; i < NFFT; i += blockDim.x) win[i] = __ldg(p.tab.win + i);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = __ldg(p.tab.tw + i);
+  for (int i = threadIdx.x; i <= N; i += blockDim.x) tw2[i] = __ldg(p.tab.tw2 + i);
   // coalesced load of the spectrum block: consecutive threads -> consecutive frames of one bin
   const float2* sp = p.spec + (long long)b * bins * p.frames;
   for (int i = threadIdx.x; i < bins * SLOTS; i += blockDim.x) {
@@ -311,8 +348,9 @@ istft_kernel(const IstftParams p) {
       const float2 xnk = k == 0 ? xn : mybuf[pad(N - k)];
       return irfft_pack(xk, cconj(xnk), tw2[k]);
     };
-    transform<N, true>(t, load0, mybuf, tw, [] { __syncthreads(); });
+    transform<N, true>(t, load0, mybuf, tw, [g] { group_sync(g, T); });
   }
+  __syncthreads();
   // gather overlap-add
   const float inv_n = 1.0f / N;
   float* o = p.wav + (long long)b * p.Nout;
@@ -400,6 +438,7 @@ int b200voc_istft(const float* spec_ri, int B, int frames, int n_fft, int hop, i
   IstftParams p{};
   p.spec = reinterpret_cast<const float2*>(spec_ri); p.wav = wav; p.B = B; p.frames = frames; p.hop = hop; p.Nout = N;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (n_fft == 512 || n_fft == 1024 || n_fft == 2048) B200_TRY(get_fft_tables(n_fft, &p.tab));
   switch (n_fft) {
     case 512: return launch_istft<512>(p, st);
     case 1024: return launch_istft<1024>(p, st);
