@@ -131,6 +131,9 @@ int b200voc_resblock(const void* a16, const void* w_packed, const float* b_conv,
 
 /* experiment: UMMA descriptors whose start address is offset by whole 128B rows. */
 int b200voc_exp_rowshift(const void* a16_144x64, const void* b16_64x64, float* out_2x16x128x64, void* stream);
+/* debug: when non-NULL, the narrow-stage residual-block kernel records a clock64 timeline of CTA 0
+ * ([5 roles][64 tiles][4] int64) into dev_buf; NULL switches it off. */
+int b200voc_debug_set_trace(int64_t* dev_buf);
 /* experiment: cycles for iters x 4 tcgen05.mma (M=128, N=n, K=16, operands in shared memory). */
 int b200voc_exp_mma_rate(int n, int iters, int blocks, int64_t* out_cycles, void* stream);
 

@@ -629,6 +629,11 @@ int b200voc_resblock(const void* a16, const void* w_packed, const float* b_conv,
   return resblock_launch(a16, w_packed, b_conv, b_proj, film, 2 * C, N, L, C, dilation, T, num_bands, fmt, fmt, store_lrelu,
                          out16, reinterpret_cast<cudaStream_t>(stream));
 }
+namespace b200 { extern long long* g_rb2_trace; }
+int b200voc_debug_set_trace(int64_t* dev_buf) {
+  b200::g_rb2_trace = reinterpret_cast<long long*>(dev_buf);
+  return B200VOC_OK;
+}
 int b200voc_exp_mma_rate(int n, int iters, int blocks, int64_t* out_cycles, void* stream) {
   B200_CHECK_ARG(out_cycles && iters > 0 && blocks > 0, "exp_mma_rate: bad argument");
   return exp_mma_rate_launch(n, iters, blocks, reinterpret_cast<long long*>(out_cycles),

@@ -27,7 +27,14 @@ struct Resblock2Params {
   const float* film;     // [B, T, film_stride]
   int film_stride;
   uint16_t* out;         // [N, L, C]
+  long long* trace;      // optional clock64 timeline of CTA 0 (debug), [5 roles][64 tiles][4]
 };
+
+#define RB2_TRACE(slot, i, k)                                                             \
+  do {                                                                                    \
+    if (p.trace && blockIdx.x == 0 && (i) < 64 && (threadIdx.x & 31) == 0)                 \
+      p.trace[(((slot) * 64 + (i)) << 2) + (k)] = clock64();                               \
+  } while (0)
 
 template <int C>
 struct Rb2Cfg {
@@ -125,6 +132,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int ab = i % NA;
         const int seq = tile / p.tiles_per_seq, l0 = (tile - seq * p.tiles_per_seq) * 128;
         mbar_wait(&a_empty[ab], ((i / NA) & 1) ^ 1);
+        RB2_TRACE(0, i, 0);
         mbar_expect_tx(&a_full[ab], K::A_BYTES);
         tma_load_3d(sA + ab * K::A_SLOT, &tmX, &a_full[ab], 0, l0 - K::HALO, seq);
       }
@@ -139,7 +147,9 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int b = i % ND;
         const uint32_t ph = (i / ND) & 1;
         mbar_wait(&h_full[b], ph);
+        RB2_TRACE(2, i, 0);
         mbar_wait(&d2_empty[b], ph ^ 1);
+        RB2_TRACE(2, i, 1);
         tc_fence_after();
         const uint64_t a_desc = make_kmajor_desc<K::ROWB>(smem_u32(sH + b * K::H_BYTES));
         const uint64_t b_desc = make_kmajor_desc<K::ROWB>(smem_u32(sW2));
@@ -154,7 +164,9 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int b = i % ND, ab = i % NA;
         const uint32_t ph = (i / ND) & 1;
         mbar_wait(&a_full[ab], (i / NA) & 1);
+        RB2_TRACE(1, i, 0);
         mbar_wait(&d1_empty[b], ph ^ 1);
+        RB2_TRACE(1, i, 1);
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + ab * K::A_SLOT);
 #pragma unroll
@@ -166,6 +178,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             umma_f16(tmem_base + b * K::N1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (tap | k) != 0);
         }
         umma_commit(&d1_full[b]);
+        RB2_TRACE(1, i, 2);
         if (i >= ND - 1) issue_g2(i - (ND - 1));     // GEMM2 trails GEMM1 by ND-1 tiles
       }
       for (int j = (i >= ND - 1 ? i - (ND - 1) : 0); j < i; ++j) issue_g2(j);
@@ -193,7 +206,9 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
       for (int k = 0; k < (2 * C) / 32; ++k) prefetch_l1(film + k * 32);     // this row's FiLM line(s) -> L1
       mbar_wait(&d1_full[b], ph);
+      if (q == 0) RB2_TRACE(3, i, 0);
       mbar_wait(&h_empty[b], ph ^ 1);
+      if (q == 0) RB2_TRACE(3, i, 1);
       tc_fence_after();
       uint8_t* hrow = sH + b * K::H_BYTES + row * K::ROWB;
 #pragma unroll
@@ -234,6 +249,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the UMMA (async proxy)
       mbar_arrive(&h_full[b]);
       mbar_arrive(&d1_empty[b]);
+      if (q == 0) RB2_TRACE(3, i, 2);
     }
   } else {
     // ------------------------------------------------------------ epilogue 2 (warps 10..17): residual + store
@@ -252,6 +268,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const bool valid = l < p.L;
       mbar_wait(&a_full[ab], (i / NA) & 1);   // visibility of the TMA-written tile to this thread
       mbar_wait(&d2_full[b], ph);
+      if (q == 0) RB2_TRACE(4, i, 0);
       tc_fence_after();
       const uint8_t* xrow = sA + ab * K::A_SLOT + (row + K::HALO) * K::ROWB;
       uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)seq * p.L + (valid ? l : 0)) * C);
@@ -287,12 +304,15 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tc_fence_before();
       mbar_arrive(&d2_empty[b]);
       mbar_arrive(&a_empty[ab]);
+      if (q == 0) RB2_TRACE(4, i, 1);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, K::TMEM_COLS);
 }
+
+long long* g_rb2_trace = nullptr;   // set through b200voc_debug_set_trace (debug only)
 
 static int num_sms() {
   static int n[16] = {};
@@ -320,6 +340,7 @@ static int launch_resblock2(const void* a16, const void* w_packed, const float* 
   p.total_tiles = p.tiles_per_seq * N;
   p.b_conv = b_conv; p.b_proj = b_proj; p.film = film; p.film_stride = film_stride;
   p.out = reinterpret_cast<uint16_t*>(out16);
+  p.trace = g_rb2_trace;
   static bool configured[16] = {};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
