@@ -99,6 +99,7 @@ int cvt16_launch(const float*, void*, long long, int, cudaStream_t, float mul = 
 int attention_launch(const void* x16, const void* wqkv, const float* bqkv, const void* wo, const float* bo, int N,
                      int L, int C, int window, int fmt, void* scratch, void* out16, cudaStream_t st);
 long long attention_scratch_elems(int N, int L, int C);
+extern long long* g_rb2_trace;
 
 }  // namespace b200
 
@@ -629,7 +630,6 @@ int b200voc_resblock(const void* a16, const void* w_packed, const float* b_conv,
   return resblock_launch(a16, w_packed, b_conv, b_proj, film, 2 * C, N, L, C, dilation, T, num_bands, fmt, fmt, store_lrelu,
                          out16, reinterpret_cast<cudaStream_t>(stream));
 }
-namespace b200 { extern long long* g_rb2_trace; }
 int b200voc_debug_set_trace(int64_t* dev_buf) {
   b200::g_rb2_trace = reinterpret_cast<long long*>(dev_buf);
   return B200VOC_OK;
