@@ -200,6 +200,15 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid(g) = 0.5 + 0.5 * tanh(g / 2): ONE MUFU op (tanh.approx, max rel. error 2^-11, below the
+// fp16 rounding of the value it multiplies -- oracle/emulate.py shows no change in waveform error).
+// Pass hg = g / 2.
+__device__ __forceinline__ float sigmoid_from_half_g(float hg) { return fmaf(tanh_approx(hg), 0.5f, 0.5f); }
 // sigmoid(g) with g already scaled: pass t = -log2(e) * g
 __device__ __forceinline__ float sigmoid_from_neg_log2e_g(float t) { return rcp_approx(1.0f + ex2_approx(t)); }
 

@@ -51,19 +51,22 @@ struct Rb2Cfg {
   static constexpr int OFF_W1 = 0;
   static constexpr int OFF_W2 = 3 * W1_TILE;
   static constexpr int OFF_A = (OFF_W2 + W2_BYTES + 1023) & ~1023;
-  static constexpr int ND = C == 32 ? 4 : 2;         // ring depth of the TMEM accumulators and of h
-  static constexpr int NA = ND + 2;                 // ring depth of the input tiles (TMA prefetch distance)
+  static constexpr int ND1 = C == 32 ? 4 : 3;        // ring depth of the GEMM1 accumulators and of h
+  static constexpr int ND2 = C == 32 ? 4 : 2;        // ring depth of the GEMM2 accumulators
+  static constexpr int NA = ND1 + 2;                // ring depth of the input tiles (TMA prefetch distance)
   static constexpr int OFF_H = OFF_A + NA * A_SLOT;
-  static constexpr int OFF_BAR = OFF_H + ND * H_BYTES;
+  static constexpr int OFF_BAR = OFF_H + ND1 * H_BYTES;
   static constexpr int OFF_PAR = OFF_BAR + 512;
   static constexpr int SMEM = OFF_PAR + 3 * C * 4 + 1024;
-  static constexpr int D2_COL = ND * N1;
-  static constexpr int TMEM_NEED = ND * N1 + ND * C;
+  static constexpr int D2_COL = ND1 * N1;
+  static constexpr int TMEM_NEED = ND1 * N1 + ND2 * C;
+  static_assert(TMEM_NEED <= 512, "TMEM budget");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static constexpr uint32_t TMEM_COLS = TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
 };
 
 template <int C, int FMT, int OFMT, bool LRELU>
-__global__ void __launch_bounds__(576, 1)
+__global__ void __launch_bounds__(608, 1)
 resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const Resblock2Params p) {
   using K = Rb2Cfg<C>;
@@ -74,26 +77,25 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* sA = smem + K::OFF_A;
   uint8_t* sH = smem + K::OFF_H;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_BAR);
-  constexpr int ND = K::ND, NA = K::NA;
+  constexpr int ND1 = K::ND1, ND2 = K::ND2, NA = K::NA;
   uint64_t* w_full = bars;                 // [1]
   uint64_t* a_full = bars + 1;             // [NA]
   uint64_t* a_empty = a_full + NA;         // [NA]
-  uint64_t* d1_full = a_empty + NA;        // [ND]
-  uint64_t* d1_empty = d1_full + ND;       // [ND]
-  uint64_t* h_full = d1_empty + ND;        // [ND]
-  uint64_t* h_empty = h_full + ND;         // [ND]
-  uint64_t* d2_full = h_empty + ND;        // [ND]
-  uint64_t* d2_empty = d2_full + ND;       // [ND]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + ND);
-  float* sPar = reinterpret_cast<float*>(smem + K::OFF_PAR);   // [ba | -log2e*bg | b2], C floats each
+  uint64_t* d1_full = a_empty + NA;        // [ND1]
+  uint64_t* d1_empty = d1_full + ND1;      // [ND1]
+  uint64_t* h_full = d1_empty + ND1;       // [ND1]
+  uint64_t* h_empty = h_full + ND1;        // [ND1]
+  uint64_t* d2_full = h_empty + ND1;       // [ND2]
+  uint64_t* d2_empty = d2_full + ND2;      // [ND2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + ND2);
+  float* sPar = reinterpret_cast<float*>(smem + K::OFF_PAR);   // [ba | bg/2 | b2], C floats each
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr float kNegLog2e = -1.4426950408889634f;
   constexpr int kEpiThreads = 128;          // per tile: the 4 warps (one per TMEM lane quadrant) of one parity set
 
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     sPar[i] = p.b_conv[i];
-    sPar[C + i] = kNegLog2e * p.b_conv[C + i];
+    sPar[C + i] = 0.5f * p.b_conv[C + i];
     sPar[2 * C + i] = p.b_proj[i];
   }
   if (warp == 0 && lane == 0) {
@@ -105,11 +107,13 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_init(&a_full[b], 1);
       mbar_init(&a_empty[b], kEpiThreads);
     }
-    for (int b = 0; b < ND; ++b) {
+    for (int b = 0; b < ND1; ++b) {
       mbar_init(&d1_full[b], 1);
       mbar_init(&d1_empty[b], kEpiThreads);
       mbar_init(&h_full[b], kEpiThreads);
       mbar_init(&h_empty[b], 1);
+    }
+    for (int b = 0; b < ND2; ++b) {
       mbar_init(&d2_full[b], 1);
       mbar_init(&d2_empty[b], kEpiThreads);
     }
@@ -137,35 +141,37 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tma_load_3d(sA + ab * K::A_SLOT, &tmX, &a_full[ab], 0, l0 - K::HALO, seq);
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 || warp == 18) {
+    // ------------------------------------------------------------ MMA issuers: warp 1 owns the even tiles,
+    // warp 18 the odd ones (tcgen05.mma may be issued by any thread; the per-tile barrier round trips
+    // of a single issuing thread were the bottleneck of the C=32 stage, see profiles/).
     if (lane == 0) {
+      const int mpar = warp == 1 ? 0 : 1;
       const uint32_t idesc1 = make_idesc_f16(FMT, K::N1);
       const uint32_t idesc2 = make_idesc_f16(FMT, C);
       mbar_wait(w_full, 0);
       auto issue_g2 = [&](int i) {
-        const int b = i % ND;
-        const uint32_t ph = (i / ND) & 1;
-        mbar_wait(&h_full[b], ph);
+        const int b1 = i % ND1, b2 = i % ND2;
+        mbar_wait(&h_full[b1], (i / ND1) & 1);
         RB2_TRACE(2, i, 0);
-        mbar_wait(&d2_empty[b], ph ^ 1);
+        mbar_wait(&d2_empty[b2], ((i / ND2) & 1) ^ 1);
         RB2_TRACE(2, i, 1);
         tc_fence_after();
-        const uint64_t a_desc = make_kmajor_desc<K::ROWB>(smem_u32(sH + b * K::H_BYTES));
+        const uint64_t a_desc = make_kmajor_desc<K::ROWB>(smem_u32(sH + b1 * K::H_BYTES));
         const uint64_t b_desc = make_kmajor_desc<K::ROWB>(smem_u32(sW2));
 #pragma unroll
         for (int k = 0; k < K::KB / 16; ++k)
-          umma_f16(tmem_base + K::D2_COL + b * C, a_desc + 2 * k, b_desc + 2 * k, idesc2, k != 0);
-        umma_commit(&d2_full[b]);
-        umma_commit(&h_empty[b]);
+          umma_f16(tmem_base + K::D2_COL + b2 * C, a_desc + 2 * k, b_desc + 2 * k, idesc2, k != 0);
+        umma_commit(&d2_full[b2]);
+        umma_commit(&h_empty[b1]);
       };
-      int i = 0;
+      int i = 0, prev = -1;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
-        const int b = i % ND, ab = i % NA;
-        const uint32_t ph = (i / ND) & 1;
+        if ((i & 1) != mpar) continue;
+        const int b = i % ND1, ab = i % NA;
         mbar_wait(&a_full[ab], (i / NA) & 1);
         RB2_TRACE(1, i, 0);
-        mbar_wait(&d1_empty[b], ph ^ 1);
+        mbar_wait(&d1_empty[b], ((i / ND1) & 1) ^ 1);
         RB2_TRACE(1, i, 1);
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + ab * K::A_SLOT);
@@ -179,9 +185,10 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         umma_commit(&d1_full[b]);
         RB2_TRACE(1, i, 2);
-        if (i >= ND - 1) issue_g2(i - (ND - 1));     // GEMM2 trails GEMM1 by ND-1 tiles
+        if (prev >= 0) issue_g2(prev);        // GEMM2 trails GEMM1 by one own tile (= 2 tiles)
+        prev = i;
       }
-      for (int j = (i >= ND - 1 ? i - (ND - 1) : 0); j < i; ++j) issue_g2(j);
+      if (prev >= 0) issue_g2(prev);
     }
   } else if (warp < 10) {
     // ------------------------------------------------------------ epilogue 1 (warps 2..9): GLU + FiLM -> h
@@ -197,8 +204,8 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     int i = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
       if ((i & 1) != par) continue;
-      const int b = i % ND;
-      const uint32_t ph = (i / ND) & 1;
+      const int b = i % ND1;
+      const uint32_t ph = (i / ND1) & 1;
       const int seq = tile / p.tiles_per_seq, l = (tile - seq * p.tiles_per_seq) * 128 + row;
       int t = l / p.P;
       if (t > p.T - 1) t = p.T - 1;
@@ -234,7 +241,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float a = __uint_as_float(va[i4 * 4 + e]) + av[e];
-              const float sg = sigmoid_from_neg_log2e_g(fmaf(__uint_as_float(vg[i4 * 4 + e]), kNegLog2e, gv[e]));
+              const float sg = sigmoid_from_half_g(fmaf(__uint_as_float(vg[i4 * 4 + e]), 0.5f, gv[e]));
               hv[h4 * 4 + e] = fmaf(a * sg, sv[e], tv[e]);
             }
           }
@@ -251,7 +258,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_arrive(&d1_empty[b]);
       if (q == 0) RB2_TRACE(3, i, 2);
     }
-  } else {
+  } else if (warp < 18) {
     // ------------------------------------------------------------ epilogue 2 (warps 10..17): residual + store
     const int q = warp & 3, par = (warp - 10) >> 2;
     const int row = q * 32 + lane;
@@ -262,8 +269,8 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     int i = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
       if ((i & 1) != par) continue;
-      const int b = i % ND, ab = i % NA;
-      const uint32_t ph = (i / ND) & 1;
+      const int b = i % ND2, ab = i % NA;
+      const uint32_t ph = (i / ND2) & 1;
       const int seq = tile / p.tiles_per_seq, l = (tile - seq * p.tiles_per_seq) * 128 + row;
       const bool valid = l < p.L;
       mbar_wait(&a_full[ab], (i / NA) & 1);   // visibility of the TMA-written tile to this thread
@@ -350,7 +357,7 @@ static int launch_resblock2(const void* a16, const void* w_packed, const float* 
     configured[dev & 15] = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  resblock2_kernel<C, FMT, OFMT, LRELU><<<grid, 576, K::SMEM, stream>>>(tmX, tmW1, tmW2, p);
+  resblock2_kernel<C, FMT, OFMT, LRELU><<<grid, 608, K::SMEM, stream>>>(tmX, tmW1, tmW2, p);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
