@@ -14,6 +14,8 @@
 //     8 warps residual+store epilogue, so tile i+1's GEMM1 and GLU overlap tile i's GEMM2/store;
 //     operand format / output format / stored activation are template parameters (no per-element
 //     branches in the epilogues, which are the instruction-issue bottleneck of these stages).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -28,6 +30,7 @@ struct Resblock2Params {
   int film_stride;
   uint16_t* out;         // [N, L, C]
   long long* trace;      // optional clock64 timeline of CTA 0 (debug), [5 roles][64 tiles][4]
+  int dbg;               // debug-only experiment switches (B200VOC_DBG): 1 = no FiLM loads, 2 = no E2 stores
 };
 
 #define RB2_TRACE(slot, i, k)                                                             \
@@ -227,7 +230,10 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const float4* fh = reinterpret_cast<const float4*>(film + C + c0);
         float4 S[4], H[4];
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) { S[i4] = __ldg(fs + i4); H[i4] = __ldg(fh + i4); }
+        for (int i4 = 0; i4 < 4; ++i4) {
+          if (p.dbg & 1) { S[i4] = make_float4(1.f, 1.f, 1.f, 1.f); H[i4] = make_float4(0.f, 0.f, 0.f, 0.f); }
+          else { S[i4] = __ldg(fs + i4); H[i4] = __ldg(fh + i4); }
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int i8 = 0; i8 < 2; ++i8) {
@@ -305,7 +311,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
             ow[e2] = pack2t<OFMT>(y0, y1);
           }
-          if (valid) dst[(c0 >> 3) + i8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          if (valid && !(p.dbg & 2)) dst[(c0 >> 3) + i8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
       }
       tc_fence_before();
@@ -348,6 +354,10 @@ static int launch_resblock2(const void* a16, const void* w_packed, const float* 
   p.b_conv = b_conv; p.b_proj = b_proj; p.film = film; p.film_stride = film_stride;
   p.out = reinterpret_cast<uint16_t*>(out16);
   p.trace = g_rb2_trace;
+  {
+    const char* e = getenv("B200VOC_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   static bool configured[16] = {};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
