@@ -71,7 +71,8 @@ struct Rb2Cfg {
 template <int C, int FMT, int OFMT, bool LRELU>
 __global__ void __launch_bounds__(608, 1)
 resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                 const __grid_constant__ CUtensorMap tmW2, const Resblock2Params p) {
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
+                 const Resblock2Params p) {
   using K = Rb2Cfg<C>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
@@ -105,10 +106,11 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmOut);
     mbar_init(w_full, 1);
     for (int b = 0; b < NA; ++b) {
       mbar_init(&a_full[b], 1);
-      mbar_init(&a_empty[b], kEpiThreads);
+      mbar_init(&a_empty[b], 1);
     }
     for (int b = 0; b < ND1; ++b) {
       mbar_init(&d1_full[b], 1);
@@ -278,23 +280,26 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const int b = i % ND2, ab = i % NA;
       const uint32_t ph = (i / ND2) & 1;
       const int seq = tile / p.tiles_per_seq, l = (tile - seq * p.tiles_per_seq) * 128 + row;
-      const bool valid = l < p.L;
       mbar_wait(&a_full[ab], (i / NA) & 1);   // visibility of the TMA-written tile to this thread
       mbar_wait(&d2_full[b], ph);
       if (q == 0) RB2_TRACE(4, i, 0);
       tc_fence_after();
-      const uint8_t* xrow = sA + ab * K::A_SLOT + (row + K::HALO) * K::ROWB;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)seq * p.L + (valid ? l : 0)) * C);
+      // The output tile is staged IN PLACE over the centre rows of the input tile (each thread
+      // overwrites exactly the 16-byte chunks it read) and leaves through one TMA store: no
+      // strided per-thread global stores, and rows past the end of the sequence are clipped by TMA.
+      uint8_t* xrow = sA + ab * K::A_SLOT + (row + K::HALO) * K::ROWB;
 #pragma unroll
       for (int c0 = cbase; c0 < cbase + CW; c0 += 16) {
         uint32_t vd[16];
         tmem_ld16(lane_addr + K::D2_COL + b * C + c0, vd);
         uint4 xa[2];
+        uint4* xp[2];
 #pragma unroll
         for (int i8 = 0; i8 < 2; ++i8) {
           const int chunk = (c0 >> 3) + i8;
           const int phys = K::ROWB == 128 ? (chunk ^ (row & 7)) : (chunk ^ ((row >> 1) & 3));
-          xa[i8] = *reinterpret_cast<const uint4*>(xrow + phys * 16);
+          xp[i8] = reinterpret_cast<uint4*>(xrow + phys * 16);
+          xa[i8] = *xp[i8];
         }
         tmem_ld_wait();
 #pragma unroll
@@ -311,12 +316,19 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
             ow[e2] = pack2t<OFMT>(y0, y1);
           }
-          if (valid && !(p.dbg & 2)) dst[(c0 >> 3) + i8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          *xp[i8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
       }
       tc_fence_before();
       mbar_arrive(&d2_empty[b]);
-      mbar_arrive(&a_empty[ab]);
+      fence_proxy_async_smem();                     // staged tile -> visible to the TMA engine
+      named_bar_sync(1 + par, 128);                 // the 4 warps of this parity set
+      if (q == 0 && lane == 0 && !(p.dbg & 2)) {
+        tma_store_3d(&tmOut, sA + ab * K::A_SLOT + K::HALO * K::ROWB, 0, l - row, seq);
+        tma_store_commit();
+        tma_store_wait_read();                      // smem has been read: the A slot may be refilled
+      }
+      if (q == 0 && lane == 0) mbar_arrive(&a_empty[ab]);
       if (q == 0) RB2_TRACE(4, i, 1);
     }
   }
@@ -340,8 +352,9 @@ static int launch_resblock2(const void* a16, const void* w_packed, const float* 
                             const float* film, int film_stride, int N, int L, int dilation, int T, int num_bands,
                             void* out16, cudaStream_t stream) {
   using K = Rb2Cfg<C>;
-  CUtensorMap tmX, tmW1, tmW2;
+  CUtensorMap tmX, tmW1, tmW2, tmOut;
   B200_TRY(make_tmap_3d(&tmX, a16, C, L, N, (uint64_t)C * 2, (uint64_t)L * C * 2, K::KB, K::A_ROWS, K::ROWB));
+  B200_TRY(make_tmap_3d(&tmOut, out16, C, L, N, (uint64_t)C * 2, (uint64_t)L * C * 2, K::KB, 128, K::ROWB));
   const uint16_t* w1 = reinterpret_cast<const uint16_t*>(w_packed);
   const uint16_t* w2 = w1 + 2ll * C * 3 * C;
   B200_TRY(make_tmap_2d(&tmW1, w1, 3 * C, 2 * C, (uint64_t)3 * C * 2, K::KB, K::N1, K::ROWB));
@@ -367,7 +380,7 @@ static int launch_resblock2(const void* a16, const void* w_packed, const float* 
     configured[dev & 15] = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  resblock2_kernel<C, FMT, OFMT, LRELU><<<grid, 608, K::SMEM, stream>>>(tmX, tmW1, tmW2, p);
+  resblock2_kernel<C, FMT, OFMT, LRELU><<<grid, 608, K::SMEM, stream>>>(tmX, tmW1, tmW2, tmOut, p);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
