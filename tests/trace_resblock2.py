@@ -35,3 +35,7 @@ for i in range(20, 40):
     print(f"{i:3d} | {r(0,0):7d} | {r(1,0):7d} {r(1,1):7d} {r(1,2):7d} | {r(2,0):7d} {r(2,1):7d} | {r(3,0):7d} {r(3,1):7d} {r(3,2):7d} | {r(4,0):7d} {r(4,1):7d}")
 per_tile = (int(t[1, 60, 2]) - int(t[1, 20, 2])) / 40
 print("steady-state cycles per tile:", per_tile)
+print("E1 detail: tile | d1_full->h_empty | ->first LDTM done | ->first group stored | ->all groups | ->arrive")
+for i in range(30, 38):
+    a, b, c, d, e, f = int(t[3, i, 0]), int(t[3, i, 1]), int(t[3, i, 3]), int(t[4, i, 2]), int(t[4, i, 3]), int(t[3, i, 2])
+    print(i, b - a, c - b, d - c, e - d, f - e)

@@ -237,6 +237,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           else { S[i4] = __ldg(fs + i4); H[i4] = __ldg(fh + i4); }
         }
         tmem_ld_wait();
+        if (q == 0 && c0 == 0) RB2_TRACE(3, i, 3);
 #pragma unroll
         for (int i8 = 0; i8 < 2; ++i8) {
           float hv[8];
@@ -259,7 +260,9 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               make_uint4(pack2t<FMT>(hv[0], hv[1]), pack2t<FMT>(hv[2], hv[3]), pack2t<FMT>(hv[4], hv[5]),
                          pack2t<FMT>(hv[6], hv[7]));
         }
+        if (q == 0 && c0 == 0) RB2_TRACE(4, i, 2);
       }
+      if (q == 0) RB2_TRACE(4, i, 3);
       tc_fence_before();
       fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the UMMA (async proxy)
       mbar_arrive(&h_full[b]);
