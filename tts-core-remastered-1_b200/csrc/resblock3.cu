@@ -37,10 +37,11 @@ struct Rb3Cfg {
   static constexpr int A_ROWS = 128 + 2 * HALO;
   static constexpr int A_KB_BYTES = A_ROWS * 128;    // 18 KB per k-block
   static constexpr int A_BYTES = KPT * A_KB_BYTES;
-  static constexpr int NA = C == 128 ? 2 : 1;
+  static constexpr bool INPLACE = C == 128;          // stage the output over the input tile + TMA store
+  static constexpr int NA = C == 128 ? 3 : 1;
   static constexpr int H_KB_BYTES = 128 * 128;       // 16 KB per k-block
   static constexpr int W_TILE = 128 * 128;           // 16 KB ring slot: [128 rows x 64 k]
-  static constexpr int NW = C == 128 ? 6 : 4;
+  static constexpr int NW = 4;
   static constexpr int ND2 = C == 128 ? 2 : 1;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_H = OFF_A + NA * A_BYTES;
@@ -50,7 +51,7 @@ struct Rb3Cfg {
   static constexpr int SMEM = OFF_PAR + 3 * C * 4 + 1024;
   static constexpr int D2_COL = 256;
   static constexpr uint32_t TMEM_COLS = 512;
-  static constexpr int A_PREFETCH_AFTER_CHUNK = NA == 2 ? 0 : NCH - 1;
+  static constexpr int A_PREFETCH_AFTER_CHUNK = NA >= 2 ? 0 : NCH - 1;
   static_assert(OFF_H % 1024 == 0 && OFF_W % 1024 == 0 && A_KB_BYTES % 1024 == 0, "1024B alignment for SWIZZLE_128B");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -58,7 +59,8 @@ struct Rb3Cfg {
 template <int C, int FMT, int OFMT, bool LRELU>
 __global__ void __launch_bounds__(576, 1)
 resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                 const __grid_constant__ CUtensorMap tmW2, const Resblock3Params p) {
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
+                 const Resblock3Params p) {
   using K = Rb3Cfg<C>;
   constexpr int KPT = K::KPT, NCH = K::NCH, NH = K::NH, NA = K::NA, NW = K::NW, ND2 = K::ND2;
   extern __shared__ uint8_t smem_raw[];
@@ -78,26 +80,27 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* d2_full = h_empty + KPT;        // [ND2]
   uint64_t* d2_empty = d2_full + ND2;       // [ND2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + ND2);
-  float* sPar = reinterpret_cast<float*>(smem + K::OFF_PAR);   // [ba | -log2e*bg | b2]
+  float* sPar = reinterpret_cast<float*>(smem + K::OFF_PAR);   // [ba | bg/2 | b2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr float kNegLog2e = -1.4426950408889634f;
-  constexpr int kEpiThreads = 256;
+  constexpr int kE1Threads = 128;                       // one chunk-parity set (4 warps)
+  constexpr int kE2Threads = K::INPLACE ? 128 : 256;     // tile-parity set, or all 8 warps (C=256)
 
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     sPar[i] = p.b_conv[i];
-    sPar[C + i] = kNegLog2e * p.b_conv[C + i];
+    sPar[C + i] = 0.5f * p.b_conv[C + i];
     sPar[2 * C + i] = p.b_proj[i];
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmOut);
     for (int b = 0; b < NA; ++b) { mbar_init(&a_full[b], 1); mbar_init(&a_empty[b], 1); }
     for (int b = 0; b < NW; ++b) { mbar_init(&w_full[b], 1); mbar_init(&w_empty[b], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&d1_full[b], 1); mbar_init(&d1_empty[b], kEpiThreads); }
-    for (int b = 0; b < KPT; ++b) { mbar_init(&h_full[b], kEpiThreads); mbar_init(&h_empty[b], 1); }
-    for (int b = 0; b < ND2; ++b) { mbar_init(&d2_full[b], 1); mbar_init(&d2_empty[b], kEpiThreads); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&d1_full[b], 1); mbar_init(&d1_empty[b], kE1Threads); }
+    for (int b = 0; b < KPT; ++b) { mbar_init(&h_full[b], kE1Threads); mbar_init(&h_empty[b], 1); }
+    for (int b = 0; b < ND2; ++b) { mbar_init(&d2_full[b], 1); mbar_init(&d2_empty[b], kE2Threads); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, K::TMEM_COLS);
@@ -199,7 +202,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               ++wi;
             }
           umma_commit(&d1_full[b]);
-          if (j == NCH - 1) umma_commit(&a_empty[ab]);
+          if (!K::INPLACE && j == NCH - 1) umma_commit(&a_empty[ab]);   // INPLACE: released by the store epilogue
           if (gc >= 1) g2((gc - 1) / NCH, (gc - 1) % NCH);
         }
       }
@@ -207,7 +210,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   } else if (warp < 10) {
     // ------------------------------------------------------------ epilogue 1 (warps 2..9): GLU + FiLM -> h
-    const int q = warp & 3, hsel = (warp - 2) >> 2;
+    // two warps per TMEM lane quadrant: warp set `par` owns the chunks with (global chunk index & 1)
+    // == par, i.e. the accumulator buffer D1[par]; the two sets' epilogues overlap in time
+    const int q = warp & 3, par = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float4* sBA = reinterpret_cast<const float4*>(sPar);
@@ -223,12 +228,13 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       for (int k = 0; k < (2 * C) / 32; ++k) prefetch_l1(film + k * 32);     // this row's FiLM line(s) -> L1
       for (int j = 0; j < NCH; ++j, ++gc) {
         const int b = gc & 1;
+        if (b != par) continue;
         mbar_wait(&d1_full[b], (gc >> 1) & 1);
         mbar_wait(&h_empty[j], (it & 1) ^ 1);
         tc_fence_after();
         uint8_t* hrow = sH + j * K::H_KB_BYTES + row * 128;
 #pragma unroll
-        for (int cl = hsel * 32; cl < hsel * 32 + 32; cl += 16) {   // column inside the chunk's 64 value channels
+        for (int cl = 0; cl < 64; cl += 16) {   // column inside the chunk's 64 value channels
           uint32_t va[16], vg[16];
           tmem_ld16(lane_addr + b * 128 + cl, va);
           tmem_ld16(lane_addr + b * 128 + 64 + cl, vg);
@@ -251,7 +257,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float a = __uint_as_float(va[i4 * 4 + e]) + av[e];
-                const float sg = sigmoid_from_neg_log2e_g(fmaf(__uint_as_float(vg[i4 * 4 + e]), kNegLog2e, gv[e]));
+                const float sg = sigmoid_from_half_g(fmaf(__uint_as_float(vg[i4 * 4 + e]), 0.5f, gv[e]));
                 hv[h4 * 4 + e] = fmaf(a * sg, sv[e], tv[e]);
               }
             }
@@ -267,8 +273,68 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_arrive(&d1_empty[b]);
       }
     }
+  } else if (K::INPLACE) {
+    // ------------------------------------------------------------ epilogue 2, in-place variant (C = 128):
+    // warp set `par` owns the tiles with it % 2 == par.  The residual x comes from the shared-memory
+    // input tile; the output is staged over the same chunks and leaves through TMA stores.
+    const int q = warp & 3, par = (warp - 10) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float4* sB2 = reinterpret_cast<const float4*>(sPar + 2 * C);
+    for (int it = par; it < n_my_tiles; it += 2) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int seq = tile / p.tiles_per_seq, l0 = (tile - seq * p.tiles_per_seq) * 128;
+      const int db = it % ND2, ab = it % NA;
+      mbar_wait(&a_full[ab], (it / NA) & 1);      // visibility of the TMA-written tile to this thread
+      mbar_wait(&d2_full[db], (it / ND2) & 1);
+      tc_fence_after();
+      uint8_t* abase = sA + ab * K::A_BYTES + (row + K::HALO) * 128;
+#pragma unroll 2
+      for (int c0 = 0; c0 < C; c0 += 16) {
+        uint32_t vd[16];
+        tmem_ld16(lane_addr + K::D2_COL + db * C + c0, vd);
+        uint4 xa[2];
+        uint4* xp[2];
+#pragma unroll
+        for (int i8 = 0; i8 < 2; ++i8) {
+          const int kb = c0 >> 6, chunk = ((c0 & 63) >> 3) + i8;
+          xp[i8] = reinterpret_cast<uint4*>(abase + kb * K::A_KB_BYTES + ((chunk ^ (row & 7)) << 4));
+          xa[i8] = *xp[i8];
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i8 = 0; i8 < 2; ++i8) {
+          const uint32_t xw[4] = {xa[i8].x, xa[i8].y, xa[i8].z, xa[i8].w};
+          const float4 B0 = sB2[(c0 >> 2) + i8 * 2], B1 = sB2[(c0 >> 2) + i8 * 2 + 1];
+          const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const float2 xs = unpack2t<FMT>(xw[e2]);
+            float y0 = (lrelu_inv_fast(xs.x) + bv[e2 * 2]) + __uint_as_float(vd[i8 * 8 + e2 * 2]);
+            float y1 = (lrelu_inv_fast(xs.y) + bv[e2 * 2 + 1]) + __uint_as_float(vd[i8 * 8 + e2 * 2 + 1]);
+            if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
+            ow[e2] = pack2t<OFMT>(y0, y1);
+          }
+          *xp[i8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&d2_empty[db]);
+      fence_proxy_async_smem();
+      named_bar_sync(1 + par, 128);
+      if (q == 0 && lane == 0) {
+#pragma unroll
+        for (int kb = 0; kb < KPT; ++kb)
+          tma_store_3d(&tmOut, sA + ab * K::A_BYTES + kb * K::A_KB_BYTES + K::HALO * 128, kb * 64, l0, seq);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(&a_empty[ab]);
+      }
+    }
   } else {
-    // ------------------------------------------------------------ epilogue 2 (warps 10..17): residual + store
+    // ------------------------------------------------------------ epilogue 2 (warps 10..17), C = 256:
+    // residual from global (L2), direct stores; the two warps of a quadrant split the channels
     const int q = warp & 3, hsel = (warp - 10) >> 2;
     const int row = q * 32 + lane;
     constexpr int CW = C / 2;
@@ -340,8 +406,9 @@ static int launch_resblock3(const void* a16, const void* w_packed, const float* 
                             const float* film, int film_stride, int N, int L, int dilation, int T, int num_bands,
                             void* out16, cudaStream_t stream) {
   using K = Rb3Cfg<C>;
-  CUtensorMap tmX, tmW1, tmW2;
+  CUtensorMap tmX, tmW1, tmW2, tmOut;
   B200_TRY(make_tmap_3d(&tmX, a16, C, L, N, (uint64_t)C * 2, (uint64_t)L * C * 2, 64, K::A_ROWS, 128));
+  B200_TRY(make_tmap_3d(&tmOut, out16, C, L, N, (uint64_t)C * 2, (uint64_t)L * C * 2, 64, 128, 128));
   const uint16_t* w1 = reinterpret_cast<const uint16_t*>(w_packed);
   const uint16_t* w2 = w1 + 2ll * C * 3 * C;
   B200_TRY(make_tmap_2d(&tmW1, w1, 3 * C, 2 * C, (uint64_t)3 * C * 2, 64, 128, 128));
@@ -362,7 +429,7 @@ static int launch_resblock3(const void* a16, const void* w_packed, const float* 
     configured[dev & 15] = true;
   }
   const int grid = p.total_tiles < num_sms3() ? p.total_tiles : num_sms3();
-  resblock3_kernel<C, FMT, OFMT, LRELU><<<grid, 576, K::SMEM, stream>>>(tmX, tmW1, tmW2, p);
+  resblock3_kernel<C, FMT, OFMT, LRELU><<<grid, 576, K::SMEM, stream>>>(tmX, tmW1, tmW2, tmOut, p);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
