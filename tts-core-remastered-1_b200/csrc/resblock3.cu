@@ -157,6 +157,17 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(FMT, 128);
       int wi = 0;
+      // The weight-ring wait is software pipelined: while the MMAs of slot wi are being issued, a
+      // non-blocking probe of slot wi+1 is already in flight, so a ready slot costs no round trip.
+      bool w_ready = false;
+      auto acquire_w = [&]() -> int {
+        const int s = wi % NW;
+        if (!w_ready) mbar_wait(&w_full[s], (wi / NW) & 1);
+        tc_fence_after();
+        const int wn = wi + 1;
+        w_ready = mbar_test(&w_full[wn % NW], (wn / NW) & 1);
+        return s;
+      };
       auto g2 = [&](int it2, int kb) {
         const int db = it2 % ND2;
         mbar_wait(&h_full[kb], it2 & 1);
@@ -164,9 +175,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tc_fence_after();
         const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sH + kb * K::H_KB_BYTES));
         for (int half = 0; half < NH; ++half) {
-          const int s = wi % NW;
-          mbar_wait(&w_full[s], (wi / NW) & 1);
-          tc_fence_after();
+          const int s = acquire_w();
           const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + s * K::W_TILE));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -188,9 +197,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tc_fence_after();
           for (int tap = 0; tap < 3; ++tap)
             for (int kb = 0; kb < KPT; ++kb) {
-              const int s = wi % NW;
-              mbar_wait(&w_full[s], (wi / NW) & 1);
-              tc_fence_after();
+              const int s = acquire_w();
               const uint32_t a_addr = smem_u32(sA + ab * K::A_BYTES + kb * K::A_KB_BYTES) +
                                       (K::HALO + (tap - 1) * p.dilation) * 128;
               const uint64_t a_desc = make_kmajor_desc<128>(a_addr);
