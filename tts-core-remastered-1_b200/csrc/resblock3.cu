@@ -153,8 +153,10 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       if (gc >= 1) load_w2((gc - 1) % NCH);
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer.  The whole warp runs the
+    // (warp-uniform) control flow so that indices and descriptors live in uniform registers; only the
+    // tcgen05.mma / commit instructions are executed by one elected lane.
+    {
       const uint32_t idesc = make_idesc_f16(FMT, 128);
       int wi = 0;
       // The weight-ring wait is software pipelined: while the MMAs of slot wi are being issued, a
@@ -177,15 +179,21 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int half = 0; half < NH; ++half) {
           const int s = acquire_w();
           const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + s * K::W_TILE));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + K::D2_COL + db * C + half * 128, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                     (kb | k) != 0);
-          umma_commit(&w_empty[s]);
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_base + K::D2_COL + db * C + half * 128, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                       (kb | k) != 0);
+            umma_commit(&w_empty[s]);
+          }
+          __syncwarp();
           ++wi;
         }
-        umma_commit(&h_empty[kb]);
-        if (kb == NCH - 1) umma_commit(&d2_full[db]);
+        if (elect_one()) {
+          umma_commit(&h_empty[kb]);
+          if (kb == NCH - 1) umma_commit(&d2_full[db]);
+        }
+        __syncwarp();
       };
       int gc = 0;
       for (int it = 0; it < n_my_tiles; ++it) {
@@ -202,14 +210,20 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                                       (K::HALO + (tap - 1) * p.dilation) * 128;
               const uint64_t a_desc = make_kmajor_desc<128>(a_addr);
               const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + s * K::W_TILE));
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(tmem_base + b * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, (tap | kb | k) != 0);
-              umma_commit(&w_empty[s]);
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(tmem_base + b * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, (tap | kb | k) != 0);
+                umma_commit(&w_empty[s]);
+              }
+              __syncwarp();
               ++wi;
             }
-          umma_commit(&d1_full[b]);
-          if (!K::INPLACE && j == NCH - 1) umma_commit(&a_empty[ab]);   // INPLACE: released by the store epilogue
+          if (elect_one()) {
+            umma_commit(&d1_full[b]);
+            if (!K::INPLACE && j == NCH - 1) umma_commit(&a_empty[ab]);   // INPLACE: released by the store epilogue
+          }
+          __syncwarp();
           if (gc >= 1) g2((gc - 1) / NCH, (gc - 1) % NCH);
         }
       }
