@@ -150,45 +150,58 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // ------------------------------------------------------------ MMA issuers: warp 1 owns the even tiles,
     // warp 18 the odd ones (tcgen05.mma may be issued by any thread; the per-tile barrier round trips
     // of a single issuing thread were the bottleneck of the C=32 stage, see profiles/).
-    if (lane == 0) {
+    // Whole warp runs the (warp-uniform) control flow, one elected lane issues tcgen05.mma / commit:
+    // indices and descriptors stay in uniform registers; independent barrier probes are issued
+    // together so their round trips overlap.
+    {
       const int mpar = warp == 1 ? 0 : 1;
       const uint32_t idesc1 = make_idesc_f16(FMT, K::N1);
       const uint32_t idesc2 = make_idesc_f16(FMT, C);
       mbar_wait(w_full, 0);
       auto issue_g2 = [&](int i) {
         const int b1 = i % ND1, b2 = i % ND2;
-        mbar_wait(&h_full[b1], (i / ND1) & 1);
+        const uint32_t ph1 = (i / ND1) & 1, ph2 = ((i / ND2) & 1) ^ 1;
+        const bool r1 = mbar_test(&h_full[b1], ph1), r2 = mbar_test(&d2_empty[b2], ph2);
+        if (!r1) mbar_wait(&h_full[b1], ph1);
         RB2_TRACE(2, i, 0);
-        mbar_wait(&d2_empty[b2], ((i / ND2) & 1) ^ 1);
+        if (!r2) mbar_wait(&d2_empty[b2], ph2);
         RB2_TRACE(2, i, 1);
         tc_fence_after();
         const uint64_t a_desc = make_kmajor_desc<K::ROWB>(smem_u32(sH + b1 * K::H_BYTES));
         const uint64_t b_desc = make_kmajor_desc<K::ROWB>(smem_u32(sW2));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < K::KB / 16; ++k)
-          umma_f16(tmem_base + K::D2_COL + b2 * C, a_desc + 2 * k, b_desc + 2 * k, idesc2, k != 0);
-        umma_commit(&d2_full[b2]);
-        umma_commit(&h_empty[b1]);
+          for (int k = 0; k < K::KB / 16; ++k)
+            umma_f16(tmem_base + K::D2_COL + b2 * C, a_desc + 2 * k, b_desc + 2 * k, idesc2, k != 0);
+          umma_commit(&d2_full[b2]);
+          umma_commit(&h_empty[b1]);
+        }
+        __syncwarp();
       };
       int i = 0, prev = -1;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
         if ((i & 1) != mpar) continue;
         const int b = i % ND1, ab = i % NA;
-        mbar_wait(&a_full[ab], (i / NA) & 1);
+        const uint32_t pha = (i / NA) & 1, phd = ((i / ND1) & 1) ^ 1;
+        const bool ra = mbar_test(&a_full[ab], pha), rd = mbar_test(&d1_empty[b], phd);
+        if (!ra) mbar_wait(&a_full[ab], pha);
         RB2_TRACE(1, i, 0);
-        mbar_wait(&d1_empty[b], ((i / ND1) & 1) ^ 1);
+        if (!rd) mbar_wait(&d1_empty[b], phd);
         RB2_TRACE(1, i, 1);
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + ab * K::A_SLOT);
+        if (elect_one()) {
 #pragma unroll
-        for (int tap = 0; tap < 3; ++tap) {
-          const uint64_t a_desc = make_kmajor_desc<K::ROWB>(a_base + (K::HALO + (tap - 1) * p.dilation) * K::ROWB);
-          const uint64_t b_desc = make_kmajor_desc<K::ROWB>(smem_u32(sW1 + tap * K::W1_TILE));
+          for (int tap = 0; tap < 3; ++tap) {
+            const uint64_t a_desc = make_kmajor_desc<K::ROWB>(a_base + (K::HALO + (tap - 1) * p.dilation) * K::ROWB);
+            const uint64_t b_desc = make_kmajor_desc<K::ROWB>(smem_u32(sW1 + tap * K::W1_TILE));
 #pragma unroll
-          for (int k = 0; k < K::KB / 16; ++k)
-            umma_f16(tmem_base + b * K::N1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (tap | k) != 0);
+            for (int k = 0; k < K::KB / 16; ++k)
+              umma_f16(tmem_base + b * K::N1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (tap | k) != 0);
+          }
+          umma_commit(&d1_full[b]);
         }
-        umma_commit(&d1_full[b]);
+        __syncwarp();
         RB2_TRACE(1, i, 2);
         if (prev >= 0) issue_g2(prev);        // GEMM2 trails GEMM1 by one own tile (= 2 tiles)
         prev = i;

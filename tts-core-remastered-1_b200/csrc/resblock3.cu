@@ -172,8 +172,10 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       };
       auto g2 = [&](int it2, int kb) {
         const int db = it2 % ND2;
-        mbar_wait(&h_full[kb], it2 & 1);
-        if (kb == 0) mbar_wait(&d2_empty[db], ((it2 / ND2) & 1) ^ 1);
+        const uint32_t phh = it2 & 1, phd = ((it2 / ND2) & 1) ^ 1;
+        const bool rh = mbar_test(&h_full[kb], phh), rd = kb == 0 ? mbar_test(&d2_empty[db], phd) : true;
+        if (!rh) mbar_wait(&h_full[kb], phh);
+        if (!rd) mbar_wait(&d2_empty[db], phd);
         tc_fence_after();
         const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sH + kb * K::H_KB_BYTES));
         for (int half = 0; half < NH; ++half) {
@@ -200,8 +202,12 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int ab = it % NA;
         for (int j = 0; j < NCH; ++j, ++gc) {
           const int b = gc & 1;
-          if (j == 0) mbar_wait(&a_full[ab], (it / NA) & 1);
-          mbar_wait(&d1_empty[b], ((gc >> 1) & 1) ^ 1);
+          {
+            const uint32_t pha = (it / NA) & 1, phd = ((gc >> 1) & 1) ^ 1;
+            const bool ra = j == 0 ? mbar_test(&a_full[ab], pha) : true, rd = mbar_test(&d1_empty[b], phd);
+            if (!ra) mbar_wait(&a_full[ab], pha);
+            if (!rd) mbar_wait(&d1_empty[b], phd);
+          }
           tc_fence_after();
           for (int tap = 0; tap < 3; ++tap)
             for (int kb = 0; kb < KPT; ++kb) {
