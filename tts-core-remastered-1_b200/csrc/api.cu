@@ -304,9 +304,14 @@ int b200voc_gen_create(const b200voc_gen_config* cfg, b200voc_gen** out) {
     g->stages.push_back(sw);
     c /= 2;
   }
+  film_cols = (film_cols + 127) / 128 * 128;      // padded to the SGEMM tile; pad rows are zero
   g->film_cols = film_cols;
   A(g->film_w, (long long)film_cols * cd);
   A(g->film_b, film_cols);
+  if (st == B200VOC_OK) {
+    cudaMemset(g->film_w, 0, (size_t)film_cols * cd * sizeof(float));
+    cudaMemset(g->film_b, 0, (size_t)film_cols * sizeof(float));
+  }
   A(g->merge_w, (long long)c * nb * 7);
   A(g->merge_b, 1);
   add_slot(g, "band_merge.weight", (long long)c * nb * 7, W_MERGE_W);
@@ -316,11 +321,7 @@ int b200voc_gen_create(const b200voc_gen_config* cfg, b200voc_gen** out) {
     b200voc_gen_destroy(g);
     return st;
   }
-  if (film_cols % 64 != 0) {
-    set_error("film column count %d not a multiple of 64", film_cols);
-    b200voc_gen_destroy(g);
-    return B200VOC_ERR_UNSUPPORTED;
-  }
+
   *out = g;
   return B200VOC_OK;
 }

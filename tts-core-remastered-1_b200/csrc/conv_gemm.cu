@@ -36,7 +36,7 @@ struct GemmTapsParams {
 
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 x 2B
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int FMT, bool LRELU>
 __global__ void __launch_bounds__(192, 1)
 gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmTapsParams p) {
@@ -85,22 +85,26 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(p.fmt, BN);
-      for (int kb = 0; kb < num_k; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t a_desc = make_kmajor_desc<128>(a_addr);
-        const uint64_t b_desc = make_kmajor_desc<128>(a_addr + kATileBytes);
+    // whole warp runs the uniform control flow; one elected lane issues the MMAs (descriptors in
+    // uniform registers); the probe of the next stage overlaps the issue of the current one
+    const uint32_t idesc = make_idesc_f16(FMT, BN);
+    bool ready = false;
+    for (int kb = 0; kb < num_k; ++kb) {
+      const int s = kb % STAGES;
+      if (!ready) mbar_wait(&full[s], (kb / STAGES) & 1);
+      tc_fence_after();
+      ready = mbar_test(&full[(kb + 1) % STAGES], ((kb + 1) / STAGES) & 1);
+      const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+      const uint64_t a_desc = make_kmajor_desc<128>(a_addr);
+      const uint64_t b_desc = make_kmajor_desc<128>(a_addr + kATileBytes);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // UMMA_K = 16 elements = 32 bytes = +2 in the >>4 start field
           umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
         umma_commit(&empty[s]);
+        if (kb == num_k - 1) umma_commit(accum_full);
       }
-      umma_commit(accum_full);
+      __syncwarp();
     }
   } else {
     // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
@@ -126,9 +130,9 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const float4 bb = __ldg(b4 + i);
           float y0 = __uint_as_float(v[4 * i + 0]) + bb.x, y1 = __uint_as_float(v[4 * i + 1]) + bb.y;
           float y2 = __uint_as_float(v[4 * i + 2]) + bb.z, y3 = __uint_as_float(v[4 * i + 3]) + bb.w;
-          if (p.store_lrelu) { y0 = lrelu(y0); y1 = lrelu(y1); y2 = lrelu(y2); y3 = lrelu(y3); }
-          w[2 * i] = pack2(y0, y1, p.fmt);
-          w[2 * i + 1] = pack2(y2, y3, p.fmt);
+          if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); y2 = lrelu_fast(y2); y3 = lrelu_fast(y3); }
+          w[2 * i] = pack2t<FMT>(y0, y1);
+          w[2 * i + 1] = pack2t<FMT>(y2, y3);
         }
         uint4* dst = reinterpret_cast<uint4*>(out + idx);
 #pragma unroll
@@ -141,21 +145,33 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int STAGES>
-static int launch_gemm_taps(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTapsParams& p, int n_seq,
-                            cudaStream_t stream) {
+template <int BN, int STAGES, int FMT, bool LRELU>
+static int launch_gemm_taps_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTapsParams& p, int n_seq,
+                              cudaStream_t stream) {
   constexpr int SMEM = STAGES * (kATileBytes + BN * 128) + 256 + 1024;
   static bool configured[16] = {};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 15]) {
-    B200_CUDA(cudaFuncSetAttribute(gemm_taps_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    B200_CUDA(cudaFuncSetAttribute(gemm_taps_kernel<BN, STAGES, FMT, LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   SMEM));
     configured[dev & 15] = true;
   }
   dim3 grid(ceil_div(p.rows_per_seq, 128), p.n_total / BN, n_seq);
-  gemm_taps_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(tmA, tmB, p);
+  gemm_taps_kernel<BN, STAGES, FMT, LRELU><<<grid, 192, SMEM, stream>>>(tmA, tmB, p);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm_taps(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTapsParams& p, int n_seq,
+                            cudaStream_t stream) {
+  if (p.fmt == 0) {
+    if (p.store_lrelu) return launch_gemm_taps_t<BN, STAGES, 0, true>(tmA, tmB, p, n_seq, stream);
+    return launch_gemm_taps_t<BN, STAGES, 0, false>(tmA, tmB, p, n_seq, stream);
+  }
+  if (p.store_lrelu) return launch_gemm_taps_t<BN, STAGES, 1, true>(tmA, tmB, p, n_seq, stream);
+  return launch_gemm_taps_t<BN, STAGES, 1, false>(tmA, tmB, p, n_seq, stream);
 }
 
 // ---------------------------------------------------------------------------- ConvT packing

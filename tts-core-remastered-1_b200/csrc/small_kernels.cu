@@ -77,45 +77,51 @@ __global__ void __launch_bounds__(128) cond_kernel(const float* __restrict__ pro
 }
 
 // ------------------------------------------------------------------ FiLM projection (fp32 SGEMM)
-// out[r, n] = sum_k A[r, k] * W[n, k] + bias[n],  K = 128 fixed, r < M, n < Ncols (multiple of 64).
-// 64x64 tile per block, 4x4 per thread, both operands transposed into smem ([k][m], [k][n]).
+// out[r, n] = sum_k A[r, k] * W[n, k] + bias[n],  K = 128 fixed, r < M, n < Ncols (multiple of 128).
+// 128x128 tile per block, 8x8 per thread (16 FMA per shared-memory vector load), K in chunks of 16,
+// operands transposed into smem ([k][m], [k][n]).  fp32 on CUDA cores: the FiLM projection is one
+// of the precision-sensitive layers.
 __global__ void __launch_bounds__(256) film_sgemm_kernel(const float* __restrict__ A, const float* __restrict__ W,
                                                          const float* __restrict__ bias, int M, int Ncols,
                                                          float* __restrict__ out) {
-  constexpr int K = 128, KH = 64, BM = 64, BN = 64, PAD = 4;
-  __shared__ float sA[KH][BM + PAD];
-  __shared__ float sB[KH][BN + PAD];
+  constexpr int K = 128, BK = 16, BM = 128, BN = 128, PAD = 4;
+  __shared__ __align__(16) float sA[BK][BM + PAD];
+  __shared__ __align__(16) float sB[BK][BN + PAD];
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int tm = (threadIdx.x / 16) * 4, tn = (threadIdx.x % 16) * 4;
-  float acc[4][4] = {};
-  for (int kh = 0; kh < K; kh += KH) {
-    if (kh) __syncthreads();
-    for (int i = threadIdx.x; i < BM * (KH / 4); i += 256) {
-      const int r = i / (KH / 4), k4 = i % (KH / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m0 + r < M) v = *reinterpret_cast<const float4*>(A + (long long)(m0 + r) * K + kh + k4 * 4);
-      sA[k4 * 4 + 0][r] = v.x; sA[k4 * 4 + 1][r] = v.y; sA[k4 * 4 + 2][r] = v.z; sA[k4 * 4 + 3][r] = v.w;
-      const float4 w = *reinterpret_cast<const float4*>(W + (long long)(n0 + r) * K + kh + k4 * 4);
+  const int tm = (threadIdx.x / 16) * 8, tn = (threadIdx.x % 16) * 8;
+  float acc[8][8] = {};
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    if (k0) __syncthreads();
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int i = threadIdx.x + v * 256;         // 512 float4 per operand chunk
+      const int r = i >> 2, k4 = i & 3;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < M) a = __ldg(reinterpret_cast<const float4*>(A + (long long)(m0 + r) * K + k0 + k4 * 4));
+      sA[k4 * 4 + 0][r] = a.x; sA[k4 * 4 + 1][r] = a.y; sA[k4 * 4 + 2][r] = a.z; sA[k4 * 4 + 3][r] = a.w;
+      const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)(n0 + r) * K + k0 + k4 * 4));
       sB[k4 * 4 + 0][r] = w.x; sB[k4 * 4 + 1][r] = w.y; sB[k4 * 4 + 2][r] = w.z; sB[k4 * 4 + 3][r] = w.w;
     }
     __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < KH; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&sA[k][tm]);
-      const float4 b = *reinterpret_cast<const float4*>(&sB[k][tn]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sA[k][tm]), a1 = *reinterpret_cast<const float4*>(&sA[k][tm + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&sB[k][tn]), b1 = *reinterpret_cast<const float4*>(&sB[k][tn + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
   }
-  const float4 bb = *reinterpret_cast<const float4*>(bias + n0 + tn);
+  const float4 c0 = *reinterpret_cast<const float4*>(bias + n0 + tn), c1 = *reinterpret_cast<const float4*>(bias + n0 + tn + 4);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     if (m0 + tm + i < M) {
-      float4 o = make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
-      *reinterpret_cast<float4*>(out + (long long)(m0 + tm + i) * Ncols + n0 + tn) = o;
+      float* o = out + (long long)(m0 + tm + i) * Ncols + n0 + tn;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[i][0] + c0.x, acc[i][1] + c0.y, acc[i][2] + c0.z, acc[i][3] + c0.w);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[i][4] + c1.x, acc[i][5] + c1.y, acc[i][6] + c1.z, acc[i][7] + c1.w);
     }
   }
 }
@@ -171,43 +177,64 @@ __global__ void pack_split_kernel(const float* __restrict__ w, int band_size, in
 
 // ------------------------------------------------------------------ K4: band_merge + tanh
 // wav[b, l] = tanh(bias + sum_{band,c,k} w[band*Cb + c][k] * x[(b*nb+band), l+k-3, c]); x16 raw,
-// channels-last with Cb = 32 channels (64-byte rows).  Thread = output sample.
-template <int CB>
+// channels-last, Cb = 32 channels per band (64-byte rows), nb = 4 bands (= 128 input channels).
+// One warp produces 32 consecutive samples: lane = (band, 4 channels) keeps its 4x7 weights in
+// registers, slides over the 38 input rows (each warp load = four full 64-byte rows, one per band)
+// accumulating 32 partial outputs, then a 5-stage transpose-reduce leaves output j in lane j
+// (31 shuffles per 32 outputs), tanh, one coalesced 128-byte store.  HBM-bound by design.
+template <int FMT>
 __global__ void __launch_bounds__(256) band_merge_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w,
-                                                         const float* __restrict__ bias, int B, int nb, int L,
-                                                         int fmt, float* __restrict__ wav) {
-  extern __shared__ float s_w[];   // [nb][7][CB]
-  for (int i = threadIdx.x; i < nb * 7 * CB; i += blockDim.x) {
-    const int band = i / (7 * CB), k = (i / CB) % 7, c = i % CB;
-    s_w[i] = w[(band * CB + c) * 7 + k];
-  }
-  __syncthreads();
-  const int b = blockIdx.y;
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= L) return;
-  float acc = bias[0];
-  for (int band = 0; band < nb; ++band) {
-    const uint16_t* xs = x + ((long long)(b * nb + band) * L) * CB;
+                                                         const float* __restrict__ bias, int B, int L,
+                                                         float* __restrict__ wav) {
+  constexpr int CB = 32, NB = 4;
+  const int lane = threadIdx.x & 31;
+  const int tiles = (L + 31) / 32;
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= (long long)B * tiles) return;
+  const int b = (int)(gw / tiles), l0 = (int)(gw % tiles) * 32;
+  const int band = lane >> 3, c0 = (lane & 7) * 4;
+  float wr[4][7];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) wr[i][k] = __ldg(w + (band * CB + c0 + i) * 7 + k);
+  const uint16_t* xs = x + ((long long)(b * NB + band) * L) * CB + c0;
+  float p[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) p[j] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 38; ++r) {
+    const int l = l0 + r - 3;
+    float xf[4] = {0.f, 0.f, 0.f, 0.f};
+    if (l >= 0 && l < L) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(xs + (long long)l * CB));
+      const float2 f0 = unpack2t<FMT>(u.x), f1 = unpack2t<FMT>(u.y);
+      xf[0] = f0.x; xf[1] = f0.y; xf[2] = f1.x; xf[3] = f1.y;
+    }
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
-      const int ll = l + k - 3;
-      if (ll < 0 || ll >= L) continue;
-      const uint4* row = reinterpret_cast<const uint4*>(xs + (long long)ll * CB);
-      const float* wk = s_w + (band * 7 + k) * CB;
+      const int j = r - k;               // output l0 + j uses input row l0 + j + k - 3 = row index r
+      if (j >= 0 && j < 32) {
+        float a = p[j];
 #pragma unroll
-      for (int v = 0; v < CB / 8; ++v) {
-        const uint4 u = __ldg(row + v);
-        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack2(uw[e], fmt);
-          acc = fmaf(f.x, wk[v * 8 + e * 2], acc);
-          acc = fmaf(f.y, wk[v * 8 + e * 2 + 1], acc);
-        }
+        for (int i = 0; i < 4; ++i) a = fmaf(wr[i][k], xf[i], a);
+        p[j] = a;
       }
     }
   }
-  wav[(long long)b * L + l] = tanhf(acc);
+  // transpose-reduce over the 32 lanes: after stage s each lane keeps s values
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? p[i] : p[i + s];
+      const float keep = up ? p[i + s] : p[i];
+      p[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  const int l = l0 + lane;
+  if (l < L) wav[(long long)b * L + l] = tanhf(p[0] + __ldg(bias));
 }
 
 // ------------------------------------------------------------------ helpers
@@ -262,8 +289,8 @@ int cond_launch(const float* prosody, const float* w0, const float* b0, const fl
 }
 int film_launch(const float* cond, const float* w_all, const float* b_all, int M, int ncols, float* out,
                 cudaStream_t st) {
-  B200_CHECK_ARG(ncols % 64 == 0, "film: ncols=%d must be a multiple of 64", ncols);
-  dim3 grid(ceil_div(M, 64), ncols / 64);
+  B200_CHECK_ARG(ncols % 128 == 0, "film: ncols=%d must be a multiple of 128", ncols);
+  dim3 grid(ceil_div(M, 128), ncols / 128);
   film_sgemm_kernel<<<grid, 256, 0, st>>>(cond, w_all, b_all, M, ncols, out);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
@@ -284,10 +311,13 @@ int pack_split_launch(const float* w, int band_size, int H, float* wt_band, cuda
 }
 int band_merge_launch(const void* x16, const float* w, const float* bias, int B, int nb, int L, int Cb, int fmt,
                       float* wav, cudaStream_t st) {
-  B200_CHECK_ARG(Cb == 32, "band_merge: per-band channels %d unsupported (32)", Cb);
-  dim3 grid(ceil_div(L, 256), B);
-  band_merge_kernel<32><<<grid, 256, (size_t)nb * 7 * 32 * sizeof(float), st>>>(
-      reinterpret_cast<const uint16_t*>(x16), w, bias, B, nb, L, fmt, wav);
+  B200_CHECK_ARG(Cb == 32 && nb == 4, "band_merge: %d bands x %d channels unsupported (4 x 32)", nb, Cb);
+  const long long warps = (long long)B * ceil_div(L, 32);
+  const int grid = (int)((warps + 7) / 8);
+  if (fmt == 0)
+    band_merge_kernel<0><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(x16), w, bias, B, L, wav);
+  else
+    band_merge_kernel<1><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(x16), w, bias, B, L, wav);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
