@@ -54,9 +54,9 @@ struct Rb2Cfg {
   static constexpr int OFF_W1 = 0;
   static constexpr int OFF_W2 = 3 * W1_TILE;
   static constexpr int OFF_A = (OFF_W2 + W2_BYTES + 1023) & ~1023;
-  static constexpr int ND1 = C == 32 ? 4 : 3;        // ring depth of the GEMM1 accumulators and of h
+  static constexpr int ND1 = C == 32 ? 6 : 3;        // ring depth of the GEMM1 accumulators and of h
   static constexpr int ND2 = C == 32 ? 4 : 2;        // ring depth of the GEMM2 accumulators
-  static constexpr int NA = ND1 + 2;                // ring depth of the input tiles (TMA prefetch distance)
+  static constexpr int NA = C == 32 ? 10 : ND1 + 2;  // ring depth of the input tiles (TMA prefetch distance)
   static constexpr int OFF_H = OFF_A + NA * A_SLOT;
   static constexpr int OFF_BAR = OFF_H + ND1 * H_BYTES;
   static constexpr int OFF_PAR = OFF_BAR + 512;
