@@ -46,7 +46,7 @@ static int encode(CUtensorMap* out, const void* base, int rank, const cuuint64_t
     set_error("TMA base pointer %p is not 16-byte aligned", base);
     return B200VOC_ERR_BAD_ARG;
   }
-  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
@@ -73,6 +73,15 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {box0, box1, 1};
   return encode(out, base, 3, dims, strides, box, swizzle_bytes);
+}
+
+int make_tmap_4d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint64_t stride3_bytes, uint32_t box0, uint32_t box1,
+                 uint32_t box2, int swizzle_bytes) {
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {stride1_bytes, stride2_bytes, stride3_bytes};
+  cuuint32_t box[4] = {box0, box1, box2, 1};
+  return encode(out, base, 4, dims, strides, box, swizzle_bytes);
 }
 
 // ------------------------------------------------------------------ launchers defined elsewhere

@@ -44,6 +44,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
 int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                  uint64_t stride2_bytes, uint32_t box0, uint32_t box1, int swizzle_bytes);
 
+int make_tmap_4d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint64_t stride3_bytes, uint32_t box0, uint32_t box1,
+                 uint32_t box2, int swizzle_bytes);
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace b200

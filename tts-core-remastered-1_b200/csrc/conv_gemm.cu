@@ -25,13 +25,11 @@ struct GemmTapsParams {
   int k_per_tap;      // Cin (multiple of 64)
   int n_total;        // GEMM columns (s * Cout)
   int cout;           // bias period
-  long long out_seq_stride;  // elements between sequences in the output
-  long long out_valid;       // valid output elements per sequence (Lout * Cout)
-  int out_shift;      // p * Cout: GEMM (m, c) -> flat m*n_total + c - out_shift
+  int stride;         // s  (1 for a plain projection)
+  int pad;            // p = s/2 (0 for a plain projection)
   int fmt;            // B200VOC_FMT_*
   int store_lrelu;
   const float* bias;
-  void* out;
 };
 
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 x 2B
@@ -39,7 +37,7 @@ constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 x 2B
 template <int BN, int STAGES, int FMT, bool LRELU>
 __global__ void __launch_bounds__(192, 1)
 gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmTapsParams p) {
+                 const __grid_constant__ CUtensorMap tmOut, const GemmTapsParams p) {
   constexpr int B_TILE = BN * 128;
   constexpr int STAGE_BYTES = kATileBytes + B_TILE;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
@@ -107,37 +105,59 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
     }
   } else {
-    // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
+    // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4).  The accumulator tile is converted in
+    // registers (+bias, leaky-ReLU, 16-bit) and staged in shared memory (the operand ring is idle
+    // by now) as [128 rows x 64 ch] swizzled blocks -- one block per (output phase, 64-channel group)
+    // -- which leave through TMA stores on a 4-D view (co, l mod s, l / s, n) of the output: the
+    // polyphase pixel shuffle, the -p offset and both sequence ends are handled by the TMA unit.
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const long long m = (long long)m0 + row;
     mbar_wait(accum_full, 0);
     tc_fence_after();
-    uint16_t* out = reinterpret_cast<uint16_t*>(p.out) + (long long)seq * p.out_seq_stride;
+    const bool narrow = p.cout < 64;                 // Cout = 32: 64-byte rows, SWIZZLE_64B, one block per phase
+    const int blk_bytes = narrow ? 128 * 64 : 128 * 128;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
       tmem_ld_wait();
       const int col0 = n0 + c * 32;
-      const long long idx = m * p.n_total + col0 - p.out_shift;
-      const bool valid = (m < p.rows_per_seq) && idx >= 0 && idx < p.out_valid;
-      if (valid) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + (col0 % p.cout));
-        uint32_t w[16];
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + (col0 % p.cout));
+      uint32_t w[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bb = __ldg(b4 + i);
-          float y0 = __uint_as_float(v[4 * i + 0]) + bb.x, y1 = __uint_as_float(v[4 * i + 1]) + bb.y;
-          float y2 = __uint_as_float(v[4 * i + 2]) + bb.z, y3 = __uint_as_float(v[4 * i + 3]) + bb.w;
-          if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); y2 = lrelu_fast(y2); y3 = lrelu_fast(y3); }
-          w[2 * i] = pack2t<FMT>(y0, y1);
-          w[2 * i + 1] = pack2t<FMT>(y2, y3);
-        }
-        uint4* dst = reinterpret_cast<uint4*>(out + idx);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+      for (int i = 0; i < 8; ++i) {
+        const float4 bb = __ldg(b4 + i);
+        float y0 = __uint_as_float(v[4 * i + 0]) + bb.x, y1 = __uint_as_float(v[4 * i + 1]) + bb.y;
+        float y2 = __uint_as_float(v[4 * i + 2]) + bb.z, y3 = __uint_as_float(v[4 * i + 3]) + bb.w;
+        if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); y2 = lrelu_fast(y2); y3 = lrelu_fast(y3); }
+        w[2 * i] = pack2t<FMT>(y0, y1);
+        w[2 * i + 1] = pack2t<FMT>(y2, y3);
       }
+      if (narrow) {
+        uint8_t* dst = smem + c * blk_bytes + row * 64;        // block c = one phase of 32 channels
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(dst + ((i ^ ((row >> 1) & 3)) << 4)) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+      } else {
+        uint8_t* dst = smem + (c >> 1) * blk_bytes + row * 128;  // block = 64 channels, this chunk = half of it
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(dst + ((((c & 1) * 4 + i) ^ (row & 7)) << 4)) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (warp == 2 && lane == 0) {
+      const int bw = narrow ? 32 : 64;                 // GEMM columns per block
+      for (int j = 0; j < BN / bw; ++j) {
+        const int col = n0 + j * bw;
+        const int r = col / p.cout, co0 = col % p.cout;
+        const int rr = r >= p.pad ? r - p.pad : r - p.pad + p.stride;
+        const int mm = r >= p.pad ? m0 : m0 - 1;
+        tma_store_4d(&tmOut, smem + j * blk_bytes, co0, rr, mm, seq);
+      }
+      tma_store_commit();
+      tma_store_wait_read();
     }
   }
   tc_fence_before();
@@ -146,8 +166,8 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int BN, int STAGES, int FMT, bool LRELU>
-static int launch_gemm_taps_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTapsParams& p, int n_seq,
-                              cudaStream_t stream) {
+static int launch_gemm_taps_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                              const GemmTapsParams& p, int n_seq, cudaStream_t stream) {
   constexpr int SMEM = STAGES * (kATileBytes + BN * 128) + 256 + 1024;
   static bool configured[16] = {};
   int dev = 0;
@@ -158,20 +178,20 @@ static int launch_gemm_taps_t(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     configured[dev & 15] = true;
   }
   dim3 grid(ceil_div(p.rows_per_seq, 128), p.n_total / BN, n_seq);
-  gemm_taps_kernel<BN, STAGES, FMT, LRELU><<<grid, 192, SMEM, stream>>>(tmA, tmB, p);
+  gemm_taps_kernel<BN, STAGES, FMT, LRELU><<<grid, 192, SMEM, stream>>>(tmA, tmB, tmOut, p);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
 
 template <int BN, int STAGES>
-static int launch_gemm_taps(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTapsParams& p, int n_seq,
-                            cudaStream_t stream) {
+static int launch_gemm_taps(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                            const GemmTapsParams& p, int n_seq, cudaStream_t stream) {
   if (p.fmt == 0) {
-    if (p.store_lrelu) return launch_gemm_taps_t<BN, STAGES, 0, true>(tmA, tmB, p, n_seq, stream);
-    return launch_gemm_taps_t<BN, STAGES, 0, false>(tmA, tmB, p, n_seq, stream);
+    if (p.store_lrelu) return launch_gemm_taps_t<BN, STAGES, 0, true>(tmA, tmB, tmOut, p, n_seq, stream);
+    return launch_gemm_taps_t<BN, STAGES, 0, false>(tmA, tmB, tmOut, p, n_seq, stream);
   }
-  if (p.store_lrelu) return launch_gemm_taps_t<BN, STAGES, 1, true>(tmA, tmB, p, n_seq, stream);
-  return launch_gemm_taps_t<BN, STAGES, 1, false>(tmA, tmB, p, n_seq, stream);
+  if (p.store_lrelu) return launch_gemm_taps_t<BN, STAGES, 1, true>(tmA, tmB, tmOut, p, n_seq, stream);
+  return launch_gemm_taps_t<BN, STAGES, 1, false>(tmA, tmB, tmOut, p, n_seq, stream);
 }
 
 // ---------------------------------------------------------------------------- ConvT packing
@@ -198,8 +218,12 @@ int convt1d_launch(const void* x16, const void* w_packed, const float* bias, int
   B200_CHECK_ARG(s >= 2 && s % 2 == 0, "convt1d: stride %d must be even", s);
   B200_CHECK_ARG(N > 0 && Lin > 0, "convt1d: empty input");
   const int n_total = s * Cout;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmOut;
   B200_TRY(make_tmap_3d(&tmA, x16, Cin, Lin, N, (uint64_t)Cin * 2, (uint64_t)Lin * Cin * 2, 64, 128, 128));
+  // output [N, s*Lin, Cout] viewed as (co, l mod s, l / s, n)
+  const int obox = Cout < 64 ? Cout : 64;
+  B200_TRY(make_tmap_4d(&tmOut, out16, Cout, s, Lin, N, (uint64_t)Cout * 2, (uint64_t)s * Cout * 2,
+                        (uint64_t)s * Lin * Cout * 2, obox, 1, 128, obox * 2));
   GemmTapsParams p{};
   p.rows_per_seq = Lin + 1;
   p.n_taps = 2;
@@ -208,22 +232,20 @@ int convt1d_launch(const void* x16, const void* w_packed, const float* bias, int
   p.k_per_tap = Cin;
   p.n_total = n_total;
   p.cout = Cout;
-  p.out_seq_stride = (long long)s * Lin * Cout;
-  p.out_valid = (long long)s * Lin * Cout;
-  p.out_shift = (s / 2) * Cout;
+  p.stride = s;
+  p.pad = s / 2;
   p.fmt = fmt;
   p.store_lrelu = store_lrelu;
   p.bias = bias;
-  p.out = out16;
   if (n_total % 256 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 256, 128));
-    return launch_gemm_taps<256, 2>(tmA, tmB, p, N, stream);
+    return launch_gemm_taps<256, 2>(tmA, tmB, tmOut, p, N, stream);
   } else if (n_total % 128 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 128, 128));
-    return launch_gemm_taps<128, 3>(tmA, tmB, p, N, stream);
+    return launch_gemm_taps<128, 3>(tmA, tmB, tmOut, p, N, stream);
   } else if (n_total % 64 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 64, 128));
-    return launch_gemm_taps<64, 2>(tmA, tmB, p, N, stream);
+    return launch_gemm_taps<64, 2>(tmA, tmB, tmOut, p, N, stream);
   }
   set_error("convt1d: s*Cout=%d must be a multiple of 64", n_total);
   return B200VOC_ERR_UNSUPPORTED;
@@ -233,29 +255,30 @@ int convt1d_launch(const void* x16, const void* w_packed, const float* bias, int
 int linear_launch(const void* x16, const void* w_packed /*[Cout][Cin]*/, const float* bias, int N, int L, int Cin,
                   int Cout, int fmt, int store_lrelu, void* out16, cudaStream_t stream) {
   B200_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0, "linear: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmOut;
   B200_TRY(make_tmap_3d(&tmA, x16, Cin, L, N, (uint64_t)Cin * 2, (uint64_t)L * Cin * 2, 64, 128, 128));
+  B200_TRY(make_tmap_4d(&tmOut, out16, Cout, 1, L, N, (uint64_t)Cout * 2, (uint64_t)Cout * 2, (uint64_t)L * Cout * 2,
+                        64, 1, 128, 128));
   GemmTapsParams p{};
   p.rows_per_seq = L;
   p.n_taps = 1;
   p.k_per_tap = Cin;
   p.n_total = Cout;
   p.cout = Cout;
-  p.out_seq_stride = (long long)L * Cout;
-  p.out_valid = (long long)L * Cout;
+  p.stride = 1;
+  p.pad = 0;
   p.fmt = fmt;
   p.store_lrelu = store_lrelu;
   p.bias = bias;
-  p.out = out16;
   if (Cout % 256 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, Cin, Cout, (uint64_t)Cin * 2, 64, 256, 128));
-    return launch_gemm_taps<256, 2>(tmA, tmB, p, N, stream);
+    return launch_gemm_taps<256, 2>(tmA, tmB, tmOut, p, N, stream);
   } else if (Cout % 128 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, Cin, Cout, (uint64_t)Cin * 2, 64, 128, 128));
-    return launch_gemm_taps<128, 3>(tmA, tmB, p, N, stream);
+    return launch_gemm_taps<128, 3>(tmA, tmB, tmOut, p, N, stream);
   }
   B200_TRY(make_tmap_2d(&tmB, w_packed, Cin, Cout, (uint64_t)Cin * 2, 64, 64, 128));
-  return launch_gemm_taps<64, 2>(tmA, tmB, p, N, stream);
+  return launch_gemm_taps<64, 2>(tmA, tmB, tmOut, p, N, stream);
 }
 
 // ---------------------------------------------------------------------------- experiment
