@@ -13,6 +13,8 @@
 //   y[m*s + r - p, co] = sum_ci x[m, ci] W[ci, co, r] + x[m-1, ci] W[ci, co, r+s],  m in [0, Lin]
 // i.e. 2 taps (shift 0, -1), GEMM column c = r*Cout + co, and because the output is channels-last
 // the GEMM output row m IS the contiguous run out[(m*s - p)*Cout ...] -- the pixel shuffle is free.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -30,6 +32,7 @@ struct GemmTapsParams {
   int fmt;            // B200VOC_FMT_*
   int store_lrelu;
   const float* bias;
+  int dbg;            // debug switches (B200VOC_DBG): 4 = skip the TMA stores, 8 = skip stores with a negative row coordinate
 };
 
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 x 2B
@@ -41,6 +44,7 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int B_TILE = BN * 128;
   constexpr int STAGE_BYTES = kATileBytes + B_TILE;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "tile width");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -49,7 +53,12 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN, seq = blockIdx.z;
+  const int n0 = blockIdx.y * BN, seq = blockIdx.z;
+  // Column tiles whose output phase r < p map to the previous input row (l = (m-1)*s + r - p + s): they
+  // run over GEMM rows m = 1 + 128*i so that the TMA store coordinate (m - 1) is never negative (row
+  // m = 0 of those phases is entirely out of range anyway).  The launcher keeps tiles phase-pure.
+  const bool part_b = (n0 / p.cout) < p.pad;
+  const int m0 = blockIdx.x * 128 + (part_b ? 1 : 0);
   const int kpt = p.k_per_tap >> 6;
   const int num_k = p.n_taps * kpt;
 
@@ -152,8 +161,9 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int j = 0; j < BN / bw; ++j) {
         const int col = n0 + j * bw;
         const int r = col / p.cout, co0 = col % p.cout;
-        const int rr = r >= p.pad ? r - p.pad : r - p.pad + p.stride;
-        const int mm = r >= p.pad ? m0 : m0 - 1;
+        const int rr = part_b ? r - p.pad + p.stride : r - p.pad;
+        const int mm = part_b ? m0 - 1 : m0;
+        if (p.dbg & 4) continue;
         tma_store_4d(&tmOut, smem + j * blk_bytes, co0, rr, mm, seq);
       }
       tma_store_commit();
@@ -178,7 +188,12 @@ static int launch_gemm_taps_t(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     configured[dev & 15] = true;
   }
   dim3 grid(ceil_div(p.rows_per_seq, 128), p.n_total / BN, n_seq);
-  gemm_taps_kernel<BN, STAGES, FMT, LRELU><<<grid, 192, SMEM, stream>>>(tmA, tmB, tmOut, p);
+  GemmTapsParams pp = p;
+  {
+    const char* e = getenv("B200VOC_DBG");
+    pp.dbg = e ? atoi(e) : 0;
+  }
+  gemm_taps_kernel<BN, STAGES, FMT, LRELU><<<grid, 192, SMEM, stream>>>(tmA, tmB, tmOut, pp);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
@@ -225,7 +240,7 @@ int convt1d_launch(const void* x16, const void* w_packed, const float* bias, int
   B200_TRY(make_tmap_4d(&tmOut, out16, Cout, s, Lin, N, (uint64_t)Cout * 2, (uint64_t)s * Cout * 2,
                         (uint64_t)s * Lin * Cout * 2, obox, 1, 128, obox * 2));
   GemmTapsParams p{};
-  p.rows_per_seq = Lin + 1;
+  p.rows_per_seq = Lin;      // phases r >= p use rows m = 0..Lin-1, phases r < p use m = 1..Lin (see kernel)
   p.n_taps = 2;
   p.tap_shift[0] = 0;
   p.tap_shift[1] = -1;
@@ -237,17 +252,22 @@ int convt1d_launch(const void* x16, const void* w_packed, const float* bias, int
   p.fmt = fmt;
   p.store_lrelu = store_lrelu;
   p.bias = bias;
-  if (n_total % 256 == 0) {
+  // tiles must be phase-pure w.r.t. the padding boundary: BN divides p*Cout
+  const int pc = p.pad * Cout;
+  if (pc % 256 == 0 && n_total % 256 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 256, 128));
     return launch_gemm_taps<256, 2>(tmA, tmB, tmOut, p, N, stream);
-  } else if (n_total % 128 == 0) {
+  } else if (pc % 128 == 0 && n_total % 128 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 128, 128));
     return launch_gemm_taps<128, 3>(tmA, tmB, tmOut, p, N, stream);
-  } else if (n_total % 64 == 0) {
+  } else if (pc % 64 == 0 && n_total % 64 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 64, 128));
-    return launch_gemm_taps<64, 2>(tmA, tmB, tmOut, p, N, stream);
+    return launch_gemm_taps<64, 3>(tmA, tmB, tmOut, p, N, stream);
+  } else if (pc % 32 == 0 && n_total % 32 == 0) {
+    B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 32, 128));
+    return launch_gemm_taps<32, 2>(tmA, tmB, tmOut, p, N, stream);
   }
-  set_error("convt1d: s*Cout=%d must be a multiple of 64", n_total);
+  set_error("convt1d: (s/2)*Cout=%d must be a multiple of 32", pc);
   return B200VOC_ERR_UNSUPPORTED;
 }
 
@@ -278,7 +298,7 @@ int linear_launch(const void* x16, const void* w_packed /*[Cout][Cin]*/, const f
     return launch_gemm_taps<128, 3>(tmA, tmB, tmOut, p, N, stream);
   }
   B200_TRY(make_tmap_2d(&tmB, w_packed, Cin, Cout, (uint64_t)Cin * 2, 64, 64, 128));
-  return launch_gemm_taps<64, 2>(tmA, tmB, tmOut, p, N, stream);
+  return launch_gemm_taps<64, 3>(tmA, tmB, tmOut, p, N, stream);
 }
 
 // ---------------------------------------------------------------------------- experiment
