@@ -21,16 +21,14 @@ void run_pass(Loader load, float2* buf, const float2* tw) {
 template <int N, bool INV>
 double test_complex() {
   std::vector<float2> in(N), tw(N), buf(N + N / 8 + 8);
-  for (int i = 0; i < N; ++i) {
-    in[i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
-    tw[i] = make_float2((float)cos(-2.0 * M_PI * i / N), (float)sin(-2.0 * M_PI * i / N));
-  }
+  for (int i = 0; i < N; ++i) in[i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+  fill_pass_twiddles<N>(tw.data());
   using PL = Plan<N>;
   auto load0 = [&](int i) { return in[i]; };
   auto from_buf = [&](int i) { return buf[pad(i)]; };
   run_pass<N, PL::R0, 1, INV>(load0, buf.data(), tw.data());
-  run_pass<N, PL::R1, PL::R0, INV>(from_buf, buf.data(), tw.data());
-  run_pass<N, PL::R2, PL::R0 * PL::R1, INV>(from_buf, buf.data(), tw.data());
+  run_pass<N, PL::R1, PL::R0, INV>(from_buf, buf.data(), tw.data() + tw_offset1<N>());
+  run_pass<N, PL::R2, PL::R0 * PL::R1, INV>(from_buf, buf.data(), tw.data() + tw_offset2<N>());
   double maxerr = 0;
   for (int k = 0; k < N; ++k) {
     double re = 0, im = 0;
@@ -51,14 +49,14 @@ double test_real(double* inv_err) {
   std::vector<float> x(n);
   std::vector<float2> tw(N), tw2(N + 1), buf(N + N / 8 + 8);
   for (int i = 0; i < n; ++i) x[i] = (float)rand() / RAND_MAX - 0.5f;
-  for (int i = 0; i < N; ++i) tw[i] = make_float2((float)cos(-2.0 * M_PI * i / N), (float)sin(-2.0 * M_PI * i / N));
+  fill_pass_twiddles<N>(tw.data());
   for (int i = 0; i <= N; ++i) tw2[i] = make_float2((float)cos(-M_PI * i / N), (float)sin(-M_PI * i / N));
   using PL = Plan<N>;
   auto load0 = [&](int m) { return make_float2(x[2 * m], x[2 * m + 1]); };
   auto from_buf = [&](int i) { return buf[pad(i)]; };
   run_pass<N, PL::R0, 1, false>(load0, buf.data(), tw.data());
-  run_pass<N, PL::R1, PL::R0, false>(from_buf, buf.data(), tw.data());
-  run_pass<N, PL::R2, PL::R0 * PL::R1, false>(from_buf, buf.data(), tw.data());
+  run_pass<N, PL::R1, PL::R0, false>(from_buf, buf.data(), tw.data() + tw_offset1<N>());
+  run_pass<N, PL::R2, PL::R0 * PL::R1, false>(from_buf, buf.data(), tw.data() + tw_offset2<N>());
   std::vector<float2> X(N + 1);
   double maxerr = 0;
   for (int k = 0; k <= N; ++k) {
@@ -75,8 +73,8 @@ double test_real(double* inv_err) {
   for (int k = 0; k < N; ++k) Z[k] = irfft_pack(X[k], cconj(X[N - k]), tw2[k]);
   auto loadz = [&](int i) { return Z[i]; };
   run_pass<N, PL::R0, 1, true>(loadz, buf.data(), tw.data());
-  run_pass<N, PL::R1, PL::R0, true>(from_buf, buf.data(), tw.data());
-  run_pass<N, PL::R2, PL::R0 * PL::R1, true>(from_buf, buf.data(), tw.data());
+  run_pass<N, PL::R1, PL::R0, true>(from_buf, buf.data(), tw.data() + tw_offset1<N>());
+  run_pass<N, PL::R2, PL::R0 * PL::R1, true>(from_buf, buf.data(), tw.data() + tw_offset2<N>());
   double ie = 0;
   for (int m = 0; m < N; ++m) {
     ie = fmax(ie, fabs(buf[pad(m)].x / N - x[2 * m]));

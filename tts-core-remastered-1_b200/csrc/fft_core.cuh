@@ -34,13 +34,27 @@ B200_HD float2 w16() {
   else return make_float2(-c1, -s1);
 }
 
+// x * exp(-+2*pi*i*K16/16) with the trivial cases (1, -+i, (1 -+ i)/sqrt2) strength-reduced: without
+// fast-math the compiler may not fold multiplications by 0 and 1.
+template <int K16, bool INV>
+B200_HD float2 mul_w16(float2 x) {
+  constexpr float h = 0.70710678118654752440f;
+  if constexpr (K16 == 0) return x;
+  else if constexpr (K16 == 4) return INV ? make_float2(-x.y, x.x) : make_float2(x.y, -x.x);
+  else if constexpr (K16 == 2) return INV ? make_float2(h * (x.x - x.y), h * (x.x + x.y)) : make_float2(h * (x.x + x.y), h * (x.y - x.x));
+  else if constexpr (K16 == 6) return INV ? make_float2(-h * (x.x + x.y), h * (x.x - x.y)) : make_float2(h * (x.y - x.x), -h * (x.x + x.y));
+  else {
+    float2 w = w16<K16>();
+    if (INV) w = cconj(w);
+    return cmul(x, w);
+  }
+}
+
 template <int R, bool INV, int K>
 struct Combine {
   B200_HD static void run(const float2* e, const float2* o, float2* v) {
     if constexpr (K < R / 2) {
-      float2 w = w16<K * (16 / R)>();
-      if (INV) w = cconj(w);
-      const float2 t = cmul(o[K], w);
+      const float2 t = mul_w16<K * (16 / R), INV>(o[K]);
       v[K] = cadd(e[K], t);
       v[K + R / 2] = csub(e[K], t);
       Combine<R, INV, K + 1>::run(e, o, v);
@@ -91,7 +105,7 @@ struct Pass {
         for (int r = 0; r < R; ++r) {
           float2 x = load(j + r * NB);
           if (NS > 1 && r > 0) {
-            float2 w = tw[r * k * (N / (NS * R))];
+            float2 w = tw[(r - 1) * NS + k];          // pass table: conflict-free in k
             if (INV) w = cconj(w);
             x = cmul(x, w);
           }
@@ -121,6 +135,30 @@ template <> struct Plan<256> { static constexpr int R0 = 4, R1 = 8, R2 = 8; };
 template <> struct Plan<512> { static constexpr int R0 = 8, R1 = 8, R2 = 8; };
 template <> struct Plan<1024> { static constexpr int R0 = 8, R1 = 8, R2 = 16; };
 
+// Twiddle storage: per pass p (previous radices multiply to NS, radix R) a table
+//   T_p[(r-1)*NS + k] = exp(-2*pi*i * r*k / (NS*R)),  r = 1..R-1, k = 0..NS-1
+// laid out so that the threads of a pass (k = j % NS consecutive) read consecutive words.
+// Pass 0 needs none; pass 1 starts at offset 0, pass 2 after it.
+template <int N> B200_HD constexpr int tw_offset1() { return 0; }
+template <int N> B200_HD constexpr int tw_offset2() { return (Plan<N>::R1 - 1) * Plan<N>::R0; }
+template <int N> B200_HD constexpr int tw_total() {
+  return (Plan<N>::R1 - 1) * Plan<N>::R0 + (Plan<N>::R2 - 1) * Plan<N>::R0 * Plan<N>::R1;
+}
+// host helper: fill the pass tables
+template <int N>
+inline void fill_pass_twiddles(float2* out) {
+  using P = Plan<N>;
+  int o = 0;
+  for (int pass = 1; pass <= 2; ++pass) {
+    const int NS = pass == 1 ? P::R0 : P::R0 * P::R1, R = pass == 1 ? P::R1 : P::R2;
+    for (int r = 1; r < R; ++r)
+      for (int k = 0; k < NS; ++k) {
+        const double a = -2.0 * 3.14159265358979323846 * (double)r * k / ((double)NS * R);
+        out[o++] = make_float2((float)cos(a), (float)sin(a));
+      }
+  }
+}
+
 // Full N-point transform by the N/8 threads of one frame group.  `sync` is the barrier between
 // the phases (a no-op lambda in the sequential host emulation, which instead loops over t per
 // phase).  After the call `buf[pad(k)]` holds bin k.
@@ -136,11 +174,11 @@ B200_HD void transform(int t, Loader load0, float2* buf, const float2* tw, Sync 
   sync();
   P0::write(t, buf, v);
   sync();
-  P1::read(t, from_buf, tw, v);
+  P1::read(t, from_buf, tw + tw_offset1<N>(), v);
   sync();
   P1::write(t, buf, v);
   sync();
-  P2::read(t, from_buf, tw, v);
+  P2::read(t, from_buf, tw + tw_offset2<N>(), v);
   sync();
   P2::write(t, buf, v);
   sync();

@@ -33,7 +33,7 @@ struct MelTable {      // CSR by mel bin over frequency bins
 
 struct FftTables {     // per (device, n_fft), built once on the host in double precision
   const float* win;    // [n_fft] periodic Hann
-  const float2* tw;    // [n_fft/2]   exp(-2 pi i m / (n_fft/2))
+  const float2* tw;    // [<= n_fft/2] per-pass Stockham twiddle tables (fft_core.cuh)
   const float2* tw2;   // [n_fft/2+1] exp(-pi i k / (n_fft/2))
 };
 
@@ -210,7 +210,9 @@ static int get_fft_tables(int n_fft, FftTables* out) {
     std::vector<float> win(n_fft);
     std::vector<float2> tw(N), tw2(N + 1);
     for (int i = 0; i < n_fft; ++i) win[i] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * i / n_fft));
-    for (int i = 0; i < N; ++i) tw[i] = make_float2((float)std::cos(-2.0 * M_PI * i / N), (float)std::sin(-2.0 * M_PI * i / N));
+    if (N == 256) fill_pass_twiddles<256>(tw.data());
+    else if (N == 512) fill_pass_twiddles<512>(tw.data());
+    else fill_pass_twiddles<1024>(tw.data());   // per-pass tables, conflict-free layout (fft_core.cuh)
     for (int i = 0; i <= N; ++i) tw2[i] = make_float2((float)std::cos(-M_PI * i / N), (float)std::sin(-M_PI * i / N));
     float* dwin;
     float2 *dtw, *dtw2;
