@@ -6,6 +6,8 @@
 //   stft:  frame = reflect-padded wav[f*hop - n/2 ...] * periodic Hann  ->  rFFT (packed complex
 //          FFT of n/2 points + split)  ->  |X|*gain  |  re,im  |  |X|^2 -> sparse HTK mel -> log
 //   istft: spectrum block -> inverse packed FFT -> * window, gather overlap-add, / sum w^2
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -14,6 +16,7 @@
 
 #include "common.cuh"
 #include "fft_core.cuh"
+#include "fft_warp.cuh"
 
 namespace b200 {
 
@@ -151,6 +154,135 @@ stft_kernel(const StftParams p) {
   }
 }
 
+// ------------------------------------------------------------------ fast path, n_fft = 1024
+// One warp per frame (fft_warp.cuh), 8 warps = 8 consecutive frames per round, kRounds rounds per
+// CTA.  Window samples and the per-lane twiddles live in registers for the whole CTA.
+constexpr int kFastWarps = 8, kFastRounds = 4;
+
+template <int MODE>
+__global__ void __launch_bounds__(kFastWarps * 32)
+stft1024_kernel(const StftParams p) {
+  constexpr int NFFT = 1024, N = 512, BINS = 513;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int span_len = (kFastWarps - 1) * p.hop + NFFT;
+  float* span = reinterpret_cast<float*>(smem_raw);                              // one round's samples
+  float2* tw2 = reinterpret_cast<float2*>(span + ((span_len + 3) & ~3));         // [N + 1]
+  float2* wbuf = tw2 + (N + 2);                                                  // [warps][576]
+  float* stage = reinterpret_cast<float*>(wbuf + kFastWarps * 576);              // [BINS][kFastWarps + 1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  float2* T = wbuf + warp * 576;       // 16 x 33 transpose scratch, later Z[512] linear
+
+  for (int i = threadIdx.x; i <= N; i += blockDim.x) tw2[i] = __ldg(p.tab.tw2 + i);
+  // per-lane constants: window for samples (2n, 2n+1), n = 32*n1 + lane, and W_512^(lane*k1)
+  float2 win[16], tw1[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) {
+    win[n1] = __ldg(reinterpret_cast<const float2*>(p.tab.win) + n1 * 32 + lane);
+    float s, c;
+    sincospif(-2.0f * (float)((lane * n1) & 511) / 512.0f, &s, &c);
+    tw1[n1] = make_float2(c, s);
+  }
+  float l1_acc = 0.f;
+  constexpr int NPASS = MODE == MODE_L1 ? 2 : 1;
+#pragma unroll 1
+  for (int round = 0; round < kFastRounds; ++round) {
+    const int f0 = (blockIdx.x * kFastRounds + round) * kFastWarps;
+    if (f0 >= p.frames) break;
+#pragma unroll 1
+    for (int pass = 0; pass < NPASS; ++pass) {
+      const float* w = (pass == 0 ? p.wav : p.wav2) + (long long)b * p.Nsamp;
+      __syncthreads();                                   // previous users of span / stage are done
+      for (int i = threadIdx.x; i < span_len; i += blockDim.x) span[i] = __ldg(w + reflect(f0 * p.hop - N + i, p.Nsamp));
+      __syncthreads();
+      const float2* fr = reinterpret_cast<const float2*>(span + warp * p.hop);   // hop is even (checked on the host)
+      float2 v[16];
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const float2 x = fr[n1 * 32 + lane];
+        v[n1] = make_float2(x.x * win[n1].x, x.y * win[n1].y);
+      }
+      warp_fft512<false>(v, T, tw1, lane);
+      // Z -> linear per-warp buffer (reusing the transpose scratch), then the real-FFT split
+      const int k1 = lane & 15, pp = lane >> 4;
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) T[pad(k1 + 16 * k2 + 256 * pp)] = v[k2];
+      __syncwarp();
+#pragma unroll 4
+      for (int j = 0; j <= 16; ++j) {
+        const int k = lane + 32 * j;
+        if (k > N) break;
+        const float2 X = rfft_bin(T, tw2, N, k);
+        float* st = stage + k * (kFastWarps + 1) + warp;
+        if (MODE == MODE_COMPLEX) {
+          reinterpret_cast<float2*>(stage)[k * (kFastWarps + 1) + warp] = X;
+        } else if (MODE == MODE_MEL) {
+          *st = X.x * X.x + X.y * X.y;
+        } else {
+          float mag = sqrtf(X.x * X.x + X.y * X.y);
+          if (p.gain) mag *= __ldg(p.gain + k);
+          if (MODE == MODE_L1) {
+            if (pass == 0) *st = mag;
+            else if (f0 + warp < p.frames) l1_acc += fabsf(*st - mag);
+          } else {
+            *st = mag;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    if (MODE == MODE_MAG) {
+      float* o = p.out + (long long)b * BINS * p.frames;
+      for (int i = threadIdx.x; i < BINS * kFastWarps; i += blockDim.x) {
+        const int k = i / kFastWarps, f = i % kFastWarps;
+        if (f0 + f < p.frames) o[(long long)k * p.frames + f0 + f] = stage[k * (kFastWarps + 1) + f];
+      }
+    } else if (MODE == MODE_COMPLEX) {
+      float2* o = reinterpret_cast<float2*>(p.out) + (long long)b * BINS * p.frames;
+      for (int i = threadIdx.x; i < BINS * kFastWarps; i += blockDim.x) {
+        const int k = i / kFastWarps, f = i % kFastWarps;
+        if (f0 + f < p.frames) o[(long long)k * p.frames + f0 + f] = reinterpret_cast<float2*>(stage)[k * (kFastWarps + 1) + f];
+      }
+    } else if (MODE == MODE_MEL) {
+      float* o = p.out + (long long)b * p.mel.n_mels * p.frames;
+      for (int i = threadIdx.x; i < p.mel.n_mels * kFastWarps; i += blockDim.x) {
+        const int m = i / kFastWarps, f = i % kFastWarps;
+        const int lo = __ldg(p.mel.lo + m), cnt = __ldg(p.mel.cnt + m);
+        const float* wv = p.mel.w + __ldg(p.mel.off + m);
+        float acc = 0.f;
+        for (int k = 0; k < cnt; ++k) acc = fmaf(__ldg(wv + k), stage[(lo + k) * (kFastWarps + 1) + f], acc);
+        if (p.log_compress) acc = logf(fmaxf(acc, 1e-5f));
+        if (f0 + f < p.frames) o[(long long)m * p.frames + f0 + f] = acc;
+      }
+    }
+  }
+  if (MODE == MODE_L1) {
+    __shared__ float red[32];
+    for (int o = 16; o > 0; o >>= 1) l1_acc += __shfl_xor_sync(0xffffffffu, l1_acc, o);
+    if (lane == 0) red[warp] = l1_acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float vv = threadIdx.x < kFastWarps ? red[threadIdx.x] : 0.f;
+      for (int o = 16; o > 0; o >>= 1) vv += __shfl_xor_sync(0xffffffffu, vv, o);
+      if (threadIdx.x == 0) atomicAdd(p.out_sum, (double)vv);
+    }
+  }
+}
+
+template <int MODE>
+static int launch_stft1024(const StftParams& p, cudaStream_t st) {
+  const int span_len = (kFastWarps - 1) * p.hop + 1024;
+  const size_t smem = (size_t)((span_len + 3) & ~3) * 4 + 514 * 8 + (size_t)kFastWarps * 576 * 8 +
+                      (size_t)513 * (kFastWarps + 1) * (MODE == MODE_COMPLEX ? 8 : 4) + 64;
+  B200_CHECK_ARG(smem <= 227 * 1024, "stft: hop %d needs %zu bytes of shared memory", p.hop, smem);
+  B200_CUDA(cudaFuncSetAttribute(stft1024_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(p.frames, kFastWarps * kFastRounds), p.B);
+  stft1024_kernel<MODE><<<grid, kFastWarps * 32, smem, st>>>(p);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
 template <int NFFT>
 static size_t stft_smem(int hop, int mode) {
   constexpr int N = NFFT / 2, NPAD = N + N / 8, BINS = N + 1;
@@ -180,7 +312,9 @@ static int dispatch_stft(int n_fft, StftParams p, cudaStream_t st) {
   B200_TRY(get_fft_tables(n_fft, &p.tab));
   switch (n_fft) {
     case 512: return launch_stft<512, MODE>(p, st);
-    case 1024: return launch_stft<1024, MODE>(p, st);
+    case 1024:
+      if (p.hop % 2 == 0 && !getenv("B200VOC_STFT_V1")) return launch_stft1024<MODE>(p, st);
+      return launch_stft<1024, MODE>(p, st);
     case 2048: return launch_stft<2048, MODE>(p, st);
   }
   set_error("stft: n_fft=%d unsupported (512/1024/2048, vocoder7/config.py:39 stft_sizes)", n_fft);
