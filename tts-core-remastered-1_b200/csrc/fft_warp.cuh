@@ -39,12 +39,16 @@ struct OddTwiddle {
   }
 };
 
-// T: per-warp scratch of 16 x 33 float2.  tw1[k1] = exp(-2*pi*i*lane*k1/512).
+// T: per-warp scratch of 16 x 33 float2.  tw1[k1 * 32 + lane] = exp(-2*pi*i*lane*k1/512) (shared memory,
+// conflict-free: consecutive lanes read consecutive words).
 template <bool INV>
-__device__ __forceinline__ void warp_fft512(float2 (&v)[16], float2* T, const float2 (&tw1)[16], int lane) {
+__device__ __forceinline__ void warp_fft512(float2 (&v)[16], float2* T, const float2* tw1, int lane) {
   fft_reg<16, INV>(v);
 #pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], INV ? cconj(tw1[k1]) : tw1[k1]);
+  for (int k1 = 1; k1 < 16; ++k1) {
+    const float2 w = tw1[k1 * 32 + lane];
+    v[k1] = cmul(v[k1], INV ? cconj(w) : w);
+  }
 #pragma unroll
   for (int k1 = 0; k1 < 16; ++k1) T[k1 * 33 + lane] = v[k1];
   __syncwarp();

@@ -160,28 +160,28 @@ stft_kernel(const StftParams p) {
 constexpr int kFastWarps = 8, kFastRounds = 4;
 
 template <int MODE>
-__global__ void __launch_bounds__(kFastWarps * 32)
+__global__ void __launch_bounds__(kFastWarps * 32, 3)
 stft1024_kernel(const StftParams p) {
-  constexpr int NFFT = 1024, N = 512, BINS = 513;
+  constexpr int NFFT = 1024, N = 512, BINS = 513, SW = kFastWarps + 1;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int span_len = (kFastWarps - 1) * p.hop + NFFT;
   float* span = reinterpret_cast<float*>(smem_raw);                              // one round's samples
-  float2* tw2 = reinterpret_cast<float2*>(span + ((span_len + 3) & ~3));         // [N + 1]
-  float2* wbuf = tw2 + (N + 2);                                                  // [warps][576]
-  float* stage = reinterpret_cast<float*>(wbuf + kFastWarps * 576);              // [BINS][kFastWarps + 1]
+  float2* tw2 = reinterpret_cast<float2*>(span + ((span_len + 3) & ~3));         // [N + 1] (padded to N + 2)
+  float2* win2 = tw2 + (N + 2);                                                  // [N] window pairs (w[2n], w[2n+1])
+  float2* tw1 = win2 + N;                                                        // [16][32] W_512^(lane*k1)
+  float2* wbuf = tw1 + 512;                                                      // [warps][576]
+  float* stage = reinterpret_cast<float*>(wbuf + kFastWarps * 576);              // [BINS][SW]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
-  float2* T = wbuf + warp * 576;       // 16 x 33 transpose scratch, later Z[512] linear
+  float2* T = wbuf + warp * 576;       // 16 x 33 transpose scratch, later Z[512] linear (padded)
 
   for (int i = threadIdx.x; i <= N; i += blockDim.x) tw2[i] = __ldg(p.tab.tw2 + i);
-  // per-lane constants: window for samples (2n, 2n+1), n = 32*n1 + lane, and W_512^(lane*k1)
-  float2 win[16], tw1[16];
-#pragma unroll
-  for (int n1 = 0; n1 < 16; ++n1) {
-    win[n1] = __ldg(reinterpret_cast<const float2*>(p.tab.win) + n1 * 32 + lane);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    win2[i] = __ldg(reinterpret_cast<const float2*>(p.tab.win) + i);
+    const int k1 = i >> 5, t = i & 31;
     float s, c;
-    sincospif(-2.0f * (float)((lane * n1) & 511) / 512.0f, &s, &c);
-    tw1[n1] = make_float2(c, s);
+    sincospif(-2.0f * (float)((t * k1) & 511) / 512.0f, &s, &c);
+    tw1[i] = make_float2(c, s);
   }
   float l1_acc = 0.f;
   constexpr int NPASS = MODE == MODE_L1 ? 2 : 1;
@@ -193,67 +193,77 @@ stft1024_kernel(const StftParams p) {
     for (int pass = 0; pass < NPASS; ++pass) {
       const float* w = (pass == 0 ? p.wav : p.wav2) + (long long)b * p.Nsamp;
       __syncthreads();                                   // previous users of span / stage are done
-      for (int i = threadIdx.x; i < span_len; i += blockDim.x) span[i] = __ldg(w + reflect(f0 * p.hop - N + i, p.Nsamp));
+      const int s0 = f0 * p.hop - N;                     // first sample of the span (may be < 0: reflect)
+      if (s0 >= 0 && s0 + span_len <= p.Nsamp && ((s0 | p.Nsamp) & 3) == 0) {
+        const float4* src = reinterpret_cast<const float4*>(w + s0);     // interior: plain vector loads
+        for (int i = threadIdx.x; i < (span_len >> 2); i += blockDim.x) reinterpret_cast<float4*>(span)[i] = __ldg(src + i);
+      } else {
+        for (int i = threadIdx.x; i < span_len; i += blockDim.x) span[i] = __ldg(w + reflect(s0 + i, p.Nsamp));
+      }
       __syncthreads();
       const float2* fr = reinterpret_cast<const float2*>(span + warp * p.hop);   // hop is even (checked on the host)
       float2 v[16];
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
-        const float2 x = fr[n1 * 32 + lane];
-        v[n1] = make_float2(x.x * win[n1].x, x.y * win[n1].y);
+        const float2 x = fr[n1 * 32 + lane], wn = win2[n1 * 32 + lane];
+        v[n1] = make_float2(x.x * wn.x, x.y * wn.y);
       }
       warp_fft512<false>(v, T, tw1, lane);
       // Z -> linear per-warp buffer (reusing the transpose scratch), then the real-FFT split
-      const int k1 = lane & 15, pp = lane >> 4;
+      {
+        float2* zp = T + pad((lane & 15) + 256 * (lane >> 4));
 #pragma unroll
-      for (int k2 = 0; k2 < 16; ++k2) T[pad(k1 + 16 * k2 + 256 * pp)] = v[k2];
+        for (int k2 = 0; k2 < 16; ++k2) zp[18 * k2] = v[k2];          // pad(k + 16*k2) = pad(k) + 18*k2
+      }
       __syncwarp();
+      float* st = stage + lane * SW + warp;
 #pragma unroll 4
       for (int j = 0; j <= 16; ++j) {
         const int k = lane + 32 * j;
         if (k > N) break;
         const float2 X = rfft_bin(T, tw2, N, k);
-        float* st = stage + k * (kFastWarps + 1) + warp;
         if (MODE == MODE_COMPLEX) {
-          reinterpret_cast<float2*>(stage)[k * (kFastWarps + 1) + warp] = X;
+          reinterpret_cast<float2*>(stage)[k * SW + warp] = X;
         } else if (MODE == MODE_MEL) {
-          *st = X.x * X.x + X.y * X.y;
+          st[32 * SW * j] = X.x * X.x + X.y * X.y;
         } else {
           float mag = sqrtf(X.x * X.x + X.y * X.y);
           if (p.gain) mag *= __ldg(p.gain + k);
           if (MODE == MODE_L1) {
-            if (pass == 0) *st = mag;
-            else if (f0 + warp < p.frames) l1_acc += fabsf(*st - mag);
+            if (pass == 0) st[32 * SW * j] = mag;
+            else if (f0 + warp < p.frames) l1_acc += fabsf(st[32 * SW * j] - mag);
           } else {
-            *st = mag;
+            st[32 * SW * j] = mag;
           }
         }
       }
       __syncwarp();
     }
     __syncthreads();
+    // cooperative write-out: thread = (frame f = tid & 7, bin k = tid >> 3 + 32*i): 8 frames of one bin are
+    // one 32-byte sector of out[b, k, f0 .. f0+7]
+    const int f = threadIdx.x & (kFastWarps - 1), kk = threadIdx.x >> 3;
+    const bool fok = f0 + f < p.frames;
     if (MODE == MODE_MAG) {
-      float* o = p.out + (long long)b * BINS * p.frames;
-      for (int i = threadIdx.x; i < BINS * kFastWarps; i += blockDim.x) {
-        const int k = i / kFastWarps, f = i % kFastWarps;
-        if (f0 + f < p.frames) o[(long long)k * p.frames + f0 + f] = stage[k * (kFastWarps + 1) + f];
-      }
+      float* o = p.out + ((long long)b * BINS + kk) * p.frames + f0 + f;
+      const float* sp = stage + kk * SW + f;
+      for (int k = kk; k < BINS; k += 32, o += 32ll * p.frames, sp += 32 * SW)
+        if (fok) *o = *sp;
     } else if (MODE == MODE_COMPLEX) {
-      float2* o = reinterpret_cast<float2*>(p.out) + (long long)b * BINS * p.frames;
-      for (int i = threadIdx.x; i < BINS * kFastWarps; i += blockDim.x) {
-        const int k = i / kFastWarps, f = i % kFastWarps;
-        if (f0 + f < p.frames) o[(long long)k * p.frames + f0 + f] = reinterpret_cast<float2*>(stage)[k * (kFastWarps + 1) + f];
-      }
+      float2* o = reinterpret_cast<float2*>(p.out) + ((long long)b * BINS + kk) * p.frames + f0 + f;
+      const float2* sp = reinterpret_cast<const float2*>(stage) + kk * SW + f;
+      for (int k = kk; k < BINS; k += 32, o += 32ll * p.frames, sp += 32 * SW)
+        if (fok) *o = *sp;
     } else if (MODE == MODE_MEL) {
-      float* o = p.out + (long long)b * p.mel.n_mels * p.frames;
-      for (int i = threadIdx.x; i < p.mel.n_mels * kFastWarps; i += blockDim.x) {
-        const int m = i / kFastWarps, f = i % kFastWarps;
+      float* o = p.out + (long long)b * p.mel.n_mels * p.frames + f0 + f;
+      for (int m = kk; m < p.mel.n_mels; m += 32) {
         const int lo = __ldg(p.mel.lo + m), cnt = __ldg(p.mel.cnt + m);
         const float* wv = p.mel.w + __ldg(p.mel.off + m);
+        const float* sp = stage + lo * SW + f;
         float acc = 0.f;
-        for (int k = 0; k < cnt; ++k) acc = fmaf(__ldg(wv + k), stage[(lo + k) * (kFastWarps + 1) + f], acc);
+        for (int k = 0; k < cnt; ++k) acc = fmaf(__ldg(wv + k), sp[k * SW], acc);
         if (p.log_compress) acc = logf(fmaxf(acc, 1e-5f));
-        if (f0 + f < p.frames) o[(long long)m * p.frames + f0 + f] = acc;
+        if (fok) o[(long long)m * p.frames] = acc;
       }
     }
   }
@@ -273,7 +283,7 @@ stft1024_kernel(const StftParams p) {
 template <int MODE>
 static int launch_stft1024(const StftParams& p, cudaStream_t st) {
   const int span_len = (kFastWarps - 1) * p.hop + 1024;
-  const size_t smem = (size_t)((span_len + 3) & ~3) * 4 + 514 * 8 + (size_t)kFastWarps * 576 * 8 +
+  const size_t smem = (size_t)((span_len + 3) & ~3) * 4 + 514 * 8 + 512 * 8 + 512 * 8 + (size_t)kFastWarps * 576 * 8 +
                       (size_t)513 * (kFastWarps + 1) * (MODE == MODE_COMPLEX ? 8 : 4) + 64;
   B200_CHECK_ARG(smem <= 227 * 1024, "stft: hop %d needs %zu bytes of shared memory", p.hop, smem);
   B200_CUDA(cudaFuncSetAttribute(stft1024_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
