@@ -216,26 +216,38 @@ stft1024_kernel(const StftParams p) {
         for (int k2 = 0; k2 < 16; ++k2) zp[18 * k2] = v[k2];          // pad(k + 16*k2) = pad(k) + 18*k2
       }
       __syncwarp();
-      float* st = stage + lane * SW + warp;
-#pragma unroll 4
-      for (int j = 0; j <= 16; ++j) {
-        const int k = lane + 32 * j;
-        if (k > N) break;
-        const float2 X = rfft_bin(T, tw2, N, k);
+      // real-FFT split, two bins per pair of loads: with a = (Z[k] + conj Z[N-k])/2, d = (Z[k] - conj Z[N-k])/2,
+      // t = i * exp(-i pi k / N) * d:   X[k] = a - t,   X[N-k] = conj(a + t)
+      auto emit = [&](int k, float2 X) {
         if (MODE == MODE_COMPLEX) {
           reinterpret_cast<float2*>(stage)[k * SW + warp] = X;
         } else if (MODE == MODE_MEL) {
-          st[32 * SW * j] = X.x * X.x + X.y * X.y;
+          stage[k * SW + warp] = X.x * X.x + X.y * X.y;
         } else {
           float mag = sqrtf(X.x * X.x + X.y * X.y);
           if (p.gain) mag *= __ldg(p.gain + k);
           if (MODE == MODE_L1) {
-            if (pass == 0) st[32 * SW * j] = mag;
-            else if (f0 + warp < p.frames) l1_acc += fabsf(st[32 * SW * j] - mag);
+            if (pass == 0) stage[k * SW + warp] = mag;
+            else if (f0 + warp < p.frames) l1_acc += fabsf(stage[k * SW + warp] - mag);
           } else {
-            st[32 * SW * j] = mag;
+            stage[k * SW + warp] = mag;
           }
         }
+      };
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = lane + 32 * j;                       // 0 .. 255, partner bin N - k
+        const float2 zk = T[pad(k)], zn = T[pad((N - k) & (N - 1))], wk = tw2[k];
+        const float2 a = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        const float2 d = make_float2(0.5f * (zk.x - zn.x), 0.5f * (zk.y + zn.y));
+        const float2 wd = cmul(wk, d);
+        const float2 t = make_float2(-wd.y, wd.x);        // i * wd
+        emit(k, make_float2(a.x - t.x, a.y - t.y));
+        emit(N - k, make_float2(a.x + t.x, -(a.y + t.y)));
+      }
+      if (lane == 0) {
+        const float2 zm = T[pad(N / 2)];
+        emit(N / 2, make_float2(zm.x, -zm.y));
       }
       __syncwarp();
     }
