@@ -32,7 +32,8 @@ struct GemmTapsParams {
   int fmt;            // B200VOC_FMT_*
   int store_lrelu;
   const float* bias;
-  int dbg;            // debug switches (B200VOC_DBG): 4 = skip the TMA stores, 8 = skip stores with a negative row coordinate
+  int dbg;            // debug switch (B200VOC_DBG): 4 = skip the TMA stores
+  int m_tiles, n_tiles, n_seq;   // tile grid walked by the persistent CTAs
 };
 
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 x 2B
@@ -41,35 +42,54 @@ template <int BN, int STAGES, int FMT, bool LRELU>
 __global__ void __launch_bounds__(192, 1)
 gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const GemmTapsParams p) {
+  // Persistent: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (column tile fastest,
+  // so CTAs working on the same input rows run together and share them through L2).  The operand
+  // ring runs continuously across tiles; the accumulator is double buffered in TMEM so the
+  // epilogue of tile i (TMEM -> registers -> swizzled smem staging -> TMA store) overlaps the
+  // MMAs of tile i+1.
   constexpr int B_TILE = BN * 128;
   constexpr int STAGE_BYTES = kATileBytes + B_TILE;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int STAGING = 128 * BN * 2;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "tile width");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + STAGING);
   uint64_t* empty = full + STAGES;
-  uint64_t* accum_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  uint64_t* acc_full = empty + STAGES;      // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * BN, seq = blockIdx.z;
-  // Column tiles whose output phase r < p map to the previous input row (l = (m-1)*s + r - p + s): they
-  // run over GEMM rows m = 1 + 128*i so that the TMA store coordinate (m - 1) is never negative (row
-  // m = 0 of those phases is entirely out of range anyway).  The launcher keeps tiles phase-pure.
-  const bool part_b = (n0 / p.cout) < p.pad;
-  const int m0 = blockIdx.x * 128 + (part_b ? 1 : 0);
   const int kpt = p.k_per_tap >> 6;
   const int num_k = p.n_taps * kpt;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.n_seq;
+
+  // tile -> (m0, n0, seq).  Column tiles whose output phase r < p map to the previous input row
+  // (l = (m-1)*s + r - p + s): they run over GEMM rows m = 1 + 128*i so that the TMA store
+  // coordinate (m - 1) is never negative (row m = 0 of those phases is entirely out of range
+  // anyway).  The launcher keeps tiles phase-pure.
+  auto decode = [&](int t, int& m0, int& n0, int& seq, bool& part_b) {
+    const int nt = t % p.n_tiles, rest = t / p.n_tiles;
+    n0 = nt * BN;
+    seq = rest / p.m_tiles;
+    part_b = (n0 / p.cout) < p.pad;
+    m0 = (rest - seq * p.m_tiles) * 128 + (part_b ? 1 : 0);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(accum_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -80,15 +100,20 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_k; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], STAGE_BYTES);
-        const int tap = kb / kpt, kk = kb - tap * kpt;
-        uint8_t* st = smem + s * STAGE_BYTES;
-        tma_load_3d(st, &tmA, &full[s], kk * 64, m0 + p.tap_shift[tap], seq);
-        tma_load_2d(st + kATileBytes, &tmB, &full[s], tap * p.k_per_tap + kk * 64, n0);
+      int g = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, n0, seq;
+        bool part_b;
+        decode(t, m0, n0, seq, part_b);
+        for (int kb = 0; kb < num_k; ++kb, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          const int tap = kb / kpt, kk = kb - tap * kpt;
+          uint8_t* st = smem + s * STAGE_BYTES;
+          tma_load_3d(st, &tmA, &full[s], kk * 64, m0 + p.tap_shift[tap], seq);
+          tma_load_2d(st + kATileBytes, &tmB, &full[s], tap * p.k_per_tap + kk * 64, n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -96,79 +121,98 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // uniform registers); the probe of the next stage overlaps the issue of the current one
     const uint32_t idesc = make_idesc_f16(FMT, BN);
     bool ready = false;
-    for (int kb = 0; kb < num_k; ++kb) {
-      const int s = kb % STAGES;
-      if (!ready) mbar_wait(&full[s], (kb / STAGES) & 1);
+    int g = 0, i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      const int buf = i & 1;
+      mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);
       tc_fence_after();
-      ready = mbar_test(&full[(kb + 1) % STAGES], ((kb + 1) / STAGES) & 1);
-      const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-      const uint64_t a_desc = make_kmajor_desc<128>(a_addr);
-      const uint64_t b_desc = make_kmajor_desc<128>(a_addr + kATileBytes);
-      if (elect_one()) {
+      for (int kb = 0; kb < num_k; ++kb, ++g) {
+        const int s = g % STAGES;
+        if (!ready) mbar_wait(&full[s], (g / STAGES) & 1);
+        tc_fence_after();
+        ready = mbar_test(&full[(g + 1) % STAGES], ((g + 1) / STAGES) & 1);
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t a_desc = make_kmajor_desc<128>(a_addr);
+        const uint64_t b_desc = make_kmajor_desc<128>(a_addr + kATileBytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // UMMA_K = 16 elements = 32 bytes = +2 in the >>4 start field
-          umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-        umma_commit(&empty[s]);
-        if (kb == num_k - 1) umma_commit(accum_full);
+          for (int k = 0; k < 4; ++k)  // UMMA_K = 16 elements = 32 bytes = +2 in the >>4 start field
+            umma_f16(tmem_base + buf * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty[s]);
+          if (kb == num_k - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4).  The accumulator tile is converted in
-    // registers (+bias, leaky-ReLU, 16-bit) and staged in shared memory (the operand ring is idle
-    // by now) as [128 rows x 64 ch] swizzled blocks -- one block per (output phase, 64-channel group)
-    // -- which leave through TMA stores on a 4-D view (co, l mod s, l / s, n) of the output: the
-    // polyphase pixel shuffle, the -p offset and both sequence ends are handled by the TMA unit.
+    // registers (+bias, leaky-ReLU, 16-bit) and staged in shared memory as [128 rows x 64 ch]
+    // swizzled blocks -- one block per (output phase, 64-channel group) -- which leave through TMA
+    // stores on a 4-D view (co, l mod s, l / s, n) of the output: the polyphase pixel shuffle, the -p
+    // offset and both sequence ends are handled by the TMA unit.
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    mbar_wait(accum_full, 0);
-    tc_fence_after();
     const bool narrow = p.cout < 64;                 // Cout = 32: 64-byte rows, SWIZZLE_64B, one block per phase
     const int blk_bytes = narrow ? 128 * 64 : 128 * 128;
+    const bool issuer = warp == 2 && lane == 0;
+    int i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      int m0, n0, seq;
+      bool part_b;
+      decode(t, m0, n0, seq, part_b);
+      const int buf = i & 1;
+      mbar_wait(&acc_full[buf], (i >> 1) & 1);
+      tc_fence_after();
+      if (i > 0) {                                   // staging is free once the previous stores have read it
+        if (issuer) tma_store_wait_read();
+        named_bar_sync(1, 128);
+      }
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      const int col0 = n0 + c * 32;
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + (col0 % p.cout));
-      uint32_t w[16];
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + (col0 % p.cout));
+        uint32_t w[16];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 bb = __ldg(b4 + i);
-        float y0 = __uint_as_float(v[4 * i + 0]) + bb.x, y1 = __uint_as_float(v[4 * i + 1]) + bb.y;
-        float y2 = __uint_as_float(v[4 * i + 2]) + bb.z, y3 = __uint_as_float(v[4 * i + 3]) + bb.w;
-        if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); y2 = lrelu_fast(y2); y3 = lrelu_fast(y3); }
-        w[2 * i] = pack2t<FMT>(y0, y1);
-        w[2 * i + 1] = pack2t<FMT>(y2, y3);
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = __ldg(b4 + j);
+          float y0 = __uint_as_float(v[4 * j + 0]) + bb.x, y1 = __uint_as_float(v[4 * j + 1]) + bb.y;
+          float y2 = __uint_as_float(v[4 * j + 2]) + bb.z, y3 = __uint_as_float(v[4 * j + 3]) + bb.w;
+          if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); y2 = lrelu_fast(y2); y3 = lrelu_fast(y3); }
+          w[2 * j] = pack2t<FMT>(y0, y1);
+          w[2 * j + 1] = pack2t<FMT>(y2, y3);
+        }
+        if (narrow) {
+          uint8_t* dst = staging + c * blk_bytes + row * 64;        // block c = one phase of 32 channels
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(dst + ((j ^ ((row >> 1) & 3)) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        } else {
+          uint8_t* dst = staging + (c >> 1) * blk_bytes + row * 128;  // block = 64 channels, this chunk = half of it
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(dst + ((((c & 1) * 4 + j) ^ (row & 7)) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        }
       }
-      if (narrow) {
-        uint8_t* dst = smem + c * blk_bytes + row * 64;        // block c = one phase of 32 channels
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(dst + ((i ^ ((row >> 1) & 3)) << 4)) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-      } else {
-        uint8_t* dst = smem + (c >> 1) * blk_bytes + row * 128;  // block = 64 channels, this chunk = half of it
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(dst + ((((c & 1) * 4 + i) ^ (row & 7)) << 4)) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+      tc_fence_before();
+      mbar_arrive(&acc_empty[buf]);                  // accumulator drained: the MMAs of tile i+2 may start
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (issuer && !(p.dbg & 4)) {
+        const int bw = narrow ? 32 : 64;             // GEMM columns per block
+        for (int j = 0; j < BN / bw; ++j) {
+          const int col = n0 + j * bw;
+          const int r = col / p.cout, co0 = col % p.cout;
+          const int rr = part_b ? r - p.pad + p.stride : r - p.pad;
+          const int mm = part_b ? m0 - 1 : m0;
+          tma_store_4d(&tmOut, staging + j * blk_bytes, co0, rr, mm, seq);
+        }
+        tma_store_commit();
       }
     }
-    fence_proxy_async_smem();
-    named_bar_sync(1, 128);
-    if (warp == 2 && lane == 0) {
-      const int bw = narrow ? 32 : 64;                 // GEMM columns per block
-      for (int j = 0; j < BN / bw; ++j) {
-        const int col = n0 + j * bw;
-        const int r = col / p.cout, co0 = col % p.cout;
-        const int rr = part_b ? r - p.pad + p.stride : r - p.pad;
-        const int mm = part_b ? m0 - 1 : m0;
-        if (p.dbg & 4) continue;
-        tma_store_4d(&tmOut, smem + j * blk_bytes, co0, rr, mm, seq);
-      }
-      tma_store_commit();
-      tma_store_wait_read();
-    }
+    if (issuer) tma_store_wait_read();
   }
   tc_fence_before();
   __syncthreads();
@@ -178,21 +222,30 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BN, int STAGES, int FMT, bool LRELU>
 static int launch_gemm_taps_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                               const GemmTapsParams& p, int n_seq, cudaStream_t stream) {
-  constexpr int SMEM = STAGES * (kATileBytes + BN * 128) + 256 + 1024;
+  constexpr int SMEM = STAGES * (kATileBytes + BN * 128) + 128 * BN * 2 + 256 + 1024;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static bool configured[16] = {};
+  static int sms[16] = {};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 15]) {
     B200_CUDA(cudaFuncSetAttribute(gemm_taps_kernel<BN, STAGES, FMT, LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    SMEM));
+    B200_CUDA(cudaDeviceGetAttribute(&sms[dev & 15], cudaDevAttrMultiProcessorCount, dev));
     configured[dev & 15] = true;
   }
-  dim3 grid(ceil_div(p.rows_per_seq, 128), p.n_total / BN, n_seq);
   GemmTapsParams pp = p;
   {
     const char* e = getenv("B200VOC_DBG");
     pp.dbg = e ? atoi(e) : 0;
   }
+  pp.m_tiles = ceil_div(p.rows_per_seq, 128);
+  pp.n_tiles = p.n_total / BN;
+  pp.n_seq = n_seq;
+  const long long total = (long long)pp.m_tiles * pp.n_tiles * n_seq;
+  const int per_sm = SMEM <= 110 * 1024 ? 2 : 1;        // CTAs that fit per SM (smem and TMEM: 2 x 2*BN <= 512)
+  const long long cap = (long long)sms[dev & 15] * per_sm;
+  const int grid = (int)(total < cap ? total : cap);
   gemm_taps_kernel<BN, STAGES, FMT, LRELU><<<grid, 192, SMEM, stream>>>(tmA, tmB, tmOut, pp);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
@@ -256,16 +309,16 @@ int convt1d_launch(const void* x16, const void* w_packed, const float* bias, int
   const int pc = p.pad * Cout;
   if (pc % 256 == 0 && n_total % 256 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 256, 128));
-    return launch_gemm_taps<256, 2>(tmA, tmB, tmOut, p, N, stream);
+    return launch_gemm_taps<256, 3>(tmA, tmB, tmOut, p, N, stream);
   } else if (pc % 128 == 0 && n_total % 128 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 128, 128));
-    return launch_gemm_taps<128, 3>(tmA, tmB, tmOut, p, N, stream);
+    return launch_gemm_taps<128, 4>(tmA, tmB, tmOut, p, N, stream);
   } else if (pc % 64 == 0 && n_total % 64 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 64, 128));
     return launch_gemm_taps<64, 3>(tmA, tmB, tmOut, p, N, stream);
   } else if (pc % 32 == 0 && n_total % 32 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 32, 128));
-    return launch_gemm_taps<32, 2>(tmA, tmB, tmOut, p, N, stream);
+    return launch_gemm_taps<32, 3>(tmA, tmB, tmOut, p, N, stream);
   }
   set_error("convt1d: (s/2)*Cout=%d must be a multiple of 32", pc);
   return B200VOC_ERR_UNSUPPORTED;
@@ -292,10 +345,10 @@ int linear_launch(const void* x16, const void* w_packed /*[Cout][Cin]*/, const f
   p.bias = bias;
   if (Cout % 256 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, Cin, Cout, (uint64_t)Cin * 2, 64, 256, 128));
-    return launch_gemm_taps<256, 2>(tmA, tmB, tmOut, p, N, stream);
+    return launch_gemm_taps<256, 3>(tmA, tmB, tmOut, p, N, stream);
   } else if (Cout % 128 == 0) {
     B200_TRY(make_tmap_2d(&tmB, w_packed, Cin, Cout, (uint64_t)Cin * 2, 64, 128, 128));
-    return launch_gemm_taps<128, 3>(tmA, tmB, tmOut, p, N, stream);
+    return launch_gemm_taps<128, 4>(tmA, tmB, tmOut, p, N, stream);
   }
   B200_TRY(make_tmap_2d(&tmB, w_packed, Cin, Cout, (uint64_t)Cin * 2, 64, 64, 128));
   return launch_gemm_taps<64, 3>(tmA, tmB, tmOut, p, N, stream);
