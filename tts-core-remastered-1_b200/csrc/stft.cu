@@ -531,6 +531,109 @@ istft_kernel(const IstftParams p) {
   }
 }
 
+// ------------------------------------------------------------------ fast iSTFT, n_fft = 1024
+// 16 frame slots per CTA (2 rounds x 8 warps), one warp per frame (fft_warp.cuh, inverse).  The
+// spectrum block is loaded coalesced (frames are the contiguous axis), every warp packs its frame's
+// half spectrum into the 512-point complex input on the fly, runs the inverse FFT in registers and
+// writes the windowed, scaled samples back over its slot; then every thread gathers n_fft/hop
+// contributions per output sample and divides by the window envelope.
+constexpr int kISlots = 16, kISlotStride = 577;     // float2 per slot (odd stride: conflict-free block load)
+
+__global__ void __launch_bounds__(kFastWarps * 32)
+istft1024_kernel(const IstftParams p) {
+  constexpr int NFFT = 1024, N = 512;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float2* tw2 = reinterpret_cast<float2*>(smem_raw);      // [N + 2]
+  float2* win2 = tw2 + (N + 2);                            // [N]
+  float2* tw1 = win2 + N;                                  // [16][32]
+  float2* xN = tw1 + 512;                                  // [kISlots] Nyquist bins
+  float2* slots = xN + kISlots;                            // [kISlots][kISlotStride]: X[k] (padded), later y[m]
+  float2* tbuf = slots + kISlots * kISlotStride;           // [warps][528] transpose scratch
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int ratio = NFFT / p.hop;
+  const int opb = (kISlots - ratio + 1) * p.hop;
+  const int n0 = blockIdx.x * opb;
+  const int f_lo = (n0 - N) / p.hop + 1;                   // may be negative
+  const int bins = N + 1;
+
+  for (int i = threadIdx.x; i <= N; i += blockDim.x) tw2[i] = __ldg(p.tab.tw2 + i);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    win2[i] = __ldg(reinterpret_cast<const float2*>(p.tab.win) + i);
+    const int k1 = i >> 5, t = i & 31;
+    float s, c;
+    sincospif(-2.0f * (float)((t * k1) & 511) / 512.0f, &s, &c);
+    tw1[i] = make_float2(c, s);
+  }
+  const float2* sp = p.spec + (long long)b * bins * p.frames;
+  for (int i = threadIdx.x; i < bins * kISlots; i += blockDim.x) {
+    const int k = i / kISlots, s = i % kISlots;
+    const int f = f_lo + s;
+    float2 v = make_float2(0.f, 0.f);
+    if (f >= 0 && f < p.frames) v = __ldg(sp + (long long)k * p.frames + f);
+    if (k == 0 || k == N) v.y = 0.f;                       // c2r ignores the imaginary part of DC / Nyquist
+    if (k < N) slots[s * kISlotStride + pad(k)] = v;
+    else xN[s] = v;
+  }
+  __syncthreads();
+  const float inv_n = 1.0f / N;
+#pragma unroll 1
+  for (int r = 0; r < kISlots / kFastWarps; ++r) {
+    const int slot = r * kFastWarps + warp;
+    float2* X = slots + slot * kISlotStride;
+    const float2 xn = xN[slot];
+    float2 v[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+      const int k = 32 * n1 + lane;
+      const float2 xk = X[pad(k)];
+      const float2 xnk = k == 0 ? xn : X[pad(N - k)];
+      v[n1] = irfft_pack(xk, cconj(xnk), tw2[k]);
+    }
+    __syncwarp();                                          // all reads of X done before it is overwritten
+    warp_fft512<true>(v, tbuf + warp * 528, tw1, lane);
+    // lane (k1, p) holds z[m], m = k1 + 16*k2 + 256*p  ->  samples (2m, 2m+1), windowed and scaled
+    const int mb = (lane & 15) + 256 * (lane >> 4);
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+      const int m = mb + 16 * k2;
+      const float2 w = win2[m];
+      X[pad(m)] = make_float2(v[k2].x * w.x * inv_n, v[k2].y * w.y * inv_n);
+    }
+  }
+  __syncthreads();
+  float* o = p.wav + (long long)b * p.Nout;
+  const float* wv = reinterpret_cast<const float*>(win2);
+  for (int i = threadIdx.x; i < opb; i += blockDim.x) {
+    const int n = n0 + i;
+    if (n >= p.Nout) break;
+    const int j = n + N;                                   // padded-signal coordinate
+    const int f_hi = j / p.hop;
+    float acc = 0.f, env = 0.f;
+    for (int q = 0; q < ratio; ++q) {
+      const int f = f_hi - q;
+      const int idx = j - f * p.hop;
+      if (f < 0 || f >= p.frames || idx >= NFFT) continue;
+      const float w = wv[idx];
+      const float2 z = slots[(f - f_lo) * kISlotStride + pad(idx >> 1)];
+      acc += (idx & 1) ? z.y : z.x;
+      env = fmaf(w, w, env);
+    }
+    o[n] = env > 1e-11f ? acc / env : 0.f;
+  }
+}
+
+static int launch_istft1024(const IstftParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)(514 + 512 + 512 + kISlots + kISlots * kISlotStride + kFastWarps * 528) * 8 + 64;
+  B200_CUDA(cudaFuncSetAttribute(istft1024_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int ratio = 1024 / p.hop;
+  const int opb = (kISlots - ratio + 1) * p.hop;
+  dim3 grid(ceil_div(p.Nout, opb), p.B);
+  istft1024_kernel<<<grid, kFastWarps * 32, smem, st>>>(p);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
 template <int NFFT>
 static int launch_istft(const IstftParams& p, cudaStream_t st) {
   constexpr int N = NFFT / 2, NPAD = N + N / 8, SLOTS = 2 * kFPB;
@@ -599,7 +702,9 @@ int b200voc_istft(const float* spec_ri, int B, int frames, int n_fft, int hop, i
   if (n_fft == 512 || n_fft == 1024 || n_fft == 2048) B200_TRY(get_fft_tables(n_fft, &p.tab));
   switch (n_fft) {
     case 512: return launch_istft<512>(p, st);
-    case 1024: return launch_istft<1024>(p, st);
+    case 1024:
+      if (n_fft / hop <= kISlots / 2 && !getenv("B200VOC_STFT_V1")) return launch_istft1024(p, st);
+      return launch_istft<1024>(p, st);
     case 2048: return launch_istft<2048>(p, st);
   }
   set_error("istft: n_fft=%d unsupported (512/1024/2048)", n_fft);
