@@ -539,7 +539,7 @@ istft_kernel(const IstftParams p) {
 // contributions per output sample and divides by the window envelope.
 constexpr int kISlots = 16, kISlotStride = 577;     // float2 per slot (odd stride: conflict-free block load)
 
-__global__ void __launch_bounds__(kFastWarps * 32)
+__global__ void __launch_bounds__(kISlots * 32, 2)
 istft1024_kernel(const IstftParams p) {
   constexpr int NFFT = 1024, N = 512;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -547,8 +547,7 @@ istft1024_kernel(const IstftParams p) {
   float2* win2 = tw2 + (N + 2);                            // [N]
   float2* tw1 = win2 + N;                                  // [16][32]
   float2* xN = tw1 + 512;                                  // [kISlots] Nyquist bins
-  float2* slots = xN + kISlots;                            // [kISlots][kISlotStride]: X[k] (padded), later y[m]
-  float2* tbuf = slots + kISlots * kISlotStride;           // [warps][528] transpose scratch
+  float2* slots = xN + kISlots;                            // [kISlots][kISlotStride]: X[k] (padded) -> transpose scratch -> y[m]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int ratio = NFFT / p.hop;
@@ -577,9 +576,8 @@ istft1024_kernel(const IstftParams p) {
   }
   __syncthreads();
   const float inv_n = 1.0f / N;
-#pragma unroll 1
-  for (int r = 0; r < kISlots / kFastWarps; ++r) {
-    const int slot = r * kFastWarps + warp;
+  {
+    const int slot = warp;                                 // one warp per frame slot
     float2* X = slots + slot * kISlotStride;
     const float2 xn = xN[slot];
     float2 v[16];
@@ -591,7 +589,7 @@ istft1024_kernel(const IstftParams p) {
       v[n1] = irfft_pack(xk, cconj(xnk), tw2[k]);
     }
     __syncwarp();                                          // all reads of X done before it is overwritten
-    warp_fft512<true>(v, tbuf + warp * 528, tw1, lane);
+    warp_fft512<true>(v, X, tw1, lane);                  // the slot doubles as the transpose scratch
     // lane (k1, p) holds z[m], m = k1 + 16*k2 + 256*p  ->  samples (2m, 2m+1), windowed and scaled
     const int mb = (lane & 15) + 256 * (lane >> 4);
 #pragma unroll
@@ -624,12 +622,12 @@ istft1024_kernel(const IstftParams p) {
 }
 
 static int launch_istft1024(const IstftParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)(514 + 512 + 512 + kISlots + kISlots * kISlotStride + kFastWarps * 528) * 8 + 64;
+  const size_t smem = (size_t)(514 + 512 + 512 + kISlots + kISlots * kISlotStride) * 8 + 64;
   B200_CUDA(cudaFuncSetAttribute(istft1024_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ratio = 1024 / p.hop;
   const int opb = (kISlots - ratio + 1) * p.hop;
   dim3 grid(ceil_div(p.Nout, opb), p.B);
-  istft1024_kernel<<<grid, kFastWarps * 32, smem, st>>>(p);
+  istft1024_kernel<<<grid, kISlots * 32, smem, st>>>(p);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
