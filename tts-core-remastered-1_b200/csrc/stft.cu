@@ -564,15 +564,30 @@ istft1024_kernel(const IstftParams p) {
     sincospif(-2.0f * (float)((t * k1) & 511) / 512.0f, &s, &c);
     tw1[i] = make_float2(c, s);
   }
-  const float2* sp = p.spec + (long long)b * bins * p.frames;
-  for (int i = threadIdx.x; i < bins * kISlots; i += blockDim.x) {
-    const int k = i / kISlots, s = i % kISlots;
-    const int f = f_lo + s;
-    float2 v = make_float2(0.f, 0.f);
-    if (f >= 0 && f < p.frames) v = __ldg(sp + (long long)k * p.frames + f);
-    if (k == 0 || k == N) v.y = 0.f;                       // c2r ignores the imaginary part of DC / Nyquist
-    if (k < N) slots[s * kISlotStride + pad(k)] = v;
-    else xN[s] = v;
+  {
+    // thread = (frame slot s = tid & 15, bin k = tid >> 4 + 32*j): 16 slots of one bin are one 128-byte
+    // line of spec[b, k, f_lo ..]; loads are issued 9 at a time so their latencies overlap
+    const int sidx = threadIdx.x & (kISlots - 1), k0 = threadIdx.x >> 4;
+    const int f = f_lo + sidx;
+    const bool fok = f >= 0 && f < p.frames;
+    const float2* sp = p.spec + (long long)b * bins * p.frames + (fok ? f : 0);
+    float2* dst = slots + sidx * kISlotStride;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      float2 v[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int k = k0 + 32 * (jj * 9 + j);
+        v[j] = (fok && k < bins) ? __ldg(sp + (long long)k * p.frames) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int k = k0 + 32 * (jj * 9 + j);
+        if (k == 0 || k == N) v[j].y = 0.f;                // c2r ignores the imaginary part of DC / Nyquist
+        if (k < N) dst[pad(k)] = v[j];
+        else if (k == N) xN[sidx] = v[j];
+      }
+    }
   }
   __syncthreads();
   const float inv_n = 1.0f / N;
