@@ -119,10 +119,15 @@ int b200voc_convt1d(const void* x16, const void* w_packed, const float* bias, in
                     int s, int fmt, int store_lrelu, void* out16, void* stream);
 
 /* ResidualBlock(C, dilation, cond_dim).forward(x, cond) (generator.py:40-41,89-90; body = repair
- * R2).  a16 holds leaky_relu(x) (the form the producer stores); film[B,T,2C] fp32 holds
- * (1+scale | shift) at frame rate; N = num_bands*B sequences, sequence n uses film row n/num_bands.
- * w1_packed [2C rows (GLU-interleaved)][3C], w2_packed [C][C]. */
+ * R2).  a16 is the activation in the form its producer stores it: leaky_relu(x) for the wide
+ * stages (C >= 128), raw x for the narrow ones (C <= 64, where the kernel applies leaky_relu on
+ * chip and adds the residual on the tensor core) -- b200voc_resblock_input_is_lrelu(C) tells.
+ * film[B,T,2C] fp32 holds (1+scale | shift) at frame rate; N = num_bands*B sequences, sequence n
+ * uses film row n/num_bands.  w1_packed [2C rows (GLU-interleaved)][3C]; w2_packed [C][C], or
+ * [C][2C] = [W_proj | I] with w1 pre-scaled by 1/2 for C <= 64.  store_lrelu != 0 stores
+ * leaky_relu(y). */
 int64_t b200voc_resblock_packed_elems(int C);   /* elements of w1_packed + w2_packed */
+int b200voc_resblock_input_is_lrelu(int C);
 int b200voc_pack_resblock_weights(const float* w_conv, const float* w_proj, int C, int fmt, void* w_packed,
                                   void* stream);
 int b200voc_resblock(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,

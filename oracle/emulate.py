@@ -5,8 +5,10 @@ error of a given operand/storage plan.  It follows the *kernel* data flow docume
 DESIGN.md section "Numerics plan":
 
   * every inter-layer activation is stored once in HBM as a 16-bit tensor (fp16 or bf16, per
-    stage); when the consumer is a residual block the stored value is leaky_relu(x) and the raw x
-    is recovered exactly-invertibly (x = a if a >= 0 else 10*a);
+    stage); in the wide stages (C >= 128), when the consumer is a residual block the stored value
+    is leaky_relu(x) and the raw x is recovered exactly-invertibly (x = a if a >= 0 else 10*a); the
+    narrow stages (C <= 64) store raw x, apply leaky_relu in 16-bit arithmetic on chip and add the
+    residual x on the tensor core;
   * tensor-core operands (activations and weights) are rounded to the stage's 16-bit format,
     accumulation, bias, GLU, FiLM and the residual add are fp32;
   * conditioning MLPs, FiLM projections, band_split and band_merge + tanh are fp32 CUDA-core
@@ -34,6 +36,16 @@ def _store_lrelu(x, fmt):
     return a, torch.where(a >= 0, a, a * 10.0)
 
 
+def _store_raw(x, fmt):
+    """narrow stages: raw x rounded to fmt; the MMA operand is leaky_relu evaluated in the 16-bit
+    format (slope constant and product rounded to fmt)."""
+    xs = _q(x, fmt)
+    if fmt == "fp32":
+        return F.leaky_relu(xs, O.LRELU_SLOPE), xs
+    slope = _q(torch.tensor(O.LRELU_SLOPE), fmt)
+    return torch.maximum(xs, _q(xs * slope, fmt)), xs
+
+
 def emulated_forward(sd: Dict[str, torch.Tensor], cfg: O.OracleConfig, mel, prosody, style, emotion,
                      stage_fmt: List[str], split_fmt: str = None, **kw) -> torch.Tensor:
     """stage_fmt[i] = 16-bit format of stage i's operands AND of the activations it writes."""
@@ -51,7 +63,8 @@ def emulated_forward(sd: Dict[str, torch.Tensor], cfg: O.OracleConfig, mel, pros
             fmt = stage_fmt[i]
             p = f"upsample_blocks.{i}"
             x = F.conv_transpose1d(_q(x, fmt), _q(sd[f"{p}.0.weight"], fmt), sd[f"{p}.0.bias"], stride=f, padding=f // 2)
-            a, x = _store_lrelu(x, fmt)
+            narrow = x.shape[1] <= 64
+            a, x = _store_raw(x, fmt) if narrow else _store_lrelu(x, fmt)
             nres = len(cfg.res_dilations)
             for j, d in enumerate(cfg.res_dilations):
                 q = f"{p}.{j + 1}"
@@ -66,7 +79,7 @@ def emulated_forward(sd: Dict[str, torch.Tensor], cfg: O.OracleConfig, mel, pros
                     nxt = stage_fmt[i + 1] if i + 1 < len(stage_fmt) else fmt
                     x = _q(y, nxt)                 # raw store for the next ConvT / band_merge
                 else:
-                    a, x = _store_lrelu(y, fmt)
+                    a, x = _store_raw(y, fmt) if narrow else _store_lrelu(y, fmt)
         outs.append(x)
     wav = F.conv1d(torch.cat(outs, 1), sd["band_merge.weight"], sd["band_merge.bias"], padding=3)
     return torch.tanh(wav)

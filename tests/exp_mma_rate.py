@@ -1,4 +1,5 @@
-"""Experiment driver (test infrastructure): raw tcgen05.mma SS-mode issue rate vs N."""
+"""Experiment driver (test infrastructure): raw tcgen05.mma SS-mode issue rate vs N, and the cost of
+switching accumulator / shape between short groups of MMAs."""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tts-core-remastered-1_b200"))
@@ -6,15 +7,15 @@ import torch
 from b200voc import _lib
 lib = _lib.load()
 res = {}
-for blocks in (1, 148):
-    for n in (64, 128, 256):
-        out = torch.zeros(blocks, dtype=torch.int64, device="cuda")
-        iters = 2000
-        for _ in range(2):
-            _lib.check(lib.b200voc_exp_mma_rate(n, iters, blocks, out.data_ptr(), _lib.current_stream()))
-        torch.cuda.synchronize()
-        cyc = float(out.float().mean())
-        per_mma = cyc / (iters * 4)
-        ideal = 128 * n * 16 / 4096.0          # 8192 flop/clk/SM -> 4096 MAC/clk
-        res[f"blocks{blocks}_N{n}"] = dict(cycles_per_mma=round(per_mma, 1), ideal=ideal, frac_of_peak=round(ideal / per_mma, 3))
-print(json.dumps(res, indent=1))
+blocks = 148
+def run(n, iters):
+    out = torch.zeros(blocks, dtype=torch.int64, device="cuda")
+    for _ in range(2):
+        _lib.check(lib.b200voc_exp_mma_rate(n, iters, blocks, out.data_ptr(), _lib.current_stream()))
+    torch.cuda.synchronize()
+    return float(out.float().mean())
+for shape, name in enumerate(["32x32b.x32", "16x256b.x8", "16x128b.x16", "16x64b.x32"]):
+    for nw in (1, 4, 16):
+        cyc = run(20000 + 100 * shape + nw, 2000)
+        res[f"tmem_ld_{name}_{nw}warps"] = dict(cycles_per_ld=round(cyc / 2000, 1), bytes_per_clk_per_sm=round(nw * 4096 * 2000 / cyc, 1))
+print(json.dumps(res, indent=0))

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "b200voc_pack_convt_weight": (C.c_int, [_P, _I, _I, _I, _I, _P, _P]),
     "b200voc_convt1d": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "b200voc_resblock_packed_elems": (_I64, [_I]),
+    "b200voc_resblock_input_is_lrelu": (_I, [_I]),
     "b200voc_pack_resblock_weights": (C.c_int, [_P, _P, _I, _I, _P, _P]),
     "b200voc_resblock": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "b200voc_exp_rowshift": (C.c_int, [_P, _P, _P, _P]),

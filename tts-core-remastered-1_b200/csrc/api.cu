@@ -543,19 +543,22 @@ int b200voc_gen_forward(b200voc_gen* g, const float* mel, const float* prosody, 
     const StageW& s = g->stages[i];
     char nm[32];
     snprintf(nm, sizeof nm, "up%d", (int)i);
-    // ConvT: 2 taps per output sample (generator.py:35-38,87); stores leaky_relu(y) for the res blocks
+    // ConvT: 2 taps per output sample (generator.py:35-38,87).  Wide stages (C >= 128) carry
+    // leaky_relu(x) between kernels (the residual block's MMA operand), narrow stages carry raw x
+    // (resblock2.cu applies leaky_relu on chip and adds the residual on the tensor core).
+    const int carry_lrelu = s.Cout <= 64 ? 0 : 1;
     RUN(nm, 2.0 * N * (double)L * s.s * 2.0 * s.Cin * s.Cout, (double)N * L * (s.Cin + (double)s.s * s.Cout) * 2,
-        convt1d_launch(act[cur], s.up_w, s.up_b, N, L, s.Cin, s.Cout, s.s, s.fmt, 1, act[cur ^ 1], st));
+        convt1d_launch(act[cur], s.up_w, s.up_b, N, L, s.Cin, s.Cout, s.s, s.fmt, carry_lrelu, act[cur ^ 1], st));
     cur ^= 1;
     L *= s.s;
-    if (tap == nm && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, s.Cout, s.fmt, 1, tap_out, st));
+    if (tap == nm && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, s.Cout, s.fmt, carry_lrelu, tap_out, st));
     const bool att_here = (int)i == g->att_stage && g->cfg.use_attention;
     for (size_t j = 0; j < s.res.size(); ++j) {
       const ResW& r = s.res[j];
       const bool last = j + 1 == s.res.size();
       // last block of a stage stores raw x (for the next ConvT / attention / band_merge);
-      // inner blocks store leaky_relu(x).
-      const int store_lrelu = last ? 0 : 1;
+      // inner blocks of the wide stages store leaky_relu(x).
+      const int store_lrelu = last ? 0 : carry_lrelu;
       const int out_fmt = (last && i + 1 < g->stages.size()) ? g->stages[i + 1].fmt : s.fmt;
       snprintf(nm, sizeof nm, "res%d.%d", (int)i, (int)j);
       RUN(nm, 2.0 * N * (double)L * (6.0 * r.C * r.C + (double)r.C * r.C), (double)N * L * r.C * 2 * 2.0,
@@ -627,7 +630,8 @@ int b200voc_convt1d(const void* x16, const void* w_packed, const float* bias, in
   return convt1d_launch(x16, w_packed, bias, N, Lin, Cin, Cout, s, fmt, store_lrelu, out16,
                         reinterpret_cast<cudaStream_t>(stream));
 }
-int64_t b200voc_resblock_packed_elems(int C) { return 2ll * C * 3 * C + (int64_t)C * C; }
+int64_t b200voc_resblock_packed_elems(int C) { return 2ll * C * 3 * C + (int64_t)C * (C <= 64 ? 2 * C : C); }
+int b200voc_resblock_input_is_lrelu(int C) { return C <= 64 ? 0 : 1; }
 int b200voc_pack_resblock_weights(const float* w_conv, const float* w_proj, int C, int fmt, void* w_packed,
                                   void* stream) {
   B200_CHECK_ARG(w_conv && w_proj && w_packed, "pack_resblock_weights: null argument");

@@ -425,7 +425,7 @@ int exp_rowshift_launch(const void* a16, const void* b16, float* out, cudaStream
 // Raw tcgen05.mma issue rate from shared-memory operands (SS mode), M = 128, K = 16 per MMA, for a
 // given N: one thread per CTA issues `iters` x 4 MMAs on a fixed (uninitialised) operand tile and
 // times them with clock64.  out[blockIdx.x] = cycles.  DESIGN.md uses the result to pick N.
-__global__ void __launch_bounds__(128, 1) exp_mma_rate_kernel(int n, int iters, long long* out) {
+__global__ void __launch_bounds__(512, 1) exp_mma_rate_kernel(int n, int iters, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;               // 128 rows x 128 B
@@ -444,14 +444,56 @@ __global__ void __launch_bounds__(128, 1) exp_mma_rate_kernel(int n, int iters, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (n >= 20000) {
+    // TMEM read bandwidth: (n - 20000) warps issue `iters` x (tcgen05.ld 32x32b.x32 + wait) on their lane quadrant
+    const int nw = (n - 20000) % 100, shape = (n - 20000) / 100;
+    if (warp < nw) {
+      uint32_t v[32], acc = 0;
+      const uint32_t addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + ((warp >> 2) & 3) * 32;
+      __syncwarp();
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+        if (shape == 0) tmem_ld32(addr, v);
+        else if (shape == 1) tmem_ld_16x256b_x8(addr, v);
+        else if (shape == 2) tmem_ld_16x128b_x16(addr, v);
+        else tmem_ld_16x64b_x32(addr, v);
+        tmem_ld_wait();
+        acc += v[0] ^ v[31];
+      }
+      const long long t1 = clock64();
+      if ((threadIdx.x & 31) == 0 && warp == 0) out[blockIdx.x] = (t1 - t0) + (acc == 0x12345u ? 1 : 0);
+    }
+  } else
   if (threadIdx.x == 0) {
+    // n >= 1000 selects 64-byte rows / SWIZZLE_64B operands (the C=32 layout), 2 k-steps per row
+    const int shift_rows = n / 10000;       // n >= 10000: A descriptor starts shift_rows rows into the tile
+    n %= 10000;
+    const bool sw64 = n >= 1000;
+    if (sw64) n -= 1000;
     const uint32_t idesc = make_idesc_f16(0, n);
-    const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sA));
-    const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sB));
+    const uint64_t a_desc = sw64 ? make_kmajor_desc<64>(smem_u32(sA) + shift_rows * 64)
+                                 : make_kmajor_desc<128>(smem_u32(sA) + shift_rows * 128);
+    const uint64_t b_desc = sw64 ? make_kmajor_desc<64>(smem_u32(sB)) : make_kmajor_desc<128>(smem_u32(sB));
+    const int kmask = sw64 ? 1 : 3;
+    // iters >= 1000000: group experiment.  iters = 1000000*mode + 1000*G + reps: issue `reps` rounds of
+    // two groups of G MMAs; mode 1: the groups alternate between two accumulators (same shape);
+    // mode 2: same accumulator, second group starts with accumulate = 0; mode 3: two accumulators AND
+    // the second group has N/2; mode 4: one accumulator, all accumulate (control).
+    const int mode = iters / 1000000, G = (iters / 1000) % 1000, reps = iters % 1000;
     const long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
+    if (mode == 0) {
+      for (int it = 0; it < iters; ++it) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, 1);
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a_desc + 2 * (k & kmask), b_desc + 2 * (k & kmask), idesc, 1);
+      }
+    } else {
+      const uint32_t idesc_b = mode == 3 ? make_idesc_f16(0, n / 2) : idesc;
+      const uint32_t d_b = (mode == 1 || mode == 3) ? tmem_base + 128 : tmem_base;
+      for (int it = 0; it < reps; ++it) {
+        for (int k = 0; k < G; ++k) umma_f16(tmem_base, a_desc + 2 * (k & kmask), b_desc + 2 * (k & kmask), idesc, 1);
+        for (int k = 0; k < G; ++k)
+          umma_f16(d_b, a_desc + 2 * (k & kmask), b_desc + 2 * (k & kmask), idesc_b, (mode == 2 && k == 0) ? 0 : 1);
+      }
     }
     umma_commit(bar);
     mbar_wait(bar, 0);
@@ -463,13 +505,13 @@ __global__ void __launch_bounds__(128, 1) exp_mma_rate_kernel(int n, int iters, 
 }
 
 int exp_mma_rate_launch(int n, int iters, int blocks, long long* out, cudaStream_t stream) {
-  B200_CHECK_ARG(n % 16 == 0 && n >= 16 && n <= 256, "exp_mma_rate: N=%d", n);
+  B200_CHECK_ARG(n >= 20000 || ((n % 1000) % 16 == 0 && (n % 1000) >= 16 && (n % 1000) <= 256 && n / 10000 <= 16), "exp_mma_rate: N=%d", n);
   static bool configured = false;
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(exp_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024));
     configured = true;
   }
-  exp_mma_rate_kernel<<<blocks, 128, 52 * 1024, stream>>>(n, iters, out);
+  exp_mma_rate_kernel<<<blocks, 512, 52 * 1024, stream>>>(n, iters, out);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }

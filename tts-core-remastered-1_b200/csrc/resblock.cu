@@ -271,10 +271,15 @@ resblock_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // ---------------------------------------------------------------------------- packing
 // w_conv [2C][C][3] (value rows 0..C-1, gate rows C..2C-1)  ->  w1[row][tap*C + ci] with rows
 // GLU-interleaved per chunk of CH channels: row = j*2CH + {0..CH-1: value ch j*CH+i | CH..: gate}.
-// w_proj [C][C][1] -> w2[co][ci].  Layout of w_packed: w1 (2C*3C elems) then w2 (C*C elems).
+// w_proj [C][C][1] -> w2[co][ci].  Layout of w_packed: w1 (2C*3C elems) then w2.
+// Narrow stages (C <= 64, resblock2.cu): w1 is pre-scaled by 1/2 (exact; the kernel evaluates
+// sigmoid through tanh(g/2) and folds the other 1/2 into the value half), and w2 is [C][2C] =
+// [W_proj | I]: the identity block adds the residual x on the tensor core.
 __global__ void pack_resblock_kernel(const float* __restrict__ w_conv, const float* __restrict__ w_proj, int C,
                                      int CH, int fmt, uint16_t* __restrict__ out) {
-  const long long n1 = 2ll * C * 3 * C, total = n1 + (long long)C * C;
+  const bool narrow = C <= 64;
+  const int w2_cols = narrow ? 2 * C : C;
+  const long long n1 = 2ll * C * 3 * C, total = n1 + (long long)C * w2_cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     float v;
@@ -284,8 +289,10 @@ __global__ void pack_resblock_kernel(const float* __restrict__ w_conv, const flo
       const int j = row / (2 * CH), within = row % (2 * CH);
       const int src_row = within < CH ? (j * CH + within) : (C + j * CH + within - CH);
       v = w_conv[((long long)src_row * C + ci) * 3 + tap];
+      if (narrow) v *= 0.5f;
     } else {
-      v = w_proj[i - n1];
+      const int col = (int)((i - n1) % w2_cols), row = (int)((i - n1) / w2_cols);
+      v = col < C ? w_proj[(long long)row * C + col] : (col - C == row ? 1.0f : 0.0f);
     }
     out[i] = fmt == 0 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
   }
@@ -365,12 +372,9 @@ int resblock_launch(const void* a16, const void* w_packed, const float* b_conv, 
   switch (C) {
     case 32:
     case 64:
-      if (dilation <= 8 && !force_v1())
-        return resblock2_launch(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, C, dilation, T, num_bands, fmt,
-                                out_fmt, store_lrelu, out16, stream);
-      if (C == 32)
-        return launch_resblock<32>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, out_fmt, store_lrelu, out16, stream);
-      return launch_resblock<64>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation, T, num_bands, fmt, out_fmt, store_lrelu, out16, stream);
+      // narrow stages: RAW input convention, weights packed for resblock2.cu only
+      return resblock2_launch(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, C, dilation, T, num_bands, fmt,
+                              out_fmt, store_lrelu, out16, stream);
     case 128:
     case 256:
       if (dilation <= 8 && !force_v1())
