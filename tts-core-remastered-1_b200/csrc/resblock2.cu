@@ -22,6 +22,7 @@
 //     awaited one tile later (off the critical path) before the h slot is recycled;
 //   * W1 (3 taps), W2 and I stay resident in shared memory; the roles are specialised warps:
 //     TMA | 2 GEMM issuers (even/odd tiles) | identity-MMA issuer | 4 prep | 4 store | 8 GLU+FiLM;
+//   * FiLM coefficients of a tile (one frame when P % 128 == 0) are staged per warp in shared memory;
 //   * multi-thread barriers are arrived on once per WARP (fence, __syncwarp, lane 0 arrives): a
 //     128-arrival barrier wakes its waiter ~25 times per phase, which alone was ~20 % of all
 //     issued instructions.
@@ -75,7 +76,10 @@ struct Rb2Cfg {
   static constexpr int OFF_H = OFF_R + NR * A_SLOT;
   static constexpr int OFF_BAR = OFF_H + NH * H_BYTES;
   static constexpr int OFF_PAR = OFF_BAR + 1024;
-  static constexpr int SMEM = OFF_PAR + 3 * C * 4 + 1024;
+  static constexpr bool SPLIT = C == 64;             // GLU epilogue: both warp sets share a tile (column halves)
+  static constexpr int E1_CH = SPLIT ? C / 2 : C;    // channels per GLU warp
+  static constexpr int OFF_FILM = OFF_PAR + 3 * C * 4;     // per GLU warp: (1+scale | shift) of its channels, 2*E1_CH floats
+  static constexpr int SMEM = OFF_FILM + 8 * 2 * E1_CH * 4 + 1024;
   static constexpr int NBARS = 1 + 4 * NR + 2 * ND1 + 2 * NH + 2 * ND2;
   static constexpr int D2_COL = ND1 * N1;
   static constexpr int TMEM_NEED = ND1 * N1 + ND2 * C;
@@ -199,10 +203,10 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
     for (int b = 0; b < ND1; ++b) {
       mbar_init(&d1_full[b], 1);
-      mbar_init(&d1_empty[b], kSetWarps);
+      mbar_init(&d1_empty[b], K::SPLIT ? 2 * kSetWarps : kSetWarps);
     }
     for (int b = 0; b < NH; ++b) {
-      mbar_init(&h_full[b], kSetWarps);
+      mbar_init(&h_full[b], K::SPLIT ? 2 * kSetWarps : kSetWarps);
       mbar_init(&h_empty[b], 1);
     }
     for (int b = 0; b < ND2; ++b) {
@@ -317,48 +321,80 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (prev >= 0) issue_g2(prev);
   } else if (warp >= 12) {
     // ------------------------------------------------------------ epilogue 1 (warps 12..19): GLU + FiLM -> h
-    // two warps per TMEM lane quadrant; warp set `par` owns the tiles with i % 2 == par, so two
-    // tiles' GLU epilogues are in flight per quadrant and their latencies overlap
-    const int q = warp & 3, par = (warp - 12) >> 2;
+    // Two warps per TMEM lane quadrant.  C = 32: warp set `set` owns the tiles with i % 2 == set, so
+    // two tiles' GLU epilogues are in flight per quadrant.  C = 64 (only two GEMM1 accumulators fit
+    // in TMEM next to the D2 ring): both sets work on EVERY tile, one half of the channels each,
+    // which halves the time an accumulator is held.
+    const int q = warp & 3, set = (warp - 12) >> 2;
     const int row = q * 32 + lane;
+    constexpr int CH = K::E1_CH;
+    const int cbeg = K::SPLIT ? set * CH : 0;
+    const int first = K::SPLIT ? 0 : set, stride = K::SPLIT ? 1 : 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float4* sBA = reinterpret_cast<const float4*>(sPar);
-    const float4* sBG = reinterpret_cast<const float4*>(sPar + C);
-    FilmWalk fw(blockIdx.x + par * grid, p.tiles_per_seq, 2 * grid, p.P, p.num_bands);
-    for (int i = par; blockIdx.x + (long long)i * grid < p.total_tiles; i += 2, fw.next()) {
+    float* scratch = reinterpret_cast<float*>(smem + K::OFF_FILM) + (warp - 12) * 2 * CH;   // [S(CH) | T(CH)]
+    FilmWalk fw(blockIdx.x + first * grid, p.tiles_per_seq, stride * grid, p.P, p.num_bands);
+    for (int i = first; blockIdx.x + (long long)i * grid < p.total_tiles; i += stride, fw.next()) {
       const int b = i % ND1, hb = i % NH;
-      int t = fw.t0;
-      {
-        const int r = fw.rem0 + row;
-        if (r >= fw.P) t += r / fw.P;                           // only when the tile straddles a frame boundary
+      // FiLM: when all 128 rows of the tile lie in one frame (always, in the generator: P is a
+      // multiple of 128) the frame's coefficients are staged once per warp in shared memory and
+      // read back as broadcasts; a warp-wide LDG.128 of one address costs 4-5 L1 wavefronts, and
+      // 2 per 4 elements of them made the L1 data pipe the busiest unit of this kernel.
+      const bool uniform = fw.rem0 + 127 < fw.P;
+      float4 stage = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* film_row;
+      if (uniform) {
+        film_row = p.film + ((long long)fw.b * p.T + fw.t0) * p.film_stride;
+        if (lane < CH / 2) {                       // lanes [0, CH/4): S, [CH/4, CH/2): T
+          const int j = lane < CH / 4 ? lane : lane - CH / 4;
+          stage = __ldg(reinterpret_cast<const float4*>(film_row + (lane < CH / 4 ? 0 : C) + cbeg) + j);
+        }
+      } else {
+        int t = fw.t0 + (fw.rem0 + row) / fw.P;
+        if (t > p.T - 1) t = p.T - 1;
+        film_row = p.film + ((long long)fw.b * p.T + t) * p.film_stride;
       }
-      if (t > p.T - 1) t = p.T - 1;
-      const float* film = p.film + ((long long)fw.b * p.T + t) * p.film_stride;
       mbar_wait(&d1_full[b], (i / ND1) & 1);
       if (q == 0) RB2_TRACE(3, i, 0);
       mbar_wait(&h_empty[hb], ((i / NH) & 1) ^ 1);
       if (q == 0) RB2_TRACE(3, i, 1);
       tc_fence_after();
+      if (uniform) {
+        if (lane < CH / 2) reinterpret_cast<float4*>(scratch)[lane] = stage;
+        __syncwarp();
+      }
       uint8_t* hrow = sH + hb * K::H_BYTES + row * K::ROWB;
+      const float* srcS = film_row + cbeg;
+      const float* srcT = film_row + C + cbeg;
 #pragma unroll
-      for (int c0 = 0; c0 < C; c0 += 16) {
+      for (int cc = 0; cc < CH; cc += 16) {
+        const int c0 = cbeg + cc;
         uint32_t va[16], vg[16];
         tmem_ld16(lane_addr + b * K::N1 + c0, va);
         tmem_ld16(lane_addr + b * K::N1 + C + c0, vg);
-        const float4* fs = reinterpret_cast<const float4*>(film + c0);
-        const float4* fh = reinterpret_cast<const float4*>(film + C + c0);
         float4 S[4], H[4];
+        if (uniform) {
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) { S[i4] = __ldg(fs + i4); H[i4] = __ldg(fh + i4); }
+          for (int i4 = 0; i4 < 4; ++i4) {
+            S[i4] = reinterpret_cast<const float4*>(scratch + cc)[i4];
+            H[i4] = reinterpret_cast<const float4*>(scratch + CH + cc)[i4];
+          }
+        } else {
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            S[i4] = __ldg(reinterpret_cast<const float4*>(srcS + cc) + i4);
+            H[i4] = __ldg(reinterpret_cast<const float4*>(srcT + cc) + i4);
+          }
+        }
         tmem_ld_wait();
-        if (q == 0 && c0 == 0) RB2_TRACE(3, i, 3);
+        if (q == 0 && cc == 0) RB2_TRACE(3, i, 3);
 #pragma unroll
         for (int i8 = 0; i8 < 2; ++i8) {
           float hv[8];
 #pragma unroll
           for (int h4 = 0; h4 < 2; ++h4) {
             const int i4 = i8 * 2 + h4;
-            const float4 A = sBA[(c0 >> 2) + i4], G = sBG[(c0 >> 2) + i4];
+            const float4 A = *reinterpret_cast<const float4*>(sPar + c0 + i4 * 4);
+            const float4 G = *reinterpret_cast<const float4*>(sPar + C + c0 + i4 * 4);
             const float av[4] = {A.x, A.y, A.z, A.w}, gv[4] = {G.x, G.y, G.z, G.w};
             const float sv[4] = {S[i4].x, S[i4].y, S[i4].z, S[i4].w}, tv[4] = {H[i4].x, H[i4].y, H[i4].z, H[i4].w};
 #pragma unroll
@@ -374,12 +410,12 @@ resblock2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               make_uint4(pack2t<FMT>(hv[0], hv[1]), pack2t<FMT>(hv[2], hv[3]), pack2t<FMT>(hv[4], hv[5]),
                          pack2t<FMT>(hv[6], hv[7]));
         }
-        if (q == 0 && c0 == 0) RB2_TRACE(6, i, 2);
+        if (q == 0 && cc == 0) RB2_TRACE(6, i, 2);
       }
       if (q == 0) RB2_TRACE(6, i, 3);
       tc_fence_before();             // TMEM reads of D1 are complete
       fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the UMMA (async proxy)
-      __syncwarp();
+      __syncwarp();                  // (also: every lane is done with the FiLM scratch)
       if (lane == 0) {
         mbar_arrive(&h_full[hb]);
         mbar_arrive(&d1_empty[b]);
