@@ -93,6 +93,39 @@ int b200voc_gen_forward(b200voc_gen* g, const float* mel, const float* prosody, 
                         const float* emotion, int B, int T, int style_drop, int emo_drop, float w_style,
                         float w_emo, float* wav_out, void* workspace, int64_t workspace_bytes,
                         const char* tap_name, float* tap_out, void* stream);
+/* Generator.forward with the wire formats either side of the path:
+ *   io->mel_time_major  1: `mel` is [B,T,channels], the layout the refiner / acoustic model emit
+ *                          (sde_refiner5/model.py:304-306); vocoder7/trainer.py:77 transposes it on
+ *                          the host, here the transpose is folded into the band-split load;
+ *   io->out_format      B200VOC_OUT_F32: wav_out is float[B,1,hop*T] in (-1,1);
+ *                       B200VOC_OUT_PCM16: wav_out is int16[B,1,hop*T] = round(clamp(wav)*32767);
+ *   io->valid_samples   optional int32[B] (device): samples at or past valid_samples[b] are written
+ *                       as 0 (the collator's wav_length = hop*frame_length of a padded batch,
+ *                       batching2/colate.py:140-146,184-191).
+ * io == NULL is b200voc_gen_forward. */
+#define B200VOC_OUT_F32 0
+#define B200VOC_OUT_PCM16 1
+typedef struct {
+  int32_t mel_time_major;
+  int32_t out_format;
+  const int32_t* valid_samples;
+  int32_t reserved[4];
+} b200voc_gen_io;
+int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosody, const float* style,
+                           const float* emotion, int B, int T, int style_drop, int emo_drop, float w_style,
+                           float w_emo, const b200voc_gen_io* io, void* wav_out, void* workspace,
+                           int64_t workspace_bytes, const char* tap_name, float* tap_out, void* stream);
+
+/* GlobalStyleTokens.forward (vocoder7/gst.py:24-35; the step before the Generator in its only caller,
+ * vocoder7/trainer.py:73): style[B,style_dim] from mel[B,channels,T] (or [B,T,channels]).
+ * conv0_w[style_dim,channels,3] conv0_b[style_dim] (attn_conv.0), conv2_w[num_tokens,style_dim]
+ * conv2_b[num_tokens] (attn_conv.2), tokens[num_tokens,style_dim]; all fp32 device pointers. */
+int64_t b200voc_gst_scratch_bytes(int B, int T, int num_tokens);
+int b200voc_gst_forward(const float* mel, int mel_time_major, int B, int T, int channels, int style_dim,
+                        int num_tokens, const float* conv0_w, const float* conv0_b, const float* conv2_w,
+                        const float* conv2_b, const float* tokens, void* scratch, int64_t scratch_bytes,
+                        float* style_out, void* stream);
+
 /* Per-launch CUDA-event timing of the LAST forward (bench.py's roofline numbers).  Enable, run a
  * forward, synchronise the stream, then read entry i: layer name (oracle tap names), elapsed ms,
  * algorithmic FLOPs and algorithmic HBM bytes (DESIGN.md states the per-unit figures). */

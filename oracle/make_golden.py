@@ -170,6 +170,28 @@ def main():
     for f in sorted(os.listdir(GOLD)):
         print(f"  {f}: {os.path.getsize(os.path.join(GOLD, f)) / 1024:.1f} KiB")
 
+    # ---- GlobalStyleTokens: reference class vs restatement, golden vectors -------
+    from vocoder7 import gst as rgst
+    torch.manual_seed(1234)
+    ref_gst = rgst.GlobalStyleTokens(rcfg.GANConfig()).eval()
+    sd_ref = {k: v.detach() for k, v in ref_gst.state_dict().items()}
+    sd_ora = O.make_gst_state(seed=1234)
+    assert list(sd_ref.keys()) == list(sd_ora.keys())
+    for k in sd_ref:
+        assert torch.equal(sd_ref[k], sd_ora[k]), k
+    g = torch.Generator().manual_seed(77)
+    mel_ref = torch.randn(3, 80, 150, generator=g) * 2.0 - 4.0     # log-mel-like range
+    with torch.no_grad():
+        y_ref = ref_gst(mel_ref)
+        y_ora = O.gst_forward(sd_ora, mel_ref)
+    d = float((y_ref - y_ora).abs().max())
+    d0 = float((y_ref - sd_ref["tokens"].sum(0)).abs().max())
+    print(f"gst: |reference - restatement|max = {d:.3e};  |reference - sum_n tokens|max = {d0:.3e} "
+          "(softmax and einsum run over the same axis: the style is input-independent up to fp32 rounding)")
+    assert d <= 1e-6
+    np.savez_compressed(os.path.join(GOLD, "gst_b3_t150.npz"), mel=mel_ref.numpy(), style=y_ref.numpy(),
+                        **{"sd." + k: v.numpy() for k, v in sd_ref.items()})
+
 
 if __name__ == "__main__":
     main()

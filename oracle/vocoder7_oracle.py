@@ -357,6 +357,33 @@ def istft(spec: torch.Tensor, n_fft: int, hop: int, length: int) -> torch.Tensor
 # --------------------------------------------------------------------------------------
 # Synthetic inputs -- shared by tests, smoke() and bench.py.
 # --------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------- GST (vocoder7/gst.py)
+def gst_forward(sd: Dict[str, torch.Tensor], mel_ref: torch.Tensor) -> torch.Tensor:
+    """Functional restatement of ``GlobalStyleTokens.forward`` (vocoder7/gst.py:24-35):
+    attn_conv = Conv1d(channels, style_dim, 3, padding=1) -> ReLU -> Conv1d(style_dim, tokens, 1)
+    (gst.py:18-22); softmax over TIME (gst.py:32, dim=-1); einsum('bnt,nd->bd') (gst.py:34).
+    ``sd`` uses the reference's state_dict keys: tokens, attn_conv.0.{weight,bias}, attn_conv.2.{weight,bias}."""
+    h = F.relu(F.conv1d(mel_ref, sd["attn_conv.0.weight"], sd["attn_conv.0.bias"], padding=1))
+    logits = F.conv1d(h, sd["attn_conv.2.weight"], sd["attn_conv.2.bias"])
+    weights = F.softmax(logits, dim=-1)
+    return torch.einsum("bnt,nd->bd", weights, sd["tokens"])
+
+
+def make_gst_state(seed: int = 1234, channels: int = 80, style_dim: int = 128, num_tokens: int = 10):
+    """Default init of the reference module under ``seed`` (construction order of gst.py:15-22)."""
+    torch.manual_seed(seed)
+    tokens = torch.randn(num_tokens, style_dim)
+    c0 = nn.Conv1d(channels, style_dim, kernel_size=3, padding=1)
+    c2 = nn.Conv1d(style_dim, num_tokens, kernel_size=1)
+    return {"tokens": tokens, "attn_conv.0.weight": c0.weight.detach(), "attn_conv.0.bias": c0.bias.detach(),
+            "attn_conv.2.weight": c2.weight.detach(), "attn_conv.2.bias": c2.bias.detach()}
+
+
+def pcm16(wav: torch.Tensor) -> torch.Tensor:
+    """16-bit PCM wire format: round-half-even(clamp(wav, -1, 1) * 32767)."""
+    return torch.round(wav.clamp(-1.0, 1.0) * 32767.0).to(torch.int16)
+
+
 def make_generator(cfg: OracleConfig, seed: int = 1234) -> OracleGenerator:
     torch.manual_seed(seed)
     return OracleGenerator(cfg).eval()

@@ -65,6 +65,21 @@ def test_kernel_plan_expects_exactly_the_state_dict():
     lib.b200voc_gen_destroy(h)
 
 
+def test_gst_module_layout_matches_reference():
+    from b200voc import GANConfig, GlobalStyleTokens, _lib
+    from oracle import vocoder7_oracle as O
+    torch.manual_seed(1234)
+    gst = GlobalStyleTokens(GANConfig())
+    sd, ref = gst.state_dict(), O.make_gst_state(seed=1234)
+    assert list(sd.keys()) == list(ref.keys())
+    for k in sd:
+        assert torch.equal(sd[k], ref[k]), k
+    with pytest.raises(_lib.B200VocError):          # no CPU path
+        gst(torch.zeros(1, 80, 4))
+    with pytest.raises(ValueError):
+        gst(torch.zeros(1, 80, 4), mel_layout="TBC")
+
+
 def test_no_cpu_fallback():
     from b200voc import GANConfig, Generator, _lib
     gen = Generator(GANConfig(use_attention=False))

@@ -1,0 +1,87 @@
+"""GPU parity tests for the callers / wire formats either side of the hot path (SURVEY.md 8f ranks
+1-2): GlobalStyleTokens (vocoder7/gst.py), time-major mel input, 16-bit PCM output and the padded
+batch length mask -- all through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vocoder7_oracle as O  # noqa: E402
+
+
+def _gst():
+    from b200voc import GANConfig, GlobalStyleTokens
+    gst = GlobalStyleTokens(GANConfig()).eval()
+    gst.load_state_dict(O.make_gst_state(seed=1234))
+    return gst.cuda()
+
+
+def test_gst_matches_reference_golden(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "gst_b3_t150.npz"))
+    gst = _gst()
+    mel = torch.from_numpy(gold["mel"]).cuda()
+    want = torch.from_numpy(gold["style"])
+    with torch.no_grad():
+        got = gst(mel).cpu()
+        got_t = gst(mel.transpose(1, 2).contiguous(), mel_layout="BTC").cpu()
+    assert got.shape == want.shape
+    # fp32 everywhere; the only differences are summation order and expf vs torch's exp
+    assert float((got - want).abs().max()) <= 1e-5
+    assert torch.equal(got, got_t)
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 7), (1, 64), (3, 65), (2, 861)])
+def test_gst_matches_oracle_ragged(B, T):
+    gst = _gst()
+    sd = O.make_gst_state(seed=1234)
+    g = torch.Generator().manual_seed(T)
+    mel = torch.randn(B, 80, T, generator=g) * 3.0
+    with torch.no_grad():
+        got = gst(mel.cuda()).cpu()
+    want = O.gst_forward(sd, mel)
+    assert float((got - want).abs().max()) <= 1e-5
+
+
+@pytest.fixture(scope="module")
+def models():
+    from b200voc import GANConfig, Generator
+    ocfg = O.OracleConfig(use_attention=False)
+    ora = O.make_generator(ocfg, seed=1234)
+    gen = Generator(GANConfig(use_attention=False)).eval()
+    gen.load_state_dict(ora.state_dict())
+    return ocfg, ora, gen.cuda()
+
+
+def test_time_major_mel_is_bit_identical(models):
+    _, _, gen = models
+    mel, pros, sty, emo = [x.cuda() for x in O.synthetic_inputs(3, 37, seed=5)]
+    with torch.no_grad():
+        a = gen(mel, pros, sty, emo).clone()
+        b = gen(mel.transpose(1, 2).contiguous(), pros, sty, emo, mel_layout="BTC").clone()
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        gen(mel, pros, sty, emo, mel_layout="BTC")          # channels on the wrong axis
+
+
+def test_pcm16_output_and_length_mask(models):
+    ocfg, ora, gen = models
+    B, T = 4, 40
+    mel, pros, sty, emo = O.synthetic_inputs(B, T, seed=6)
+    lens = torch.tensor([40, 17, 1, 33])
+    with torch.no_grad():
+        f32 = gen(mel.cuda(), pros.cuda(), sty.cuda(), emo.cuda()).clone()
+        pcm = gen(mel.cuda(), pros.cuda(), sty.cuda(), emo.cuda(), out_dtype=torch.int16).clone()
+        msk = gen(mel.cuda(), pros.cuda(), sty.cuda(), emo.cuda(), frame_lengths=lens.cuda()).clone()
+        both = gen(mel.cuda(), pros.cuda(), sty.cuda(), emo.cuda(), out_dtype=torch.int16, frame_lengths=lens).clone()
+        ref = O.generator_forward(ora.state_dict(), ocfg, mel, pros, sty, emo)
+    assert pcm.dtype == torch.int16 and pcm.shape == f32.shape
+    assert torch.equal(pcm.cpu(), O.pcm16(f32.cpu()))                       # same rounding as the oracle's wire format
+    assert int((pcm.cpu().int() - O.pcm16(ref).int()).abs().max()) <= 34     # 1e-3 * 32767 + rounding
+    for b in range(B):
+        n = int(lens[b]) * 256
+        assert torch.equal(msk[b, 0, :n], f32[b, 0, :n])
+        assert not bool(msk[b, 0, n:].any())
+        assert torch.equal(both[b, 0, :n], pcm[b, 0, :n]) and not bool(both[b, 0, n:].any())

@@ -112,3 +112,23 @@ def test_emulated_fp16_plan_meets_gate():
         ref = O.generator_forward(sd, cfg, mel, pros, sty, emo)
         y = E.emulated_forward(sd, cfg, mel, pros, sty, emo, E.PLANS["fp16"])
     assert float((y - ref).abs().max()) <= 1e-3 and O.snr_db(ref, y) >= 40.0
+
+
+def test_gst_restatement_matches_reference_golden(golden_dir):
+    """GlobalStyleTokens (vocoder7/gst.py): golden made by the reference class itself."""
+    gold = np.load(os.path.join(golden_dir, "gst_b3_t150.npz"))
+    sd = {k[3:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("sd.")}
+    seeded = O.make_gst_state(seed=1234)
+    assert list(seeded.keys()) == ["tokens", "attn_conv.0.weight", "attn_conv.0.bias", "attn_conv.2.weight",
+                                   "attn_conv.2.bias"]
+    for k in seeded:
+        assert torch.equal(seeded[k], sd[k]), k
+    y = O.gst_forward(sd, torch.from_numpy(gold["mel"]))
+    assert float((y - torch.from_numpy(gold["style"])).abs().max()) <= 1e-6
+    # the reference's softmax runs over the axis the einsum sums over: the style is sum_n tokens[n]
+    assert float((y - sd["tokens"].sum(0)).abs().max()) <= 1e-5
+
+
+def test_pcm16_wire_format():
+    w = torch.tensor([-1.5, -1.0, -0.5, 0.0, 0.25, 0.99999, 1.0, 2.0, 1.5 / 32767.0, 2.5 / 32767.0])
+    assert O.pcm16(w).tolist() == [-32767, -32767, -16384, 0, 8192, 32767, 32767, 32767, 2, 2]

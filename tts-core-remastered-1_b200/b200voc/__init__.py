@@ -3,8 +3,9 @@ ChiefTriston/TTS-Core-Remastered-1: Generator inference and the STFT / mel / iST
 behind the reference's Python API.  See DESIGN.md."""
 from .config import GANConfig
 from .generator import Generator, ResidualBlock, SelfAttention
+from .gst import GlobalStyleTokens
 from .stft import LearnableSTFT, STFTLoss, stft, istft, mel_spectrogram, log_mel, stft_magnitude
 from . import _lib
 
-__all__ = ["GANConfig", "Generator", "ResidualBlock", "SelfAttention", "LearnableSTFT", "STFTLoss", "stft", "istft",
+__all__ = ["GANConfig", "Generator", "GlobalStyleTokens", "ResidualBlock", "SelfAttention", "LearnableSTFT", "STFTLoss", "stft", "istft",
            "mel_spectrogram", "log_mel", "stft_magnitude"]

@@ -25,6 +25,13 @@ class GenConfig(C.Structure):
     ]
 
 
+class GenIO(C.Structure):
+    """b200voc_gen_io (include/b200voc.h): wire formats either side of Generator.forward."""
+    _fields_ = [("mel_time_major", C.c_int32), ("out_format", C.c_int32), ("valid_samples", C.c_void_p),
+                ("reserved", C.c_int32 * 4)]
+
+
+OUT_F32, OUT_PCM16 = 0, 1
 _P, _I, _I64, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _SIGNATURES = {
     "b200voc_version": (C.c_int, []),
@@ -38,6 +45,10 @@ _SIGNATURES = {
     "b200voc_gen_finalize": (C.c_int, [_P]),
     "b200voc_gen_workspace_bytes": (_I64, [_P, _I, _I]),
     "b200voc_gen_forward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _I64, C.c_char_p, _P, _P]),
+    "b200voc_gen_forward_ex": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, C.POINTER(GenIO), _P, _P, _I64,
+                                         C.c_char_p, _P, _P]),
+    "b200voc_gst_scratch_bytes": (_I64, [_I, _I, _I]),
+    "b200voc_gst_forward": (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "b200voc_gen_launch_count": (C.c_int, [_P]),
     "b200voc_gen_profile_enable": (C.c_int, [_P, _I]),
     "b200voc_gen_profile_count": (C.c_int, [_P]),

@@ -156,13 +156,28 @@ class Generator(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, mel: torch.Tensor, prosody: torch.Tensor, style: torch.Tensor, emotion: torch.Tensor,
                 style_drop: bool = False, emo_drop: bool = False, w_style: float = 1.0, w_emo: float = 1.0,
-                *, out: Optional[torch.Tensor] = None, _tap: Optional[str] = None) -> torch.Tensor:
+                *, out: Optional[torch.Tensor] = None, _tap: Optional[str] = None, mel_layout: str = "BCT",
+                out_dtype: torch.dtype = torch.float32, frame_lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
         """mel[B,channels,T], prosody[B,T,18], style[B,style_dim], emotion[B,6] -> wav[B,1,hop*T]
-        (generator.py:50-98)."""
+        (generator.py:50-98).
+
+        Keyword-only extras are the wire formats either side of the path (none changes the math):
+        ``mel_layout="BTC"`` takes the mel as the refiner / acoustic model emit it, [B,T,channels]
+        (sde_refiner5/model.py:304-306; vocoder7/trainer.py:77 transposes on the host -- here the
+        transpose is folded into the first kernel's load); ``out_dtype=torch.int16`` writes 16-bit
+        PCM ``round(clamp(wav,-1,1)*32767)``; ``frame_lengths[B]`` (valid mel frames of a padded
+        batch, the collator's frame_length, batching2/colate.py:140-146) zeroes every sample at or
+        past ``hop*frame_lengths[b]``."""
         _lib.require_cuda(mel, prosody, style, emotion)
-        if mel.dim() != 3 or mel.shape[1] != self.cfg.channels:
-            raise ValueError(f"mel must be [B,{self.cfg.channels},T], got {tuple(mel.shape)}")
-        B, _, T = mel.shape
+        if mel_layout not in ("BCT", "BTC"):
+            raise ValueError(f"mel_layout must be 'BCT' or 'BTC', got {mel_layout!r}")
+        if out_dtype not in (torch.float32, torch.int16):
+            raise ValueError(f"out_dtype must be torch.float32 or torch.int16, got {out_dtype}")
+        ch_axis = 1 if mel_layout == "BCT" else 2
+        if mel.dim() != 3 or mel.shape[ch_axis] != self.cfg.channels:
+            want = f"[B,{self.cfg.channels},T]" if mel_layout == "BCT" else f"[B,T,{self.cfg.channels}]"
+            raise ValueError(f"mel must be {want}, got {tuple(mel.shape)}")
+        B, T = mel.shape[0], mel.shape[3 - ch_axis]
         if tuple(prosody.shape) != (B, T, 18):
             raise ValueError(f"prosody must be [B,T,18]=({B},{T},18), got {tuple(prosody.shape)}")
         if tuple(style.shape) != (B, self.cfg.style_dim):
@@ -175,7 +190,19 @@ class Generator(nn.Module):
             f32 = lambda t: t.detach().to(torch.float32).contiguous()
             mel_, pros_, sty_, emo_ = f32(mel), f32(prosody), f32(style), f32(emotion)
             if out is None:
-                out = torch.empty(B, 1, self.hop * T, device=mel.device, dtype=torch.float32)
+                out = torch.empty(B, 1, self.hop * T, device=mel.device, dtype=out_dtype)
+            elif out.dtype != out_dtype or out.numel() != B * self.hop * T or not out.is_contiguous():
+                raise ValueError("out must be a contiguous tensor of B*hop*T elements of dtype out_dtype")
+            io = _lib.GenIO()
+            io.mel_time_major = int(mel_layout == "BTC")
+            io.out_format = _lib.OUT_PCM16 if out_dtype == torch.int16 else _lib.OUT_F32
+            valid = None
+            if frame_lengths is not None:
+                if tuple(frame_lengths.shape) != (B,):
+                    raise ValueError(f"frame_lengths must be [B]=({B},), got {tuple(frame_lengths.shape)}")
+                valid = (frame_lengths.to(device=mel.device, dtype=torch.int64) * self.hop).clamp_(0, self.hop * T)
+                valid = valid.to(torch.int32).contiguous()
+            io.valid_samples = _lib.ptr(valid)
             need = self.workspace_bytes(B, T)
             ws = self._workspace
             if ws is None or ws.numel() < need or ws.device != mel.device:
@@ -184,9 +211,9 @@ class Generator(nn.Module):
             tap_out = None
             if _tap is not None:
                 tap_out = torch.empty(self._tap_numel(_tap, B, T), device=mel.device, dtype=torch.float32)
-            _lib.check(lib.b200voc_gen_forward(
+            _lib.check(lib.b200voc_gen_forward_ex(
                 h, _lib.ptr(mel_), _lib.ptr(pros_), _lib.ptr(sty_), _lib.ptr(emo_), B, T, int(style_drop),
-                int(emo_drop), float(w_style), float(w_emo), _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                int(emo_drop), float(w_style), float(w_emo), C.byref(io), _lib.ptr(out), _lib.ptr(ws), ws.numel(),
                 _tap.encode() if _tap else None, _lib.ptr(tap_out), _lib.current_stream()), "gen_forward")
         if _tap is not None:
             return out, tap_out

@@ -99,9 +99,13 @@ int style_emo_launch(const float*, const float*, const float*, const float*, con
 int cond_launch(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int,
                 int, float*, cudaStream_t);
 int film_launch(const float*, const float*, const float*, int, int, float*, cudaStream_t);
-int band_split_launch(const float*, const float*, const float*, int, int, int, int, int, int, void*, cudaStream_t);
+int band_split_launch(const float*, const float*, const float*, int, int, int, int, int, int, int, void*, cudaStream_t);
 int pack_split_launch(const float*, int, int, float*, cudaStream_t);
-int band_merge_launch(const void*, const float*, const float*, int, int, int, int, int, float*, cudaStream_t);
+int band_merge_launch(const void*, const float*, const float*, int, int, int, int, int, int, const int*, void*, cudaStream_t);
+long long gst_scratch_floats(int B, int T, int nt);
+int gst_launch(const float* mel, int time_major, int B, int T, int channels, int sd, int nt, const float* w0,
+               const float* b0, const float* w1, const float* b1, const float* tokens, float* scratch, float* style,
+               cudaStream_t st);
 int tap_extract_launch(const void*, int, int, int, int, int, float*, cudaStream_t);
 int copy_f32_launch(const float*, float*, long long, float add, cudaStream_t, float mul = 1.0f);
 int cvt16_launch(const float*, void*, long long, int, cudaStream_t, float mul = 1.0f);
@@ -467,6 +471,19 @@ int b200voc_gen_forward(b200voc_gen* g, const float* mel, const float* prosody, 
                         const float* emotion, int B, int T, int style_drop, int emo_drop, float w_style,
                         float w_emo, float* wav_out, void* workspace, int64_t workspace_bytes,
                         const char* tap_name, float* tap_out, void* stream) {
+  return b200voc_gen_forward_ex(g, mel, prosody, style, emotion, B, T, style_drop, emo_drop, w_style, w_emo, nullptr,
+                                wav_out, workspace, workspace_bytes, tap_name, tap_out, stream);
+}
+
+int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosody, const float* style,
+                           const float* emotion, int B, int T, int style_drop, int emo_drop, float w_style,
+                           float w_emo, const b200voc_gen_io* io, void* wav_out, void* workspace,
+                           int64_t workspace_bytes, const char* tap_name, float* tap_out, void* stream) {
+  const int mel_time_major = io ? io->mel_time_major : 0;
+  const int pcm16 = io ? io->out_format == B200VOC_OUT_PCM16 : 0;
+  const int* valid_samples = io ? io->valid_samples : nullptr;
+  B200_CHECK_ARG(!io || io->out_format == B200VOC_OUT_F32 || io->out_format == B200VOC_OUT_PCM16,
+                 "gen_forward: unknown out_format %d", io ? io->out_format : 0);
   B200_CHECK_ARG(g && mel && prosody && style && emotion && wav_out && workspace, "gen_forward: null argument");
   B200_CHECK_ARG(B > 0 && T > 0, "gen_forward: empty batch (B=%d, T=%d)", B, T);
   if (!g->finalized) {
@@ -535,7 +552,7 @@ int b200voc_gen_forward(b200voc_gen* g, const float* mel, const float* prosody, 
   int cur = 0;
   RUN("band_split", 2.0 * dBT * nb * g->band_size * 7 * g->H, dBT * (g->cfg.channels * 4 + nb * g->H * 2.0),
       band_split_launch(mel, g->split_wt, g->split_b, B, g->cfg.channels, g->band_size, T, g->H, g->stages[0].fmt,
-                        act[cur], st));
+                        mel_time_major, act[cur], st));
   if (tap == "split" && tap_out) B200_TRY(tap_extract_launch(act[cur], N, T, g->H, g->stages[0].fmt, 0, tap_out, st));
 
   int L = T;
@@ -581,7 +598,8 @@ int b200voc_gen_forward(b200voc_gen* g, const float* mel, const float* prosody, 
   }
   const StageW& last = g->stages.back();
   RUN("band_merge", 2.0 * B * (double)L * nb * last.Cout * 7, (double)N * L * last.Cout * 2 + (double)B * L * 4,
-      band_merge_launch(act[cur], g->merge_w, g->merge_b, B, nb, L, last.Cout, last.fmt, wav_out, st));
+      band_merge_launch(act[cur], g->merge_w, g->merge_b, B, nb, L, last.Cout, last.fmt, pcm16, valid_samples, wav_out,
+                        st));
 #undef RUN
   g->launches = launches;
   return B200VOC_OK;
@@ -643,6 +661,21 @@ int b200voc_resblock(const void* a16, const void* w_packed, const float* b_conv,
   B200_CHECK_ARG(a16 && w_packed && b_conv && b_proj && film && out16, "resblock: null argument");
   return resblock_launch(a16, w_packed, b_conv, b_proj, film, 2 * C, N, L, C, dilation, T, num_bands, fmt, fmt, store_lrelu,
                          out16, reinterpret_cast<cudaStream_t>(stream));
+}
+/* GlobalStyleTokens.forward (vocoder7/gst.py:24-35) */
+int64_t b200voc_gst_scratch_bytes(int B, int T, int num_tokens) {
+  return (B > 0 && T > 0 && num_tokens > 0) ? gst_scratch_floats(B, T, num_tokens) * 4 : 0;
+}
+int b200voc_gst_forward(const float* mel, int mel_time_major, int B, int T, int channels, int style_dim,
+                        int num_tokens, const float* conv0_w, const float* conv0_b, const float* conv2_w,
+                        const float* conv2_b, const float* tokens, void* scratch, int64_t scratch_bytes,
+                        float* style_out, void* stream) {
+  B200_CHECK_ARG(mel && conv0_w && conv0_b && conv2_w && conv2_b && tokens && scratch && style_out,
+                 "gst_forward: null argument");
+  B200_CHECK_ARG(B > 0 && T > 0, "gst_forward: empty batch (B=%d, T=%d)", B, T);
+  B200_CHECK_ARG(scratch_bytes >= b200voc_gst_scratch_bytes(B, T, num_tokens), "gst_forward: scratch too small");
+  return gst_launch(mel, mel_time_major, B, T, channels, style_dim, num_tokens, conv0_w, conv0_b, conv2_w, conv2_b,
+                    tokens, reinterpret_cast<float*>(scratch), style_out, reinterpret_cast<cudaStream_t>(stream));
 }
 int b200voc_debug_set_trace(int64_t* dev_buf) {
   b200::g_rb2_trace = reinterpret_cast<long long*>(dev_buf);

@@ -83,8 +83,10 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   float* sPar = reinterpret_cast<float*>(smem + K::OFF_PAR);   // [ba | bg/2 | b2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kE1Threads = 128;                       // one chunk-parity set (4 warps)
-  constexpr int kE2Threads = K::INPLACE ? 128 : 256;     // tile-parity set, or all 8 warps (C=256)
+  // multi-thread barriers are arrived on once per WARP (fence, __syncwarp, lane 0): a 128-arrival
+  // barrier wakes the waiting MMA issuer ~25 times per phase (measured in resblock2.cu)
+  constexpr int kE1Warps = 4;                           // one chunk-parity set (4 warps)
+  constexpr int kE2Warps = K::INPLACE ? 4 : 8;          // tile-parity set, or all 8 warps (C=256)
 
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     sPar[i] = p.b_conv[i];
@@ -98,9 +100,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmOut);
     for (int b = 0; b < NA; ++b) { mbar_init(&a_full[b], 1); mbar_init(&a_empty[b], 1); }
     for (int b = 0; b < NW; ++b) { mbar_init(&w_full[b], 1); mbar_init(&w_empty[b], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&d1_full[b], 1); mbar_init(&d1_empty[b], kE1Threads); }
-    for (int b = 0; b < KPT; ++b) { mbar_init(&h_full[b], kE1Threads); mbar_init(&h_empty[b], 1); }
-    for (int b = 0; b < ND2; ++b) { mbar_init(&d2_full[b], 1); mbar_init(&d2_empty[b], kE2Threads); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&d1_full[b], 1); mbar_init(&d1_empty[b], kE1Warps); }
+    for (int b = 0; b < KPT; ++b) { mbar_init(&h_full[b], kE1Warps); mbar_init(&h_empty[b], 1); }
+    for (int b = 0; b < ND2; ++b) { mbar_init(&d2_full[b], 1); mbar_init(&d2_empty[b], kE2Warps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, K::TMEM_COLS);
@@ -296,8 +298,11 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         tc_fence_before();
         fence_proxy_async_smem();
-        mbar_arrive(&h_full[j]);
-        mbar_arrive(&d1_empty[b]);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&h_full[j]);
+          mbar_arrive(&d1_empty[b]);
+        }
       }
     }
   } else if (K::INPLACE) {
@@ -347,8 +352,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&d2_empty[db]);
       fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d2_empty[db]);
       named_bar_sync(1 + par, 128);
       if (q == 0 && lane == 0) {
 #pragma unroll
@@ -412,7 +418,8 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&d2_empty[db]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d2_empty[db]);
     }
   }
   tc_fence_before();

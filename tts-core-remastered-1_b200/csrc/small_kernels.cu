@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) film_sgemm_kernel(const float* __restrict
 constexpr int kSplitTT = 32;
 __global__ void __launch_bounds__(256) band_split_kernel(const float* __restrict__ mel, const float* __restrict__ wt,
                                                          const float* __restrict__ bias, int B, int channels,
-                                                         int band_size, int T, int H, int fmt,
+                                                         int band_size, int T, int H, int fmt, int time_major,
                                                          uint16_t* __restrict__ out) {
   extern __shared__ float s_mel[];   // [band_size][kSplitTT + 8]
   constexpr int W = kSplitTT + 8;
@@ -141,7 +141,11 @@ __global__ void __launch_bounds__(256) band_split_kernel(const float* __restrict
   for (int i = threadIdx.x; i < band_size * W; i += blockDim.x) {
     const int ci = i / W, tt = i % W;
     const int t = t0 + tt - 3;
-    s_mel[i] = (t >= 0 && t < T && tt < kSplitTT + 6) ? mel[((long long)b * channels + band * band_size + ci) * T + t] : 0.f;
+    // time_major: mel is [B, T, channels] (the refiner / acoustic output layout, sde_refiner5/model.py:304-306;
+    // vocoder7/trainer.py:77 transposes it on the host) -- the transpose is folded into this load
+    const long long src = time_major ? ((long long)b * T + t) * channels + band * band_size + ci
+                                     : ((long long)b * channels + band * band_size + ci) * T + t;
+    s_mel[i] = (t >= 0 && t < T && tt < kSplitTT + 6) ? mel[src] : 0.f;
   }
   __syncthreads();
   const float* wb = wt + (long long)band * band_size * 7 * H;
@@ -182,10 +186,13 @@ __global__ void pack_split_kernel(const float* __restrict__ w, int band_size, in
 // registers, slides over the 38 input rows (each warp load = four full 64-byte rows, one per band)
 // accumulating 32 partial outputs, then a 5-stage transpose-reduce leaves output j in lane j
 // (31 shuffles per 32 outputs), tanh, one coalesced 128-byte store.  HBM-bound by design.
-template <int FMT>
+// Output formats (the wire formats after the path): fp32 in (-1, 1), or 16-bit PCM
+// round(clamp(wav, -1, 1) * 32767).  `valid` (optional, [B]) = number of valid samples per utterance
+// (hop * frame_length from the collator, batching2/colate.py:140-146,184-191): the padded tail is zeroed.
+template <int FMT, int PCM16>
 __global__ void __launch_bounds__(256) band_merge_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, int B, int L,
-                                                         float* __restrict__ wav) {
+                                                         const int* __restrict__ valid, void* __restrict__ wav_out) {
   constexpr int CB = 32, NB = 4;
   const int lane = threadIdx.x & 31;
   const int tiles = (L + 31) / 32;
@@ -234,7 +241,16 @@ __global__ void __launch_bounds__(256) band_merge_kernel(const uint16_t* __restr
     }
   }
   const int l = l0 + lane;
-  if (l < L) wav[(long long)b * L + l] = tanhf(p[0] + __ldg(bias));
+  if (l < L) {
+    float y = tanhf(p[0] + __ldg(bias));
+    if (valid != nullptr && l >= __ldg(valid + b)) y = 0.f;
+    if (PCM16) {
+      const float c = fminf(fmaxf(y, -1.f), 1.f) * 32767.f;
+      reinterpret_cast<int16_t*>(wav_out)[(long long)b * L + l] = (int16_t)__float2int_rn(c);
+    } else {
+      reinterpret_cast<float*>(wav_out)[(long long)b * L + l] = y;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ helpers
@@ -296,10 +312,10 @@ int film_launch(const float* cond, const float* w_all, const float* b_all, int M
   return B200VOC_OK;
 }
 int band_split_launch(const float* mel, const float* wt, const float* bias, int B, int channels, int band_size, int T,
-                      int H, int fmt, void* out16, cudaStream_t st) {
+                      int H, int fmt, int time_major, void* out16, cudaStream_t st) {
   dim3 grid(ceil_div(T, kSplitTT), channels / band_size, B);
   size_t smem = (size_t)band_size * (kSplitTT + 8) * sizeof(float);
-  band_split_kernel<<<grid, 256, smem, st>>>(mel, wt, bias, B, channels, band_size, T, H, fmt,
+  band_split_kernel<<<grid, 256, smem, st>>>(mel, wt, bias, B, channels, band_size, T, H, fmt, time_major,
                                              reinterpret_cast<uint16_t*>(out16));
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
@@ -310,14 +326,18 @@ int pack_split_launch(const float* w, int band_size, int H, float* wt_band, cuda
   return B200VOC_OK;
 }
 int band_merge_launch(const void* x16, const float* w, const float* bias, int B, int nb, int L, int Cb, int fmt,
-                      float* wav, cudaStream_t st) {
+                      int pcm16, const int* valid, void* wav, cudaStream_t st) {
   B200_CHECK_ARG(Cb == 32 && nb == 4, "band_merge: %d bands x %d channels unsupported (4 x 32)", nb, Cb);
   const long long warps = (long long)B * ceil_div(L, 32);
   const int grid = (int)((warps + 7) / 8);
-  if (fmt == 0)
-    band_merge_kernel<0><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(x16), w, bias, B, L, wav);
-  else
-    band_merge_kernel<1><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(x16), w, bias, B, L, wav);
+  const uint16_t* x = reinterpret_cast<const uint16_t*>(x16);
+  if (fmt == 0) {
+    if (pcm16) band_merge_kernel<0, 1><<<grid, 256, 0, st>>>(x, w, bias, B, L, valid, wav);
+    else band_merge_kernel<0, 0><<<grid, 256, 0, st>>>(x, w, bias, B, L, valid, wav);
+  } else {
+    if (pcm16) band_merge_kernel<1, 1><<<grid, 256, 0, st>>>(x, w, bias, B, L, valid, wav);
+    else band_merge_kernel<1, 0><<<grid, 256, 0, st>>>(x, w, bias, B, L, valid, wav);
+  }
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
@@ -334,6 +354,121 @@ int copy_f32_launch(const float* src, float* dst, long long n, float add, cudaSt
 }
 int cvt16_launch(const float* src, void* dst, long long n, int fmt, cudaStream_t st, float mul) {
   cvt16_kernel<<<grid_for(n), 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(dst), n, fmt, mul);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
+
+// ------------------------------------------------------------------ GlobalStyleTokens (vocoder7/gst.py:16-35)
+// logits[b, n, t] = W1 relu(conv3(mel))[.., t] + b1; weights = softmax over t; style[b, :] =
+// sum_n sum_t weights[b, n, t] * tokens[n, :].  (Because the softmax runs over the same axis the
+// einsum sums over, sum_t weights = 1 and the reference's style is sum_n tokens[n] up to fp32
+// rounding -- reproduced here as it is written, not simplified.)
+// Pass 1: one CTA per (64-frame chunk, utterance): hidden = relu(conv) for its frames, the 10 token
+// logits per frame, and per token the chunk's online-softmax partial (max, sum exp).  Pass 2 combines.
+constexpr int kGstTT = 64;
+__global__ void __launch_bounds__(128) gst_partial_kernel(const float* __restrict__ mel, int time_major, int B, int T,
+                                                          int channels, int sd, int nt, const float* __restrict__ w0,
+                                                          const float* __restrict__ b0, const float* __restrict__ w1,
+                                                          const float* __restrict__ b1, float* __restrict__ part) {
+  extern __shared__ float sm[];
+  float* s_mel = sm;                               // [channels][kGstTT + 2]
+  float* s_hid = sm + channels * (kGstTT + 2);     // [kGstTT][sd + 1]
+  float* s_log = s_hid + kGstTT * (sd + 1);        // [nt][kGstTT]
+  constexpr int W = kGstTT + 2;
+  const int t0 = blockIdx.x * kGstTT, b = blockIdx.y;
+  for (int i = threadIdx.x; i < channels * W; i += blockDim.x) {
+    const int ci = i / W, t = t0 + i % W - 1;
+    const long long src = time_major ? ((long long)b * T + t) * channels + ci : ((long long)b * channels + ci) * T + t;
+    s_mel[i] = (t >= 0 && t < T) ? mel[src] : 0.f;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < sd; d += blockDim.x) {
+    float acc[kGstTT];
+    const float bv = b0[d];
+#pragma unroll
+    for (int i = 0; i < kGstTT; ++i) acc[i] = bv;
+    for (int ci = 0; ci < channels; ++ci)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float w = __ldg(w0 + ((long long)d * channels + ci) * 3 + k);
+        const float* m = s_mel + ci * W + k;
+#pragma unroll
+        for (int i = 0; i < kGstTT; ++i) acc[i] = fmaf(w, m[i], acc[i]);
+      }
+#pragma unroll
+    for (int i = 0; i < kGstTT; ++i) s_hid[i * (sd + 1) + d] = fmaxf(acc[i], 0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nt * kGstTT; i += blockDim.x) {
+    const int n = i / kGstTT, tt = i % kGstTT;
+    float a = b1[n];
+    for (int d = 0; d < sd; ++d) a = fmaf(__ldg(w1 + n * sd + d), s_hid[tt * (sd + 1) + d], a);
+    s_log[i] = (t0 + tt < T) ? a : -INFINITY;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int n = warp; n < nt; n += blockDim.x >> 5) {
+    float m = -INFINITY;
+    for (int tt = lane; tt < kGstTT; tt += 32) m = fmaxf(m, s_log[n * kGstTT + tt]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int tt = lane; tt < kGstTT; tt += 32) sum += expf(s_log[n * kGstTT + tt] - m);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) {
+      float* dst = part + (((long long)b * gridDim.x + blockIdx.x) * nt + n) * 2;
+      dst[0] = m;
+      dst[1] = sum;
+    }
+  }
+}
+__global__ void __launch_bounds__(128) gst_combine_kernel(const float* __restrict__ part, int chunks, int sd, int nt,
+                                                          const float* __restrict__ tokens, float* __restrict__ style) {
+  __shared__ float s_r[64];
+  const int b = blockIdx.x;
+  for (int n = threadIdx.x; n < nt; n += blockDim.x) {
+    float M = -INFINITY;
+    for (int c = 0; c < chunks; ++c) M = fmaxf(M, part[(((long long)b * chunks + c) * nt + n) * 2]);
+    float Z = 0.f;
+    for (int c = 0; c < chunks; ++c) {
+      const float* q = part + (((long long)b * chunks + c) * nt + n) * 2;
+      Z += q[1] * expf(q[0] - M);
+    }
+    // sum_t softmax_t: each chunk contributes (its sum of exponentials) / Z
+    float r = 0.f;
+    for (int c = 0; c < chunks; ++c) {
+      const float* q = part + (((long long)b * chunks + c) * nt + n) * 2;
+      r += q[1] * expf(q[0] - M) / Z;
+    }
+    s_r[n] = r;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < sd; d += blockDim.x) {
+    float a = 0.f;
+    for (int n = 0; n < nt; ++n) a = fmaf(s_r[n], __ldg(tokens + n * sd + d), a);
+    style[(long long)b * sd + d] = a;
+  }
+}
+long long gst_scratch_floats(int B, int T, int nt) { return (long long)B * ceil_div(T, kGstTT) * nt * 2; }
+int gst_launch(const float* mel, int time_major, int B, int T, int channels, int sd, int nt, const float* w0,
+               const float* b0, const float* w1, const float* b1, const float* tokens, float* scratch, float* style,
+               cudaStream_t st) {
+  B200_CHECK_ARG(nt >= 1 && nt <= 64 && sd >= 1 && channels >= 1, "gst: bad sizes (tokens %d, style_dim %d)", nt, sd);
+  const int chunks = ceil_div(T, kGstTT);
+  const size_t smem = ((size_t)channels * (kGstTT + 2) + (size_t)kGstTT * (sd + 1) + (size_t)nt * kGstTT) * sizeof(float);
+  B200_CHECK_ARG(smem <= 200 * 1024, "gst: style_dim %d / channels %d too large", sd, channels);
+  static bool configured[16] = {};
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 15]) {
+    B200_CUDA(cudaFuncSetAttribute(gst_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured[dev & 15] = true;
+  }
+  gst_partial_kernel<<<dim3(chunks, B), 128, smem, st>>>(mel, time_major, B, T, channels, sd, nt, w0, b0, w1, b1, scratch);
+  B200_CUDA(cudaGetLastError());
+  gst_combine_kernel<<<B, 128, 0, st>>>(scratch, chunks, sd, nt, tokens, style);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
