@@ -198,6 +198,42 @@ def secondary_measurements(dev, dev_in, B, T):
     except Exception as e:  # keep the headline line even if the secondary run fails
         out["with_attention"] = {"error": str(e)[:200]}
     try:
+        # callers / wire formats either side of the path: GlobalStyleTokens on the
+        # time-major mel, Generator fed the same time-major mel, 16-bit PCM out with a length mask
+        from b200voc import GlobalStyleTokens
+        torch.manual_seed(1234)
+        gst = GlobalStyleTokens(GANConfig()).eval().to(dev)
+        gen_f = Generator(GANConfig(use_attention=False)).eval().to(dev)
+        mel_btc = dev_in[0].transpose(1, 2).contiguous()
+        lens = torch.full((B,), T, device=dev, dtype=torch.int32)
+        pcm = torch.empty(B, 1, HOP * T, device=dev, dtype=torch.int16)
+
+        def pipeline():
+            style = gst(mel_btc, mel_layout="BTC")
+            return gen_f(mel_btc, dev_in[1], style, dev_in[3], mel_layout="BTC", out_dtype=torch.int16,
+                         frame_lengths=lens, out=pcm)
+        with torch.no_grad():
+            for _ in range(2):
+                pipeline()
+            torch.cuda.synchronize()
+            a, b_, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            for _ in range(5):
+                gst(mel_btc, mel_layout="BTC")
+            b_.record()
+            for _ in range(5):
+                pipeline()
+            c.record()
+            torch.cuda.synchronize()
+        out["frontend"] = {
+            "gst_ms": a.elapsed_time(b_) / 5, "gst_mel_bytes": int(mel_btc.numel() * 4),
+            "mel_btc_gst_generator_pcm16": {"ms_per_step": b_.elapsed_time(c) / 5,
+                                             "value": B * HOP * T / SR / (b_.elapsed_time(c) / 5 / 1e3), "unit": UNIT},
+            "note": "GlobalStyleTokens (vocoder7/gst.py) + Generator on [B,T,80] mels, int16 PCM out, length mask"}
+        del gst, gen_f
+    except Exception as e:
+        out["frontend"] = {"error": str(e)[:200]}
+    try:
         Bw, Nw = 1024, 88200
         x = torch.rand(Bw, Nw, device=dev) * 2 - 1
         res = {}

@@ -12,6 +12,8 @@
 //     k-block j of GEMM2's A operand; GEMM2's k-block j is issued one chunk later, the last
 //     one after the first chunk of the NEXT tile, so the tensor pipe never waits for an epilogue;
 //   * the residual/store epilogue (8 more warps) drains D2 while the next tile's GEMM1 runs.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -26,7 +28,14 @@ struct Resblock3Params {
   const float* film;     // [B, T, film_stride]
   int film_stride;
   uint16_t* out;         // [N, L, C]
+  int dbg;               // knock-out experiment switches, only with -DB200VOC_TRACE (B200VOC_DBG)
 };
+
+#ifdef B200VOC_TRACE
+#define RB3_DBG(bit) (p.dbg & (bit))
+#else
+#define RB3_DBG(bit) false
+#endif
 
 template <int C>
 struct Rb3Cfg {
@@ -41,7 +50,7 @@ struct Rb3Cfg {
   static constexpr int NA = C == 128 ? 3 : 1;
   static constexpr int H_KB_BYTES = 128 * 128;       // 16 KB per k-block
   static constexpr int W_TILE = 128 * 128;           // 16 KB ring slot: [128 rows x 64 k]
-  static constexpr int NW = 4;
+  static constexpr int NW = 5;                       // 5 x 16 KB in flight: covers the L2 -> SMEM round trip of the weight stream
   static constexpr int ND2 = C == 128 ? 2 : 1;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_H = OFF_A + NA * A_BYTES;
@@ -119,6 +128,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       auto w_slot = [&]() -> uint8_t* {
         const int s = wi % NW;
         mbar_wait(&w_empty[s], ((wi / NW) & 1) ^ 1);
+        if (RB3_DBG(4) && wi >= NW) { mbar_arrive(&w_full[s]); return nullptr; }
         mbar_expect_tx(&w_full[s], K::W_TILE);
         return sW + s * K::W_TILE;
       };
@@ -127,6 +137,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int seq = tile / p.tiles_per_seq, l0 = (tile - seq * p.tiles_per_seq) * 128;
         const int ab = it % NA;
         mbar_wait(&a_empty[ab], ((it / NA) & 1) ^ 1);
+        if (RB3_DBG(16) && it >= NA) { mbar_arrive(&a_full[ab]); return; }
         mbar_expect_tx(&a_full[ab], K::A_BYTES);
         for (int kb = 0; kb < KPT; ++kb)
           tma_load_3d(sA + ab * K::A_BYTES + kb * K::A_KB_BYTES, &tmX, &a_full[ab], kb * 64, l0 - K::HALO, seq);
@@ -134,7 +145,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       auto load_w2 = [&](int kb) {
         for (int half = 0; half < NH; ++half) {
           uint8_t* dst = w_slot();
-          tma_load_2d(dst, &tmW2, &w_full[wi % NW], kb * 64, half * 128);
+          if (dst) tma_load_2d(dst, &tmW2, &w_full[wi % NW], kb * 64, half * 128);
           ++wi;
         }
       };
@@ -145,7 +156,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int tap = 0; tap < 3; ++tap)
             for (int kb = 0; kb < KPT; ++kb) {
               uint8_t* dst = w_slot();
-              tma_load_2d(dst, &tmW1, &w_full[wi % NW], tap * C + kb * 64, j * 128);
+              if (dst) tma_load_2d(dst, &tmW1, &w_full[wi % NW], tap * C + kb * 64, j * 128);
               ++wi;
             }
           if (j == K::A_PREFETCH_AFTER_CHUNK && it + 1 < n_my_tiles) load_a(it + 1);
@@ -184,6 +195,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int s = acquire_w();
           const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + s * K::W_TILE));
           if (elect_one()) {
+            if (!RB3_DBG(8))
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_f16(tmem_base + K::D2_COL + db * C + half * 128, a_desc + 2 * k, b_desc + 2 * k, idesc,
@@ -219,6 +231,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               const uint64_t a_desc = make_kmajor_desc<128>(a_addr);
               const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + s * K::W_TILE));
               if (elect_one()) {
+                if (!RB3_DBG(32))
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   umma_f16(tmem_base + b * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, (tap | kb | k) != 0);
@@ -262,6 +275,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(&h_empty[j], (it & 1) ^ 1);
         tc_fence_after();
         uint8_t* hrow = sH + j * K::H_KB_BYTES + row * 128;
+        if (!RB3_DBG(1))
 #pragma unroll
         for (int cl = 0; cl < 64; cl += 16) {   // column inside the chunk's 64 value channels
           uint32_t va[16], vg[16];
@@ -321,6 +335,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_wait(&d2_full[db], (it / ND2) & 1);
       tc_fence_after();
       uint8_t* abase = sA + ab * K::A_BYTES + (row + K::HALO) * 128;
+      if (!RB3_DBG(2))
 #pragma unroll 2
       for (int c0 = 0; c0 < C; c0 += 16) {
         uint32_t vd[16];
@@ -454,6 +469,10 @@ static int launch_resblock3(const void* a16, const void* w_packed, const float* 
   p.a16 = reinterpret_cast<const uint16_t*>(a16);
   p.b_conv = b_conv; p.b_proj = b_proj; p.film = film; p.film_stride = film_stride;
   p.out = reinterpret_cast<uint16_t*>(out16);
+  {
+    const char* e = getenv("B200VOC_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   static bool configured[16] = {};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
