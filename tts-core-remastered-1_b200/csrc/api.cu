@@ -215,15 +215,26 @@ int b200voc_version(void) { return 100; }
 const char* b200voc_last_error_string(void) { return get_error(); }
 
 int b200voc_device_supported(int dev) {
-  cudaDeviceProp prop;
-  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
-  if (e != cudaSuccess) {
-    set_error("cudaGetDeviceProperties(%d): %s", dev, cudaGetErrorString(e));
-    return B200VOC_ERR_CUDA;
+  // cached per device: cudaGetDeviceProperties costs milliseconds, and the host wrappers call this
+  // on every forward of the handle-less entry points
+  static int cached_major[64];
+  static bool have[64] = {};
+  int major = 0;
+  if (dev >= 0 && dev < 64 && have[dev]) {
+    major = cached_major[dev];
+  } else {
+    cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) {
+      set_error("cudaDeviceGetAttribute(%d): %s", dev, cudaGetErrorString(e));
+      return B200VOC_ERR_CUDA;
+    }
+    if (dev >= 0 && dev < 64) {
+      cached_major[dev] = major;
+      have[dev] = true;
+    }
   }
-  if (prop.major != 10) {
-    set_error("device %d is sm_%d%d; b200voc kernels are built for sm_100a only (no fallback)", dev, prop.major,
-              prop.minor);
+  if (major != 10) {
+    set_error("device %d is sm_%dx; b200voc kernels are built for sm_100a only (no fallback)", dev, major);
     return B200VOC_ERR_UNSUPPORTED;
   }
   return B200VOC_OK;

@@ -94,7 +94,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // multi-thread barriers are arrived on once per WARP (fence, __syncwarp, lane 0): a 128-arrival
   // barrier wakes the waiting MMA issuer ~25 times per phase (measured in resblock2.cu)
-  constexpr int kE1Warps = 4;                           // one chunk-parity set (4 warps)
+  constexpr int kE1Warps = 8;                           // both GLU warp sets share every chunk (32 channels each)
   constexpr int kE2Warps = K::INPLACE ? 4 : 8;          // tile-parity set, or all 8 warps (C=256)
 
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -252,8 +252,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   } else if (warp < 10) {
     // ------------------------------------------------------------ epilogue 1 (warps 2..9): GLU + FiLM -> h
-    // two warps per TMEM lane quadrant: warp set `par` owns the chunks with (global chunk index & 1)
-    // == par, i.e. the accumulator buffer D1[par]; the two sets' epilogues overlap in time
+    // two warps per TMEM lane quadrant; BOTH sets work on every chunk, warp set `par` on 32 of its 64
+    // value channels: the time an accumulator buffer is held (which gates the MMAs of chunk j+2)
+    // halves, and knocking this epilogue out entirely is worth ~9 % (tests/knock_resblock3.py)
     const int q = warp & 3, par = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -270,14 +271,13 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       for (int k = 0; k < (2 * C) / 32; ++k) prefetch_l1(film + k * 32);     // this row's FiLM line(s) -> L1
       for (int j = 0; j < NCH; ++j, ++gc) {
         const int b = gc & 1;
-        if (b != par) continue;
         mbar_wait(&d1_full[b], (gc >> 1) & 1);
         mbar_wait(&h_empty[j], (it & 1) ^ 1);
         tc_fence_after();
         uint8_t* hrow = sH + j * K::H_KB_BYTES + row * 128;
         if (!RB3_DBG(1))
 #pragma unroll
-        for (int cl = 0; cl < 64; cl += 16) {   // column inside the chunk's 64 value channels
+        for (int cl = par * 32; cl < par * 32 + 32; cl += 16) {   // column inside the chunk's 64 value channels
           uint32_t va[16], vg[16];
           tmem_ld16(lane_addr + b * 128 + cl, va);
           tmem_ld16(lane_addr + b * 128 + 64 + cl, vg);

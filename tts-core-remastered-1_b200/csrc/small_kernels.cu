@@ -138,14 +138,15 @@ __global__ void __launch_bounds__(256) band_split_kernel(const float* __restrict
   constexpr int W = kSplitTT + 8;
   const int t0 = blockIdx.x * kSplitTT, band = blockIdx.y, b = blockIdx.z;
   const int nb = channels / band_size;
+  // time_major: mel is [B, T, channels] (the refiner / acoustic output layout, sde_refiner5/model.py:304-306;
+  // vocoder7/trainer.py:77 transposes it on the host) -- the transpose is folded into this load.
+  // Either way consecutive threads read consecutive addresses (t fastest, or channel fastest).
   for (int i = threadIdx.x; i < band_size * W; i += blockDim.x) {
-    const int ci = i / W, tt = i % W;
+    const int ci = time_major ? i % band_size : i / W, tt = time_major ? i / band_size : i % W;
     const int t = t0 + tt - 3;
-    // time_major: mel is [B, T, channels] (the refiner / acoustic output layout, sde_refiner5/model.py:304-306;
-    // vocoder7/trainer.py:77 transposes it on the host) -- the transpose is folded into this load
     const long long src = time_major ? ((long long)b * T + t) * channels + band * band_size + ci
                                      : ((long long)b * channels + band * band_size + ci) * T + t;
-    s_mel[i] = (t >= 0 && t < T && tt < kSplitTT + 6) ? mel[src] : 0.f;
+    s_mel[ci * W + tt] = (t >= 0 && t < T && tt < kSplitTT + 6) ? mel[src] : 0.f;
   }
   __syncthreads();
   const float* wb = wt + (long long)band * band_size * 7 * H;
@@ -377,10 +378,11 @@ __global__ void __launch_bounds__(128) gst_partial_kernel(const float* __restric
   float* s_log = s_hid + kGstTT * (sd + 1);        // [nt][kGstTT]
   constexpr int W = kGstTT + 2;
   const int t0 = blockIdx.x * kGstTT, b = blockIdx.y;
-  for (int i = threadIdx.x; i < channels * W; i += blockDim.x) {
-    const int ci = i / W, t = t0 + i % W - 1;
+  for (int i = threadIdx.x; i < channels * W; i += blockDim.x) {   // consecutive threads -> consecutive addresses
+    const int ci = time_major ? i % channels : i / W, tt = time_major ? i / channels : i % W;
+    const int t = t0 + tt - 1;
     const long long src = time_major ? ((long long)b * T + t) * channels + ci : ((long long)b * channels + ci) * T + t;
-    s_mel[i] = (t >= 0 && t < T) ? mel[src] : 0.f;
+    s_mel[ci * W + tt] = (t >= 0 && t < T) ? mel[src] : 0.f;
   }
   __syncthreads();
   for (int d = threadIdx.x; d < sd; d += blockDim.x) {
