@@ -14,8 +14,7 @@ def run(n, iters):
         _lib.check(lib.b200voc_exp_mma_rate(n, iters, blocks, out.data_ptr(), _lib.current_stream()))
     torch.cuda.synchronize()
     return float(out.float().mean())
-for shape, name in enumerate(["32x32b.x32", "16x256b.x8", "16x128b.x16", "16x64b.x32"]):
-    for nw in (1, 4, 16):
-        cyc = run(20000 + 100 * shape + nw, 2000)
-        res[f"tmem_ld_{name}_{nw}warps"] = dict(cycles_per_ld=round(cyc / 2000, 1), bytes_per_clk_per_sm=round(nw * 4096 * 2000 / cyc, 1))
+for variant, name in enumerate(["pingpong_try_wait_suspend", "pingpong_poll", "mma_commit_poll"]):
+    cyc = run(30000 + variant, 2000)
+    res[name] = dict(cycles_per_round_trip=round(cyc / 2000, 1))
 print(json.dumps(res, indent=0))

@@ -58,3 +58,17 @@ def test_synthesize_batch_ragged(gen):
         for (m, p, s, e), w in zip(items, outs):
             one = gen(m.cuda(), p.cuda(), s.cuda(), e.cuda())[0]
             assert w.shape == one.shape and torch.equal(w, one)
+
+
+def test_streaming_synthesizer_matches_direct_calls(gen):
+    """host-in / host-out pipelined loop (uploads and downloads overlapping the kernels): every batch
+    equals the direct call bit for bit, including when slots and host buffers are recycled."""
+    from b200voc import scheduler as S
+    batches = [tuple(t.pin_memory() for t in O.synthetic_inputs(3, 50, seed=200 + k)) for k in range(5)]
+    outs = [torch.empty(3, 1, 256 * 50).pin_memory() for _ in batches]
+    with torch.no_grad():
+        S.StreamingSynthesizer(gen, torch.device("cuda"), depth=2).run(batches, outs)
+        torch.cuda.synchronize()
+        for b, o in zip(batches, outs):
+            want = gen(*[t.cuda() for t in b]).cpu()
+            assert torch.equal(o, want)

@@ -34,6 +34,25 @@ def test_group_by_length_exact_and_bounded():
         assert len(b) <= 2 and len({lengths[i] for i in b}) == 1
 
 
+def test_streaming_synthesizer_host_logic():
+    """CPU device: the streaming loop degenerates to the sequential one (stand-in synthesizer)."""
+    calls = []
+
+    def synth(mel, pros, sty, emo, scale=1.0):
+        calls.append(mel.shape)
+        return (mel.sum(1, keepdim=True) * scale).repeat_interleave(4, -1)
+    batches = [O.synthetic_inputs(2, 5, seed=k) for k in range(3)]
+    outs = [torch.empty(2, 1, 20) for _ in batches]
+    S.StreamingSynthesizer(synth, torch.device("cpu"), depth=2, scale=2.0).run(batches, outs)
+    assert len(calls) == 3
+    for b, o in zip(batches, outs):
+        assert torch.equal(o, (b[0].sum(1, keepdim=True) * 2.0).repeat_interleave(4, -1))
+    with pytest.raises(ValueError):
+        S.StreamingSynthesizer(synth, torch.device("cpu")).run(batches, outs[:2])
+    with pytest.raises(ValueError):
+        S.StreamingSynthesizer(synth, torch.device("cpu"), depth=0)
+
+
 def test_chunk_plan_tiles_the_utterance():
     for T, chunk, halo in [(5167, 512, 8), (100, 512, 8), (513, 512, 6), (1024, 256, 0)]:
         plan = S.chunk_plan(T, chunk, halo)

@@ -113,6 +113,76 @@ def synthesize_long(synth: Synth, mel: torch.Tensor, prosody: torch.Tensor, styl
     return out
 
 
+# ------------------------------------------------------------------ host-to-host streaming loop
+class StreamingSynthesizer:
+    """Host-in / host-out synthesis of a stream of equally shaped batches, software pipelined over
+    three CUDA streams: the upload of batch i+1 (pinned host -> device) and the download of batch i-1
+    (device -> pinned host) overlap the kernels of batch i.  Device input / output tensors are
+    double buffered (`depth` slots, allocated once), so a serving loop's steady-state step time is
+    the kernel time, not kernel + PCIe time.  `synth` must accept ``out=`` (Generator.forward does)
+    and launch on the current stream.  On a CPU device (unit tests with a stand-in callable) the
+    loop degenerates to the sequential one -- same results, no streams."""
+
+    def __init__(self, synth: Synth, device: torch.device, depth: int = 2, **kw):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.synth, self.device, self.depth, self.kw = synth, torch.device(device), depth, kw
+        self._slots = None
+        self._shape_key = None
+
+    def _alloc(self, batch, out_like: torch.Tensor):
+        key = tuple((tuple(t.shape), t.dtype) for t in batch) + ((tuple(out_like.shape), out_like.dtype),)
+        if self._slots is not None and key == self._shape_key:
+            return
+        self._shape_key = key
+        self._slots = [dict(inp=[torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in batch],
+                            out=torch.empty(out_like.shape, dtype=out_like.dtype, device=self.device))
+                       for _ in range(self.depth)]
+
+    def run(self, batches: Sequence[Sequence[torch.Tensor]], host_outs: Sequence[torch.Tensor]) -> None:
+        """batches[i] = (mel, prosody, style, emotion) host tensors (pinned for true overlap);
+        host_outs[i] = preallocated host tensor that receives batch i's waveforms.  Returns when every
+        waveform has landed in host memory."""
+        if len(batches) != len(host_outs):
+            raise ValueError("one output buffer per batch")
+        if not batches:
+            return
+        if self.device.type != "cuda":
+            for b, o in zip(batches, host_outs):
+                o.copy_(self.synth(*[t.to(self.device) for t in b], **self.kw))
+            return
+        self._alloc(batches[0], host_outs[0])
+        main = torch.cuda.current_stream(self.device)
+        s_in, s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        ev_in = [torch.cuda.Event() for _ in batches]
+        ev_comp = [torch.cuda.Event() for _ in batches]
+        ev_out = [torch.cuda.Event() for _ in batches]
+        start = torch.cuda.Event()
+        start.record(main)
+        s_in.wait_event(start)
+        s_out.wait_event(start)
+        for i, (b, o) in enumerate(zip(batches, host_outs)):
+            slot = self._slots[i % self.depth]
+            with torch.cuda.stream(s_in):
+                if i >= self.depth:
+                    s_in.wait_event(ev_comp[i - self.depth])      # the slot's inputs have been consumed
+                for d, h in zip(slot["inp"], b):
+                    d.copy_(h, non_blocking=True)
+                ev_in[i].record(s_in)
+            main.wait_event(ev_in[i])
+            if i >= self.depth:
+                main.wait_event(ev_out[i - self.depth])          # the slot's output has been downloaded
+            self.synth(*slot["inp"], out=slot["out"], **self.kw)
+            ev_comp[i].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_comp[i])
+                o.copy_(slot["out"], non_blocking=True)
+                ev_out[i].record(s_out)
+        main.wait_event(ev_out[-1])
+        for e in ev_out[-self.depth:]:
+            main.wait_event(e)
+
+
 # ------------------------------------------------------------------ multi-GPU (one process per GPU)
 def sharded_synthesize(synth: Synth, mels: Sequence[torch.Tensor], prosodies: Sequence[torch.Tensor],
                        styles: Sequence[torch.Tensor], emotions: Sequence[torch.Tensor], max_batch: int = 16,

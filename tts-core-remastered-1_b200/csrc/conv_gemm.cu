@@ -444,6 +444,44 @@ __global__ void __launch_bounds__(512, 1) exp_mma_rate_kernel(int n, int iters, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (n >= 30000) {
+    // mbarrier hand-off latency.  variant 0/1: warps 0 and 1 ping-pong through two mbarriers (one lane each),
+    // waiting with the suspending try_wait (0) or by polling test_wait (1); variant 2: one thread issues one
+    // M128 N64 K16 MMA + tcgen05.commit and polls for its completion (issue -> barrier round trip).
+    const int variant = n - 30000;
+    uint64_t* ping = bar;                                     // reuse the kernel's barrier + one more
+    uint64_t* pong = reinterpret_cast<uint64_t*>(smem + 49152 + 64);
+    if (threadIdx.x == 0) {
+      mbar_init(pong, 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (variant < 2) {
+      if ((threadIdx.x & 31) == 0 && warp < 2) {
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+          if (warp == 0) {
+            mbar_arrive(ping);
+            if (variant == 0) mbar_wait(pong, it & 1); else mbar_wait_poll(pong, it & 1);
+          } else {
+            if (variant == 0) mbar_wait(ping, it & 1); else mbar_wait_poll(ping, it & 1);
+            mbar_arrive(pong);
+          }
+        }
+        if (warp == 0) out[blockIdx.x] = clock64() - t0;
+      }
+    } else if (threadIdx.x == 0) {
+      const uint32_t idesc = make_idesc_f16(0, 64);
+      const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sA)), b_desc = make_kmajor_desc<128>(smem_u32(sB));
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+        umma_f16(tmem_base, a_desc, b_desc, idesc, 0);
+        umma_commit(ping);
+        mbar_wait_poll(ping, it & 1);
+      }
+      out[blockIdx.x] = clock64() - t0;
+    }
+  } else
   if (n >= 20000) {
     // TMEM read bandwidth: (n - 20000) warps issue `iters` x (tcgen05.ld 32x32b.x32 + wait) on their lane quadrant
     const int nw = (n - 20000) % 100, shape = (n - 20000) / 100;
