@@ -190,6 +190,16 @@ int b200voc_stft_logmel(const float* wav, int B, int N, int n_fft, int hop, int 
                         int log_compress, float* out, void* stream);
 /* torch.istft semantics (center, hann, length=N): spec_ri[B,bins,frames,2] -> wav[B,N]. */
 int b200voc_istft(const float* spec_ri, int B, int frames, int n_fft, int hop, int N, float* wav, void* stream);
+
+/* Backward of one resolution of STFTLoss.forward (vocoder7/stft.py:48-54), the first training-side
+ * consumer of the STFT kernels:  L = scale * mean_{b,k,m} | |STFT(wav_fake)| g_k - |STFT(wav_real)| g_k |.
+ * grad_wav[B,N] += dL/dwav_fake and grad_gain[n_fft/2+1] += dL/dg (grad_gain may be NULL); both are
+ * ACCUMULATED so the three resolutions sum in place.  `gain` is the signed per-bin gain (LearnableSTFT.filterbank),
+ * `scale` = lambda_stft * upstream gradient.  Workspace from the query below, 16-byte aligned. */
+int64_t b200voc_stft_l1_backward_workspace_bytes(int B, int N, int n_fft, int hop);
+int b200voc_stft_l1_backward(const float* wav_fake, const float* wav_real, int B, int N, int n_fft, int hop,
+                             const float* gain, float scale, float* grad_wav, float* grad_gain, void* workspace,
+                             int64_t workspace_bytes, void* stream);
 /* STFTLoss.forward (stft.py:48-54) partial sums: out_sum[0] += sum |mag(fake)-mag(real)|*|gain|
  * for one resolution (host divides by numel and multiplies lambda). */
 int b200voc_stft_l1(const float* wav_fake, const float* wav_real, int B, int N, int n_fft, int hop,

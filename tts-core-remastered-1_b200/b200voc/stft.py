@@ -1,7 +1,8 @@
 """STFT family: drop-ins for ``vocoder7.stft.LearnableSTFT`` / ``STFTLoss`` (vocoder7/stft.py:9-54)
 and the functional transforms north_star names (stft, istft, mel_spectrogram, log_mel), all running
-the hand-written sm_100a kernels of csrc/stft.cu through the C ABI.  fp32 throughout; inference
-only (no autograd); no CPU fallback.
+the hand-written sm_100a kernels of csrc/stft.cu through the C ABI.  fp32 throughout; no CPU
+fallback.  The transforms are inference-only; ``STFTLoss`` is differentiable w.r.t. ``wav_fake`` and
+the learnable per-bin gains (its backward is a CUDA kernel chain too, b200voc_stft_l1_backward).
 
 Semantics (identical to what the reference calls, see oracle/vocoder7_oracle.py):
   STFT  = torch.stft(center=True, pad_mode="reflect", win_length=n_fft, periodic Hann, onesided,
@@ -100,8 +101,58 @@ class LearnableSTFT(nn.Module):
         return stft_magnitude(wav, self.n_fft, self.hop_length, self.filterbank)
 
 
+def _stft_loss_values(f: torch.Tensor, r: torch.Tensor, gains, n_ffts, hop: int) -> torch.Tensor:
+    """sum over resolutions of mean(|g| * ||X_f| - |X_r||) (fused STFT + L1 kernels)."""
+    B, N = f.shape
+    lib = _lib.load()
+    sums = torch.zeros(len(n_ffts), device=f.device, dtype=torch.float64)
+    loss = torch.zeros((), device=f.device, dtype=torch.float32)
+    with torch.cuda.device(f.device):
+        for i, (g, n_fft) in enumerate(zip(gains, n_ffts)):
+            # L1(|X_f| g, |X_r| g) = mean(|g| * | |X_f| - |X_r| |): the kernel is given |g|
+            ga = g.detach().abs().to(torch.float32).contiguous()
+            _lib.check(lib.b200voc_stft_l1(_lib.ptr(f), _lib.ptr(r), B, N, n_fft, hop, _lib.ptr(ga),
+                                           sums[i:i + 1].data_ptr(), _lib.current_stream()), "stft_l1")
+            numel = B * (n_fft // 2 + 1) * (1 + N // hop)
+            loss = loss + (sums[i] / numel).to(torch.float32)
+    return loss
+
+
+class _STFTLossFn(torch.autograd.Function):
+    """loss = lambda * sum_res mean | |STFT(fake)| g - |STFT(real)| g |; gradients w.r.t. ``wav_fake`` and
+    every gain vector come from b200voc_stft_l1_backward (STFT -> spectral gradient -> adjoint STFT as
+    an un-normalised overlap-add -> reflect fold), accumulated over the resolutions in place."""
+
+    @staticmethod
+    def forward(ctx, wav_fake, wav_real, lam, hop, n_ffts, *gains):
+        f, r = _prep(wav_fake), _prep(wav_real)
+        ctx.save_for_backward(f, r, *[g.detach() for g in gains])
+        ctx.meta = (float(lam), int(hop), tuple(int(n) for n in n_ffts), tuple(wav_fake.shape))
+        return _stft_loss_values(f, r, gains, n_ffts, hop) * lam
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        f, r, *gains = ctx.saved_tensors
+        lam, hop, n_ffts, shape = ctx.meta
+        B, N = f.shape
+        lib = _lib.load()
+        grad_wav = torch.zeros_like(f)
+        grad_gains = [torch.zeros(n // 2 + 1, device=f.device, dtype=torch.float32) for n in n_ffts]
+        scale = float(grad_out) * lam
+        with torch.cuda.device(f.device):
+            need = max(int(lib.b200voc_stft_l1_backward_workspace_bytes(B, N, n, hop)) for n in n_ffts)
+            ws = torch.empty(need, dtype=torch.uint8, device=f.device)
+            for g, gg, n in zip(gains, grad_gains, n_ffts):
+                gs = g.to(torch.float32).contiguous()
+                _lib.check(lib.b200voc_stft_l1_backward(_lib.ptr(f), _lib.ptr(r), B, N, n, hop, _lib.ptr(gs), scale,
+                                                        _lib.ptr(grad_wav), _lib.ptr(gg), _lib.ptr(ws), ws.numel(),
+                                                        _lib.current_stream()), "stft_l1_backward")
+        return (grad_wav.view(shape), None, None, None, None, *grad_gains)
+
+
 class STFTLoss(nn.Module):
-    """Multi-resolution STFT L1 loss (stft.py:36-54), forward value only."""
+    """Multi-resolution STFT L1 loss (stft.py:36-54).  Differentiable w.r.t. ``wav_fake`` and the
+    per-resolution ``filterbank`` gains (``wav_real`` is data)."""
 
     def __init__(self, cfg: GANConfig):
         super().__init__()
@@ -109,19 +160,18 @@ class STFTLoss(nn.Module):
         self.lambda_stft = cfg.lambda_stft
 
     def forward(self, wav_fake: torch.Tensor, wav_real: torch.Tensor) -> torch.Tensor:
+        _lib.require_cuda(wav_fake, wav_real)
+        if wav_fake.shape != wav_real.shape:
+            raise ValueError(f"shape mismatch {tuple(wav_fake.shape)} vs {tuple(wav_real.shape)}")
+        _prep(wav_fake)                                  # shape validation
+        n_ffts = [m.n_fft for m in self.stfts]
+        hops = {m.hop_length for m in self.stfts}
+        gains = [m.filterbank for m in self.stfts]
+        needs_grad = torch.is_grad_enabled() and (wav_fake.requires_grad or any(g.requires_grad for g in gains))
+        if needs_grad and len(hops) == 1:
+            return _STFTLossFn.apply(wav_fake, wav_real, self.lambda_stft, hops.pop(), n_ffts, *gains)
         f, r = _prep(wav_fake), _prep(wav_real)
-        if f.shape != r.shape:
-            raise ValueError(f"shape mismatch {tuple(f.shape)} vs {tuple(r.shape)}")
-        B, N = f.shape
-        lib = _lib.load()
-        sums = torch.zeros(len(self.stfts), device=f.device, dtype=torch.float64)
         loss = torch.zeros((), device=f.device, dtype=torch.float32)
-        with torch.cuda.device(f.device):
-            for i, m in enumerate(self.stfts):
-                # L1(|X_f| g, |X_r| g) = mean(|g| * | |X_f| - |X_r| |): the kernel is given |g|
-                g = m.filterbank.detach().abs().to(torch.float32).contiguous()
-                _lib.check(lib.b200voc_stft_l1(_lib.ptr(f), _lib.ptr(r), B, N, m.n_fft, m.hop_length, _lib.ptr(g),
-                                               sums[i:i + 1].data_ptr(), _lib.current_stream()), "stft_l1")
-                numel = B * (m.n_fft // 2 + 1) * (1 + N // m.hop_length)
-                loss = loss + (sums[i] / numel).to(torch.float32)
+        for m in self.stfts:
+            loss = loss + _stft_loss_values(f, r, [m.filterbank], [m.n_fft], m.hop_length)
         return loss * self.lambda_stft

@@ -461,6 +461,8 @@ struct IstftParams {
   const float2* spec;   // [B, bins, frames]
   float* wav;           // [B, Nout]
   int B, frames, hop, Nout;
+  int joff;             // padded-signal coordinate of output sample 0: n_fft/2 (iSTFT: centre trimmed) or 0 (adjoint)
+  int normalize;        // 1: divide by the window envelope (torch.istft); 0: plain overlap-add (adjoint of the STFT)
 };
 
 template <int NFFT>
@@ -478,7 +480,7 @@ istft_kernel(const IstftParams p) {
   const int ratio = NFFT / p.hop;
   const int opb = (SLOTS - ratio + 1) * p.hop;
   const int n0 = blockIdx.x * opb;                       // first output sample of this CTA
-  const int f_lo = (n0 - N) / p.hop + 1;                 // may be negative (n0 - N is a multiple of hop)
+  const int f_lo = (n0 + p.joff - NFFT) / p.hop + 1;     // may be negative (the numerator is a multiple of hop)
   const int bins = N + 1;
 
   for (int i = threadIdx.x; i < NFFT; i += blockDim.x) win[i] = __ldg(p.tab.win + i);
@@ -515,7 +517,7 @@ istft_kernel(const IstftParams p) {
   for (int i = threadIdx.x; i < opb; i += blockDim.x) {
     const int n = n0 + i;
     if (n >= p.Nout) break;
-    const int j = n + N;                                 // padded-signal coordinate
+    const int j = n + p.joff;                            // padded-signal coordinate
     const int f_hi = j / p.hop;
     float acc = 0.f, env = 0.f;
     for (int q = 0; q < ratio; ++q) {
@@ -527,7 +529,7 @@ istft_kernel(const IstftParams p) {
       acc = fmaf((idx & 1) ? z.y : z.x, w * inv_n, acc);
       env = fmaf(w, w, env);
     }
-    o[n] = env > 1e-11f ? acc / env : 0.f;
+    o[n] = !p.normalize ? acc : env > 1e-11f ? acc / env : 0.f;
   }
 }
 
@@ -553,7 +555,7 @@ istft1024_kernel(const IstftParams p) {
   const int ratio = NFFT / p.hop;
   const int opb = (kISlots - ratio + 1) * p.hop;
   const int n0 = blockIdx.x * opb;
-  const int f_lo = (n0 - N) / p.hop + 1;                   // may be negative
+  const int f_lo = (n0 + p.joff - NFFT) / p.hop + 1;       // may be negative (the numerator is a multiple of hop)
   const int bins = N + 1;
 
   for (int i = threadIdx.x; i <= N; i += blockDim.x) tw2[i] = __ldg(p.tab.tw2 + i);
@@ -620,7 +622,7 @@ istft1024_kernel(const IstftParams p) {
   for (int i = threadIdx.x; i < opb; i += blockDim.x) {
     const int n = n0 + i;
     if (n >= p.Nout) break;
-    const int j = n + N;                                   // padded-signal coordinate
+    const int j = n + p.joff;                              // padded-signal coordinate
     const int f_hi = j / p.hop;
     float acc = 0.f, env = 0.f;
     for (int q = 0; q < ratio; ++q) {
@@ -632,7 +634,7 @@ istft1024_kernel(const IstftParams p) {
       acc += (idx & 1) ? z.y : z.x;
       env = fmaf(w, w, env);
     }
-    o[n] = env > 1e-11f ? acc / env : 0.f;
+    o[n] = !p.normalize ? acc : env > 1e-11f ? acc / env : 0.f;
   }
 }
 
@@ -658,6 +660,63 @@ static int launch_istft(const IstftParams& p, cudaStream_t st) {
   istft_kernel<NFFT><<<grid, kFPB * (NFFT / 16), smem, st>>>(p);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
+}
+
+
+// ------------------------------------------------------------------ STFTLoss backward (stft.py:48-54)
+// One resolution of  loss = scale * mean_{b,k,m} | |X_f| g_k - |X_r| g_k |  (scale = lambda * upstream grad):
+//   dL/dX_f[k,m]   = scale/numel * |g_k| * sign(|X_f| - |X_r|) * X_f / |X_f|
+//   dL/dwav_f      = STFT^T (dL/dX_f): per frame  w[n] * sum_{k=0..N/2} Re(G_k e^{+2 pi i k n / N}),  overlap-added
+//                    on the padded signal, then folded back through the reflect padding.
+// The per-frame sum is evaluated by the inverse real FFT of this file with Y_0 = N G_0, Y_{N/2} = N G_{N/2}
+// (real parts only: Im X_0 = Im X_{N/2} = 0 identically), Y_k = (N/2) G_k  (irfft weights undone).
+__global__ void __launch_bounds__(256) stft_l1_grad_spec_kernel(float2* __restrict__ xf, const float* __restrict__ magr,
+                                                                 const float* __restrict__ gain, int bins, int frames,
+                                                                 long long total, float w_elem, int n_fft,
+                                                                 float* __restrict__ grad_gain) {
+  // block = 256 consecutive elements of [B, bins, frames]; grad_gain accumulates per-bin |d| sums
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float contrib = 0.f;
+  int k = -1;
+  if (i < total) {
+    k = (int)((i / frames) % bins);
+    const float2 x = xf[i];
+    const float a = sqrtf(x.x * x.x + x.y * x.y);
+    const float d = a - magr[i];
+    const float g = __ldg(gain + k);
+    const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    const bool edge = k == 0 || k == bins - 1;
+    const float coef = (edge ? (float)n_fft : 0.5f * n_fft) * w_elem * fabsf(g) * sgn;
+    const float inv = a > 0.f ? coef / a : 0.f;
+    xf[i] = make_float2(x.x * inv, edge ? 0.f : x.y * inv);
+    contrib = w_elem * (g > 0.f ? 1.f : (g < 0.f ? -1.f : 0.f)) * fabsf(d);
+  }
+  if (grad_gain != nullptr) {
+    // consecutive threads mostly share k (frames >> 32): reduce runs of equal k inside the warp
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int k0 = __shfl_sync(full, k, 0);
+    if (__all_sync(full, k == k0)) {
+      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(full, contrib, o);
+      if (lane == 0 && k0 >= 0) atomicAdd(grad_gain + k0, contrib);
+    } else if (k >= 0) {
+      atomicAdd(grad_gain + k, contrib);
+    }
+  }
+}
+
+// grad_wav[b, n] += P[b, pad + n] + reflected contributions of the two padded ends (P is the overlap-add on
+// the padded signal of length N + 2 pad):  x_pad[j] = x[pad - j] (j < pad),  x_pad[pad + N + i] = x[N - 2 - i].
+__global__ void __launch_bounds__(256) stft_fold_reflect_kernel(const float* __restrict__ P, int B, int N, int pad,
+                                                                 float* __restrict__ grad_wav) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * N) return;
+  const int b = (int)(i / N), n = (int)(i % N);
+  const float* p = P + (long long)b * (N + 2 * pad);
+  float g = p[pad + n];
+  if (n >= 1 && n <= pad) g += p[pad - n];
+  if (n >= N - 1 - pad && n <= N - 2) g += p[pad + 2 * N - 2 - n];
+  grad_wav[i] += g;
 }
 
 }  // namespace b200
@@ -711,6 +770,7 @@ int b200voc_istft(const float* spec_ri, int B, int frames, int n_fft, int hop, i
                  "istft: length %d exceeds the signal the %d frames cover", N, frames);
   IstftParams p{};
   p.spec = reinterpret_cast<const float2*>(spec_ri); p.wav = wav; p.B = B; p.frames = frames; p.hop = hop; p.Nout = N;
+  p.joff = n_fft / 2; p.normalize = 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (n_fft == 512 || n_fft == 1024 || n_fft == 2048) B200_TRY(get_fft_tables(n_fft, &p.tab));
   switch (n_fft) {
@@ -722,6 +782,60 @@ int b200voc_istft(const float* spec_ri, int B, int frames, int n_fft, int hop, i
   }
   set_error("istft: n_fft=%d unsupported (512/1024/2048)", n_fft);
   return B200VOC_ERR_UNSUPPORTED;
+}
+
+
+/* STFTLoss backward, one resolution (see the kernels above).  grad_wav and grad_gain are ACCUMULATED. */
+int64_t b200voc_stft_l1_backward_workspace_bytes(int B, int N, int n_fft, int hop) {
+  if (B <= 0 || N <= 0 || n_fft <= 0 || hop <= 0) return 0;
+  const long long bins = n_fft / 2 + 1, frames = 1 + N / hop;
+  const long long e = (long long)B * bins * frames;
+  return e * 8 + e * 4 + (long long)B * (N + n_fft) * 4 + 1024;
+}
+int b200voc_stft_l1_backward(const float* wav_fake, const float* wav_real, int B, int N, int n_fft, int hop,
+                             const float* gain, float scale, float* grad_wav, float* grad_gain, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+  B200_TRY(check_stft_args(wav_fake, B, N, n_fft, hop));
+  B200_CHECK_ARG(wav_real && gain && grad_wav && workspace, "stft_l1_backward: null argument");
+  B200_CHECK_ARG(workspace_bytes >= b200voc_stft_l1_backward_workspace_bytes(B, N, n_fft, hop),
+                 "stft_l1_backward: workspace too small");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "stft_l1_backward: workspace must be 16B aligned");
+  B200_CHECK_ARG((n_fft / 2) % hop == 0 && n_fft / hop <= 2 * kFPB, "stft_l1_backward: hop %d must divide n_fft/2", hop);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int bins = n_fft / 2 + 1, frames = 1 + N / hop, pad = n_fft / 2;
+  const long long e = (long long)B * bins * frames;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float2* xf = reinterpret_cast<float2*>(ws);
+  float* magr = reinterpret_cast<float*>(ws + e * 8);
+  float* P = reinterpret_cast<float*>(ws + ((e * 12 + 15) & ~15ll));
+  {  // X_f (complex) and |X_r|
+    StftParams p{};
+    p.wav = wav_fake; p.B = B; p.Nsamp = N; p.hop = hop; p.frames = frames; p.out = reinterpret_cast<float*>(xf);
+    B200_TRY(dispatch_stft<MODE_COMPLEX>(n_fft, p, st));
+    StftParams q{};
+    q.wav = wav_real; q.B = B; q.Nsamp = N; q.hop = hop; q.frames = frames; q.gain = nullptr; q.out = magr;
+    B200_TRY(dispatch_stft<MODE_MAG>(n_fft, q, st));
+  }
+  const float w_elem = scale / (float)e;
+  stft_l1_grad_spec_kernel<<<(unsigned)((e + 255) / 256), 256, 0, st>>>(xf, magr, gain, bins, frames, e, w_elem, n_fft,
+                                                                        grad_gain);
+  B200_CUDA(cudaGetLastError());
+  {  // adjoint: plain overlap-add on the padded signal
+    IstftParams p{};
+    p.spec = xf; p.wav = P; p.B = B; p.frames = frames; p.hop = hop; p.Nout = N + n_fft; p.joff = 0; p.normalize = 0;
+    B200_TRY(get_fft_tables(n_fft, &p.tab));
+    int rc;
+    switch (n_fft) {
+      case 512: rc = launch_istft<512>(p, st); break;
+      case 1024: rc = (n_fft / hop <= kISlots / 2) ? launch_istft1024(p, st) : launch_istft<1024>(p, st); break;
+      case 2048: rc = launch_istft<2048>(p, st); break;
+      default: set_error("stft_l1_backward: n_fft=%d unsupported (512/1024/2048)", n_fft); return B200VOC_ERR_UNSUPPORTED;
+    }
+    B200_TRY(rc);
+  }
+  stft_fold_reflect_kernel<<<(unsigned)(((long long)B * N + 255) / 256), 256, 0, st>>>(P, B, N, pad, grad_wav);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
 }
 
 }  // extern "C"
