@@ -262,6 +262,21 @@ def secondary_measurements(dev, dev_in, B, T):
         ms, y = timeit(lambda: b200voc.istft(sp, 1024, 256, Nw))
         res["istft"] = {"ms": ms, "algorithmic_gb": by / 1e9, "gbs": by / ms / 1e6, "frac_of_hbm": by / ms / 1e6 / peaks["hbm_gbs"],
                         "roundtrip_maxabs": float((y - x).abs().max())}
+        # training-side consumer: STFTLoss forward + backward, 3 resolutions, 256 x 4 s
+        try:
+            lm_mod = b200voc.STFTLoss(GANConfig()).to(dev)
+            xf = x[:256].clone().requires_grad_(True)
+            xr = torch.rand(256, Nw, device=dev) * 2 - 1
+
+            def fb():
+                with torch.enable_grad():
+                    lm_mod(xf, xr).backward()
+                return xf.grad
+            ms, _ = timeit(fb, reps=3)
+            res["stft_loss_fwd_bwd"] = {"ms": ms, "batch": 256, "audio_seconds": 256 * Nw / SR,
+                                        "note": "STFTLoss(cfg) forward + backward (wav and gain gradients), n_fft 512/1024/2048"}
+        except Exception as e:
+            res["stft_loss_fwd_bwd"] = {"error": str(e)[:200]}
         res["audio_seconds"] = Bw * Nw / SR
         res["workload"] = "BASELINE configs[2]: 1024 x 4 s uniform(-1,1) waveforms, n_fft 1024, hop 256, 80 HTK mels"
         out["stft"] = res

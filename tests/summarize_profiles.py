@@ -1,6 +1,6 @@
 """Turn ncu reports brought back in gpurun_out/ into the small text summaries kept under profiles/
 (test infrastructure; runs in the authoring container, no GPU needed).
-    python tests/summarize_profiles.py <launches.csv> <full.ncu-rep> <tag>"""
+    python tests/summarize_profiles.py <launches.csv> <full.ncu-rep>[,<more.ncu-rep>...] <tag>"""
 import collections
 import csv
 import json
@@ -35,8 +35,17 @@ with open(os.path.join(out_dir, f"{tag}_launch_shares.txt"), "w") as f:
         f.write(f"{k[:70]:70s} {cnt[k]:8d} {v/1e3:12.1f} {v/1e3/cnt[k]:10.1f} {100*v/total:6.1f}%\n")
 
 # ---- full capture: key metrics per kernel instance
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
+reps = rep.split(",")
+rep = reps[0]
+rr = None
+for one in reps:                      # later reports append their kernel rows (same metric set)
+    raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    part = list(csv.reader(raw.splitlines()))
+    if rr is None:
+        rr = part
+    else:
+        assert part[0] == rr[0], "metric sets differ between reports"
+        rr += part[2:]
 h = rr[0]
 want = ["Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "dram__bytes_read.sum",
@@ -49,6 +58,8 @@ seen = collections.OrderedDict()
 for r in rr[2:]:
     d = {h[i]: r[i] for i in idx}
     key = re.sub(r"\(CUtensor.*", "", d["Kernel Name"])
+    if key.startswith("pack_") or "copy_f32" in key or "cvt16" in key:
+        continue                      # weight packing (load time), not part of the step
     seen.setdefault(key, d)
 with open(os.path.join(out_dir, f"{tag}_resblock_kernels_ncu.txt"), "w") as f:
     f.write("# ncu --set full --clock-control none --import-source on : python tests/prof_step.py --B 16 --T 861 --iters 2\n")
