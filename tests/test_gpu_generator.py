@@ -168,11 +168,13 @@ def test_convt1d_layer(Cin, Cout, s, fmt):
     assert float(((got - ref).abs() / (ref.abs() + 1.0)).max()) <= 1.2 * ulp
 
 
-@pytest.mark.parametrize("C", [32, 64, 128, 256])
-@pytest.mark.parametrize("d", [1, 3, 5])
-def test_resblock_layer(C, d):
+@pytest.mark.parametrize("C,d,fmt,store_lrelu", [(C, d, 0, 0) for C in (32, 64, 128, 256) for d in (1, 3, 5)] +
+                         [(32, 3, 1, 0), (64, 5, 1, 0), (128, 3, 1, 0), (32, 5, 0, 1), (64, 1, 0, 1), (128, 5, 0, 1),
+                          (256, 3, 0, 1)])
+def test_resblock_layer(C, d, fmt, store_lrelu):
+    """every channel width / dilation in fp16, plus bf16 operands and the leaky_relu-stored output form"""
     _l, lib = _lib()
-    fmt, dt = 0, torch.float16
+    dt = torch.float16 if fmt == 0 else torch.bfloat16
     B, nb, T, P = 2, 4, 6, 55
     N, L = B * nb, T * P
     g = torch.Generator().manual_seed(10 + d)
@@ -204,12 +206,15 @@ def test_resblock_layer(C, d):
     _l.check(lib.b200voc_pack_resblock_weights(_l.ptr(wcd), _l.ptr(wpd), C, fmt, _l.ptr(wpk), st))
     out = torch.full((N, L, C), float("nan"), dtype=dt, device="cuda")
     _l.check(lib.b200voc_resblock(_l.ptr(a_cl), _l.ptr(wpk), _l.ptr(bcd), _l.ptr(bpd), _l.ptr(film_cl), N, L, C, d, T,
-                                  nb, fmt, 0, _l.ptr(out), st))
+                                  nb, fmt, store_lrelu, _l.ptr(out), st))
     torch.cuda.synchronize()
     got = out.float().cpu().transpose(1, 2).double()
     assert not bool(torch.isnan(got).any())
-    # h is rounded to fp16 before GEMM2 and the output to fp16: a few ulps of the output scale
-    assert float(((got - ref).abs() / (ref.abs() + 1.0)).max()) <= 3 * 2.0 ** -11
+    if store_lrelu:
+        ref = F.leaky_relu(ref, 0.1)
+    # h is rounded to 16 bits before GEMM2 and the output to 16 bits: a few ulps of the output scale
+    ulp = 2.0 ** -11 if fmt == 0 else 2.0 ** -8
+    assert float(((got - ref).abs() / (ref.abs() + 1.0)).max()) <= 3 * ulp
 
 
 def test_rowshifted_umma_descriptors():

@@ -50,12 +50,13 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int B_TILE = BN * 128;
   constexpr int STAGE_BYTES = kATileBytes + B_TILE;
   constexpr int STAGING = 128 * BN * 2;
+  constexpr int NSTG = BN <= 128 ? 2 : 1;     // output staging buffers: the TMA store of tile i-1 drains while tile i is converted
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "tile width");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-  uint8_t* staging = smem + STAGES * STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(staging + STAGING);
+  uint8_t* staging0 = smem + STAGES * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging0 + NSTG * STAGING);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;      // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
@@ -163,8 +164,11 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int buf = i & 1;
       mbar_wait(&acc_full[buf], (i >> 1) & 1);
       tc_fence_after();
-      if (i > 0) {                                   // staging is free once the previous stores have read it
-        if (issuer) tma_store_wait_read();
+      uint8_t* staging = staging0 + (i % NSTG) * STAGING;
+      if (i >= NSTG) {                               // this staging buffer is free once its previous stores have read it
+        if (issuer) {
+          if (NSTG == 2) tma_store_wait_read_1(); else tma_store_wait_read();
+        }
         named_bar_sync(1, 128);
       }
 #pragma unroll 1
@@ -222,7 +226,7 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BN, int STAGES, int FMT, bool LRELU>
 static int launch_gemm_taps_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                               const GemmTapsParams& p, int n_seq, cudaStream_t stream) {
-  constexpr int SMEM = STAGES * (kATileBytes + BN * 128) + 128 * BN * 2 + 256 + 1024;
+  constexpr int SMEM = STAGES * (kATileBytes + BN * 128) + (BN <= 128 ? 2 : 1) * 128 * BN * 2 + 256 + 1024;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static bool configured[16] = {};
   static int sms[16] = {};
