@@ -29,13 +29,21 @@ struct Resblock3Params {
   int film_stride;
   uint16_t* out;         // [N, L, C]
   int dbg;               // knock-out experiment switches, only with -DB200VOC_TRACE (B200VOC_DBG)
+  long long* trace;      // clock64 timeline of CTA 0, [7][64][4] (trace builds)
 };
 
 #ifdef B200VOC_TRACE
 #define RB3_DBG(bit) (p.dbg & (bit))
+#define RB3_TRACE(slot, i, k)                                                             \
+  do {                                                                                    \
+    if (p.trace && blockIdx.x == 0 && (i) < 64 && (threadIdx.x & 31) == 0)                 \
+      p.trace[(((slot) * 64 + (i)) << 2) + (k)] = clock64();                               \
+  } while (0)
 #else
 #define RB3_DBG(bit) false
+#define RB3_TRACE(slot, i, k) do { } while (0)
 #endif
+extern long long* g_rb2_trace;
 
 template <int C>
 struct Rb3Cfg {
@@ -47,10 +55,12 @@ struct Rb3Cfg {
   static constexpr int A_KB_BYTES = A_ROWS * 128;    // 18 KB per k-block
   static constexpr int A_BYTES = KPT * A_KB_BYTES;
   static constexpr bool INPLACE = C == 128;          // stage the output over the input tile + TMA store
-  static constexpr int NA = C == 128 ? 3 : 1;
+  static constexpr int NA = C == 128 ? 3 : 1;            // input tiles have their own producer warp (18)
   static constexpr int H_KB_BYTES = 128 * 128;       // 16 KB per k-block
   static constexpr int W_TILE = 128 * 128;           // 16 KB ring slot: [128 rows x 64 k]
-  static constexpr int NW = 5;                       // 5 x 16 KB in flight: covers the L2 -> SMEM round trip of the weight stream
+  // weight ring: a slot's round trip (MMAs complete -> commit -> producer -> TMA from L2 -> issuer) is ~1800 clk
+  // against 256 clk of MMA work per slot, measured (tests/trace_resblock3.py): the ring must hold ~7 slots
+  static constexpr int NW = 5;
   static constexpr int ND2 = C == 128 ? 2 : 1;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_H = OFF_A + NA * A_BYTES;
@@ -66,7 +76,7 @@ struct Rb3Cfg {
 };
 
 template <int C, int FMT, int OFMT, bool LRELU>
-__global__ void __launch_bounds__(576, 1)
+__global__ void __launch_bounds__(608, 1)
 resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
                  const Resblock3Params p) {
@@ -122,7 +132,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int n_my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (A tiles + weight ring)
+    // ------------------------------------------------------------ TMA producer of the weight ring
     if (lane == 0) {
       int wi = 0;
       auto w_slot = [&]() -> uint8_t* {
@@ -132,16 +142,6 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_expect_tx(&w_full[s], K::W_TILE);
         return sW + s * K::W_TILE;
       };
-      auto load_a = [&](int it) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int seq = tile / p.tiles_per_seq, l0 = (tile - seq * p.tiles_per_seq) * 128;
-        const int ab = it % NA;
-        mbar_wait(&a_empty[ab], ((it / NA) & 1) ^ 1);
-        if (RB3_DBG(16) && it >= NA) { mbar_arrive(&a_full[ab]); return; }
-        mbar_expect_tx(&a_full[ab], K::A_BYTES);
-        for (int kb = 0; kb < KPT; ++kb)
-          tma_load_3d(sA + ab * K::A_BYTES + kb * K::A_KB_BYTES, &tmX, &a_full[ab], kb * 64, l0 - K::HALO, seq);
-      };
       auto load_w2 = [&](int kb) {
         for (int half = 0; half < NH; ++half) {
           uint8_t* dst = w_slot();
@@ -149,7 +149,6 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           ++wi;
         }
       };
-      if (n_my_tiles > 0) load_a(0);
       int gc = 0;
       for (int it = 0; it < n_my_tiles; ++it) {
         for (int j = 0; j < NCH; ++j, ++gc) {
@@ -159,11 +158,26 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               if (dst) tma_load_2d(dst, &tmW1, &w_full[wi % NW], tap * C + kb * 64, j * 128);
               ++wi;
             }
-          if (j == K::A_PREFETCH_AFTER_CHUNK && it + 1 < n_my_tiles) load_a(it + 1);
           if (gc >= 1) load_w2((gc - 1) % NCH);
         }
       }
       if (gc >= 1) load_w2((gc - 1) % NCH);
+    }
+  } else if (warp == 18) {
+    // ------------------------------------------------------------ TMA producer of the input tiles (own warp: a
+    // wait for a free input slot must not hold up the weight stream)
+    if (lane == 0) {
+      for (int it = 0; it < n_my_tiles; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int seq = tile / p.tiles_per_seq, l0 = (tile - seq * p.tiles_per_seq) * 128;
+        const int ab = it % NA;
+        mbar_wait(&a_empty[ab], ((it / NA) & 1) ^ 1);
+        if (RB3_DBG(16) && it >= NA) { mbar_arrive(&a_full[ab]); continue; }
+        RB3_TRACE(0, it, 0);
+        mbar_expect_tx(&a_full[ab], K::A_BYTES);
+        for (int kb = 0; kb < KPT; ++kb)
+          tma_load_3d(sA + ab * K::A_BYTES + kb * K::A_KB_BYTES, &tmX, &a_full[ab], kb * 64, l0 - K::HALO, seq);
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer.  The whole warp runs the
@@ -188,7 +202,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t phh = it2 & 1, phd = ((it2 / ND2) & 1) ^ 1;
         const bool rh = mbar_test(&h_full[kb], phh), rd = kb == 0 ? mbar_test(&d2_empty[db], phd) : true;
         if (!rh) mbar_wait(&h_full[kb], phh);
+        RB3_TRACE(2, it2 * NCH + kb, 0);
         if (!rd) mbar_wait(&d2_empty[db], phd);
+        RB3_TRACE(2, it2 * NCH + kb, 1);
         tc_fence_after();
         const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sH + kb * K::H_KB_BYTES));
         for (int half = 0; half < NH; ++half) {
@@ -220,7 +236,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const uint32_t pha = (it / NA) & 1, phd = ((gc >> 1) & 1) ^ 1;
             const bool ra = j == 0 ? mbar_test(&a_full[ab], pha) : true, rd = mbar_test(&d1_empty[b], phd);
             if (!ra) mbar_wait(&a_full[ab], pha);
+            RB3_TRACE(1, gc, 0);
             if (!rd) mbar_wait(&d1_empty[b], phd);
+            RB3_TRACE(1, gc, 1);
           }
           tc_fence_after();
           for (int tap = 0; tap < 3; ++tap)
@@ -245,7 +263,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (!K::INPLACE && j == NCH - 1) umma_commit(&a_empty[ab]);   // INPLACE: released by the store epilogue
           }
           __syncwarp();
+          RB3_TRACE(1, gc, 2);
           if (gc >= 1) g2((gc - 1) / NCH, (gc - 1) % NCH);
+          RB3_TRACE(1, gc, 3);
         }
       }
       if (gc >= 1) g2((gc - 1) / NCH, (gc - 1) % NCH);
@@ -272,7 +292,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       for (int j = 0; j < NCH; ++j, ++gc) {
         const int b = gc & 1;
         mbar_wait(&d1_full[b], (gc >> 1) & 1);
+        if (q == 0 && par == 0) RB3_TRACE(3, gc, 0);
         mbar_wait(&h_empty[j], (it & 1) ^ 1);
+        if (q == 0 && par == 0) RB3_TRACE(3, gc, 1);
         tc_fence_after();
         uint8_t* hrow = sH + j * K::H_KB_BYTES + row * 128;
         if (!RB3_DBG(1))
@@ -317,6 +339,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_arrive(&h_full[j]);
           mbar_arrive(&d1_empty[b]);
         }
+        if (q == 0 && par == 0) RB3_TRACE(3, gc, 2);
       }
     }
   } else if (K::INPLACE) {
@@ -333,6 +356,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const int db = it % ND2, ab = it % NA;
       mbar_wait(&a_full[ab], (it / NA) & 1);      // visibility of the TMA-written tile to this thread
       mbar_wait(&d2_full[db], (it / ND2) & 1);
+      if (q == 0) RB3_TRACE(4, it, 0);
       tc_fence_after();
       uint8_t* abase = sA + ab * K::A_BYTES + (row + K::HALO) * 128;
       if (!RB3_DBG(2))
@@ -379,6 +403,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tma_store_wait_read();
         mbar_arrive(&a_empty[ab]);
       }
+      if (q == 0) RB3_TRACE(4, it, 1);
     }
   } else {
     // ------------------------------------------------------------ epilogue 2 (warps 10..17), C = 256:
@@ -473,6 +498,7 @@ static int launch_resblock3(const void* a16, const void* w_packed, const float* 
     const char* e = getenv("B200VOC_DBG");
     p.dbg = e ? atoi(e) : 0;
   }
+  p.trace = g_rb2_trace;
   static bool configured[16] = {};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
@@ -482,7 +508,7 @@ static int launch_resblock3(const void* a16, const void* w_packed, const float* 
     configured[dev & 15] = true;
   }
   const int grid = p.total_tiles < num_sms3() ? p.total_tiles : num_sms3();
-  resblock3_kernel<C, FMT, OFMT, LRELU><<<grid, 576, K::SMEM, stream>>>(tmX, tmW1, tmW2, tmOut, p);
+  resblock3_kernel<C, FMT, OFMT, LRELU><<<grid, 608, K::SMEM, stream>>>(tmX, tmW1, tmW2, tmOut, p);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
