@@ -65,6 +65,7 @@ _SIGNATURES = {
     "b200voc_pack_resblock_weights": (C.c_int, [_P, _P, _I, _I, _P, _P]),
     "b200voc_resblock": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "b200voc_exp_rowshift": (C.c_int, [_P, _P, _P, _P]),
+    "b200voc_exp_cta2": (C.c_int, [_P, _P, _I, _P, _P, _P]),
     "b200voc_debug_set_trace": (C.c_int, [_P]),
     "b200voc_exp_mma_rate": (C.c_int, [_I, _I, _I, _P, _P]),
     "b200voc_stft_mag": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P]),

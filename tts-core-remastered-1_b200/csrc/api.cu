@@ -90,6 +90,7 @@ int linear_launch(const void*, const void*, const float*, int, int, int, int, in
 int pack_convt_launch(const float*, int, int, int, int, void*, cudaStream_t);
 int exp_rowshift_launch(const void*, const void*, float*, cudaStream_t);
 int exp_mma_rate_launch(int, int, int, long long*, cudaStream_t);
+int exp_cta2_launch(const void*, const void*, int, float*, long long*, cudaStream_t);
 int pack_resblock_launch(const float*, const float*, int, int, void*, cudaStream_t);
 int resblock_launch(const void* a16, const void* w, const float* b_conv, const float* b_proj, const float* film,
                     int film_stride, int N, int L, int C, int dilation, int T, int num_bands, int fmt, int out_fmt,
@@ -696,6 +697,10 @@ int b200voc_exp_mma_rate(int n, int iters, int blocks, int64_t* out_cycles, void
   B200_CHECK_ARG(out_cycles && iters > 0 && blocks > 0, "exp_mma_rate: bad argument");
   return exp_mma_rate_launch(n, iters, blocks, reinterpret_cast<long long*>(out_cycles),
                              reinterpret_cast<cudaStream_t>(stream));
+}
+int b200voc_exp_cta2(const void* a16, const void* b16, int pairs, float* out, int64_t* cycles, void* stream) {
+  B200_CHECK_ARG(a16 && b16 && out && pairs > 0, "exp_cta2: bad argument");
+  return exp_cta2_launch(a16, b16, pairs, out, reinterpret_cast<long long*>(cycles), reinterpret_cast<cudaStream_t>(stream));
 }
 int b200voc_exp_rowshift(const void* a16, const void* b16, float* out, void* stream) {
   B200_CHECK_ARG(a16 && b16 && out, "exp_rowshift: null argument");
