@@ -21,7 +21,7 @@ namespace b200 {
 
 struct Resblock3Params {
   int L, dilation, T, P, num_bands;
-  int tiles_per_seq, total_tiles;
+  int tiles_per_seq, total_tiles, n_seq;
   const uint16_t* a16;   // [N, L, C] leaky_relu(x)
   const float* b_conv;   // [2C]
   const float* b_proj;   // [C]
@@ -45,7 +45,7 @@ struct Resblock3Params {
 #endif
 extern long long* g_rb2_trace;
 
-template <int C>
+template <int C, bool PAIR>
 struct Rb3Cfg {
   static constexpr int KPT = C / 64;                 // k-blocks per tap = GEMM1 chunks = GEMM2 k-blocks
   static constexpr int NCH = KPT;
@@ -57,16 +57,22 @@ struct Rb3Cfg {
   static constexpr bool INPLACE = C == 128;          // stage the output over the input tile + TMA store
   static constexpr int NA = C == 128 ? 3 : 1;            // input tiles have their own producer warp (18)
   static constexpr int H_KB_BYTES = 128 * 128;       // 16 KB per k-block
-  static constexpr int W_TILE = 128 * 128;           // 16 KB ring slot: [128 rows x 64 k]
+  // PAIR: two CTAs (a cluster of 2) work on two neighbouring row tiles with ONE tcgen05.mma.cta_group::2 per
+  // k-step (M = 256): each CTA stages only HALF of every weight tile (64 of its 128 rows), so the same
+  // shared-memory budget holds twice as many ring slots -- the weight ring's round trip was what paced the
+  // single-CTA kernel (tests/trace_resblock3.py).
+  static constexpr int W_ROWS = PAIR ? 64 : 128;
+  static constexpr int W_TILE = W_ROWS * 128;        // ring slot: [W_ROWS rows x 64 k]
   // weight ring: a slot's round trip (MMAs complete -> commit -> producer -> TMA from L2 -> issuer) is ~1800 clk
   // against 256 clk of MMA work per slot, measured (tests/trace_resblock3.py): the ring must hold ~7 slots
-  static constexpr int NW = 5;
+  static constexpr int NW = PAIR ? 10 : 5;
   static constexpr int ND2 = C == 128 ? 2 : 1;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_H = OFF_A + NA * A_BYTES;
   static constexpr int OFF_W = OFF_H + KPT * H_KB_BYTES;
   static constexpr int OFF_BAR = OFF_W + NW * W_TILE;
   static constexpr int OFF_PAR = OFF_BAR + 512;
+  static_assert((2 * NA + 2 * NW + 4 + 2 * KPT + 2 * (C == 128 ? 2 : 1) + NA) * 8 + 8 <= 512, "barrier block");
   static constexpr int SMEM = OFF_PAR + 3 * C * 4 + 1024;
   static constexpr int D2_COL = 256;
   static constexpr uint32_t TMEM_COLS = 512;
@@ -75,12 +81,12 @@ struct Rb3Cfg {
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-template <int C, int FMT, int OFMT, bool LRELU>
+template <int C, int FMT, int OFMT, bool LRELU, bool PAIR>
 __global__ void __launch_bounds__(608, 1)
 resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
                  const Resblock3Params p) {
-  using K = Rb3Cfg<C>;
+  using K = Rb3Cfg<C, PAIR>;
   constexpr int KPT = K::KPT, NCH = K::NCH, NH = K::NH, NA = K::NA, NW = K::NW, ND2 = K::ND2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
@@ -98,10 +104,13 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* h_empty = h_full + KPT;         // [KPT]
   uint64_t* d2_full = h_empty + KPT;        // [ND2]
   uint64_t* d2_empty = d2_full + ND2;       // [ND2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + ND2);
+  uint64_t* a_peer = d2_empty + ND2;        // [NA]  (PAIR, leader) the peer CTA's input tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_peer + NA);
   float* sPar = reinterpret_cast<float*>(smem + K::OFF_PAR);   // [ba | bg/2 | b2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;     // 0 = leader: issues the MMAs, owns the barriers the issuer waits on
+  constexpr int kCtas = PAIR ? 2 : 1;
   // multi-thread barriers are arrived on once per WARP (fence, __syncwarp, lane 0): a 128-arrival
   // barrier wakes the waiting MMA issuer ~25 times per phase (measured in resblock2.cu)
   constexpr int kE1Warps = 8;                           // both GLU warp sets share every chunk (32 channels each)
@@ -119,17 +128,29 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmOut);
     for (int b = 0; b < NA; ++b) { mbar_init(&a_full[b], 1); mbar_init(&a_empty[b], 1); }
     for (int b = 0; b < NW; ++b) { mbar_init(&w_full[b], 1); mbar_init(&w_empty[b], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&d1_full[b], 1); mbar_init(&d1_empty[b], kE1Warps); }
-    for (int b = 0; b < KPT; ++b) { mbar_init(&h_full[b], kE1Warps); mbar_init(&h_empty[b], 1); }
-    for (int b = 0; b < ND2; ++b) { mbar_init(&d2_full[b], 1); mbar_init(&d2_empty[b], kE2Warps); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&d1_full[b], 1); mbar_init(&d1_empty[b], kCtas * kE1Warps); }
+    for (int b = 0; b < KPT; ++b) { mbar_init(&h_full[b], kCtas * kE1Warps); mbar_init(&h_empty[b], 1); }
+    for (int b = 0; b < ND2; ++b) { mbar_init(&d2_full[b], 1); mbar_init(&d2_empty[b], kCtas * kE2Warps); }
+    for (int b = 0; b < NA; ++b) mbar_init(&a_peer[b], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, K::TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2cta(tmem_slot, K::TMEM_COLS); else tmem_alloc(tmem_slot, K::TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();       // barrier inits (and the pair's TMEM) visible to the peer
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // work units: a unit is one row tile (single CTA) or two neighbouring row tiles (pair: CTA `rank` takes tile
+  // 2u + rank; a tile index past the end is an all-out-of-bounds tile -- TMA zero-fills loads and clips stores)
+  const int n_units = PAIR ? (p.total_tiles + 1) / 2 : p.total_tiles;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_my_tiles = unit0 < n_units ? (n_units - unit0 + unit_stride - 1) / unit_stride : 0;
+  auto tile_of = [&](int it) { return PAIR ? 2 * (unit0 + it * unit_stride) + (int)rank : unit0 + it * unit_stride; };
+  // barriers the issuer waits on live in the leader CTA: arrive there (remote for the peer)
+  auto arrive_leader = [&](uint64_t* bar) {
+    if (!PAIR || rank == 0) mbar_arrive(bar); else mbar_arrive_remote(mapa_u32(bar, 0));
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer of the weight ring
@@ -138,14 +159,17 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       auto w_slot = [&]() -> uint8_t* {
         const int s = wi % NW;
         mbar_wait(&w_empty[s], ((wi / NW) & 1) ^ 1);
-        if (RB3_DBG(4) && wi >= NW) { mbar_arrive(&w_full[s]); return nullptr; }
-        mbar_expect_tx(&w_full[s], K::W_TILE);
+        if (RB3_DBG(4) && wi >= NW) { if (rank == 0) mbar_arrive(&w_full[s]); return nullptr; }
+        if (rank == 0) mbar_expect_tx(&w_full[s], kCtas * K::W_TILE);     // both halves land on the leader's barrier
         return sW + s * K::W_TILE;
       };
       auto load_w2 = [&](int kb) {
         for (int half = 0; half < NH; ++half) {
           uint8_t* dst = w_slot();
-          if (dst) tma_load_2d(dst, &tmW2, &w_full[wi % NW], kb * 64, half * 128);
+          if (dst) {
+            if (PAIR) tma_load_2d_2cta(dst, &tmW2, &w_full[wi % NW], kb * 64, half * 128 + rank * 64);
+            else tma_load_2d(dst, &tmW2, &w_full[wi % NW], kb * 64, half * 128);
+          }
           ++wi;
         }
       };
@@ -155,7 +179,10 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int tap = 0; tap < 3; ++tap)
             for (int kb = 0; kb < KPT; ++kb) {
               uint8_t* dst = w_slot();
-              if (dst) tma_load_2d(dst, &tmW1, &w_full[wi % NW], tap * C + kb * 64, j * 128);
+              if (dst) {
+                if (PAIR) tma_load_2d_2cta(dst, &tmW1, &w_full[wi % NW], tap * C + kb * 64, j * 128 + rank * 64);
+                else tma_load_2d(dst, &tmW1, &w_full[wi % NW], tap * C + kb * 64, j * 128);
+              }
               ++wi;
             }
           if (gc >= 1) load_w2((gc - 1) % NCH);
@@ -168,7 +195,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // wait for a free input slot must not hold up the weight stream)
     if (lane == 0) {
       for (int it = 0; it < n_my_tiles; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
+        const int tile = tile_of(it);
         const int seq = tile / p.tiles_per_seq, l0 = (tile - seq * p.tiles_per_seq) * 128;
         const int ab = it % NA;
         mbar_wait(&a_empty[ab], ((it / NA) & 1) ^ 1);
@@ -179,12 +206,30 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tma_load_3d(sA + ab * K::A_BYTES + kb * K::A_KB_BYTES, &tmX, &a_full[ab], kb * 64, l0 - K::HALO, seq);
       }
     }
+  } else if (warp == 1 && PAIR && rank != 0) {
+    // ------------------------------------------------------------ peer CTA: no MMAs to issue; tell the leader
+    // when each of our input tiles has landed
+    if (lane == 0) {
+      const uint32_t remote = mapa_u32(&a_peer[0], 0);
+      for (int it = 0; it < n_my_tiles; ++it) {
+        const int ab = it % NA;
+        mbar_wait(&a_full[ab], (it / NA) & 1);
+        mbar_arrive_remote(remote + ab * 8);
+      }
+    }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer.  The whole warp runs the
     // (warp-uniform) control flow so that indices and descriptors live in uniform registers; only the
     // tcgen05.mma / commit instructions are executed by one elected lane.
     {
-      const uint32_t idesc = make_idesc_f16(FMT, 128);
+      const uint32_t idesc = PAIR ? make_idesc_f16_m(FMT, 256, 128) : make_idesc_f16(FMT, 128);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+        if (PAIR) umma_f16_2cta(d, a, b, idesc, acc); else umma_f16(d, a, b, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (PAIR) umma_commit_2cta(bar, 0x3); else umma_commit(bar);      // PAIR: same barrier in both CTAs
+      };
+      auto wait_x = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };   // (barriers with remote arrivals)
       int wi = 0;
       // The weight-ring wait is software pipelined: while the MMAs of slot wi are being issued, a
       // non-blocking probe of slot wi+1 is already in flight, so a ready slot costs no round trip.
@@ -201,9 +246,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int db = it2 % ND2;
         const uint32_t phh = it2 & 1, phd = ((it2 / ND2) & 1) ^ 1;
         const bool rh = mbar_test(&h_full[kb], phh), rd = kb == 0 ? mbar_test(&d2_empty[db], phd) : true;
-        if (!rh) mbar_wait(&h_full[kb], phh);
+        if (!rh) wait_x(&h_full[kb], phh);
         RB3_TRACE(2, it2 * NCH + kb, 0);
-        if (!rd) mbar_wait(&d2_empty[db], phd);
+        if (!rd) wait_x(&d2_empty[db], phd);
         RB3_TRACE(2, it2 * NCH + kb, 1);
         tc_fence_after();
         const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sH + kb * K::H_KB_BYTES));
@@ -214,16 +259,15 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (!RB3_DBG(8))
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_base + K::D2_COL + db * C + half * 128, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                       (kb | k) != 0);
-            umma_commit(&w_empty[s]);
+              mma(tmem_base + K::D2_COL + db * C + half * 128, a_desc + 2 * k, b_desc + 2 * k, (kb | k) != 0);
+            commit(&w_empty[s]);
           }
           __syncwarp();
           ++wi;
         }
         if (elect_one()) {
-          umma_commit(&h_empty[kb]);
-          if (kb == NCH - 1) umma_commit(&d2_full[db]);
+          commit(&h_empty[kb]);
+          if (kb == NCH - 1) commit(&d2_full[db]);
         }
         __syncwarp();
       };
@@ -236,8 +280,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const uint32_t pha = (it / NA) & 1, phd = ((gc >> 1) & 1) ^ 1;
             const bool ra = j == 0 ? mbar_test(&a_full[ab], pha) : true, rd = mbar_test(&d1_empty[b], phd);
             if (!ra) mbar_wait(&a_full[ab], pha);
+            if (PAIR && j == 0) wait_x(&a_peer[ab], pha);
             RB3_TRACE(1, gc, 0);
-            if (!rd) mbar_wait(&d1_empty[b], phd);
+            if (!rd) wait_x(&d1_empty[b], phd);
             RB3_TRACE(1, gc, 1);
           }
           tc_fence_after();
@@ -252,15 +297,15 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 if (!RB3_DBG(32))
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(tmem_base + b * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, (tap | kb | k) != 0);
-                umma_commit(&w_empty[s]);
+                  mma(tmem_base + b * 128, a_desc + 2 * k, b_desc + 2 * k, (tap | kb | k) != 0);
+                commit(&w_empty[s]);
               }
               __syncwarp();
               ++wi;
             }
           if (elect_one()) {
-            umma_commit(&d1_full[b]);
-            if (!K::INPLACE && j == NCH - 1) umma_commit(&a_empty[ab]);   // INPLACE: released by the store epilogue
+            commit(&d1_full[b]);
+            if (!K::INPLACE && j == NCH - 1) commit(&a_empty[ab]);        // INPLACE: released by the store epilogue
           }
           __syncwarp();
           RB3_TRACE(1, gc, 2);
@@ -282,8 +327,10 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const float4* sNB = reinterpret_cast<const float4*>(sPar + C);
     int gc = 0;
     for (int it = 0; it < n_my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int seq = tile / p.tiles_per_seq, l = (tile - seq * p.tiles_per_seq) * 128 + row;
+      const int tile = tile_of(it);
+      int seq = tile / p.tiles_per_seq;
+      const int l = (tile - seq * p.tiles_per_seq) * 128 + row;
+      if (seq > p.n_seq - 1) seq = p.n_seq - 1;               // pair mode: the tile past the end is out of bounds
       int t = l / p.P;
       if (t > p.T - 1) t = p.T - 1;
       const float* film = p.film + ((long long)(seq / p.num_bands) * p.T + t) * p.film_stride;
@@ -336,8 +383,8 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&h_full[j]);
-          mbar_arrive(&d1_empty[b]);
+          arrive_leader(&h_full[j]);
+          arrive_leader(&d1_empty[b]);
         }
         if (q == 0 && par == 0) RB3_TRACE(3, gc, 2);
       }
@@ -351,7 +398,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float4* sB2 = reinterpret_cast<const float4*>(sPar + 2 * C);
     for (int it = par; it < n_my_tiles; it += 2) {
-      const int tile = blockIdx.x + it * gridDim.x;
+      const int tile = tile_of(it);
       const int seq = tile / p.tiles_per_seq, l0 = (tile - seq * p.tiles_per_seq) * 128;
       const int db = it % ND2, ab = it % NA;
       mbar_wait(&a_full[ab], (it / NA) & 1);      // visibility of the TMA-written tile to this thread
@@ -393,7 +440,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&d2_empty[db]);
+      if (lane == 0) arrive_leader(&d2_empty[db]);
       named_bar_sync(1 + par, 128);
       if (q == 0 && lane == 0) {
 #pragma unroll
@@ -414,11 +461,11 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float4* sB2 = reinterpret_cast<const float4*>(sPar + 2 * C);
     for (int it = 0; it < n_my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
+      const int tile = tile_of(it);
       const int seq = tile / p.tiles_per_seq, l = (tile - seq * p.tiles_per_seq) * 128 + row;
-      const bool valid = l < p.L;
+      const bool valid = l < p.L && seq < p.n_seq;          // (pair mode: the tile past the end is out of bounds)
       const int db = it % ND2;
-      const long long roff = ((long long)seq * p.L + (valid ? l : 0)) * C;
+      const long long roff = ((long long)(seq < p.n_seq ? seq : p.n_seq - 1) * p.L + (valid ? l : 0)) * C;
       const uint4* xin = reinterpret_cast<const uint4*>(p.a16 + roff);
       uint4* dst = reinterpret_cast<uint4*>(p.out + roff);
       // the residual operand comes from global (L2): issue the loads BEFORE waiting for the accumulator
@@ -459,12 +506,14 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&d2_empty[db]);
+      if (lane == 0) arrive_leader(&d2_empty[db]);
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, K::TMEM_COLS);
+  if (PAIR) cluster_sync_all(); else __syncthreads();       // the peer may still read our shared memory / TMEM until here
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_2cta(tmem_base, K::TMEM_COLS); else tmem_dealloc(tmem_base, K::TMEM_COLS);
+  }
 }
 
 static int num_sms3() {
@@ -475,22 +524,33 @@ static int num_sms3() {
   return n[dev & 15];
 }
 
-template <int C, int FMT, int OFMT, bool LRELU>
-static int launch_resblock3(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
-                            const float* film, int film_stride, int N, int L, int dilation, int T, int num_bands,
-                            void* out16, cudaStream_t stream) {
-  using K = Rb3Cfg<C>;
+// B200VOC_RB3_PAIR=0 forces the single-CTA kernel (A/B runs); default is the CTA-pair (cta_group::2) kernel.
+static bool use_pair() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200VOC_RB3_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int C, int FMT, int OFMT, bool LRELU, bool PAIR>
+static int launch_resblock3_t(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
+                              const float* film, int film_stride, int N, int L, int dilation, int T, int num_bands,
+                              void* out16, cudaStream_t stream) {
+  using K = Rb3Cfg<C, PAIR>;
   CUtensorMap tmX, tmW1, tmW2, tmOut;
   B200_TRY(make_tmap_3d(&tmX, a16, C, L, N, (uint64_t)C * 2, (uint64_t)L * C * 2, 64, K::A_ROWS, 128));
   B200_TRY(make_tmap_3d(&tmOut, out16, C, L, N, (uint64_t)C * 2, (uint64_t)L * C * 2, 64, 128, 128));
   const uint16_t* w1 = reinterpret_cast<const uint16_t*>(w_packed);
   const uint16_t* w2 = w1 + 2ll * C * 3 * C;
-  B200_TRY(make_tmap_2d(&tmW1, w1, 3 * C, 2 * C, (uint64_t)3 * C * 2, 64, 128, 128));
-  B200_TRY(make_tmap_2d(&tmW2, w2, C, C, (uint64_t)C * 2, 64, 128, 128));
+  B200_TRY(make_tmap_2d(&tmW1, w1, 3 * C, 2 * C, (uint64_t)3 * C * 2, 64, K::W_ROWS, 128));
+  B200_TRY(make_tmap_2d(&tmW2, w2, C, C, (uint64_t)C * 2, 64, K::W_ROWS, 128));
   Resblock3Params p{};
   p.L = L; p.dilation = dilation; p.T = T; p.P = L / T; p.num_bands = num_bands;
   p.tiles_per_seq = ceil_div(L, 128);
   p.total_tiles = p.tiles_per_seq * N;
+  p.n_seq = N;
   p.a16 = reinterpret_cast<const uint16_t*>(a16);
   p.b_conv = b_conv; p.b_proj = b_proj; p.film = film; p.film_stride = film_stride;
   p.out = reinterpret_cast<uint16_t*>(out16);
@@ -502,15 +562,44 @@ static int launch_resblock3(const void* a16, const void* w_packed, const float* 
   static bool configured[16] = {};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
+  auto kernel = resblock3_kernel<C, FMT, OFMT, LRELU, PAIR>;
   if (!configured[dev & 15]) {
-    B200_CUDA(cudaFuncSetAttribute(resblock3_kernel<C, FMT, OFMT, LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   K::SMEM));
+    B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
     configured[dev & 15] = true;
   }
-  const int grid = p.total_tiles < num_sms3() ? p.total_tiles : num_sms3();
-  resblock3_kernel<C, FMT, OFMT, LRELU><<<grid, 608, K::SMEM, stream>>>(tmX, tmW1, tmW2, tmOut, p);
+  const int sms = num_sms3();
+  if (!PAIR) {
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    kernel<<<grid, 608, K::SMEM, stream>>>(tmX, tmW1, tmW2, tmOut, p);
+  } else {
+    const int units = (p.total_tiles + 1) / 2, pairs = units < sms / 2 ? units : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(608);
+    cfg.dynamicSmemBytes = K::SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmX, tmW1, tmW2, tmOut, p));
+  }
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
+}
+
+template <int C, int FMT, int OFMT, bool LRELU>
+static int launch_resblock3(const void* a16, const void* w_packed, const float* b_conv, const float* b_proj,
+                            const float* film, int film_stride, int N, int L, int dilation, int T, int num_bands,
+                            void* out16, cudaStream_t stream) {
+  if (use_pair())
+    return launch_resblock3_t<C, FMT, OFMT, LRELU, true>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation,
+                                                         T, num_bands, out16, stream);
+  return launch_resblock3_t<C, FMT, OFMT, LRELU, false>(a16, w_packed, b_conv, b_proj, film, film_stride, N, L, dilation,
+                                                        T, num_bands, out16, stream);
 }
 
 template <int C>
