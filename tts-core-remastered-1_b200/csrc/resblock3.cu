@@ -65,12 +65,17 @@ struct Rb3Cfg {
   static constexpr int W_TILE = W_ROWS * 128;        // ring slot: [W_ROWS rows x 64 k]
   // weight ring: a slot's round trip (MMAs complete -> commit -> producer -> TMA from L2 -> issuer) is ~1800 clk
   // against 256 clk of MMA work per slot, measured (tests/trace_resblock3.py): the ring must hold ~7 slots
-  static constexpr int NW = PAIR ? 10 : 5;
+  // PAIR: a ring slot holds SUBS = 2 sub-tiles (two k-blocks of one tap, or the two column halves of a GEMM2
+  // k-block), i.e. 8 MMAs per barrier hand-off: the MMA issuer is a single warp whose per-slot instruction path
+  // (~50 dependent instructions, sharing its scheduler with 4 epilogue warps) costs about as much as 4 MMAs.
+  static constexpr int SUBS = PAIR ? 2 : 1;
+  static constexpr int W_SLOT = SUBS * W_TILE;
+  static constexpr int NW = 5;
   static constexpr int ND2 = C == 128 ? 2 : 1;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_H = OFF_A + NA * A_BYTES;
   static constexpr int OFF_W = OFF_H + KPT * H_KB_BYTES;
-  static constexpr int OFF_BAR = OFF_W + NW * W_TILE;
+  static constexpr int OFF_BAR = OFF_W + NW * W_SLOT;
   static constexpr int OFF_PAR = OFF_BAR + 512;
   static_assert((2 * NA + 2 * NW + 4 + 2 * KPT + 2 * (C == 128 ? 2 : 1) + NA) * 8 + 8 <= 512, "barrier block");
   static constexpr int SMEM = OFF_PAR + 3 * C * 4 + 1024;
@@ -156,33 +161,41 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // ------------------------------------------------------------ TMA producer of the weight ring
     if (lane == 0) {
       int wi = 0;
-      auto w_slot = [&]() -> uint8_t* {
+      auto w_slot = [&](int nsub) -> uint8_t* {
         const int s = wi % NW;
         mbar_wait(&w_empty[s], ((wi / NW) & 1) ^ 1);
         if (RB3_DBG(4) && wi >= NW) { if (rank == 0) mbar_arrive(&w_full[s]); return nullptr; }
-        if (rank == 0) mbar_expect_tx(&w_full[s], kCtas * K::W_TILE);     // both halves land on the leader's barrier
-        return sW + s * K::W_TILE;
+        (void)nsub;
+        if (rank == 0) mbar_expect_tx(&w_full[s], kCtas * nsub * K::W_TILE);   // both CTAs' bytes land on the leader's barrier
+        return sW + s * K::W_SLOT;
+      };
+      auto load_w = [&](uint8_t* dst, const CUtensorMap* tm, int c0, int c1) {
+        if (PAIR) tma_load_2d_2cta(dst, tm, &w_full[wi % NW], c0, c1 + rank * 64);
+        else tma_load_2d(dst, tm, &w_full[wi % NW], c0, c1);
       };
       auto load_w2 = [&](int kb) {
-        for (int half = 0; half < NH; ++half) {
-          uint8_t* dst = w_slot();
-          if (dst) {
-            if (PAIR) tma_load_2d_2cta(dst, &tmW2, &w_full[wi % NW], kb * 64, half * 128 + rank * 64);
-            else tma_load_2d(dst, &tmW2, &w_full[wi % NW], kb * 64, half * 128);
-          }
+        if (K::SUBS == 2) {                       // one slot: the NH column halves of this k-block
+          uint8_t* dst = w_slot(NH);
+          if (dst)
+            for (int half = 0; half < NH; ++half) load_w(dst + half * K::W_TILE, &tmW2, kb * 64, half * 128);
           ++wi;
+        } else {
+          for (int half = 0; half < NH; ++half) {
+            uint8_t* dst = w_slot(1);
+            if (dst) load_w(dst, &tmW2, kb * 64, half * 128);
+            ++wi;
+          }
         }
       };
       int gc = 0;
       for (int it = 0; it < n_my_tiles; ++it) {
         for (int j = 0; j < NCH; ++j, ++gc) {
           for (int tap = 0; tap < 3; ++tap)
-            for (int kb = 0; kb < KPT; ++kb) {
-              uint8_t* dst = w_slot();
-              if (dst) {
-                if (PAIR) tma_load_2d_2cta(dst, &tmW1, &w_full[wi % NW], tap * C + kb * 64, j * 128 + rank * 64);
-                else tma_load_2d(dst, &tmW1, &w_full[wi % NW], tap * C + kb * 64, j * 128);
-              }
+            for (int kb = 0; kb < KPT; kb += K::SUBS) {
+              uint8_t* dst = w_slot(K::SUBS);
+              if (dst)
+                for (int sub = 0; sub < K::SUBS; ++sub)
+                  load_w(dst + sub * K::W_TILE, &tmW1, tap * C + (kb + sub) * 64, j * 128);
               ++wi;
             }
           if (gc >= 1) load_w2((gc - 1) % NCH);
@@ -252,9 +265,25 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         RB3_TRACE(2, it2 * NCH + kb, 1);
         tc_fence_after();
         const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sH + kb * K::H_KB_BYTES));
+        if (K::SUBS == 2) {
+          const int s = acquire_w();
+          const uint64_t b_desc0 = make_kmajor_desc<128>(smem_u32(sW + s * K::W_SLOT));
+          if (elect_one()) {
+            if (!RB3_DBG(8))
+#pragma unroll
+            for (int half = 0; half < NH; ++half)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                mma(tmem_base + K::D2_COL + db * C + half * 128, a_desc + 2 * k, b_desc0 + (half * K::W_TILE >> 4) + 2 * k,
+                    (kb | k) != 0);
+            commit(&w_empty[s]);
+          }
+          __syncwarp();
+          ++wi;
+        } else
         for (int half = 0; half < NH; ++half) {
           const int s = acquire_w();
-          const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + s * K::W_TILE));
+          const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + s * K::W_SLOT));
           if (elect_one()) {
             if (!RB3_DBG(8))
 #pragma unroll
@@ -287,17 +316,20 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
           tc_fence_after();
           for (int tap = 0; tap < 3; ++tap)
-            for (int kb = 0; kb < KPT; ++kb) {
+            for (int kb = 0; kb < KPT; kb += K::SUBS) {
               const int s = acquire_w();
               const uint32_t a_addr = smem_u32(sA + ab * K::A_BYTES + kb * K::A_KB_BYTES) +
                                       (K::HALO + (tap - 1) * p.dilation) * 128;
               const uint64_t a_desc = make_kmajor_desc<128>(a_addr);
-              const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + s * K::W_TILE));
+              const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + s * K::W_SLOT));
               if (elect_one()) {
                 if (!RB3_DBG(32))
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  mma(tmem_base + b * 128, a_desc + 2 * k, b_desc + 2 * k, (tap | kb | k) != 0);
+                for (int sub = 0; sub < K::SUBS; ++sub)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    mma(tmem_base + b * 128, a_desc + (sub * K::A_KB_BYTES >> 4) + 2 * k,
+                        b_desc + (sub * K::W_TILE >> 4) + 2 * k, (tap | kb | sub | k) != 0);
                 commit(&w_empty[s]);
               }
               __syncwarp();
