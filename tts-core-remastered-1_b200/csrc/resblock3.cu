@@ -78,7 +78,8 @@ struct Rb3Cfg {
   static constexpr int OFF_BAR = OFF_W + NW * W_SLOT;
   static constexpr int OFF_PAR = OFF_BAR + 512;
   static_assert((2 * NA + 2 * NW + 4 + 2 * KPT + 2 * (C == 128 ? 2 : 1) + NA) * 8 + 8 <= 512, "barrier block");
-  static constexpr int SMEM = OFF_PAR + 3 * C * 4 + 1024;
+  static constexpr int OFF_FILM = OFF_PAR + 3 * C * 4;    // per GLU warp: (1+scale | shift) of its 32 channels of a chunk
+  static constexpr int SMEM = OFF_FILM + 8 * 64 * 4 + 1024;
   static constexpr int D2_COL = 256;
   static constexpr uint32_t TMEM_COLS = 512;
   static constexpr int A_PREFETCH_AFTER_CHUNK = NA >= 2 ? 0 : NCH - 1;
@@ -122,7 +123,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   constexpr int kE2Warps = K::INPLACE ? 4 : 8;          // tile-parity set, or all 8 warps (C=256)
 
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    sPar[i] = p.b_conv[i];
+    sPar[i] = 0.5f * p.b_conv[i];              // W1 is packed pre-scaled by 1/2 (see pack_resblock_kernel)
     sPar[C + i] = 0.5f * p.b_conv[C + i];
     sPar[2 * C + i] = p.b_proj[i];
   }
@@ -353,41 +354,67 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // value channels: the time an accumulator buffer is held (which gates the MMAs of chunk j+2)
     // halves, and knocking this epilogue out entirely is worth ~9 % (tests/knock_resblock3.py)
     const int q = warp & 3, par = (warp - 2) >> 2;
-    const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float4* sBA = reinterpret_cast<const float4*>(sPar);
     const float4* sNB = reinterpret_cast<const float4*>(sPar + C);
+    float* scratch = reinterpret_cast<float*>(smem + K::OFF_FILM) + (warp - 2) * 64;     // [S(32) | T(32)]
     int gc = 0;
     for (int it = 0; it < n_my_tiles; ++it) {
       const int tile = tile_of(it);
       int seq = tile / p.tiles_per_seq;
-      const int l = (tile - seq * p.tiles_per_seq) * 128 + row;
+      const int lw = (tile - seq * p.tiles_per_seq) * 128 + q * 32;   // first row of this warp
+      const int l = lw + lane;
       if (seq > p.n_seq - 1) seq = p.n_seq - 1;               // pair mode: the tile past the end is out of bounds
-      int t = l / p.P;
+      // FiLM: when the warp's 32 rows lie in one frame (P >= 32 and aligned: stage 1 of the generator) the
+      // frame's coefficients for this warp's 32 channels are staged once per chunk in shared memory and read
+      // back as broadcasts -- a warp-wide LDG.128 of one address costs 4-5 L1 wavefronts (resblock2.cu)
+      const int tw = lw / p.P;
+      const bool uniform = (lw - tw * p.P) + 31 < p.P;
+      int t = uniform ? tw : l / p.P;
       if (t > p.T - 1) t = p.T - 1;
       const float* film = p.film + ((long long)(seq / p.num_bands) * p.T + t) * p.film_stride;
+      if (!uniform) {
 #pragma unroll
-      for (int k = 0; k < (2 * C) / 32; ++k) prefetch_l1(film + k * 32);     // this row's FiLM line(s) -> L1
+        for (int k = 0; k < (2 * C) / 32; ++k) prefetch_l1(film + k * 32);   // this row's FiLM line(s) -> L1
+      }
       for (int j = 0; j < NCH; ++j, ++gc) {
         const int b = gc & 1;
+        const int ch0 = j * 64 + par * 32;                    // this warp's first channel in this chunk
+        float4 stage = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (uniform && lane < 16)                             // lanes 0-7: S, 8-15: T
+          stage = __ldg(reinterpret_cast<const float4*>(film + (lane < 8 ? 0 : C) + ch0) + (lane & 7));
         mbar_wait(&d1_full[b], (gc >> 1) & 1);
         if (q == 0 && par == 0) RB3_TRACE(3, gc, 0);
         mbar_wait(&h_empty[j], (it & 1) ^ 1);
         if (q == 0 && par == 0) RB3_TRACE(3, gc, 1);
         tc_fence_after();
-        uint8_t* hrow = sH + j * K::H_KB_BYTES + row * 128;
+        if (uniform) {
+          if (lane < 16) reinterpret_cast<float4*>(scratch)[lane] = stage;
+          __syncwarp();
+        }
+        uint8_t* hrow = sH + j * K::H_KB_BYTES + (q * 32 + lane) * 128;
+        const int row = q * 32 + lane;
         if (!RB3_DBG(1))
 #pragma unroll
-        for (int cl = par * 32; cl < par * 32 + 32; cl += 16) {   // column inside the chunk's 64 value channels
+        for (int cc = 0; cc < 32; cc += 16) {   // column inside this warp's 32 value channels
+          const int cl = par * 32 + cc;
           uint32_t va[16], vg[16];
           tmem_ld16(lane_addr + b * 128 + cl, va);
           tmem_ld16(lane_addr + b * 128 + 64 + cl, vg);
           const int ch = j * 64 + cl;
-          const float4* fs = reinterpret_cast<const float4*>(film + ch);
-          const float4* fh = reinterpret_cast<const float4*>(film + C + ch);
           float4 S[4], H[4];
+          if (uniform) {
 #pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) { S[i4] = __ldg(fs + i4); H[i4] = __ldg(fh + i4); }
+            for (int i4 = 0; i4 < 4; ++i4) {
+              S[i4] = reinterpret_cast<const float4*>(scratch + cc)[i4];
+              H[i4] = reinterpret_cast<const float4*>(scratch + 32 + cc)[i4];
+            }
+          } else {
+            const float4* fs = reinterpret_cast<const float4*>(film + ch);
+            const float4* fh = reinterpret_cast<const float4*>(film + C + ch);
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) { S[i4] = __ldg(fs + i4); H[i4] = __ldg(fh + i4); }
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int i8 = 0; i8 < 2; ++i8) {
@@ -400,9 +427,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               const float sv[4] = {S[i4].x, S[i4].y, S[i4].z, S[i4].w}, tv[4] = {H[i4].x, H[i4].y, H[i4].z, H[i4].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float a = __uint_as_float(va[i4 * 4 + e]) + av[e];
-                const float sg = sigmoid_from_half_g(fmaf(__uint_as_float(vg[i4 * 4 + e]), 0.5f, gv[e]));
-                hv[h4 * 4 + e] = fmaf(a * sg, sv[e], tv[e]);
+                const float a = __uint_as_float(va[i4 * 4 + e]) + av[e];                  // (conv_a + b_a) / 2
+                const float th = tanh_approx(__uint_as_float(vg[i4 * 4 + e]) + gv[e]);    // tanh(g / 2)
+                hv[h4 * 4 + e] = fmaf(fmaf(a, th, a), sv[e], tv[e]);                      // a sigmoid(g) (1+scale) + shift
               }
             }
             const int chunk = (cl >> 3) + i8;
