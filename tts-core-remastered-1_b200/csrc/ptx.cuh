@@ -86,6 +86,11 @@ __device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// warpgroup-wide register re-allocation (all 4 warps of the warpgroup must execute it; ptxas budgets
+// registers per region only when this is the FIRST statement of the role's branch)
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // one lane of a fully converged warp (warp-uniform control flow keeps address math in uniform registers)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
