@@ -217,6 +217,50 @@ def test_resblock_layer(C, d, fmt, store_lrelu):
     assert float(((got - ref).abs() / (ref.abs() + 1.0)).max()) <= 3 * ulp
 
 
+@pytest.mark.parametrize("C", [128, 256, 64])
+def test_resblock_layer_odd_tile_count(C):
+    """an odd number of 128-row tiles: the CTA-pair kernel's peer CTA gets one all-out-of-bounds tile
+    (TMA zero-fills its loads and clips its stores); also num_bands = 1 and a single FiLM frame per sequence."""
+    _l, lib = _lib()
+    dt = torch.float16
+    N, T, P, d = 3, 1, 300, 3
+    L = T * P                                    # 3 tiles per sequence -> 9 tiles
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(N, C, L, generator=g) * 0.5
+    if lib.b200voc_resblock_input_is_lrelu(C):
+        a = F.leaky_relu(x, 0.1).to(dt)
+        xr = torch.where(a.float() >= 0, a.float(), a.float() * 10.0)
+    else:
+        a = x.to(dt)
+        xr = a.float()
+    cond = torch.randn(N, 128, T, generator=g)
+    wc = torch.randn(2 * C, C, 3, generator=g) / (3 * C) ** 0.5
+    bc = torch.randn(2 * C, generator=g) * 0.1
+    wf = torch.randn(2 * C, 128, 1, generator=g) / 128 ** 0.5
+    bf = torch.randn(2 * C, generator=g) * 0.1
+    wp_ = torch.randn(C, C, 1, generator=g) / C ** 0.5
+    bp = torch.randn(C, generator=g) * 0.1
+    ref = O.residual_block_forward(xr.double(), cond.double(), wc.to(dt).double(), bc.double(), wf.double(),
+                                   bf.double(), wp_.to(dt).double(), bp.double(), d)
+    film = F.conv1d(cond, wf, bf)
+    film[:, :C] += 1.0
+    film_cl = film.transpose(1, 2).contiguous().cuda()
+    a_cl = a.transpose(1, 2).contiguous().cuda()
+    wpk = torch.empty(lib.b200voc_resblock_packed_elems(C), dtype=dt, device="cuda")
+    st = _l.current_stream()
+    wcd, wpd, bcd, bpd = wc.cuda(), wp_.cuda(), bc.cuda(), bp.cuda()
+    _l.check(lib.b200voc_pack_resblock_weights(_l.ptr(wcd), _l.ptr(wpd), C, 0, _l.ptr(wpk), st))
+    guard = torch.full((N * L * C + 4096,), float("nan"), dtype=dt, device="cuda")     # detects writes past the end
+    out = guard[:N * L * C].view(N, L, C)
+    _l.check(lib.b200voc_resblock(_l.ptr(a_cl), _l.ptr(wpk), _l.ptr(bcd), _l.ptr(bpd), _l.ptr(film_cl), N, L, C, d, T,
+                                  1, 0, 0, _l.ptr(out), st))
+    torch.cuda.synchronize()
+    got = out.float().cpu().transpose(1, 2).double()
+    assert not bool(torch.isnan(got).any())
+    assert bool(torch.isnan(guard[N * L * C:]).all())
+    assert float(((got - ref).abs() / (ref.abs() + 1.0)).max()) <= 3 * 2.0 ** -11
+
+
 def test_rowshifted_umma_descriptors():
     """a K-major SWIZZLE_128B descriptor may start at any 128-byte row of a TMA-written
     tile with base_offset = 0 (the swizzle is a function of the absolute smem address)."""
