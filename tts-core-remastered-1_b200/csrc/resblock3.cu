@@ -237,8 +237,11 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // tcgen05.mma / commit instructions are executed by one elected lane.
     {
       const uint32_t idesc = PAIR ? make_idesc_f16_m(FMT, 256, 128) : make_idesc_f16(FMT, 128);
-      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
-        if (PAIR) umma_f16_2cta(d, a, b, idesc, acc); else umma_f16(d, a, b, idesc, acc);
+      // descriptors as (low word, common high word): every operand tile here is K-major SWIZZLE_128B
+      const uint32_t desc_hi = (uint32_t)(make_kmajor_desc<128>(0) >> 32);
+      auto desc_lo = [](uint32_t smem_addr) { return (uint32_t)make_kmajor_desc<128>(smem_addr); };
+      auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+        if (PAIR) umma_f16_2cta_lh(d, a_lo, b_lo, desc_hi, idesc, acc); else umma_f16_lh(d, a_lo, b_lo, desc_hi, idesc, acc);
       };
       auto commit = [&](uint64_t* bar) {
         if (PAIR) umma_commit_2cta(bar, 0x3); else umma_commit(bar);      // PAIR: same barrier in both CTAs
@@ -265,10 +268,10 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (!rd) wait_x(&d2_empty[db], phd);
         RB3_TRACE(2, it2 * NCH + kb, 1);
         tc_fence_after();
-        const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sH + kb * K::H_KB_BYTES));
+        const uint32_t a_desc = desc_lo(smem_u32(sH + kb * K::H_KB_BYTES));
         if (K::SUBS == 2) {
           const int s = acquire_w();
-          const uint64_t b_desc0 = make_kmajor_desc<128>(smem_u32(sW + s * K::W_SLOT));
+          const uint32_t b_desc0 = desc_lo(smem_u32(sW + s * K::W_SLOT));
           if (elect_one()) {
             if (!RB3_DBG(8))
 #pragma unroll
@@ -284,7 +287,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         } else
         for (int half = 0; half < NH; ++half) {
           const int s = acquire_w();
-          const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + s * K::W_SLOT));
+          const uint32_t b_desc = desc_lo(smem_u32(sW + s * K::W_SLOT));
           if (elect_one()) {
             if (!RB3_DBG(8))
 #pragma unroll
@@ -321,8 +324,8 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               const int s = acquire_w();
               const uint32_t a_addr = smem_u32(sA + ab * K::A_BYTES + kb * K::A_KB_BYTES) +
                                       (K::HALO + (tap - 1) * p.dilation) * 128;
-              const uint64_t a_desc = make_kmajor_desc<128>(a_addr);
-              const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + s * K::W_SLOT));
+              const uint32_t a_desc = desc_lo(a_addr);
+              const uint32_t b_desc = desc_lo(smem_u32(sW + s * K::W_SLOT));
               if (elect_one()) {
                 if (!RB3_DBG(32))
 #pragma unroll
@@ -399,11 +402,19 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int cc = 0; cc < 32; cc += 16) {   // column inside this warp's 32 value channels
           const int cl = par * 32 + cc;
           uint32_t va[16], vg[16];
-          tmem_ld16(lane_addr + b * 128 + cl, va);
-          tmem_ld16(lane_addr + b * 128 + 64 + cl, vg);
+          if (RB3_DBG(512)) {
+#pragma unroll
+            for (int z = 0; z < 16; ++z) { va[z] = 0x3f000000u + z; vg[z] = 0x3e000000u + lane; }
+          } else {
+            tmem_ld16(lane_addr + b * 128 + cl, va);
+            tmem_ld16(lane_addr + b * 128 + 64 + cl, vg);
+          }
           const int ch = j * 64 + cl;
           float4 S[4], H[4];
-          if (uniform) {
+          if (RB3_DBG(128)) {
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) { S[i4] = make_float4(1.f, 1.f, 1.f, 1.f); H[i4] = make_float4(0.f, 0.f, 0.f, 0.f); }
+          } else if (uniform) {
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
               S[i4] = reinterpret_cast<const float4*>(scratch + cc)[i4];
@@ -428,11 +439,13 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float a = __uint_as_float(va[i4 * 4 + e]) + av[e];                  // (conv_a + b_a) / 2
-                const float th = tanh_approx(__uint_as_float(vg[i4 * 4 + e]) + gv[e]);    // tanh(g / 2)
+                const float gg = __uint_as_float(vg[i4 * 4 + e]) + gv[e];
+                const float th = RB3_DBG(64) ? gg : tanh_approx(gg);                        // tanh(g / 2)
                 hv[h4 * 4 + e] = fmaf(fmaf(a, th, a), sv[e], tv[e]);                      // a sigmoid(g) (1+scale) + shift
               }
             }
             const int chunk = (cl >> 3) + i8;
+            if (!RB3_DBG(256) || hv[0] == 123.456f)
             *reinterpret_cast<uint4*>(hrow + ((chunk ^ (row & 7)) << 4)) =
                 make_uint4(pack2t<FMT>(hv[0], hv[1]), pack2t<FMT>(hv[2], hv[3]), pack2t<FMT>(hv[4], hv[5]),
                            pack2t<FMT>(hv[6], hv[7]));
