@@ -400,7 +400,7 @@ def run_b200(args):
         "config": workload_config(world),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "kernel": "resblock3_kernel<128,...> (stage-1 fused residual block: conv k3 + GLU + FiLM + 1x1 + residual, 3 launches/step)",
+                     "kernel": "resblock3_kernel<128,...,PAIR> (stage-1 fused residual block on CTA pairs, tcgen05.mma.cta_group::2: conv k3 + GLU + FiLM + 1x1 + residual, 3 launches/step)",
                      "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
                      "flops_per_launch": dom_flops, "ms_per_launch": dom_ms},
         "whole_step": {"algorithmic_tflop": total_flops / 1e12, "sum_kernel_ms": conv_ms,
