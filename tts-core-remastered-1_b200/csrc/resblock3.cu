@@ -1,17 +1,28 @@
 // K2c: persistent fused residual block for the wide stages (C = 128, 256) -- the tensor-bound
 // part of the network (81 % of all FLOPs live in residual blocks, stages 0-1 hold two thirds).
 //
-// Same math as resblock.cu (generator.py:40-41,89-90 / repair R2).  Schedule:
-//   * one persistent CTA per SM loops over (sequence, 128-row) tiles;
+// Same math as resblock2.cu (generator.py:40-41,89-90 / repair R2).  Schedule:
+//   * persistent CTA PAIRS (a cluster of 2, template PAIR): the two CTAs own two neighbouring 128-row
+//     tiles; the leader issues one tcgen05.mma.cta_group::2 (M = 256, N = 128) per k-step, each CTA
+//     supplies its own rows of A and HALF of the B (weight) tile, the accumulators sit at the same
+//     TMEM address in both CTAs.  Commits are multicast to both CTAs; the peer's epilogue warps arrive
+//     on the leader's barriers (mapa + mbarrier.arrive.shared::cluster); the peer's weight TMA signals
+//     the leader's barrier (cp.async.bulk.tensor ... cta_group::2).  PAIR = false is the single-CTA
+//     schedule the pair grew out of (B200VOC_RB3_PAIR=0);
 //   * the leaky_relu(x) tile (128 rows + 8-row halo each side, all channels) is loaded ONCE per
 //     tile; the three dilated taps are row-shifted UMMA descriptors over that tile;
-//   * weights do not fit in shared memory (W1 is 192/768 KB), so they stream through a TMA ring of
-//     16 KB tiles (L2-resident: every CTA walks the same 224/896 KB sequence);
+//   * weights do not fit in shared memory (W1 is 192/768 KB), so they stream from L2 through a TMA
+//     ring; what paced the single-CTA kernel was the ring (5 x 16 KB = 1.3 k clk of MMAs against a
+//     ~1.8 k clk slot round trip) and the single issuing warp's instruction path per slot (as long as
+//     the 4 MMAs it fed): a pair stages half tiles, so the same 80 KB hold 5 slots of 8 MMAs;
 //   * GEMM1 runs in chunks of 64 value + 64 gate channels into two alternating TMEM accumulators;
-//     the GLU/FiLM epilogue of chunk j (8 warps) overlaps the MMAs of chunk j+1; it writes h as
-//     k-block j of GEMM2's A operand; GEMM2's k-block j is issued one chunk later, the last
-//     one after the first chunk of the NEXT tile, so the tensor pipe never waits for an epilogue;
-//   * the residual/store epilogue (8 more warps) drains D2 while the next tile's GEMM1 runs.
+//     the GLU/FiLM epilogue of chunk j (8 warps, 32 channels each) overlaps the MMAs of chunk j+1; it
+//     writes h as k-block j of GEMM2's A operand; GEMM2's k-block j is issued one chunk later, the
+//     last one after the first chunk of the NEXT tile;
+//   * the residual/store epilogue (8 more warps) drains D2 while the next tile's GEMM1 runs;
+//   * separate producer warps for the weight ring and the input tiles; barriers are arrived on once
+//     per warp.  Measured bounds and the experiments behind these choices: DESIGN.md section 4b,
+//     profiles/r01_knockouts.txt.
 #include <stdlib.h>
 
 #include "common.cuh"
