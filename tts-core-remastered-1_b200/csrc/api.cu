@@ -2,6 +2,7 @@
 // (weight packing + layer plan + forward) and the layer-level entry points.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -98,7 +99,9 @@ int resblock_launch(const void* a16, const void* w, const float* b_conv, const f
 int style_emo_launch(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int,
                      float, float, int, int, float*, float*, cudaStream_t);
 int cond_launch(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int,
-                int, float*, cudaStream_t);
+                int, float*, void*, cudaStream_t);
+int pack_film3_launch(const float* w, long long rows, void* w3, cudaStream_t st);
+int film_tc_launch(const void* cond3, const void* w3, const float* b_all, int M, int ncols, float* out, cudaStream_t st);
 int film_launch(const float*, const float*, const float*, int, int, float*, cudaStream_t);
 int band_split_launch(const float*, const float*, const float*, int, int, int, int, int, int, int, void*, cudaStream_t);
 int pack_split_launch(const float*, int, int, float*, cudaStream_t);
@@ -164,6 +167,8 @@ struct b200voc_gen {
   float *split_wt, *split_b;     // [nb][bs*7][H], [nb][H]
   float *cp0_w, *cp0_b, *cp2_w, *cp2_b, *sty_w, *sty_b, *emo_w, *emo_b;
   float *film_w, *film_b;        // [film_cols][cond_dim], [film_cols] (scale half has +1 folded in)
+  uint16_t* film_w3;             // [film_cols][3*cond_dim] split-fp16 operand of the tensor-core FiLM GEMM
+  bool film_packed;
   int film_cols;
   float *merge_w, *merge_b;
   // attention (stage n_stages/2)
@@ -333,6 +338,8 @@ int b200voc_gen_create(const b200voc_gen_config* cfg, b200voc_gen** out) {
   g->film_cols = film_cols;
   A(g->film_w, (long long)film_cols * cd);
   A(g->film_b, film_cols);
+  A(g->film_w3, (long long)film_cols * cd * 3);
+  g->film_packed = false;
   if (st == B200VOC_OK) {
     cudaMemset(g->film_w, 0, (size_t)film_cols * cd * sizeof(float));
     cudaMemset(g->film_b, 0, (size_t)film_cols * sizeof(float));
@@ -403,6 +410,7 @@ int b200voc_gen_set_weight(b200voc_gen* g, const char* name, const float* w, int
     case W_RB_FILM_W: {
       ResW& r = g->stages[sl->a].res[sl->b];
       B200_TRY(copy_f32_launch(w, g->film_w + (long long)r.film_col * cd, numel, 0.f, st));
+      g->film_packed = false;
     } break;
     case W_RB_FILM_B: {
       ResW& r = g->stages[sl->a].res[sl->b];
@@ -445,7 +453,7 @@ int b200voc_gen_finalize(b200voc_gen* g) {
 
 namespace {
 struct WsLayout {
-  long long sty, emo, cond, film, act0, act1, att, total;
+  long long sty, emo, cond, cond3, film, act0, act1, att, total;
 };
 long long align_up(long long x) { return (x + 255) & ~255ll; }
 WsLayout ws_layout(const b200voc_gen* g, int B, int T) {
@@ -455,6 +463,7 @@ WsLayout ws_layout(const b200voc_gen* g, int B, int T) {
   w.sty = off; off = align_up(off + B * cd * 4);
   w.emo = off; off = align_up(off + B * cd * 4);
   w.cond = off; off = align_up(off + (long long)B * T * cd * 4);
+  w.cond3 = off; off = align_up(off + (long long)B * T * cd * 3 * 2);
   w.film = off; off = align_up(off + (long long)B * T * g->film_cols * 4);
   long long max_act = N * T * g->H;
   long long P = 1, attn_elems = 0;
@@ -548,14 +557,23 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
   } while (0)
 
   const double dBT = (double)B * T;
+  // FiLM projection: split-fp16 tensor-core GEMM (fp32-level accuracy); B200VOC_FILM_SGEMM=1 selects the fp32
+  // CUDA-core SGEMM it replaced (A/B runs)
+  static const bool film_sgemm = [] { const char* e = getenv("B200VOC_FILM_SGEMM"); return e && e[0] == '1'; }();
+  if (!film_sgemm && !g->film_packed) {
+    B200_TRY(pack_film3_launch(g->film_w, g->film_cols, g->film_w3, st));
+    g->film_packed = true;
+  }
   // conditioning (generator.py:65-73) and all FiLM projections (frame rate, fp32)
   RUN("style_emo", 2.0 * B * cd * (g->cfg.style_dim + 6), 0,
       style_emo_launch(style, emotion, g->sty_w, g->sty_b, g->emo_w, g->emo_b, B, g->cfg.style_dim, cd, w_style, w_emo,
                        style_drop, emo_drop, sty, emo, st));
   RUN("cond_mlp", 2.0 * dBT * (18 * (cd / 2) + (cd / 2) * cd), dBT * (18 + cd) * 4,
-      cond_launch(prosody, g->cp0_w, g->cp0_b, g->cp2_w, g->cp2_b, sty, emo, B, T, cond, st));
+      cond_launch(prosody, g->cp0_w, g->cp0_b, g->cp2_w, g->cp2_b, sty, emo, B, T, cond, film_sgemm ? nullptr : ws + w.cond3,
+                  st));
   RUN("film", 2.0 * dBT * cd * g->film_cols, dBT * (cd + g->film_cols) * 4,
-      film_launch(cond, g->film_w, g->film_b, B * T, g->film_cols, film, st));
+      film_sgemm ? film_launch(cond, g->film_w, g->film_b, B * T, g->film_cols, film, st)
+                 : film_tc_launch(ws + w.cond3, g->film_w3, g->film_b, B * T, g->film_cols, film, st));
   if (tap == "cond" && tap_out) {  // raw [B, T, cd]; the host transposes
     B200_CUDA(cudaMemcpyAsync(tap_out, cond, (size_t)B * T * cd * 4, cudaMemcpyDeviceToDevice, st));
   }

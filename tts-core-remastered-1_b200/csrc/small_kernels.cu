@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(128) cond_kernel(const float* __restrict__ pro
                                                    const float* __restrict__ b0, const float* __restrict__ w2,
                                                    const float* __restrict__ b2, const float* __restrict__ sty,
                                                    const float* __restrict__ emo, int B, int T,
-                                                   float* __restrict__ cond) {
+                                                   float* __restrict__ cond, uint16_t* __restrict__ cond3) {
   constexpr int HID = 64, CD = 128, PIN = 18;
   __shared__ float sW0[HID * PIN];
   __shared__ float sW2t[HID * CD];   // [j][c]
@@ -71,7 +71,16 @@ __global__ void __launch_bounds__(128) cond_kernel(const float* __restrict__ pro
 #pragma unroll 8
     for (int j = 0; j < HID; ++j) o = fmaf(sHid[j], sW2t[j * CD + c], o);
     o += b2[c];
-    cond[f * CD + c] = (o + sty[b * CD + c]) + emo[b * CD + c];
+    const float v = (o + sty[b * CD + c]) + emo[b * CD + c];
+    cond[f * CD + c] = v;
+    if (cond3 != nullptr) {
+      // split-fp16 operand of the tensor-core FiLM GEMM: [hi | lo | hi] (see film_tc_kernel)
+      const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+      uint16_t* r3 = cond3 + f * (3 * CD);
+      r3[c] = __half_as_ushort(hi);
+      r3[CD + c] = __half_as_ushort(lo);
+      r3[2 * CD + c] = __half_as_ushort(hi);
+    }
     __syncthreads();
   }
 }
@@ -124,6 +133,124 @@ __global__ void __launch_bounds__(256) film_sgemm_kernel(const float* __restrict
       *reinterpret_cast<float4*>(o + 4) = make_float4(acc[i][4] + c1.x, acc[i][5] + c1.y, acc[i][6] + c1.z, acc[i][7] + c1.w);
     }
   }
+}
+
+// ------------------------------------------------------------------ FiLM projection on the tensor cores
+// Same contraction with fp32-level accuracy from fp16 operands: x = hi + lo (hi = fp16(x), lo = fp16(x - hi), 22
+// significant bits), and  A W^T ~= A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T  (the lo*lo term is 2^-22 relative), i.e.
+// ONE K = 384 GEMM of A' = [A_hi | A_lo | A_hi] (written by cond_kernel) with W' = [W_hi | W_hi | W_lo] (packed at
+// load time), fp32 accumulation in TMEM, fp32 output.  One CTA = one 128 x 128 output tile: 12 TMA boxes, 24
+// tcgen05.mma, 4 epilogue warps (+bias, float4 stores).  34 TFLOP/s of CUDA-core SGEMM was 3 % of the step.
+__global__ void pack_film3_kernel(const float* __restrict__ w, long long rows, uint16_t* __restrict__ w3) {
+  const long long total = rows * 128;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / 128;
+    const int k = (int)(i % 128);
+    const float v = w[i];
+    const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+    uint16_t* o = w3 + r * 384;
+    o[k] = __half_as_ushort(hi);
+    o[128 + k] = __half_as_ushort(hi);
+    o[256 + k] = __half_as_ushort(lo);
+  }
+}
+int pack_film3_launch(const float* w, long long rows, void* w3, cudaStream_t st) {
+  const long long blocks = (rows * 128 + 255) / 256;
+  pack_film3_kernel<<<(int)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(w, rows, reinterpret_cast<uint16_t*>(w3));
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
+constexpr int kFilmSmem = 12 * 16384 + 64 + 1024;
+__global__ void __launch_bounds__(192, 1)
+film_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const float* __restrict__ bias, int M, int Ncols, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                       // 6 k-blocks x [128 rows x 64 k]
+  uint8_t* sW = smem + 6 * 16384;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 12 * 16384);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&bars[0], 12 * 16384);
+      for (int kb = 0; kb < 6; ++kb) {
+        tma_load_2d(sA + kb * 16384, &tmA, &bars[0], kb * 64, m0);      // rows past M are zero-filled
+        tma_load_2d(sW + kb * 16384, &tmW, &bars[0], kb * 64, n0);
+      }
+    }
+  } else if (warp == 1) {
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(0, 128);
+#pragma unroll
+      for (int kb = 0; kb < 6; ++kb) {
+        const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sA + kb * 16384));
+        const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + kb * 16384));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+      }
+      umma_commit(&bars[1]);
+    }
+    __syncwarp();
+  } else {
+    // epilogue warps 2..5 -> TMEM lane quadrant warp % 4; thread = output row
+    const int q = warp & 3, row = m0 + q * 32 + lane;
+    mbar_wait(&bars[1], 0);
+    tc_fence_after();
+    float* o = out + (long long)row * Ncols + n0;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      if (row < M) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = __ldg(b4 + j);
+          *reinterpret_cast<float4*>(o + c * 32 + 4 * j) =
+              make_float4(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y,
+                          __uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+int film_tc_launch(const void* cond3, const void* w3, const float* b_all, int M, int ncols, float* out, cudaStream_t st) {
+  B200_CHECK_ARG(ncols % 128 == 0, "film: ncols=%d must be a multiple of 128", ncols);
+  CUtensorMap tmA, tmW;
+  B200_TRY(make_tmap_2d(&tmA, cond3, 384, M, 384 * 2, 64, 128, 128));
+  B200_TRY(make_tmap_2d(&tmW, w3, 384, ncols, 384 * 2, 64, 128, 128));
+  static bool configured[16] = {};
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 15]) {
+    B200_CUDA(cudaFuncSetAttribute(film_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFilmSmem));
+    configured[dev & 15] = true;
+  }
+  dim3 grid(ceil_div(M, 128), ncols / 128);
+  film_tc_kernel<<<grid, 192, kFilmSmem, st>>>(tmA, tmW, b_all, M, ncols, out);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
 }
 
 // ------------------------------------------------------------------ K3: band_split
@@ -297,10 +424,10 @@ int style_emo_launch(const float* style, const float* emotion, const float* ws, 
   return B200VOC_OK;
 }
 int cond_launch(const float* prosody, const float* w0, const float* b0, const float* w2, const float* b2,
-                const float* sty, const float* emo, int B, int T, float* cond, cudaStream_t st) {
+                const float* sty, const float* emo, int B, int T, float* cond, void* cond3, cudaStream_t st) {
   long long frames = (long long)B * T;
   int grid = (int)(frames < 592 ? frames : 592);
-  cond_kernel<<<grid, 128, 0, st>>>(prosody, w0, b0, w2, b2, sty, emo, B, T, cond);
+  cond_kernel<<<grid, 128, 0, st>>>(prosody, w0, b0, w2, b2, sty, emo, B, T, cond, reinterpret_cast<uint16_t*>(cond3));
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
