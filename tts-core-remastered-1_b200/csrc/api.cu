@@ -101,6 +101,10 @@ int style_emo_launch(const float*, const float*, const float*, const float*, con
 int cond_launch(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int,
                 int, float*, void*, cudaStream_t);
 int pack_film3_launch(const float* w, long long rows, void* w3, cudaStream_t st);
+int pack_split3_launch(const float* w, int band_size, int H, void* w3, cudaStream_t st);
+long long band_split_tc_scratch_elems(int B, int T, int nb);
+int band_split_tc_launch(const float* mel, const void* w3, const float* bias, int B, int channels, int band_size, int T,
+                         int H, int fmt, int time_major, void* a3, void* out16, cudaStream_t st);
 int film_tc_launch(const void* cond3, const void* w3, const float* b_all, int M, int ncols, float* out, cudaStream_t st);
 int film_launch(const float*, const float*, const float*, int, int, float*, cudaStream_t);
 int band_split_launch(const float*, const float*, const float*, int, int, int, int, int, int, int, void*, cudaStream_t);
@@ -165,6 +169,7 @@ struct b200voc_gen {
   std::vector<StageW> stages;
   // fp32 parameters
   float *split_wt, *split_b;     // [nb][bs*7][H], [nb][H]
+  uint16_t* split_w3;            // [nb][H][448] split-fp16 operand of the tensor-core band_split GEMMs
   float *cp0_w, *cp0_b, *cp2_w, *cp2_b, *sty_w, *sty_b, *emo_w, *emo_b;
   float *film_w, *film_b;        // [film_cols][cond_dim], [film_cols] (scale half has +1 folded in)
   uint16_t* film_w3;             // [film_cols][3*cond_dim] split-fp16 operand of the tensor-core FiLM GEMM
@@ -277,6 +282,7 @@ int b200voc_gen_create(const b200voc_gen_config* cfg, b200voc_gen** out) {
   int st = B200VOC_OK;
 #define A(ptr, n) if (st == B200VOC_OK) st = dev_alloc(g, &(ptr), (n))
   A(g->split_wt, (long long)nb * bs * 7 * H);
+  A(g->split_w3, (long long)nb * H * 448);
   A(g->split_b, (long long)nb * H);
   A(g->cp0_w, (cd / 2) * 18); A(g->cp0_b, cd / 2);
   A(g->cp2_w, cd * (cd / 2)); A(g->cp2_b, cd);
@@ -377,7 +383,10 @@ int b200voc_gen_set_weight(b200voc_gen* g, const char* name, const float* w, int
                  sl->numel);
   const int cd = g->cfg.cond_dim, H = g->H, bs = g->band_size;
   switch (sl->kind) {
-    case W_SPLIT_W: B200_TRY(pack_split_launch(w, bs, H, g->split_wt + (long long)sl->a * bs * 7 * H, st)); break;
+    case W_SPLIT_W:
+      B200_TRY(pack_split_launch(w, bs, H, g->split_wt + (long long)sl->a * bs * 7 * H, st));
+      if (3 * bs * 7 <= 448) B200_TRY(pack_split3_launch(w, bs, H, g->split_w3 + (long long)sl->a * H * 448, st));
+      break;
     case W_SPLIT_B: B200_TRY(copy_f32_launch(w, g->split_b + (long long)sl->a * H, H, 0.f, st)); break;
     case W_CP0_W: B200_TRY(copy_f32_launch(w, g->cp0_w, numel, 0.f, st)); break;
     case W_CP0_B: B200_TRY(copy_f32_launch(w, g->cp0_b, numel, 0.f, st)); break;
@@ -453,7 +462,7 @@ int b200voc_gen_finalize(b200voc_gen* g) {
 
 namespace {
 struct WsLayout {
-  long long sty, emo, cond, cond3, film, act0, act1, att, total;
+  long long sty, emo, cond, cond3, film, a3, act0, act1, att, total;
 };
 long long align_up(long long x) { return (x + 255) & ~255ll; }
 WsLayout ws_layout(const b200voc_gen* g, int B, int T) {
@@ -465,6 +474,7 @@ WsLayout ws_layout(const b200voc_gen* g, int B, int T) {
   w.cond = off; off = align_up(off + (long long)B * T * cd * 4);
   w.cond3 = off; off = align_up(off + (long long)B * T * cd * 3 * 2);
   w.film = off; off = align_up(off + (long long)B * T * g->film_cols * 4);
+  w.a3 = off; off = align_up(off + band_split_tc_scratch_elems(B, T, g->cfg.num_bands) * 2);
   long long max_act = N * T * g->H;
   long long P = 1, attn_elems = 0;
   for (size_t i = 0; i < g->stages.size(); ++i) {
@@ -560,6 +570,9 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
   // FiLM projection: split-fp16 tensor-core GEMM (fp32-level accuracy); B200VOC_FILM_SGEMM=1 selects the fp32
   // CUDA-core SGEMM it replaced (A/B runs)
   static const bool film_sgemm = [] { const char* e = getenv("B200VOC_FILM_SGEMM"); return e && e[0] == '1'; }();
+  // band_split: split-fp16 tensor-core GEMMs; B200VOC_SPLIT_FP32=1 (or an unsupported shape) selects the fp32 kernel
+  static const bool split_env = [] { const char* e = getenv("B200VOC_SPLIT_FP32"); return e && e[0] == '1'; }();
+  const bool split_fp32 = split_env || g->H % 128 != 0 || 3 * g->band_size * 7 > 448;
   if (!film_sgemm && !g->film_packed) {
     B200_TRY(pack_film3_launch(g->film_w, g->film_cols, g->film_w3, st));
     g->film_packed = true;
@@ -581,8 +594,10 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
   // band split (generator.py:76-81): raw 16-bit, channels-last [N, T, H]
   int cur = 0;
   RUN("band_split", 2.0 * dBT * nb * g->band_size * 7 * g->H, dBT * (g->cfg.channels * 4 + nb * g->H * 2.0),
-      band_split_launch(mel, g->split_wt, g->split_b, B, g->cfg.channels, g->band_size, T, g->H, g->stages[0].fmt,
-                        mel_time_major, act[cur], st));
+      split_fp32 ? band_split_launch(mel, g->split_wt, g->split_b, B, g->cfg.channels, g->band_size, T, g->H,
+                                     g->stages[0].fmt, mel_time_major, act[cur], st)
+                 : band_split_tc_launch(mel, g->split_w3, g->split_b, B, g->cfg.channels, g->band_size, T, g->H,
+                                        g->stages[0].fmt, mel_time_major, ws + w.a3, act[cur], st));
   if (tap == "split" && tap_out) B200_TRY(tap_extract_launch(act[cur], N, T, g->H, g->stages[0].fmt, 0, tap_out, st));
 
   int L = T;

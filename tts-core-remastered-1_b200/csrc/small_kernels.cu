@@ -253,6 +253,161 @@ int film_tc_launch(const void* cond3, const void* w3, const float* b_all, int M,
   return B200VOC_OK;
 }
 
+// ------------------------------------------------------------------ K3 on the tensor cores: band_split as 4 GEMMs
+// The four Conv1d(20 -> H, k7) are GEMMs with K = 140 (im2col of the band's 20 mel bins x 7 taps).  Same split-fp16
+// scheme as film_tc_kernel (fp32-level accuracy): A' = [hi | lo | hi | 0] (3 x 140 padded to 448 = 7 k-blocks),
+// W' = [W_hi | W_hi | W_lo | 0], fp32 accumulation in TMEM, +bias, 16-bit channels-last store.
+constexpr int kSplitK = 448, kSplitKB = 7;
+__global__ void __launch_bounds__(256) band_im2col3_kernel(const float* __restrict__ mel, int B, int channels, int band_size,
+                                                           int T, int time_major, uint16_t* __restrict__ a3) {
+  // a3[band][b*T + t][448]; one thread per (band, frame, j): j = ci*7 + k < band_size*7
+  const int KJ = band_size * 7, nb = channels / band_size;
+  const long long total = (long long)nb * B * T * KJ;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % KJ);
+    const long long r = i / KJ;                      // band * (B*T) + b*T + t
+    const int t = (int)(r % T);
+    const int b = (int)((r / T) % B), band = (int)(r / ((long long)B * T));
+    const int ci = j / 7, tt = t + j % 7 - 3;
+    float v = 0.f;
+    if (tt >= 0 && tt < T)
+      v = time_major ? mel[((long long)b * T + tt) * channels + band * band_size + ci]
+                     : mel[((long long)b * channels + band * band_size + ci) * T + tt];
+    const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+    uint16_t* o = a3 + r * kSplitK;
+    o[j] = __half_as_ushort(hi);
+    o[KJ + j] = __half_as_ushort(lo);
+    o[2 * KJ + j] = __half_as_ushort(hi);
+    if (j < kSplitK - 3 * KJ) o[3 * KJ + j] = 0;     // zero padding (28 columns for KJ = 140)
+  }
+}
+// w[H][band_size*7] fp32 (the reference layout [H][ci][k]) -> w3[H][448] = [hi | hi | lo | 0]
+__global__ void pack_split3_kernel(const float* __restrict__ w, int KJ, int H, uint16_t* __restrict__ w3) {
+  const long long total = (long long)H * KJ;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % KJ);
+    const long long r = i / KJ;
+    const float v = w[i];
+    const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+    uint16_t* o = w3 + r * kSplitK;
+    o[j] = __half_as_ushort(hi);
+    o[KJ + j] = __half_as_ushort(hi);
+    o[2 * KJ + j] = __half_as_ushort(lo);
+    if (j < kSplitK - 3 * KJ) o[3 * KJ + j] = 0;
+  }
+}
+int pack_split3_launch(const float* w, int band_size, int H, void* w3, cudaStream_t st) {
+  B200_CHECK_ARG(3 * band_size * 7 <= kSplitK, "band_split: band of %d bins needs K > %d", band_size, kSplitK);
+  pack_split3_kernel<<<256, 256, 0, st>>>(w, band_size * 7, H, reinterpret_cast<uint16_t*>(w3));
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
+constexpr int kSplitSmem = 2 * kSplitKB * 16384 + 64 + 1024;
+__global__ void __launch_bounds__(192, 1)
+band_split_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                     const float* __restrict__ bias, int B, int T, int H, int nb, int fmt, uint16_t* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                       // 7 k-blocks x [128 rows x 64 k]
+  uint8_t* sW = smem + kSplitKB * 16384;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kSplitKB * 16384);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128, band = blockIdx.z;
+  const int M = B * T;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&bars[0], 2 * kSplitKB * 16384);
+      for (int kb = 0; kb < kSplitKB; ++kb) {
+        tma_load_3d(sA + kb * 16384, &tmA, &bars[0], kb * 64, m0, band);      // rows past M are zero-filled
+        tma_load_3d(sW + kb * 16384, &tmW, &bars[0], kb * 64, n0, band);
+      }
+    }
+  } else if (warp == 1) {
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(0, 128);
+#pragma unroll
+      for (int kb = 0; kb < kSplitKB; ++kb) {
+        const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sA + kb * 16384));
+        const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + kb * 16384));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+      }
+      umma_commit(&bars[1]);
+    }
+    __syncwarp();
+  } else {
+    // epilogue warps 2..5 -> TMEM lane quadrant warp % 4; thread = frame (b, t) of this band
+    const int q = warp & 3, m = m0 + q * 32 + lane;
+    mbar_wait(&bars[1], 0);
+    tc_fence_after();
+    const int b = m < M ? m / T : 0, t = m < M ? m - b * T : 0;
+    uint16_t* o = out + (((long long)(b * nb + band)) * T + t) * H + n0;
+    const float* bb = bias + band * H + n0;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      if (m < M) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float y0 = __uint_as_float(v[8 * j + 2 * e]) + __ldg(bb + c * 32 + 8 * j + 2 * e);
+            const float y1 = __uint_as_float(v[8 * j + 2 * e + 1]) + __ldg(bb + c * 32 + 8 * j + 2 * e + 1);
+            w[e] = pack2(y0, y1, fmt);
+          }
+          *reinterpret_cast<uint4*>(o + c * 32 + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+long long band_split_tc_scratch_elems(int B, int T, int nb) { return (long long)nb * B * T * kSplitK; }
+int band_split_tc_launch(const float* mel, const void* w3, const float* bias, int B, int channels, int band_size, int T,
+                         int H, int fmt, int time_major, void* a3, void* out16, cudaStream_t st) {
+  const int nb = channels / band_size, M = B * T;
+  B200_CHECK_ARG(H % 128 == 0 && 3 * band_size * 7 <= kSplitK, "band_split: H=%d / band_size=%d unsupported", H, band_size);
+  const long long total = (long long)nb * M * band_size * 7;
+  band_im2col3_kernel<<<(int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192), 256, 0, st>>>(
+      mel, B, channels, band_size, T, time_major, reinterpret_cast<uint16_t*>(a3));
+  B200_CUDA(cudaGetLastError());
+  CUtensorMap tmA, tmW;
+  B200_TRY(make_tmap_3d(&tmA, a3, kSplitK, M, nb, (uint64_t)kSplitK * 2, (uint64_t)M * kSplitK * 2, 64, 128, 128));
+  B200_TRY(make_tmap_3d(&tmW, w3, kSplitK, H, nb, (uint64_t)kSplitK * 2, (uint64_t)H * kSplitK * 2, 64, 128, 128));
+  static bool configured[16] = {};
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 15]) {
+    B200_CUDA(cudaFuncSetAttribute(band_split_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmem));
+    configured[dev & 15] = true;
+  }
+  dim3 grid(ceil_div(M, 128), H / 128, nb);
+  band_split_tc_kernel<<<grid, 192, kSplitSmem, st>>>(tmA, tmW, bias, B, T, H, nb, fmt, reinterpret_cast<uint16_t*>(out16));
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
 // ------------------------------------------------------------------ K3: band_split
 // out16[(b*nb + band), t, co] = bias[band][co] + sum_{ci,k} wt[band][ci*7+k][co] * mel[b][band*bs+ci][t+k-3]
 // Block = (t-tile of 32 frames, band, b); thread = output channel (co, co+256, ...).
