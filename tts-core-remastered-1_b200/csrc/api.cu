@@ -598,6 +598,7 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
                                      g->stages[0].fmt, mel_time_major, act[cur], st)
                  : band_split_tc_launch(mel, g->split_w3, g->split_b, B, g->cfg.channels, g->band_size, T, g->H,
                                         g->stages[0].fmt, mel_time_major, ws + w.a3, act[cur], st));
+  if (!split_fp32) ++launches;      // im2col + GEMM
   if (tap == "split" && tap_out) B200_TRY(tap_extract_launch(act[cur], N, T, g->H, g->stages[0].fmt, 0, tap_out, st));
 
   int L = T;
