@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128) cond_kernel(const float* __restrict__ pro
     const float v = (o + sty[b * CD + c]) + emo[b * CD + c];
     cond[f * CD + c] = v;
     if (cond3 != nullptr) {
-      // split-fp16 operand of the tensor-core FiLM GEMM: [hi | lo | hi] (see film_tc_kernel)
+      // split-fp16 operand of the tensor-core FiLM GEMM: [hi | lo | hi] (see film_tc_launch / splitgemm_kernel)
       const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
       uint16_t* r3 = cond3 + f * (3 * CD);
       r3[c] = __half_as_ushort(hi);
@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(256) film_sgemm_kernel(const float* __restrict
 // Same contraction with fp32-level accuracy from fp16 operands: x = hi + lo (hi = fp16(x), lo = fp16(x - hi), 22
 // significant bits), and  A W^T ~= A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T  (the lo*lo term is 2^-22 relative), i.e.
 // ONE K = 384 GEMM of A' = [A_hi | A_lo | A_hi] (written by cond_kernel) with W' = [W_hi | W_hi | W_lo] (packed at
-// load time), fp32 accumulation in TMEM, fp32 output.  One CTA = one 128 x 128 output tile: 12 TMA boxes, 24
-// tcgen05.mma, 4 epilogue warps (+bias, float4 stores).  34 TFLOP/s of CUDA-core SGEMM was 3 % of the step.
+// load time), fp32 accumulation in TMEM, fp32 output (splitgemm_kernel below).  34 TFLOP/s of CUDA-core SGEMM was
+// 3 % of the step.
 __global__ void pack_film3_kernel(const float* __restrict__ w, long long rows, uint16_t* __restrict__ w3) {
   const long long total = rows * 128;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -161,23 +161,38 @@ int pack_film3_launch(const float* w, long long rows, void* w3, cudaStream_t st)
   return B200VOC_OK;
 }
 
-constexpr int kFilmSmem = 12 * 16384 + 64 + 1024;
-__global__ void __launch_bounds__(192, 1)
-film_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const float* __restrict__ bias, int M, int Ncols, float* __restrict__ out) {
+// Shared mainloop of the two split-fp16 GEMMs (FiLM, band_split): one CTA = one 128 x 128 output tile, the K
+// dimension streams through a 3-stage TMA ring of (A k-block, W k-block) pairs, 96 KB of shared memory so that
+// TWO CTAs are resident per SM and one's loads / epilogue overlap the other's MMAs.
+constexpr int kSgStages = 3, kSgStageBytes = 2 * 16384, kSgSmem = kSgStages * kSgStageBytes + 128 + 1024;
+struct SplitGemmParams {
+  int M, KB;             // rows of A per band, k-blocks of 64
+  int T, H, nb, fmt;     // OUT16 (band_split): frames per utterance, row pitch, bands, 16-bit format
+  int ncols;             // !OUT16 (FiLM): row pitch of the fp32 output
+  const float* bias;
+  void* out;
+};
+template <bool OUT16>
+__global__ void __launch_bounds__(192, 2)
+splitgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ CUtensorMap tmO, const SplitGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem;                       // 6 k-blocks x [128 rows x 64 k]
-  uint8_t* sW = smem + 6 * 16384;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 12 * 16384);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSgStages * kSgStageBytes);
+  uint64_t* empty = full + kSgStages;
+  uint64_t* acc_full = empty + kSgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128, band = blockIdx.z;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < kSgStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 128);
@@ -187,75 +202,139 @@ film_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(&bars[0], 12 * 16384);
-      for (int kb = 0; kb < 6; ++kb) {
-        tma_load_2d(sA + kb * 16384, &tmA, &bars[0], kb * 64, m0);      // rows past M are zero-filled
-        tma_load_2d(sW + kb * 16384, &tmW, &bars[0], kb * 64, n0);
+      for (int kb = 0; kb < p.KB; ++kb) {
+        const int s = kb % kSgStages;
+        mbar_wait(&empty[s], ((kb / kSgStages) & 1) ^ 1);
+        mbar_expect_tx(&full[s], kSgStageBytes);
+        uint8_t* st = smem + s * kSgStageBytes;
+        tma_load_3d(st, &tmA, &full[s], kb * 64, m0, band);              // rows past M are zero-filled
+        tma_load_3d(st + 16384, &tmW, &full[s], kb * 64, n0, band);
       }
     }
   } else if (warp == 1) {
-    mbar_wait(&bars[0], 0);
-    tc_fence_after();
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_f16(0, 128);
-#pragma unroll
-      for (int kb = 0; kb < 6; ++kb) {
-        const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sA + kb * 16384));
-        const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + kb * 16384));
+    const uint32_t idesc = make_idesc_f16(0, 128);
+    for (int kb = 0; kb < p.KB; ++kb) {
+      const int s = kb % kSgStages;
+      mbar_wait(&full[s], (kb / kSgStages) & 1);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * kSgStageBytes);
+      const uint64_t a_desc = make_kmajor_desc<128>(a_addr), b_desc = make_kmajor_desc<128>(a_addr + 16384);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(&empty[s]);
+        if (kb == p.KB - 1) umma_commit(acc_full);
       }
-      umma_commit(&bars[1]);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
-    // epilogue warps 2..5 -> TMEM lane quadrant warp % 4; thread = output row
-    const int q = warp & 3, row = m0 + q * 32 + lane;
-    mbar_wait(&bars[1], 0);
+    // epilogue warps 2..5 -> TMEM lane quadrant warp % 4; thread = output row.  Each warp stages its 32 rows in the
+    // (now dead: every MMA that read it has completed) ring as 128-byte-swizzled boxes and hands them to TMA, so
+    // global writes are full lines and rows past M / past the end of an utterance are clipped by the tensor map.
+    const int q = warp & 3, row0 = m0 + q * 32;
+    mbar_wait(acc_full, 0);
     tc_fence_after();
-    float* o = out + (long long)row * Ncols + n0;
+    uint8_t* stg = smem + q * 16384;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    if (row0 < p.M) {
+      if (OUT16) {
+        const float* bb = p.bias + band * p.H + n0;
+        // TMA path only for warps whose 32 rows lie inside ONE utterance (row pitch changes at an utterance
+        // boundary; a box that starts at a negative frame index is not a legal store).  The few boundary warps
+        // (and every warp when T < 32) write their rows directly.
+        const int m = row0 + lane, b_first = row0 / p.T;
+        const bool use_tma = b_first == min(row0 + 31, p.M - 1) / p.T;
+        const int b = m < p.M ? m / p.T : 0, t = m < p.M ? m - b * p.T : 0;
+        uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + (((long long)(b * p.nb + band)) * p.T + t) * p.H + n0;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      if (row < M) {
-        const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c * 32);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+          tmem_ld_wait();
+          uint8_t* box = stg + (c >> 1) * 4096 + lane * 128;       // box = 32 rows x 64 halves
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bb = __ldg(b4 + j);
-          *reinterpret_cast<float4*>(o + c * 32 + 4 * j) =
-              make_float4(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y,
-                          __uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float y0 = __uint_as_float(v[8 * j + 2 * e]) + __ldg(bb + c * 32 + 8 * j + 2 * e);
+              const float y1 = __uint_as_float(v[8 * j + 2 * e + 1]) + __ldg(bb + c * 32 + 8 * j + 2 * e + 1);
+              w[e] = pack2(y0, y1, p.fmt);
+            }
+            if (use_tma)
+              *reinterpret_cast<uint4*>(box + ((((uint32_t)(4 * (c & 1) + j)) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            else if (m < p.M)
+              *reinterpret_cast<uint4*>(o + c * 32 + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          if (use_tma && (c & 1)) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmO, stg + (c >> 1) * 4096, n0 + 64 * (c >> 1), row0 - b_first * p.T, band, b_first);
+              tma_store_commit();
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+          tmem_ld_wait();
+          uint8_t* box = stg + c * 4096 + lane * 128;              // box = 32 rows x 32 floats
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(b4 + j);
+            *reinterpret_cast<float4*>(box + (((uint32_t)j ^ sw) << 4)) =
+                make_float4(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y,
+                            __uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmO, stg + c * 4096, 2 * (n0 + c * 32), row0, 0);   // the map counts 16-bit units
+            tma_store_commit();
+          }
         }
       }
+      if (lane == 0) tma_store_wait_all();
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 128);
 }
-int film_tc_launch(const void* cond3, const void* w3, const float* b_all, int M, int ncols, float* out, cudaStream_t st) {
-  B200_CHECK_ARG(ncols % 128 == 0, "film: ncols=%d must be a multiple of 128", ncols);
-  CUtensorMap tmA, tmW;
-  B200_TRY(make_tmap_2d(&tmA, cond3, 384, M, 384 * 2, 64, 128, 128));
-  B200_TRY(make_tmap_2d(&tmW, w3, 384, ncols, 384 * 2, 64, 128, 128));
+template <bool OUT16>
+static int launch_splitgemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO,
+                            const SplitGemmParams& p, dim3 grid, cudaStream_t st) {
   static bool configured[16] = {};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 15]) {
-    B200_CUDA(cudaFuncSetAttribute(film_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFilmSmem));
+    B200_CUDA(cudaFuncSetAttribute(splitgemm_kernel<OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgSmem));
     configured[dev & 15] = true;
   }
-  dim3 grid(ceil_div(M, 128), ncols / 128);
-  film_tc_kernel<<<grid, 192, kFilmSmem, st>>>(tmA, tmW, b_all, M, ncols, out);
+  splitgemm_kernel<OUT16><<<grid, 192, kSgSmem, st>>>(tmA, tmW, tmO, p);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
+}
+int film_tc_launch(const void* cond3, const void* w3, const float* b_all, int M, int ncols, float* out, cudaStream_t st) {
+  B200_CHECK_ARG(ncols % 128 == 0, "film: ncols=%d must be a multiple of 128", ncols);
+  CUtensorMap tmA, tmW;
+  B200_TRY(make_tmap_3d(&tmA, cond3, 384, M, 1, 384 * 2, (uint64_t)M * 384 * 2, 64, 128, 128));
+  B200_TRY(make_tmap_3d(&tmW, w3, 384, ncols, 1, 384 * 2, (uint64_t)ncols * 384 * 2, 64, 128, 128));
+  // fp32 output seen through a 16-bit map: 2 units per float, box = 32 rows x 128 bytes
+  CUtensorMap tmO;
+  B200_TRY(make_tmap_3d(&tmO, out, 2ull * ncols, M, 1, (uint64_t)ncols * 4, (uint64_t)M * ncols * 4, 64, 32, 128));
+  SplitGemmParams p{};
+  p.M = M; p.KB = 6; p.ncols = ncols; p.bias = b_all; p.out = out;
+  return launch_splitgemm<false>(tmA, tmW, tmO, p, dim3(ceil_div(M, 128), ncols / 128, 1), st);
 }
 
 // ------------------------------------------------------------------ K3 on the tensor cores: band_split as 4 GEMMs
 // The four Conv1d(20 -> H, k7) are GEMMs with K = 140 (im2col of the band's 20 mel bins x 7 taps).  Same split-fp16
-// scheme as film_tc_kernel (fp32-level accuracy): A' = [hi | lo | hi | 0] (3 x 140 padded to 448 = 7 k-blocks),
+// scheme as the FiLM GEMM (splitgemm_kernel; fp32-level accuracy): A' = [hi | lo | hi | 0] (3 x 140 padded to 448 = 7 k-blocks),
 // W' = [W_hi | W_hi | W_lo | 0], fp32 accumulation in TMEM, +bias, 16-bit channels-last store.
 constexpr int kSplitK = 448, kSplitKB = 7;
 __global__ void __launch_bounds__(256) band_im2col3_kernel(const float* __restrict__ mel, int B, int channels, int band_size,
@@ -303,86 +382,6 @@ int pack_split3_launch(const float* w, int band_size, int H, void* w3, cudaStrea
   return B200VOC_OK;
 }
 
-constexpr int kSplitSmem = 2 * kSplitKB * 16384 + 64 + 1024;
-__global__ void __launch_bounds__(192, 1)
-band_split_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                     const float* __restrict__ bias, int B, int T, int H, int nb, int fmt, uint16_t* __restrict__ out) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem;                       // 7 k-blocks x [128 rows x 64 k]
-  uint8_t* sW = smem + kSplitKB * 16384;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kSplitKB * 16384);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128, band = blockIdx.z;
-  const int M = B * T;
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmW);
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 128);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(&bars[0], 2 * kSplitKB * 16384);
-      for (int kb = 0; kb < kSplitKB; ++kb) {
-        tma_load_3d(sA + kb * 16384, &tmA, &bars[0], kb * 64, m0, band);      // rows past M are zero-filled
-        tma_load_3d(sW + kb * 16384, &tmW, &bars[0], kb * 64, n0, band);
-      }
-    }
-  } else if (warp == 1) {
-    mbar_wait(&bars[0], 0);
-    tc_fence_after();
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_f16(0, 128);
-#pragma unroll
-      for (int kb = 0; kb < kSplitKB; ++kb) {
-        const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(sA + kb * 16384));
-        const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + kb * 16384));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-      }
-      umma_commit(&bars[1]);
-    }
-    __syncwarp();
-  } else {
-    // epilogue warps 2..5 -> TMEM lane quadrant warp % 4; thread = frame (b, t) of this band
-    const int q = warp & 3, m = m0 + q * 32 + lane;
-    mbar_wait(&bars[1], 0);
-    tc_fence_after();
-    const int b = m < M ? m / T : 0, t = m < M ? m - b * T : 0;
-    uint16_t* o = out + (((long long)(b * nb + band)) * T + t) * H + n0;
-    const float* bb = bias + band * H + n0;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      if (m < M) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float y0 = __uint_as_float(v[8 * j + 2 * e]) + __ldg(bb + c * 32 + 8 * j + 2 * e);
-            const float y1 = __uint_as_float(v[8 * j + 2 * e + 1]) + __ldg(bb + c * 32 + 8 * j + 2 * e + 1);
-            w[e] = pack2(y0, y1, fmt);
-          }
-          *reinterpret_cast<uint4*>(o + c * 32 + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 128);
-}
 long long band_split_tc_scratch_elems(int B, int T, int nb) { return (long long)nb * B * T * kSplitK; }
 int band_split_tc_launch(const float* mel, const void* w3, const float* bias, int B, int channels, int band_size, int T,
                          int H, int fmt, int time_major, void* a3, void* out16, cudaStream_t st) {
@@ -395,17 +394,12 @@ int band_split_tc_launch(const float* mel, const void* w3, const float* bias, in
   CUtensorMap tmA, tmW;
   B200_TRY(make_tmap_3d(&tmA, a3, kSplitK, M, nb, (uint64_t)kSplitK * 2, (uint64_t)M * kSplitK * 2, 64, 128, 128));
   B200_TRY(make_tmap_3d(&tmW, w3, kSplitK, H, nb, (uint64_t)kSplitK * 2, (uint64_t)H * kSplitK * 2, 64, 128, 128));
-  static bool configured[16] = {};
-  int dev = 0;
-  B200_CUDA(cudaGetDevice(&dev));
-  if (!configured[dev & 15]) {
-    B200_CUDA(cudaFuncSetAttribute(band_split_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmem));
-    configured[dev & 15] = true;
-  }
-  dim3 grid(ceil_div(M, 128), H / 128, nb);
-  band_split_tc_kernel<<<grid, 192, kSplitSmem, st>>>(tmA, tmW, bias, B, T, H, nb, fmt, reinterpret_cast<uint16_t*>(out16));
-  B200_CUDA(cudaGetLastError());
-  return B200VOC_OK;
+  CUtensorMap tmO;   // out16 [B][nb][T][H]
+  B200_TRY(make_tmap_4d(&tmO, out16, H, T, nb, B, (uint64_t)H * 2, (uint64_t)T * H * 2, (uint64_t)nb * T * H * 2, 64, 32,
+                        1, 128));
+  SplitGemmParams p{};
+  p.M = M; p.KB = kSplitKB; p.T = T; p.H = H; p.nb = nb; p.fmt = fmt; p.bias = bias; p.out = out16;
+  return launch_splitgemm<true>(tmA, tmW, tmO, p, dim3(ceil_div(M, 128), H / 128, nb), st);
 }
 
 // ------------------------------------------------------------------ K3: band_split
