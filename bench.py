@@ -234,6 +234,33 @@ def secondary_measurements(dev, dev_in, B, T):
     except Exception as e:
         out["frontend"] = {"error": str(e)[:200]}
     try:
+        # SURVEY 8f rank 4 (forward half): the three critics the trainer runs on every waveform
+        # (vocoder7/trainer.py:86-92); first correct CUDA path, fp32 direct convolution
+        from b200voc import MultiPeriodDiscriminator, MultiScaleDiscriminator, MultiBandDiscriminator
+        Bc, Tc = 4, SR
+        wavc = torch.rand(Bc, 1, Tc, device=dev) * 2 - 1
+        res = {"batch": Bc, "samples": Tc, "note": "critic forwards (vocoder7/discriminators.py) on 4 x 1 s, all "
+               "feature maps written; fp32 CUDA-core direct convolution (first correct path)"}
+        for name, cls in (("mpd", MultiPeriodDiscriminator), ("msd", MultiScaleDiscriminator),
+                          ("mbd", MultiBandDiscriminator)):
+            torch.manual_seed(1234)
+            crit = cls(GANConfig()).eval().to(dev)
+            crit(wavc)
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                crit(wavc)
+            b_.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b_) / 3
+            fl = crit.forward_flops(Bc, Tc)
+            res[name] = {"ms": ms, "gflop": fl / 1e9, "tflops": fl / (ms * 1e-3) / 1e12}
+            del crit
+        out["critics"] = res
+    except Exception as e:
+        out["critics"] = {"error": str(e)[:200]}
+    try:
         Bw, Nw = 1024, 88200
         x = torch.rand(Bw, Nw, device=dev) * 2 - 1
         res = {}

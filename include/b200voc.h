@@ -126,6 +126,31 @@ int b200voc_gst_forward(const float* mel, int mel_time_major, int B, int T, int 
                         const float* conv2_b, const float* tokens, void* scratch, int64_t scratch_bytes,
                         float* style_out, void* stream);
 
+/* ---- Discriminator forwards (forward half; vocoder7/discriminators.py:8-157) ----------
+ * The three critics are stacks of strided 1-D convolutions + LeakyReLU(0.2) whose every intermediate map is
+ * returned as a feature (discriminators.py:52-59, 101-107, 148-156).  The host module (b200voc/discriminators.py)
+ * walks the layer list; these entry points are the layers.
+ *
+ * b200voc_disc_conv: y[b,co,lo,c] = bias[co] + sum_{ci,k} w[co,ci,k] * x[b,ci,lo*stride+k-pad,c] over fp32 maps
+ * laid out [B, C, L, P] with the P columns innermost and untouched by the convolution:
+ *   - MultiPeriodDiscriminator Conv2d(k=(5,1), stride=(3,1), padding=(2,0)) (discriminators.py:22-31): P = period;
+ *   - MultiScale / MultiBand Conv1d (discriminators.py:77-89, 126-138): P = 1.
+ * y_pre receives conv+bias, y_act LeakyReLU(slope) of it (either may be NULL).  in_batch_stride (elements, 0 =
+ * contiguous) lets a batch of time-chunks (torch.chunk, discriminators.py:147) be read in place; in_valid
+ * (elements per (b,ci) row, 0 = Lin*P) makes reads past the end of the waveform return zero, which is F.pad of
+ * discriminators.py:46-48 without materialising the padded copy.  w is the spectral-normalised weight. */
+int b200voc_disc_conv_out_len(int Lin, int K, int stride, int pad);
+int b200voc_disc_conv(const float* x, const float* w, const float* bias, int B, int Cin, int Cout, int Lin, int P,
+                      int K, int stride, int pad, int64_t in_batch_stride, int64_t in_valid, float slope,
+                      float* y_pre, float* y_act, void* stream);
+/* torch.nn.utils.spectral_norm as the reference wraps every critic conv (discriminators.py:21-31, 76-89,
+ * 125-138), evaluation mode (no power iteration): w_out = w_orig / sigma, sigma = u . (W v) with W = w_orig viewed
+ * as [rows = Cout][cols = Cin*K(*1)].  sigma_out: one device float. */
+int b200voc_spectral_norm_weight(const float* w_orig, const float* u, const float* v, int rows, int cols,
+                                 float* w_out, float* sigma_out, void* stream);
+/* F.avg_pool1d(x, 4, 2, 1) of discriminators.py:99 over `rows` rows of Lin samples -> (Lin-2)/2+1 samples. */
+int b200voc_avg_pool1d_k4s2p1(const float* x, int64_t rows, int Lin, float* y, void* stream);
+
 /* Per-launch CUDA-event timing of the LAST forward (bench.py's roofline numbers).  Enable, run a
  * forward, synchronise the stream, then read entry i: layer name (oracle tap names), elapsed ms,
  * algorithmic FLOPs and algorithmic HBM bytes (DESIGN.md states the per-unit figures). */

@@ -192,6 +192,40 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "gst_b3_t150.npz"), mel=mel_ref.numpy(), style=y_ref.numpy(),
                         **{"sd." + k: v.numpy() for k, v in sd_ref.items()})
 
+    # ---- critics (forward half): reference classes vs restatement, golden vectors ----------
+    from vocoder7 import discriminators as rdisc
+    cfg_ref = rcfg.GANConfig()
+    x = torch.randn(2, 1, 2403, generator=torch.Generator().manual_seed(5)) * 0.3   # 2403: ragged for p=2,5,7,11 and chunk(4)
+    save = {"x": x.numpy()}
+    for kind, cls in (("mpd", rdisc.MultiPeriodDiscriminator), ("msd", rdisc.MultiScaleDiscriminator),
+                      ("mbd", rdisc.MultiBandDiscriminator)):
+        torch.manual_seed(1234)
+        ref = cls(cfg_ref).eval()
+        sd_ref = {k: v.detach() for k, v in ref.state_dict().items()}
+        sd_ora = O.make_critic_state(kind, cfg_ref, seed=1234)
+        assert sorted(sd_ref) == sorted(sd_ora), kind
+        assert all(torch.equal(sd_ref[k], sd_ora[k]) for k in sd_ref), kind
+        with torch.no_grad():
+            o_ref, f_ref = ref(x)
+            o_ora, f_ora = O.critic_forward(kind, sd_ora, cfg_ref, x)
+        assert len(o_ref) == len(o_ora) and [len(f) for f in f_ref] == [len(f) for f in f_ora]
+        d = max([float((a - b).abs().max()) for a, b in zip(o_ref, o_ora)] +
+                [float((a - b).abs().max()) for fa, fb in zip(f_ref, f_ora) for a, b in zip(fa, fb)])
+        print(f"{kind}: |reference - restatement|max over {len(o_ref)} scores and {sum(len(f) for f in f_ref)} "
+              f"feature maps = {d:.3e}")
+        assert d <= 1e-6
+        for i, o in enumerate(o_ref):
+            save[f"{kind}.out{i}"] = o.numpy()
+            for j, fm in enumerate(f_ref[i]):
+                flat = fm.reshape(-1)
+                pick = torch.linspace(0, flat.numel() - 1, min(512, flat.numel())).long()
+                save[f"{kind}.f{i}.{j}.shape"] = np.array(fm.shape)
+                save[f"{kind}.f{i}.{j}.idx"] = pick.numpy()
+                save[f"{kind}.f{i}.{j}.val"] = flat[pick].numpy()
+                save[f"{kind}.f{i}.{j}.sum"] = np.array([float(flat.double().sum()), float(flat.double().abs().sum())])
+    np.savez_compressed(os.path.join(GOLD, "critics_b2_t2403.npz"), **save)
+    print(f"  critics_b2_t2403.npz: {os.path.getsize(os.path.join(GOLD, 'critics_b2_t2403.npz')) / 1024:.1f} KiB")
+
 
 if __name__ == "__main__":
     main()

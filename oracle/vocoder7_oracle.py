@@ -379,6 +379,118 @@ def make_gst_state(seed: int = 1234, channels: int = 80, style_dim: int = 128, n
             "attn_conv.2.weight": c2.weight.detach(), "attn_conv.2.bias": c2.bias.detach()}
 
 
+# ---------------------------------------------------------------------------- critics (vocoder7/discriminators.py)
+DISC_LRELU = 0.2           # nn.LeakyReLU(0.2): discriminators.py:26,83,132
+
+
+def critic_plans(kind: str, cfg):
+    """Layer plans of the three critics, one list per sub-discriminator, each entry
+    (Cin, Cout, K, stride, pad, leaky_relu_after); second result: True when the convs are Conv2d (K,1).
+      mpd  discriminators.py:16-32   per period: 4x Conv2d((5,1), stride (3,1), pad (2,0)), then Conv2d((3,1), pad (1,0))
+      msd  discriminators.py:71-90   per kernel size ks: 5x Conv1d(ks, stride 2,2,2,1,1, pad ks//2), then Conv1d(3, pad 1)
+      mbd  discriminators.py:119-139 per band: 4x Conv1d(15, stride 2, pad 7), then Conv1d(3, pad 1)
+    Channels go 1 -> 4 -> 16 -> ... (x4 per layer) and end in one score channel."""
+    if kind == "mpd":
+        shapes = [(4, 5, [3] * 4) for _ in cfg.disc_periods]
+    elif kind == "msd":
+        shapes = [(5, ks, [2, 2, 2, 1, 1]) for ks in cfg.disc_kernel_sizes]
+    elif kind == "mbd":
+        shapes = [(4, 15, [2] * 4) for _ in range(cfg.num_bands)]
+    else:
+        raise ValueError(kind)
+    plans = []
+    for n, k, strides in shapes:
+        plan = [(4 ** i, 4 ** (i + 1), k, strides[i], k // 2, True) for i in range(n)]
+        plan.append((4 ** n, 1, 3, 1, 1, False))
+        plans.append(plan)
+    return plans, kind == "mpd"
+
+
+def make_critic_state(kind: str, cfg, seed: int = 1234) -> Dict[str, torch.Tensor]:
+    """Default init of the reference critic under ``seed``: convs are created layer by layer, each wrapped in
+    ``nn.utils.spectral_norm`` right away (conv init, then the u and v draws), sub-discriminators in order; keys
+    follow the reference's ModuleList / Sequential nesting (``discriminators.<d>.<idx>.*`` with the LeakyReLUs
+    occupying the odd indices)."""
+    torch.manual_seed(seed)
+    plans, two_d = critic_plans(kind, cfg)
+    sd: Dict[str, torch.Tensor] = {}
+    for d, plan in enumerate(plans):
+        idx = 0
+        for cin, cout, k, st, pad, act in plan:
+            conv = (nn.Conv2d(cin, cout, (k, 1), (st, 1), (pad, 0)) if two_d else nn.Conv1d(cin, cout, k, st, pad))
+            conv = nn.utils.spectral_norm(conv)
+            for name in ("bias", "weight_orig", "weight_u", "weight_v"):
+                sd[f"discriminators.{d}.{idx}.{name}"] = getattr(conv, name).detach().clone()
+            idx += 2 if act else 1
+    return sd
+
+
+def spectral_norm_weight(w_orig: torch.Tensor, u: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """``torch.nn.utils.spectral_norm`` in evaluation mode (SpectralNorm.compute_weight without power iteration):
+    sigma = u . (W v), W = weight_orig flattened to [Cout, -1]; weight = weight_orig / sigma."""
+    sigma = torch.dot(u, torch.mv(w_orig.flatten(1), v))
+    return w_orig / sigma
+
+
+def _critic_stack(sd, d: int, plan, x: torch.Tensor, two_d: bool):
+    maps = []
+    idx = 0
+    for cin, cout, k, st, pad, act in plan:
+        pre = f"discriminators.{d}.{idx}."
+        w = spectral_norm_weight(sd[pre + "weight_orig"], sd[pre + "weight_u"], sd[pre + "weight_v"])
+        if two_d:
+            x = F.conv2d(x, w, sd[pre + "bias"], stride=(st, 1), padding=(pad, 0))
+        else:
+            x = F.conv1d(x, w, sd[pre + "bias"], stride=st, padding=pad)
+        maps.append(x)
+        if act:
+            x = F.leaky_relu(x, DISC_LRELU)
+            maps.append(x)
+        idx += 2 if act else 1
+    return maps[-1], maps[:-1]
+
+
+def critic_forward(kind: str, sd: Dict[str, torch.Tensor], cfg, x: torch.Tensor):
+    """Functional restatement of the three ``forward`` methods (discriminators.py:34-60, 92-108, 141-157):
+    returns (outputs, features) exactly as the reference does."""
+    plans, two_d = critic_plans(kind, cfg)
+    B, _, T = x.shape
+    outs, feats = [], []
+    if kind == "mpd":
+        for d, p in enumerate(cfg.disc_periods):
+            xp = F.pad(x, (0, (p - T % p) % p))                       # discriminators.py:45-49
+            o, f = _critic_stack(sd, d, plans[d], xp.view(B, 1, xp.shape[2] // p, p), True)
+            outs.append(o), feats.append(f)
+    elif kind == "msd":
+        pooled = F.avg_pool1d(x, 4, 2, 1)
+        for d, s in enumerate([x, pooled, pooled][:len(plans)]):      # discriminators.py:99: both pooled from x
+            o, f = _critic_stack(sd, d, plans[d], s, False)
+            outs.append(o), feats.append(f)
+    else:
+        for d, band in enumerate(torch.chunk(x, cfg.num_bands, dim=2)):   # discriminators.py:147: chunks of TIME
+            o, f = _critic_stack(sd, d, plans[d], band, False)
+            outs.append(o), feats.append(f)
+    return outs, feats
+
+
+def critic_flops(kind: str, cfg, B: int, T: int) -> float:
+    """Multiply-add FLOPs (2 per MAC) of one critic forward on [B, 1, T]."""
+    plans, _ = critic_plans(kind, cfg)
+    total = 0.0
+    for d, plan in enumerate(plans):
+        if kind == "mpd":
+            p = cfg.disc_periods[d]
+            L, cols = -(-T // p), p
+        elif kind == "msd":
+            L, cols = (T if d == 0 else (T - 2) // 2 + 1), 1
+        else:
+            L, cols = -(-T // cfg.num_bands), 1
+        for cin, cout, k, st, pad, _ in plan:
+            L = (L + 2 * pad - k) // st + 1
+            total += 2.0 * B * cout * cin * k * L * cols
+    return total
+
+
 def pcm16(wav: torch.Tensor) -> torch.Tensor:
     """16-bit PCM wire format: round-half-even(clamp(wav, -1, 1) * 32767)."""
     return torch.round(wav.clamp(-1.0, 1.0) * 32767.0).to(torch.int16)

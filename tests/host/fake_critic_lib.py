@@ -1,0 +1,72 @@
+"""TEST INFRASTRUCTURE: a stand-in for the four critic entry points of libb200voc.so that evaluates the SAME
+index arithmetic as csrc/disc.cu (flattened (row, column) positions, in_batch_stride / in_valid reads, output
+offsets) with numpy on host pointers.  It lets the CPU suite check the host-side layer walker of
+b200voc/discriminators.py -- pointer offsets of the time chunks, the padded period view, the pooled scales --
+against the oracle without a GPU.  It is never importable from the product package."""
+import ctypes as C
+
+import numpy as np
+
+
+def _arr(ptr: int, n: int) -> np.ndarray:
+    return np.ctypeslib.as_array((C.c_float * int(n)).from_address(int(ptr)))
+
+
+class FakeCriticLib:
+    def __init__(self):
+        self.conv_calls = []
+
+    def b200voc_device_supported(self, dev):
+        return 0
+
+    def b200voc_last_error_string(self):
+        return b"fake"
+
+    def b200voc_disc_conv_out_len(self, Lin, K, stride, pad):
+        if Lin <= 0 or K <= 0 or stride <= 0 or pad < 0 or Lin + 2 * pad < K:
+            return 0
+        return (Lin + 2 * pad - K) // stride + 1
+
+    def b200voc_disc_conv(self, x, w, bias, B, Cin, Cout, Lin, P, K, stride, pad, in_batch_stride, in_valid, slope,
+                          y_pre, y_act, stream):
+        Lout = self.b200voc_disc_conv_out_len(Lin, K, stride, pad)
+        bs = in_batch_stride if in_batch_stride > 0 else Cin * Lin * P
+        valid = in_valid if in_valid > 0 else Lin * P
+        chan = Lin * P
+        self.conv_calls.append((B, Cin, Cout, Lin, P, K, stride, pad, bs, valid))
+        wv = _arr(w, Cout * Cin * K).reshape(Cout, Cin * K)
+        bv = _arr(bias, Cout)
+        pos = np.arange(Lout * P)
+        lo = pos // P
+        col = pos - lo * P
+        li = (lo * stride - pad)[None, :] + np.arange(K)[:, None]                 # [K, pos]
+        idx = li * P + col[None, :]
+        ok = (li >= 0) & (li < Lin) & (idx < valid)
+        out = np.empty((B, Cout, Lout * P), dtype=np.float32)
+        for b in range(B):
+            cols = np.zeros((Cin, K, Lout * P), dtype=np.float32)
+            for ci in range(Cin):
+                base = b * bs + ci * chan
+                span = _arr(x + 4 * base, max(int(idx[ok].max()) + 1, 1)) if ok.any() else None
+                if span is not None:
+                    cols[ci][ok] = span[idx[ok]]
+            out[b] = wv @ cols.reshape(Cin * K, Lout * P) + bv[:, None]
+        if y_pre:
+            _arr(y_pre, out.size)[:] = out.reshape(-1)
+        if y_act:
+            _arr(y_act, out.size)[:] = np.where(out > 0, out, np.float32(slope) * out).reshape(-1)
+        return 0
+
+    def b200voc_spectral_norm_weight(self, w_orig, u, v, rows, cols, w_out, sigma_out, stream):
+        W = _arr(w_orig, rows * cols).reshape(rows, cols)
+        sigma = np.float32(_arr(u, rows) @ (W @ _arr(v, cols)))
+        _arr(sigma_out, 1)[0] = sigma
+        _arr(w_out, rows * cols)[:] = (W / sigma).reshape(-1)
+        return 0
+
+    def b200voc_avg_pool1d_k4s2p1(self, x, rows, Lin, y, stream):
+        Lout = (Lin + 2 - 4) // 2 + 1
+        xv = np.pad(_arr(x, rows * Lin).reshape(rows, Lin), ((0, 0), (1, 2 * Lout + 2 - Lin)))
+        out = sum(xv[:, k:k + 2 * Lout:2] for k in range(4)) * np.float32(0.25)
+        _arr(y, rows * Lout)[:] = out.astype(np.float32).reshape(-1)
+        return 0

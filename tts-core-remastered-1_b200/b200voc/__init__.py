@@ -4,8 +4,10 @@ behind the reference's Python API.  See DESIGN.md."""
 from .config import GANConfig
 from .generator import Generator, ResidualBlock, SelfAttention
 from .gst import GlobalStyleTokens
+from .discriminators import MultiPeriodDiscriminator, MultiScaleDiscriminator, MultiBandDiscriminator
 from .stft import LearnableSTFT, STFTLoss, stft, istft, mel_spectrogram, log_mel, stft_magnitude
 from . import _lib
 
-__all__ = ["GANConfig", "Generator", "GlobalStyleTokens", "ResidualBlock", "SelfAttention", "LearnableSTFT", "STFTLoss", "stft", "istft",
+__all__ = ["GANConfig", "Generator", "GlobalStyleTokens", "MultiPeriodDiscriminator", "MultiScaleDiscriminator",
+           "MultiBandDiscriminator", "ResidualBlock", "SelfAttention", "LearnableSTFT", "STFTLoss", "stft", "istft",
            "mel_spectrogram", "log_mel", "stft_magnitude"]
