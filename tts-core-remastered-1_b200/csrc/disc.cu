@@ -15,6 +15,8 @@
 // position x CO output channels, weights of an 8-input-channel slab staged in shared memory).  The two wide
 // layers (256 -> 1024, k41) are GEMM-shaped and belong on tcgen05 like the Generator's convolutions; that and the
 // backward kernels are the rest of rank 4.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -88,6 +90,81 @@ __global__ void __launch_bounds__(kDcThreads) disc_conv_kernel(const DiscConvPar
   }
 }
 
+// Stride-1, single-column variant (the two layers that hold > 99 % of the critics' FLOPs, MSD's 64->256 and
+// 256->1024 k15/k41 convolutions): a thread owns NP = 4 CONSECUTIVE output positions x CO = 16 channels, so that the
+// four input samples it needs for tap k+1 are three of tap k's plus one new load (sliding window in registers):
+// 64 FMAs per (1 global load + 4 shared-memory vector loads).
+constexpr int kDcNp = 4;
+template <int CO>
+__global__ void __launch_bounds__(kDcThreads) disc_conv_s1_kernel(const DiscConvParams p) {
+  extern __shared__ __align__(16) float w_s[];   // [kDcCi * K][CO]
+  const int lo0 = (blockIdx.x * kDcThreads + threadIdx.x) * kDcNp;
+  const int co0 = blockIdx.y * CO, b = blockIdx.z;
+  const bool active = lo0 < p.Lout;
+  const int lim = (int)min((long long)p.Lin, p.in_valid);   // samples of a row that exist
+  const int base = lo0 - p.pad;                              // input index of (position lo0, tap 0)
+  const float* xb = p.x + (long long)b * p.in_batch_stride;
+  float acc[kDcNp][CO];
+#pragma unroll
+  for (int j = 0; j < kDcNp; ++j)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
+
+  for (int ci0 = 0; ci0 < p.Cin; ci0 += kDcCi) {
+    const int nci = min(kDcCi, p.Cin - ci0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nci * p.K * CO; i += kDcThreads) {
+      const int c = i % CO, r = i / CO;
+      const int cc = r / p.K, k = r - cc * p.K, co = co0 + c;
+      w_s[i] = co < p.Cout ? __ldg(p.w + ((long long)co * p.Cin + ci0 + cc) * p.K + k) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      for (int cc = 0; cc < nci; ++cc) {
+        const float* xc = xb + (long long)(ci0 + cc) * p.Lin;
+        const float* wr = w_s + cc * p.K * CO;
+        float xw[kDcNp];
+#pragma unroll
+        for (int j = 0; j < kDcNp; ++j) {
+          const int li = base + j;
+          xw[j] = (li >= 0 && li < lim) ? __ldg(xc + li) : 0.f;
+        }
+        for (int k = 0; k < p.K; ++k) {
+          const int ln = base + k + kDcNp;                    // the sample tap k+1 adds to the window
+          const float xn = (ln >= 0 && ln < lim) ? __ldg(xc + ln) : 0.f;
+#pragma unroll
+          for (int c = 0; c < CO; ++c) {
+            const float wv = wr[k * CO + c];
+#pragma unroll
+            for (int j = 0; j < kDcNp; ++j) acc[j][c] = fmaf(xw[j], wv, acc[j][c]);
+          }
+#pragma unroll
+          for (int j = 0; j + 1 < kDcNp; ++j) xw[j] = xw[j + 1];
+          xw[kDcNp - 1] = xn;
+        }
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+      const int co = co0 + c;
+      if (co < p.Cout) {
+        const float bv = __ldg(p.bias + co);
+        const long long o = ((long long)b * p.Cout + co) * p.Lout + lo0;
+#pragma unroll
+        for (int j = 0; j < kDcNp; ++j) {
+          if (lo0 + j < p.Lout) {
+            const float y = acc[j][c] + bv;
+            if (p.y_pre) p.y_pre[o + j] = y;
+            if (p.y_act) p.y_act[o + j] = y > 0.f ? y : p.slope * y;
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int CO>
 static int launch_disc_conv(const DiscConvParams& p, cudaStream_t st) {
   const long long npos = (long long)p.Lout * p.P;
@@ -99,7 +176,20 @@ static int launch_disc_conv(const DiscConvParams& p, cudaStream_t st) {
   return B200VOC_OK;
 }
 
+static bool disc_s1_enabled() {
+  static const bool on = [] { const char* e = getenv("B200VOC_DISC_GENERIC"); return !(e && e[0] == '1'); }();
+  return on;
+}
 int disc_conv_launch(const DiscConvParams& p, cudaStream_t st) {
+  if (p.stride == 1 && p.P == 1 && p.Cout >= 16 && disc_s1_enabled()) {
+    constexpr int CO = 16;
+    const size_t smem = (size_t)kDcCi * p.K * CO * sizeof(float);
+    B200_CHECK_ARG(smem <= 48 * 1024, "disc_conv: kernel size %d too large for the weight slab", p.K);
+    dim3 grid((unsigned)ceil_div(p.Lout, kDcThreads * kDcNp), (unsigned)ceil_div(p.Cout, CO), (unsigned)p.B);
+    disc_conv_s1_kernel<CO><<<grid, kDcThreads, smem, st>>>(p);
+    B200_CUDA(cudaGetLastError());
+    return B200VOC_OK;
+  }
   if (p.Cout >= 16) return launch_disc_conv<16>(p, st);
   if (p.Cout >= 4) return launch_disc_conv<4>(p, st);
   return launch_disc_conv<1>(p, st);
