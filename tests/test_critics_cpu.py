@@ -113,3 +113,17 @@ def test_short_waveforms_raise():
     assert lib.b200voc_disc_conv_out_len(1, 3, 1, 1) == 1
     assert lib.b200voc_disc_conv_out_len(0, 3, 1, 1) == 0
     assert lib.b200voc_disc_conv_out_len(2, 15, 2, 3) == 0
+
+
+def test_entry_points_validate_arguments_before_touching_the_device():
+    """Bad arguments are rejected with ERR_BAD_ARG and a message, without a CUDA call (works on a CPU-only host)."""
+    from b200voc import _lib
+    lib = _lib.load()
+    assert lib.b200voc_disc_conv(0, 0, 0, 1, 1, 4, 100, 1, 5, 3, 2, 0, 0, 0.2, 0, 0, 0) == _lib.ERR_BAD_ARG
+    assert b"null" in lib.b200voc_last_error_string()
+    one = 16   # any non-null value: the shape checks come before the pointers are used
+    assert lib.b200voc_disc_conv(one, one, one, 1, 1, 4, 2, 1, 15, 2, 3, 0, 0, 0.2, one, 0, 0) == _lib.ERR_BAD_ARG
+    assert b"shorter than the kernel" in lib.b200voc_last_error_string()
+    assert lib.b200voc_disc_conv(one, one, one, 0, 1, 4, 100, 1, 5, 3, 2, 0, 0, 0.2, one, 0, 0) == _lib.ERR_BAD_ARG
+    assert lib.b200voc_spectral_norm_weight(one, one, one, 0, 5, one, one, 0) == _lib.ERR_BAD_ARG
+    assert lib.b200voc_avg_pool1d_k4s2p1(one, 1, 1, one, 0) == _lib.ERR_BAD_ARG
