@@ -16,6 +16,7 @@ ap.add_argument("--T", type=int, default=861)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--stft", action="store_true")
 ap.add_argument("--attn", action="store_true")
+ap.add_argument("--critics", action="store_true", help="also one MultiScaleDiscriminator forward on 4 x 1 s")
 a = ap.parse_args()
 torch.manual_seed(1234)
 if a.stft:
@@ -37,3 +38,8 @@ else:
             w = gen(*ins)
     torch.cuda.synchronize()
     print("gen ok", tuple(w.shape), float(w.abs().max()))
+    if a.critics:
+        msd = b200voc.MultiScaleDiscriminator(b200voc.GANConfig()).eval().cuda()
+        outs, _ = msd(torch.rand(4, 1, 22050, device="cuda") * 2 - 1)
+        torch.cuda.synchronize()
+        print("msd ok", [tuple(o.shape) for o in outs])
