@@ -112,6 +112,36 @@ def cpu_oracle_throughput(sample_B: int, sample_T: int, reps: int, threads: int)
     return audio_s / min(times), times
 
 
+def library_gpu_throughput(dev, B: int, T: int, reps: int = 3):
+    """SURVEY.md 8(d) asks for the 'library path' bar next to the CPU baseline: the same oracle module run by
+    torch eager on the GPU (cuDNN / cuBLAS kernels, bf16 autocast as vocoder7/trainer.py:75 runs the reference).
+    Part of the cpu_baseline leg: a reported baseline, never the product path.  Returns (audio-s/s, ms)."""
+    import torch
+    from oracle import vocoder7_oracle as O
+    gen = O.make_generator(O.OracleConfig(use_attention=False), seed=1234).to(dev)
+    ins = [t.to(dev) for t in O.synthetic_inputs(B, T, seed=4321)]
+    cuda = torch.device(dev).type == "cuda"
+    with torch.no_grad(), torch.autocast(torch.device(dev).type, dtype=torch.bfloat16):
+        gen(*ins)                                                   # warm-up (cuDNN heuristics, allocator)
+        if cuda:
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            gen(*ins)
+        if cuda:
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / reps
+        else:
+            ms = 1e3 * (time.perf_counter() - t0) / reps
+    del gen, ins
+    if cuda:
+        torch.cuda.empty_cache()
+    return B * HOP * T / SR / (ms / 1e3), ms
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -420,6 +450,14 @@ def run_b200(args):
             traffic = None
     cores = os.cpu_count() or 1
     cpu_val, cpu_times = cpu_oracle_throughput(1, T_FRAMES, reps=16, threads=cores)   # ~10 s of CPU work; batch 1 is the CPU path's best case
+    library = None
+    if world == 1:
+        try:   # the library-path bar of SURVEY 8(d); never allowed to cost the headline line
+            lib_val, lib_ms = library_gpu_throughput(dev, B_PER_GPU, T_FRAMES)
+            library = {"value": lib_val, "unit": UNIT, "ms_per_step": lib_ms, "dtype": "bf16 autocast",
+                       "what": "the oracle module under torch eager on this GPU (cuDNN / cuBLAS), same B x T, attention off"}
+        except Exception as e:
+            library = {"error": str(e)[:200]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -439,7 +477,8 @@ def run_b200(args):
                    for k, v in per_layer.items()},
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"best of {len(cpu_times)} forwards of 1 utterance x T={T_FRAMES} (10 s) of the same workload, "
-                                   f"fp32 torch CPU oracle, attention off; {['%.2f' % t for t in cpu_times]} s"},
+                                   f"fp32 torch CPU oracle, attention off; {['%.2f' % t for t in cpu_times]} s",
+                         "library_gpu": library},
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host)),
                 "d2h_bytes_per_step": int(host_out.numel() * 4), "ms_per_step": ms_e2e / args.steps},
