@@ -178,9 +178,8 @@ class StreamingSynthesizer:
                 s_out.wait_event(ev_comp[i])
                 o.copy_(slot["out"], non_blocking=True)
                 ev_out[i].record(s_out)
-        main.wait_event(ev_out[-1])
-        for e in ev_out[-self.depth:]:
-            main.wait_event(e)
+        main.wait_event(ev_out[-1])          # later work on the caller's stream is ordered after the downloads
+        ev_out[-1].synchronize()             # ... and the host may read host_outs as soon as run() returns
 
 
 # ------------------------------------------------------------------ multi-GPU (one process per GPU)
