@@ -159,8 +159,12 @@ stft_kernel(const StftParams p) {
 // CTA.  Window samples and the per-lane twiddles live in registers for the whole CTA.
 constexpr int kFastWarps = 8, kFastRounds = 4;
 
-template <int MODE>
-__global__ void __launch_bounds__(kFastWarps * 32, 3)
+// REGTAB (opt-in, B200VOC_STFT_REGTAB=1): the 16 window pairs and 15 stage-1 twiddles a lane needs are the same for
+// every frame, so they are read from shared memory once per CTA and kept in registers -- 31 of the ~119 64-bit
+// shared-memory accesses per frame (the LSU data pipe is this kernel's busiest unit) for ~60
+// registers, i.e. two instead of three resident CTAs per SM.
+template <int MODE, bool REGTAB>
+__global__ void __launch_bounds__(kFastWarps * 32, REGTAB ? 2 : 3)
 stft1024_kernel(const StftParams p) {
   constexpr int NFFT = 1024, N = 512, BINS = 513, SW = kFastWarps + 1;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -185,6 +189,15 @@ stft1024_kernel(const StftParams p) {
   }
   float l1_acc = 0.f;
   constexpr int NPASS = MODE == MODE_L1 ? 2 : 1;
+  float2 wreg[REGTAB ? 16 : 1], treg[REGTAB ? 16 : 1];
+  if constexpr (REGTAB) {
+    __syncthreads();                                     // the tables above are complete
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+      wreg[n1] = win2[n1 * 32 + lane];
+      treg[n1] = tw1[n1 * 32 + lane];
+    }
+  }
 #pragma unroll 1
   for (int round = 0; round < kFastRounds; ++round) {
     const int f0 = (blockIdx.x * kFastRounds + round) * kFastWarps;
@@ -205,10 +218,14 @@ stft1024_kernel(const StftParams p) {
       float2 v[16];
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
-        const float2 x = fr[n1 * 32 + lane], wn = win2[n1 * 32 + lane];
+        const float2 x = fr[n1 * 32 + lane];
+        float2 wn;
+        if constexpr (REGTAB) wn = wreg[n1];
+        else wn = win2[n1 * 32 + lane];
         v[n1] = make_float2(x.x * wn.x, x.y * wn.y);
       }
-      warp_fft512<false>(v, T, tw1, lane);
+      if constexpr (REGTAB) warp_fft512_regtw<false>(v, T, treg, lane);
+      else warp_fft512<false>(v, T, tw1, lane);
       // Z -> linear per-warp buffer (reusing the transpose scratch), then the real-FFT split
       {
         float2* zp = T + pad((lane & 15) + 256 * (lane >> 4));
@@ -298,9 +315,15 @@ static int launch_stft1024(const StftParams& p, cudaStream_t st) {
   const size_t smem = (size_t)((span_len + 3) & ~3) * 4 + 514 * 8 + 512 * 8 + 512 * 8 + (size_t)kFastWarps * 576 * 8 +
                       (size_t)513 * (kFastWarps + 1) * (MODE == MODE_COMPLEX ? 8 : 4) + 64;
   B200_CHECK_ARG(smem <= 227 * 1024, "stft: hop %d needs %zu bytes of shared memory", p.hop, smem);
-  B200_CUDA(cudaFuncSetAttribute(stft1024_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(p.frames, kFastWarps * kFastRounds), p.B);
-  stft1024_kernel<MODE><<<grid, kFastWarps * 32, smem, st>>>(p);
+  static const bool regtab = [] { const char* e = getenv("B200VOC_STFT_REGTAB"); return e && e[0] == '1'; }();
+  if (regtab) {   // opt-in A/B variant (written after the round's GPU budget was spent: not yet measured)
+    B200_CUDA(cudaFuncSetAttribute(stft1024_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stft1024_kernel<MODE, true><<<grid, kFastWarps * 32, smem, st>>>(p);
+  } else {
+    B200_CUDA(cudaFuncSetAttribute(stft1024_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stft1024_kernel<MODE, false><<<grid, kFastWarps * 32, smem, st>>>(p);
+  }
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
