@@ -131,3 +131,17 @@ def test_stft_loss_backward_matches_autograd(B, N):
     for m, fb in zip(loss_mod.stfts, fbs):
         gg, gg_ref = m.filterbank.grad.cpu().double(), fb.grad
         assert float((gg - gg_ref).abs().max()) <= 1e-4 * max(1.0, float(gg_ref.abs().max()))
+
+
+@pytest.mark.parametrize("hop", [110, 250, 128, 200])
+def test_stft1024_hops_not_multiple_of_4(hop):
+    """n_fft=1024 fast kernel with hops where 7*hop+1024 is not a multiple of 4 (hop % 4 == 2): the
+    interior vector-load path must not leave the tail of the span unwritten (round-1 ADVICE)."""
+    import b200voc
+    g = torch.Generator().manual_seed(hop)
+    wav = torch.rand(2, 8000, generator=g) * 2 - 1
+    ref = O.stft_complex(wav, 1024, hop)
+    got = b200voc.stft(wav.cuda(), 1024, hop).cpu()
+    assert got.shape == ref.shape
+    assert torch.isfinite(torch.view_as_real(got)).all()
+    assert float((got - ref).abs().max()) <= 2e-5 * 32 * 4

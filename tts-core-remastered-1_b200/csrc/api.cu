@@ -122,6 +122,8 @@ int attention_launch(const void* x16, const void* wqkv, const float* bqkv, const
 long long attention_scratch_elems(int N, int L, int C);
 extern long long* g_rb2_trace;
 
+int pack_merge_launch(const float* w, int nb, int fmt, void* out, cudaStream_t st);
+
 }  // namespace b200
 
 using namespace b200;
@@ -176,6 +178,7 @@ struct b200voc_gen {
   bool film_packed;
   int film_cols;
   float *merge_w, *merge_b;
+  uint16_t* merge_w16;           // [nb][16][32] hi | lo split of the merge taps (fused stage-3 kernel, stage_fused.cu)
   // attention (stage n_stages/2)
   int att_stage, att_C;
   uint16_t *att_wqkv, *att_wo;   // [3C][C], [C][C]
@@ -352,6 +355,7 @@ int b200voc_gen_create(const b200voc_gen_config* cfg, b200voc_gen** out) {
   }
   A(g->merge_w, (long long)c * nb * 7);
   A(g->merge_b, 1);
+  A(g->merge_w16, (long long)nb * 16 * 32);
   add_slot(g, "band_merge.weight", (long long)c * nb * 7, W_MERGE_W);
   add_slot(g, "band_merge.bias", 1, W_MERGE_B);
 #undef A
@@ -441,7 +445,10 @@ int b200voc_gen_set_weight(b200voc_gen* g, const char* name, const float* w, int
       if (sl->b < 3) B200_TRY(copy_f32_launch(w, g->att_bqkv + sl->b * C, C, 0.f, st, qs));
       else B200_TRY(copy_f32_launch(w, g->att_bo, C, 0.f, st));
     } break;
-    case W_MERGE_W: B200_TRY(copy_f32_launch(w, g->merge_w, numel, 0.f, st)); break;
+    case W_MERGE_W:
+      B200_TRY(copy_f32_launch(w, g->merge_w, numel, 0.f, st));
+      B200_TRY(pack_merge_launch(w, g->cfg.num_bands, g->stages.back().fmt, g->merge_w16, st));
+      break;
     case W_MERGE_B: B200_TRY(copy_f32_launch(w, g->merge_b, numel, 0.f, st)); break;
   }
   sl->set = true;
@@ -601,10 +608,80 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
   if (!split_fp32) ++launches;      // im2col + GEMM
   if (tap == "split" && tap_out) B200_TRY(tap_extract_launch(act[cur], N, T, g->H, g->stages[0].fmt, 0, tap_out, st));
 
+  // Narrow stages (Cout = 64 / 32, stride 2): ONE or two launches per stage with the intermediate activations on
+  // chip (stage_fused.cu); after the last stage band_merge + tanh are folded in as well.  B200VOC_FUSED=0 (or a tap
+  // inside the stage, or an unsupported shape) selects the layer-by-layer kernels.
+  static const bool fused_env = [] { const char* e = getenv("B200VOC_FUSED"); return !(e && e[0] == '0'); }();
+  auto tap_inside = [&](size_t i) {
+    if (tap.empty()) return false;
+    char a[32], b[32];
+    snprintf(a, sizeof a, "up%d", (int)i);
+    snprintf(b, sizeof b, "res%d.", (int)i);
+    if (tap == a) return true;
+    if (tap.compare(0, strlen(b), b) == 0 && tap.back() != '0' + (char)(g->cfg.n_dilations - 1)) return true;
+    return false;
+  };
+  bool merged = false;
   int L = T;
   for (size_t i = 0; i < g->stages.size(); ++i) {
     const StageW& s = g->stages[i];
     char nm[32];
+    const bool is_last = i + 1 == g->stages.size();
+    const bool fusable = fused_env && s.s == 2 && (s.Cout == 64 || s.Cout == 32) && s.res.size() == 3 &&
+                         (is_last || g->stages[i + 1].fmt == s.fmt) && !tap_inside(i) && T * (L * 2 / T) == L * 2 &&
+                         s.res[0].dilation <= 8 && s.res[1].dilation <= 8 && s.res[2].dilation <= 8;
+    if (fusable) {
+      StageFusedArgs a{};
+      a.N = N; a.C = s.Cout; a.T = T; a.num_bands = nb; a.fmt = s.fmt;
+      a.ct_w = s.up_w; a.ct_b = s.up_b; a.film = film; a.film_stride = g->film_cols;
+      const double fl_up = 2.0 * N * (double)L * s.s * 2.0 * s.Cin * s.Cout;
+      const double fl_res = 2.0 * N * (double)L * s.s * 7.0 * s.Cout * s.Cout;
+      const double by_in = (double)N * L * s.Cin * 2, by_out = (double)N * L * s.s * s.Cout * 2;
+      auto set_blk = [&](int slot, int j) {
+        const ResW& r = s.res[j];
+        a.blk_w[slot] = r.w; a.b_conv[slot] = r.b_conv; a.b_proj[slot] = r.b_proj; a.dil[slot] = r.dilation;
+        a.film_col[slot] = r.film_col;
+      };
+      const bool att_here = (int)i == g->att_stage && g->cfg.use_attention;
+      if (s.Cout == 64) {
+        // (ConvT + block 0) -> leaky_relu(x) in HBM -> (blocks 1, 2) -> raw x: the stage's weights (232 KB) do not fit
+        // next to the strip in one CTA's shared memory
+        a.x_in = act[cur]; a.Lin = L; a.in_ct = 1; a.nblk = 1; a.out_mode = 0; a.out16 = act[cur ^ 1];
+        set_blk(0, 0);
+        snprintf(nm, sizeof nm, "stage%d.a", (int)i);
+        RUN(nm, fl_up + fl_res, by_in + by_out, stage_fused_launch(a, st));
+        L *= s.s;
+        a.x_in = act[cur ^ 1]; a.Lin = L; a.in_ct = 0; a.nblk = 2; a.out_mode = 1; a.out16 = act[cur];
+        set_blk(0, 1); set_blk(1, 2);
+        snprintf(nm, sizeof nm, "stage%d.b", (int)i);
+        RUN(nm, 2 * fl_res, 2 * by_out, stage_fused_launch(a, st));
+      } else {
+        const bool merge = is_last && nb == 4 && !att_here && tap != "res3.2" && !(tap.size() > 3 && tap.compare(0, 3, "res") == 0);
+        a.x_in = act[cur]; a.Lin = L; a.in_ct = 1; a.nblk = 3; a.out_mode = merge ? 2 : 1; a.out16 = act[cur ^ 1];
+        a.merge_w16 = g->merge_w16; a.merge_b = g->merge_b; a.valid_samples = valid_samples; a.pcm16 = pcm16; a.wav = wav_out;
+        set_blk(0, 0); set_blk(1, 1); set_blk(2, 2);
+        snprintf(nm, sizeof nm, merge ? "stage%d+merge" : "stage%d", (int)i);
+        L *= s.s;
+        RUN(nm, fl_up + 3 * fl_res + (merge ? 2.0 * B * (double)L * nb * s.Cout * 7 : 0.0),
+            by_in + (merge ? (double)B * L * 4 : by_out), stage_fused_launch(a, st));
+        if (!merge) cur ^= 1;
+        merged = merge;
+      }
+      snprintf(nm, sizeof nm, "res%d.%d", (int)i, (int)s.res.size() - 1);
+      if (tap == nm && tap_out && !merged) B200_TRY(tap_extract_launch(act[cur], N, L, s.Cout, s.fmt, 0, tap_out, st));
+      if (att_here) {
+        uint16_t* sc = reinterpret_cast<uint16_t*>(ws + w.att);
+        const long long e = (long long)N * L * s.Cout;
+        const double Lw = g->cfg.attn_window > 0 && g->cfg.attn_window < L ? g->cfg.attn_window : L;
+        RUN("attn", 2.0 * N * ((double)L * Lw * 2.0 * s.Cout + 4.0 * s.Cout * s.Cout * L), (double)e * 2 * 6,
+            attention_launch(act[cur], g->att_wqkv, g->att_bqkv, g->att_wo, g->att_bo, N, L, s.Cout, g->cfg.attn_window,
+                             s.fmt, sc, act[cur ^ 1], st));
+        launches += 2;
+        cur ^= 1;
+        if (tap == "attn" && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, s.Cout, s.fmt, 0, tap_out, st));
+      }
+      continue;
+    }
     snprintf(nm, sizeof nm, "up%d", (int)i);
     // ConvT: 2 taps per output sample (generator.py:35-38,87).  Wide stages (C >= 128) carry
     // leaky_relu(x) between kernels (the residual block's MMA operand), narrow stages carry raw x
@@ -643,6 +720,7 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
     }
   }
   const StageW& last = g->stages.back();
+  if (!merged)
   RUN("band_merge", 2.0 * B * (double)L * nb * last.Cout * 7, (double)N * L * last.Cout * 2 + (double)B * L * 4,
       band_merge_launch(act[cur], g->merge_w, g->merge_b, B, nb, L, last.Cout, last.fmt, pcm16, valid_samples, wav_out,
                         st));

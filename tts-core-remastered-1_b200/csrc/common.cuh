@@ -50,4 +50,19 @@ int make_tmap_4d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// One launch of the fused narrow-stage kernel (stage_fused.cu).  x_in: in_ct ? [N, Lin, 2C] raw (ConvT stride 2 runs
+// first, L = 2 Lin) : [N, Lin, C] leaky_relu(x) (L = Lin).  out_mode: 0 = store leaky_relu(x), 1 = store raw x,
+// 2 = band_merge + tanh -> wav.
+struct StageFusedArgs {
+  const void* x_in;
+  int N, Lin, C, T, num_bands, fmt;
+  int in_ct, nblk, out_mode;
+  const void* ct_w; const float* ct_b;
+  const void* blk_w[3]; const float* b_conv[3]; const float* b_proj[3]; int dil[3]; int film_col[3];
+  const float* film; int film_stride;
+  void* out16;
+  const void* merge_w16; const float* merge_b; const int* valid_samples; int pcm16; void* wav;
+};
+int stage_fused_launch(const StageFusedArgs& a, cudaStream_t stream);
+
 }  // namespace b200

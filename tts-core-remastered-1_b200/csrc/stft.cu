@@ -207,7 +207,7 @@ stft1024_kernel(const StftParams p) {
       const float* w = (pass == 0 ? p.wav : p.wav2) + (long long)b * p.Nsamp;
       __syncthreads();                                   // previous users of span / stage are done
       const int s0 = f0 * p.hop - N;                     // first sample of the span (may be < 0: reflect)
-      if (s0 >= 0 && s0 + span_len <= p.Nsamp && ((s0 | p.Nsamp) & 3) == 0) {
+      if (s0 >= 0 && s0 + span_len <= p.Nsamp && ((s0 | p.Nsamp | span_len) & 3) == 0) {   // (hop % 4 == 2: span_len % 4 == 2)
         const float4* src = reinterpret_cast<const float4*>(w + s0);     // interior: plain vector loads
         for (int i = threadIdx.x; i < (span_len >> 2); i += blockDim.x) reinterpret_cast<float4*>(span)[i] = __ldg(src + i);
       } else {
