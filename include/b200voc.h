@@ -192,17 +192,6 @@ int b200voc_resblock(const void* a16, const void* w_packed, const float* b_conv,
                      const float* film, int N, int L, int C, int dilation, int T, int num_bands, int fmt,
                      int store_lrelu, void* out16, void* stream);
 
-/* experiment: UMMA descriptors whose start address is offset by whole 128B rows. */
-int b200voc_exp_rowshift(const void* a16_144x64, const void* b16_64x64, float* out_2x16x128x64, void* stream);
-/* debug: when non-NULL, the narrow-stage residual-block kernel records a clock64 timeline of CTA 0
- * ([5 roles][64 tiles][4] int64) into dev_buf; NULL switches it off. */
-int b200voc_debug_set_trace(int64_t* dev_buf);
-/* experiment: one cta_group::2 MMA group per CTA pair, D[256*pairs,128] = A[256*pairs,64] B[128,64]^T (fp16 in,
- * fp32 out); cycles[pairs] (optional) = issue -> completion seen by the leader. */
-int b200voc_exp_cta2(const void* a16, const void* b16, int pairs, float* out, int64_t* cycles, void* stream);
-/* experiment: cycles for iters x 4 tcgen05.mma (M=128, N=n, K=16, operands in shared memory). */
-int b200voc_exp_mma_rate(int n, int iters, int blocks, int64_t* out_cycles, void* stream);
-
 /* ----------------------------------------------------------------------------------------
  * STFT family (replaces vocoder7/stft.py:9-54 and the torchaudio MelSpectrogram call sites
  * reference_encoder/utils.py:31-36).  fp32 throughout.  frames = 1 + N / hop, bins = n_fft/2+1.

@@ -1,5 +1,6 @@
 """Experiment driver (test infrastructure): a CTA pair issuing tcgen05.mma.cta_group::2 (M=256, N=128)."""
 import os, sys
+os.environ.setdefault("B200VOC_LIB", "dev")   # experiment / trace exports live in libb200voc_dev.so
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tts-core-remastered-1_b200"))
 import torch

@@ -1,6 +1,7 @@
 """Experiment driver (test infrastructure): raw tcgen05.mma SS-mode issue rate vs N, and the cost of
 switching accumulator / shape between short groups of MMAs."""
 import os, sys, json
+os.environ.setdefault("B200VOC_LIB", "dev")   # experiment / trace exports live in libb200voc_dev.so
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tts-core-remastered-1_b200"))
 import torch

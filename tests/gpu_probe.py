@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import json
 import os
+os.environ.setdefault("B200VOC_LIB", "dev")   # experiment / trace exports live in libb200voc_dev.so
 import subprocess
 import sys
 import time

@@ -3,6 +3,7 @@ pipeline knocked out (B200VOC_DBG bits, -DB200VOC_TRACE builds only): 1 = GLU ep
 2 = store epilogue does nothing (C=128), 4 = weight ring not refilled, 8 = no GEMM2 MMAs, 16 = input
 tiles not refilled, 32 = no GEMM1 MMAs."""
 import os, sys
+os.environ.setdefault("B200VOC_LIB", "dev")   # experiment / trace exports live in libb200voc_dev.so
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tts-core-remastered-1_b200"))
 import torch

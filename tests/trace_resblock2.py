@@ -1,5 +1,6 @@
 """Debug driver (test infrastructure): clock64 timeline of CTA 0 of the narrow-stage residual block."""
 import os, sys
+os.environ.setdefault("B200VOC_LIB", "dev")   # experiment / trace exports live in libb200voc_dev.so
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tts-core-remastered-1_b200"))
 import torch

@@ -2,6 +2,7 @@
 residual block (C=128): per 64-channel chunk, when the MMA issuer passed its waits / finished issuing, when
 the GLU epilogue saw the accumulator and finished, when GEMM2's k-block was issued; per tile, the store epilogue."""
 import os, sys
+os.environ.setdefault("B200VOC_LIB", "dev")   # experiment / trace exports live in libb200voc_dev.so
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tts-core-remastered-1_b200"))
 import torch

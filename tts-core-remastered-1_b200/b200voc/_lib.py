@@ -8,6 +8,9 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb200voc.so")
+# development build (`make dev`, include/b200voc_dev.h): the product library plus experiment / trace exports;
+# only the debug drivers under tests/ select it, with B200VOC_LIB=dev
+DEV_LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb200voc_dev.so")
 
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
 FMT_FP16, FMT_BF16 = 0, 1
@@ -68,10 +71,6 @@ _SIGNATURES = {
     "b200voc_resblock_input_is_lrelu": (_I, [_I]),
     "b200voc_pack_resblock_weights": (C.c_int, [_P, _P, _I, _I, _P, _P]),
     "b200voc_resblock": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
-    "b200voc_exp_rowshift": (C.c_int, [_P, _P, _P, _P]),
-    "b200voc_exp_cta2": (C.c_int, [_P, _P, _I, _P, _P, _P]),
-    "b200voc_debug_set_trace": (C.c_int, [_P]),
-    "b200voc_exp_mma_rate": (C.c_int, [_I, _I, _I, _P, _P]),
     "b200voc_stft_mag": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "b200voc_stft_complex": (C.c_int, [_P, _I, _I, _I, _I, _P, _P]),
     "b200voc_stft_logmel": (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
@@ -81,6 +80,13 @@ _SIGNATURES = {
     "b200voc_stft_l1_backward": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _F, _P, _P, _P, _I64, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
+_DEV_SIGNATURES = {
+    "b200voc_exp_rowshift": (C.c_int, [_P, _P, _P, _P]),
+    "b200voc_exp_cta2": (C.c_int, [_P, _P, _I, _P, _P, _P]),
+    "b200voc_debug_set_trace": (C.c_int, [_P]),
+    "b200voc_exp_mma_rate": (C.c_int, [_I, _I, _I, _P, _P]),
+}
+DEV_EXPORTS = tuple(_DEV_SIGNATURES)
 
 _lib: Optional[C.CDLL] = None
 
@@ -94,12 +100,15 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    dev = os.environ.get("B200VOC_LIB", "") == "dev"
+    path = DEV_LIB_PATH if dev else LIB_PATH
+    if not os.path.exists(path):
         raise B200VocError(
-            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU / PyTorch fallback for the b200voc hot path)")
-    lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in _SIGNATURES.items():
+    lib = C.CDLL(path)
+    sigs = dict(_SIGNATURES, **_DEV_SIGNATURES) if dev else _SIGNATURES
+    for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
     _lib = lib

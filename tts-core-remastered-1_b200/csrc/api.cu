@@ -8,6 +8,9 @@
 #include <vector>
 
 #include "common.cuh"
+#ifdef B200VOC_DEV
+#include "../../include/b200voc_dev.h"
+#endif
 
 namespace b200 {
 
@@ -801,6 +804,7 @@ int b200voc_gst_forward(const float* mel, int mel_time_major, int B, int T, int 
   return gst_launch(mel, mel_time_major, B, T, channels, style_dim, num_tokens, conv0_w, conv0_b, conv2_w, conv2_b,
                     tokens, reinterpret_cast<float*>(scratch), style_out, reinterpret_cast<cudaStream_t>(stream));
 }
+#ifdef B200VOC_DEV
 int b200voc_debug_set_trace(int64_t* dev_buf) {
   b200::g_rb2_trace = reinterpret_cast<long long*>(dev_buf);
   return B200VOC_OK;
@@ -818,5 +822,7 @@ int b200voc_exp_rowshift(const void* a16, const void* b16, float* out, void* str
   B200_CHECK_ARG(a16 && b16 && out, "exp_rowshift: null argument");
   return exp_rowshift_launch(a16, b16, out, reinterpret_cast<cudaStream_t>(stream));
 }
+
+#endif  // B200VOC_DEV
 
 }  // extern "C"

@@ -358,6 +358,7 @@ int linear_launch(const void* x16, const void* w_packed /*[Cout][Cin]*/, const f
   return launch_gemm_taps<64, 3>(tmA, tmB, tmOut, p, N, stream);
 }
 
+#ifdef B200VOC_DEV
 // ---------------------------------------------------------------------------- experiment
 // Can a K-major SWIZZLE_128B descriptor start at an arbitrary 128-byte row of a TMA-written tile?
 // variant 0: base_offset field = 0; variant 1: base_offset = (start >> 7) & 7.
@@ -557,6 +558,8 @@ int exp_mma_rate_launch(int n, int iters, int blocks, long long* out, cudaStream
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
+
+#endif  // B200VOC_DEV
 
 int pack_convt_launch(const float* w, int Cin, int Cout, int s, int fmt, void* out, cudaStream_t stream) {
   const long long total = (long long)s * Cout * 2 * Cin;

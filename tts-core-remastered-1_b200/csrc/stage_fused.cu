@@ -55,7 +55,20 @@ struct StageFusedParams {
   const float* merge_bias;
   const int* valid_samples;
   int pcm16;
+  long long* trace;        // clock64 timeline of CTA 0: [16 band-strips][5 roles][32 events] (dev build only)
 };
+
+// dev build (-DB200VOC_TRACE): role 0 = MMA issuer, 1..4 = epilogue groups 0..3 (their quadrant-0 warp)
+#ifdef B200VOC_TRACE
+#define SF_TRACE(role, ev)                                                                  \
+  do {                                                                                      \
+    if (p.trace && blockIdx.x == 0 && bs < 16 && (threadIdx.x & 31) == 0)                   \
+      p.trace[((bs) * 5 + (role)) * 32 + (ev)] = clock64();                                 \
+  } while (0)
+#else
+#define SF_TRACE(role, ev) do { } while (0)
+#endif
+extern long long* g_rb2_trace;
 
 enum { SF_OUT_LRELU = 0, SF_OUT_RAW = 1, SF_OUT_MERGE = 2 };
 
@@ -86,7 +99,7 @@ struct SfCfg {
   static constexpr int OFF_IN = OFF_X + NXB * X_BYTES;
   static constexpr int OFF_Z = OFF_IN + (IN_CT ? NCHUNK * IN_CHUNK_BYTES : 0);
   static constexpr int OFF_FILM = OFF_Z + (OUT == SF_OUT_MERGE ? 7 * R * 4 : 0);
-  static constexpr int OFF_PAR = OFF_FILM + 16 * 512;                       // per epilogue warp: 2 frames x (S | T) x 32 ch
+  static constexpr int OFF_PAR = OFF_FILM + 16 * NBLK * 512;                // per epilogue warp and block: 2 frames x (S | T) x 32 ch
   static constexpr int OFF_BAR = OFF_PAR + (C + NBLK * 3 * C) * 4;
   static constexpr int NBARS = 1 + 4 * NCHUNK + 4 + 5 * NT;
   static constexpr int SMEM = ((OFF_BAR + NBARS * 8 + 16 + 1023) & ~1023) + 1024;
@@ -234,9 +247,11 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
           // the previous band-strip's last epilogues have left tensor memory (D2) and X
           for (int t = 0; t < NT; ++t) mbar_wait(&x_ready[t], (bs * XPB - 1) & 1);
         }
+        SF_TRACE(0, 0);
         if (IN_CT) {
           for (int c = 0; c < NCHUNK; ++c) {
             mbar_wait(&in_full[c], bs & 1);
+            if (c == 0) SF_TRACE(0, 1);
             tc_fence_after();
             const uint32_t a0 = smem_u32(sIn + c * K::IN_CHUNK_BYTES);
             if (elect_one()) {
@@ -255,9 +270,13 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
             }
             __syncwarp();
           }
+          SF_TRACE(0, 2);
         }
 #pragma unroll 1
         for (int blk = 0; blk < NBLK; ++blk) {
+          // [GEMM1 x NT, GEMM2 x NT] in this order: the epilogue behind GEMM2(t) rewrites tile t's rows of X in place,
+          // which GEMM1(t +- 1) read -- the tensor pipe runs in issue order.  (A polling scheduler that issued
+          // whichever of the two queues was ready was SLOWER: every mbarrier probe costs ~150 clk.)
           const int d = p.dil[blk];
           const uint32_t w1 = smem_u32(sW + blk * K::BLK_W), w2 = w1 + 3 * K::W1_TILE;
           for (int t = 0; t < NT; ++t) {
@@ -270,6 +289,7 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
               else if (t + 1 < NT) mbar_wait(&x_ready[t + 1], par);
             }
             tc_fence_after();
+            SF_TRACE(0, 3 + blk * 8 + t);
             if (elect_one()) {
 #pragma unroll
               for (int tap = 0; tap < 3; ++tap) {
@@ -286,6 +306,7 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
           for (int t = 0; t < NT; ++t) {
             mbar_wait(&h_full[t], (bs * NBLK + blk) & 1);
             tc_fence_after();
+            SF_TRACE(0, 3 + blk * 8 + 4 + t);
             if (elect_one()) {
               const uint64_t b_desc = make_kmajor_desc<ROWB>(w2);
 #pragma unroll
@@ -300,6 +321,7 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
           for (int t = 0; t < NT; ++t) {
             mbar_wait(&x_ready[t], (bs * XPB + NBLK) & 1);
             tc_fence_after();
+            SF_TRACE(0, 27 + t);
             if (elect_one()) {
               const uint64_t a_desc = make_kmajor_desc<ROWB>(xbase + (G + 128 * t) * ROWB);
               const uint64_t b_desc = make_kmajor_desc<ROWB>(smem_u32(sMW + sub * K::MW_TILE));
@@ -326,7 +348,7 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
     const int ct_mt = 2 * ct_c + (q >> 1);
     const int ct_sr = 256 * ct_c + 2 * (32 * q + lane) + ct_r;   // strip row this thread writes
     const int sr = 128 * mt + 32 * q + lane;                     // strip row of the block epilogues
-    float* scratch = reinterpret_cast<float*>(smem + K::OFF_FILM) + ew * 128;
+    float* scratch = reinterpret_cast<float*>(smem + K::OFF_FILM) + ew * NBLK * 128;
     auto sw_chunk = [](int row, int j) { return ROWB == 128 ? (j ^ (row & 7)) : (j ^ ((row >> 1) & 3)); };
     float y_acc = 0.f;
     int bs = 0;
@@ -337,75 +359,88 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
         const int seq = sg * NSUB + sub;
         const int bidx = seq / p.num_bands;                     // utterance (FiLM row)
         uint8_t* X = sX + (IN_CT ? 0 : (bs & 1)) * K::X_BYTES;
-        if (IN_CT) {
-          // ---------------------------------------------------------- ConvT epilogue: + bias, leaky_relu -> X
-          if (bs > 0) mbar_wait(&x_ready[ct_mt], (bs * XPB - 1) & 1);     // the tile's previous owner is done with its rows
-          mbar_wait(&ct_full[ct_c], bs & 1);
-          tc_fence_after();
-          uint32_t v[32];
-          tmem_ld32(lane_addr + K::CT_COL + ct_c * N1 + ct_col, v);
-          tmem_ld_wait();
-          const int l = s0 + ct_sr;
-          const bool in_seq = l >= 0 && l < p.L;
-          const int row = G + ct_sr;
-          uint8_t* xrow = X + row * ROWB;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-              const int ch = c_lo + 8 * j + 2 * e2;
-              float x0 = __uint_as_float(v[8 * j + 2 * e2]) + sPar[ch];
-              float x1 = __uint_as_float(v[8 * j + 2 * e2 + 1]) + sPar[ch + 1];
-              x0 = in_seq ? lrelu_fast(x0) : 0.f;
-              x1 = in_seq ? lrelu_fast(x1) : 0.f;
-              w[e2] = pack2t<FMT>(x0, x1);
-            }
-            *reinterpret_cast<uint4*>(xrow + (sw_chunk(row, (c_lo >> 3) + j) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-          tc_fence_before();
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&x_ready[ct_mt]);
-        } else {
-          mbar_wait(&xin_full[bs & 1], (bs >> 1) & 1);          // acquire the TMA-written strip (residual reads)
-        }
         const int l = s0 + sr;
         const bool in_seq = l >= 0 && l < p.L;
-        const int row = G + sr;
-        uint8_t* xrow = X + row * ROWB;
-        // FiLM frames of this warp's 32 rows (at most two: P >= 32)
+        const bool warp_in_seq = __all_sync(0xffffffffu, in_seq);
+        // FiLM coefficients of this warp's 32 rows (at most two frames: P >= 32) for every block of the band-strip,
+        // fetched now so that the L2 latency hides behind the ConvT phase
         const int lw = s0 + 128 * mt + 32 * q;
         const int t_first = lw < 0 ? 0 : min(lw / p.P, p.T - 1);
         const int t_last = lw + 31 < 0 ? 0 : min((lw + 31) / p.P, p.T - 1);
         const int t_mine = l < 0 ? 0 : min(l / p.P, p.T - 1);
         const float* my_film = scratch + (t_mine - t_first) * 64;
+        float4 film_st[NBLK];                                   // in flight during the ConvT phase, parked in shared memory after it
+        {
+          const int f = lane >> 4, which = (lane >> 3) & 1, j = lane & 7;
+          const float* src = p.film + ((long long)bidx * p.T + (f ? t_last : t_first)) * p.film_stride + which * C + c_lo;
+#pragma unroll
+          for (int b = 0; b < NBLK; ++b) film_st[b] = __ldg(reinterpret_cast<const float4*>(src + p.film_col[b]) + j);
+        }
+        if (IN_CT) {
+          // ---------------------------------------------------------- ConvT epilogue: + bias, leaky_relu -> X
+          if (bs > 0) mbar_wait(&x_ready[ct_mt], (bs * XPB - 1) & 1);     // the tile's previous owner is done with its rows
+          mbar_wait(&ct_full[ct_c], bs & 1);
+          tc_fence_after();
+          if (q == 0) SF_TRACE(1 + eg, 0);
+          uint32_t v[32];
+          tmem_ld32(lane_addr + K::CT_COL + ct_c * N1 + ct_col, v);
+          tmem_ld_wait();
+          const int cl = s0 + ct_sr;
+          const float keep = (cl >= 0 && cl < p.L) ? 1.f : 0.f;           // rows outside the sequence are the next conv's zero padding
+          const int crow = G + ct_sr;
+          uint8_t* cxrow = X + crow * ROWB;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 B0 = *reinterpret_cast<const float4*>(sPar + c_lo + 8 * j);
+            const float4 B1 = *reinterpret_cast<const float4*>(sPar + c_lo + 8 * j + 4);
+            const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+              const float x0 = (__uint_as_float(v[8 * j + 2 * e2]) + bv[2 * e2]) * keep;
+              const float x1 = (__uint_as_float(v[8 * j + 2 * e2 + 1]) + bv[2 * e2 + 1]) * keep;
+              w[e2] = pack2t<FMT>(lrelu_fast(x0), lrelu_fast(x1));
+            }
+            *reinterpret_cast<uint4*>(cxrow + (sw_chunk(crow, (c_lo >> 3) + j) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          tc_fence_before();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&x_ready[ct_mt]);
+          if (q == 0) SF_TRACE(1 + eg, 1);
+        } else {
+          mbar_wait(&xin_full[bs & 1], (bs >> 1) & 1);          // acquire the TMA-written strip (residual reads)
+        }
+        const int row = G + sr;
+        uint8_t* xrow = X + row * ROWB;
+        {
+          const int f = lane >> 4, which = (lane >> 3) & 1, j = lane & 7;
+#pragma unroll
+          for (int b = 0; b < NBLK; ++b) reinterpret_cast<float4*>(scratch + b * 128)[f * 16 + which * 8 + j] = film_st[b];
+          __syncwarp();
+        }
 #pragma unroll 1
         for (int blk = 0; blk < NBLK; ++blk) {
           const float* par = sPar + C + blk * 3 * C;
           // ---------------------------------------------------------- GLU + FiLM epilogue: D1 -> h (TMEM)
-          {
-            const int f = lane >> 4, which = (lane >> 3) & 1, j = lane & 7;
-            const float4 st = __ldg(reinterpret_cast<const float4*>(
-                p.film + ((long long)bidx * p.T + (f ? t_last : t_first)) * p.film_stride + p.film_col[blk] + which * C + c_lo) + j);
-            reinterpret_cast<float4*>(scratch)[f * 16 + which * 8 + j] = st;
-            __syncwarp();
-          }
+          const float* film_b = my_film + blk * 128;
           mbar_wait(&d1_full[mt], (bs * NBLK + blk) & 1);
           tc_fence_after();
+          if (q == 0) SF_TRACE(1 + eg, 2 + blk * 4);
 #pragma unroll
           for (int cc = 0; cc < 32; cc += 16) {
             uint32_t va[16], vg[16];
             tmem_ld16(lane_addr + mt * N1 + c_lo + cc, va);
             tmem_ld16(lane_addr + mt * N1 + C + c_lo + cc, vg);
             tmem_ld_wait();
+            if (q == 0 && blk == 1 && cc == 0) SF_TRACE(1 + eg, 16);
             uint32_t hw[8];
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
               const float4 A = *reinterpret_cast<const float4*>(par + c_lo + cc + 4 * i4);
               const float4 Gt = *reinterpret_cast<const float4*>(par + C + c_lo + cc + 4 * i4);
-              const float4 S = *reinterpret_cast<const float4*>(my_film + cc + 4 * i4);
-              const float4 Tt = *reinterpret_cast<const float4*>(my_film + 32 + cc + 4 * i4);
+              const float4 S = *reinterpret_cast<const float4*>(film_b + cc + 4 * i4);
+              const float4 Tt = *reinterpret_cast<const float4*>(film_b + 32 + cc + 4 * i4);
               const float av[4] = {A.x, A.y, A.z, A.w}, gv[4] = {Gt.x, Gt.y, Gt.z, Gt.w};
               const float sv[4] = {S.x, S.y, S.z, S.w}, tv[4] = {Tt.x, Tt.y, Tt.z, Tt.w};
               float hv[4];
@@ -420,41 +455,57 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
             }
             tmem_st8(lane_addr + mt * N1 + c_lo + cc, hw);     // over the value columns just read
           }
+          if (q == 0 && blk == 1) SF_TRACE(1 + eg, 17);
           tmem_st_wait();
+          if (q == 0 && blk == 1) SF_TRACE(1 + eg, 18);
           tc_fence_before();
           __syncwarp();                                         // (also: every lane is done with the FiLM scratch)
           if (lane == 0) mbar_arrive(&h_full[mt]);
+          if (q == 0) SF_TRACE(1 + eg, 3 + blk * 4);
           // ---------------------------------------------------------- epilogue 2: x + W2 h + b2
           const bool last = blk == NBLK - 1;
           mbar_wait(&d2_full[mt], (bs * NBLK + blk) & 1);
           tc_fence_after();
+          if (q == 0) SF_TRACE(1 + eg, 4 + blk * 4);
           uint32_t vd[32];
           tmem_ld32(lane_addr + mt * N1 + C + c_lo, vd);
           uint4 xa[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) xa[j] = *reinterpret_cast<const uint4*>(xrow + (sw_chunk(row, (c_lo >> 3) + j) << 4));
           tmem_ld_wait();
+          if (q == 0 && blk == 1) SF_TRACE(1 + eg, 19);
           uint4 ow[4];
+          const bool act = !last || OUT == SF_OUT_LRELU;        // store leaky_relu(y) (the next GEMM1's operand) or raw y
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t xw[4] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w};
+            const float4 B0 = *reinterpret_cast<const float4*>(par + 2 * C + c_lo + 8 * j);
+            const float4 B1 = *reinterpret_cast<const float4*>(par + 2 * C + c_lo + 8 * j + 4);
+            const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
             uint32_t o[4];
 #pragma unroll
             for (int e2 = 0; e2 < 4; ++e2) {
-              const int ch = c_lo + 8 * j + 2 * e2;
+              // (packed 16-bit leaky_relu / inverse here saves ~1.5 instructions per element but was measured to cost
+              // 3.5 dB of SNR (70.1 -> 66.6) for no change in the epilogue's latency: fp32 it is)
               const float2 xs = unpack2t<FMT>(xw[e2]);
-              float y0 = (lrelu_inv_fast(xs.x) + par[2 * C + ch]) + __uint_as_float(vd[8 * j + 2 * e2]);
-              float y1 = (lrelu_inv_fast(xs.y) + par[2 * C + ch + 1]) + __uint_as_float(vd[8 * j + 2 * e2 + 1]);
-              if (!in_seq) { y0 = 0.f; y1 = 0.f; }
-              if (!last || OUT == SF_OUT_LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
+              float y0 = (lrelu_inv_fast(xs.x) + bv[2 * e2]) + __uint_as_float(vd[8 * j + 2 * e2]);
+              float y1 = (lrelu_inv_fast(xs.y) + bv[2 * e2 + 1]) + __uint_as_float(vd[8 * j + 2 * e2 + 1]);
+              if (act) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
               o[e2] = pack2t<FMT>(y0, y1);
             }
             ow[j] = make_uint4(o[0], o[1], o[2], o[3]);
           }
+          if (!warp_in_seq && !in_seq) {                        // rows outside the sequence: the next conv's zero padding
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ow[j] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          if (q == 0 && blk == 1) SF_TRACE(1 + eg, 20);
           if (!last || OUT == SF_OUT_MERGE) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(xrow + (sw_chunk(row, (c_lo >> 3) + j) << 4)) = ow[j];
+            if (q == 0 && blk == 1) SF_TRACE(1 + eg, 21);
             fence_proxy_async_smem();
+            if (q == 0 && blk == 1) SF_TRACE(1 + eg, 22);
           } else if (in_seq && sr >= p.HL && sr < R - p.HR) {
             uint4* dst = reinterpret_cast<uint4*>(p.out16 + ((long long)seq * p.L + l) * C + c_lo);
 #pragma unroll
@@ -466,11 +517,13 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
             mbar_arrive(&x_ready[mt]);
             if (!IN_CT && last) mbar_arrive(&x_free[bs & 1]);
           }
+          if (q == 0) SF_TRACE(1 + eg, 5 + blk * 4);
         }
         if (OUT == SF_OUT_MERGE) {
           // ---------------------------------------------------------- merge: z_k[l] = m_k . x[l]  ->  y[l] += sum_k z_k[l+k-3]
           mbar_wait(&z_full[mt], bs & 1);
           tc_fence_after();
+          if (q == 0) SF_TRACE(1 + eg, 14);
           uint32_t vz[16];
           tmem_ld16(lane_addr + K::Z_COL + mt * 16, vz);
           tmem_ld_wait();
@@ -497,6 +550,7 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
             }
             y_acc = 0.f;
           }
+          if (q == 0) SF_TRACE(1 + eg, 15);
         }
       }
     }
@@ -537,6 +591,11 @@ static int launch_stage_fused_t(const StageFusedArgs& a, cudaStream_t stream) {
   p.b_ct = a.ct_b; p.film = a.film; p.film_stride = a.film_stride;
   p.out16 = reinterpret_cast<uint16_t*>(a.out16);
   p.wav = a.wav; p.merge_bias = a.merge_b; p.valid_samples = a.valid_samples; p.pcm16 = a.pcm16;
+  {   // dev build: B200VOC_SF_TRACE = 32 | 64a | 64b selects which launch of the step records its timeline
+    const char* e = getenv("B200VOC_SF_TRACE");
+    const char* me = C == 32 ? "32" : (IN_CT ? "64a" : "64b");
+    p.trace = (e ? strcmp(e, me) == 0 : C == 32) ? g_rb2_trace : nullptr;
+  }
   if (IN_CT) {
     B200_TRY(make_tmap_3d(&p.tmIn, a.x_in, 2 * C, a.Lin, a.N, (uint64_t)2 * C * 2, (uint64_t)a.Lin * 2 * C * 2, 64,
                           K::IN_ROWS, 128));
