@@ -21,7 +21,13 @@
 //     are issued before its GEMM2s and the tensor pipe executes in order;
 //   * m-tile j of the next block needs only tiles j-1, j, j+1 of this one: the MMA issuer walks
 //     [GEMM1 x NT, GEMM2 x NT] per block and waits per tile, so the epilogues of one tile overlap the MMAs of the others;
-//   * stage 3: the 4 bands of an utterance run back to back on the same strip of time; after the last block the strip
+//   * a CTA carries NCTX strips ("contexts": sequences seq, seq+1 of the same utterance over the same span of time)
+//     through the stage together: one strip alone leaves the tensor pipe idle for most of the
+//     GEMM1 -> GLU -> GEMM2 -> epilogue 2 -> next GEMM1 chain (measured, profiles/r02_stage_fused_trace.txt: 4.5 k clk
+//     per block against 1.9 k clk of MMAs, the epilogue warps busy 30 % of the time); with two strips all 512 TMEM
+//     columns hold accumulators (8 m-tiles x 2C columns), the issuer walks [GEMM1 x 8, GEMM2 x 8] and every epilogue
+//     warp alternates between its tile of strip 0 and of strip 1.  FiLM coefficients are shared by the contexts;
+//   * stage 3: the 4 bands of an utterance run on the same strip of time (two at a time); after the last block the strip
 //     (raw x, 16-bit, as band_merge reads it today) is multiplied by the 7 merge taps as ONE N = 16 MMA ([hi | lo] split
 //     of the fp32 taps: z_k = m_k . x[l]), and y[l] = sum_k z_k[l + k - 3] is gathered from shared memory into a register
 //     that accumulates over the bands; tanh (+ PCM16 / length mask) and the store follow the 4th band.  The 0.9 GB
@@ -72,16 +78,20 @@ extern long long* g_rb2_trace;
 
 enum { SF_OUT_LRELU = 0, SF_OUT_RAW = 1, SF_OUT_MERGE = 2 };
 
-template <int C, bool IN_CT, int NBLK, int OUT>
+template <int C, bool IN_CT, int NBLK, int OUT, int NCTX>
 struct SfCfg {
   static constexpr int ROWB = 2 * C;                  // bytes per X row = swizzle span (64 / 128)
   static constexpr int NT = C == 32 ? 4 : 2;          // m-tiles per strip
+  static constexpr int NTT = NCTX * NT;               // m-tiles in flight per CTA
   static constexpr int R = NT * 128;
   static constexpr int G = 8;                         // guard rows on each side of X (>= max dilation)
-  static constexpr int NXB = IN_CT ? 1 : 2;           // X buffers (TMA-loaded strips are double buffered)
+  static constexpr int NXB = IN_CT ? NCTX : 2;        // X buffers: one per context; a single TMA-loaded strip is double buffered
   static constexpr int X_BYTES = (R + 2 * G) * ROWB;
   static constexpr int CT_KB = (2 * C) / 64;          // 64-channel k-blocks of the ConvT input
-  static constexpr int NCHUNK = R / 256;              // ConvT chunks: 128 GEMM rows -> 256 strip rows
+  static constexpr int NCHUNK = R / 256;              // ConvT chunks per strip: 128 GEMM rows -> 256 strip rows
+  static constexpr int NSLOT = NCTX * NCHUNK;         // input chunk slots: every (context, chunk) has its own (two issuers must
+                                                      // not share a ring: a parity wait is only valid on a slot whose previous phase
+                                                      // the waiter has seen complete)
   static constexpr int IN_ROWS = 136;
   static constexpr int IN_KB_BYTES = IN_ROWS * 128;
   static constexpr int IN_CHUNK_BYTES = CT_KB * IN_KB_BYTES;
@@ -97,34 +107,39 @@ struct SfCfg {
   static constexpr int OFF_MW = OFF_W + NBLK * BLK_W;
   static constexpr int OFF_X = OFF_MW + (OUT == SF_OUT_MERGE ? NB * MW_TILE : 0);
   static constexpr int OFF_IN = OFF_X + NXB * X_BYTES;
-  static constexpr int OFF_Z = OFF_IN + (IN_CT ? NCHUNK * IN_CHUNK_BYTES : 0);
+  static constexpr int OFF_Z = OFF_IN + (IN_CT ? NSLOT * IN_CHUNK_BYTES : 0);
   static constexpr int OFF_FILM = OFF_Z + (OUT == SF_OUT_MERGE ? 7 * R * 4 : 0);
-  static constexpr int OFF_PAR = OFF_FILM + 16 * NBLK * 512;                // per epilogue warp and block: 2 frames x (S | T) x 32 ch
+  static constexpr int OFF_PAR = OFF_FILM + 16 * 512;                       // per epilogue warp: 2 frames x (S | T) x 32 ch of the current block
   static constexpr int OFF_BAR = OFF_PAR + (C + NBLK * 3 * C) * 4;
-  static constexpr int NBARS = 1 + 4 * NCHUNK + 4 + 5 * NT;
+  static constexpr int NBARS = 1 + 2 * NSLOT + NCTX * NCHUNK + 4 + 5 * NTT;
   static constexpr int SMEM = ((OFF_BAR + NBARS * 8 + 16 + 1023) & ~1023) + 1024;
-  static constexpr int N1 = 2 * C;                    // TMEM columns per m-tile: D1 = [0, 2C), D2 = [C, 2C), h at 16k
-  static constexpr int CT_COL = NT * N1;              // ConvT accumulators (NCHUNK x 2C columns)
-  static constexpr int Z_COL = CT_COL + (IN_CT ? NCHUNK * N1 : 0);
-  static constexpr int TMEM_NEED = Z_COL + (OUT == SF_OUT_MERGE ? NT * 16 : 0);
+  // TMEM: 2C columns per m-tile: GEMM1 accumulator = [0, 2C) (value | gate); h (packed 16-bit) over the value columns
+  // at 16k; GEMM2 accumulator = the gate columns [C, 2C); merge accumulator = [C, C + 16) once epilogue 2 has read them;
+  // the ConvT accumulator of chunk c (2C columns) = tile 2c of its context
+  static constexpr int N1 = 2 * C;
+  static constexpr int TMEM_NEED = NTT * N1;
   static constexpr uint32_t TMEM_COLS = TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
   static constexpr int XR_COUNT = C == 32 ? 4 : 8;    // warp arrivals that complete x_ready / h_full of one m-tile
-  static constexpr int XPB = IN_CT ? NBLK + 1 : NBLK; // x_ready completions per band-strip
+  // x_ready completions per iteration: [ConvT epilogue], one per block, [merge epilogue]
+  static constexpr int XPB = NBLK + (IN_CT ? 1 : 0) + (OUT == SF_OUT_MERGE ? 1 : 0);
   static_assert(C == 32 || C == 64, "narrow stages");
+  static_assert(NCTX == 1 || NCTX == 2, "contexts");
   static_assert(TMEM_NEED <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static_assert(OFF_W % 1024 == 0 && OFF_MW % 1024 == 0 && OFF_X % 1024 == 0 && OFF_IN % 1024 == 0 &&
                 X_BYTES % 1024 == 0 && W1_TILE % 1024 == 0 && W2_TILE % 1024 == 0 && IN_KB_BYTES % 1024 == 0,
                 "swizzle alignment");
   static_assert(OUT != SF_OUT_MERGE || (C == 32 && IN_CT), "merge follows the last (C = 32) stage");
+  static_assert(IN_CT || NCTX == 1, "TMA-loaded strips: one context (double-buffered X)");
 };
 
-template <int C, bool IN_CT, int NBLK, int OUT, int FMT>
-__global__ void __launch_bounds__(576, 1)
+template <int C, bool IN_CT, int NBLK, int OUT, int NCTX, int FMT>
+__global__ void __launch_bounds__(576 + 32 * (NCTX - 1), 1)
 stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
-  using K = SfCfg<C, IN_CT, NBLK, OUT>;
-  constexpr int NT = K::NT, R = K::R, G = K::G, ROWB = K::ROWB, N1 = K::N1, NCHUNK = K::NCHUNK, XPB = K::XPB;
-  constexpr int NSUB = OUT == SF_OUT_MERGE ? K::NB : 1;
+  using K = SfCfg<C, IN_CT, NBLK, OUT, NCTX>;
+  constexpr int NT = K::NT, NTT = K::NTT, R = K::R, G = K::G, ROWB = K::ROWB, N1 = K::N1, NCHUNK = K::NCHUNK, XPB = K::XPB;
+  constexpr int NSLOT = K::NSLOT;
+  constexpr int NSUB = OUT == SF_OUT_MERGE ? K::NB / NCTX : 1;      // iterations per unit (merge: all bands of the utterance)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sCtW = smem + K::OFF_CTW;
@@ -136,18 +151,17 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
   float* sPar = reinterpret_cast<float*>(smem + K::OFF_PAR);      // [b_ct (C)] then per block [ba/2 | bg/2 | b2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_BAR);
   uint64_t* w_full = bars;                      // [1]
-  uint64_t* in_full = w_full + 1;               // [NCHUNK]  TMA: input chunk landed            -> issuer
-  uint64_t* in_empty = in_full + NCHUNK;        // [NCHUNK]  ConvT MMAs have read the chunk     -> producer
-  uint64_t* ct_full = in_empty + NCHUNK;        // [NCHUNK]  ConvT accumulator complete         -> epilogue
-  uint64_t* z_pad = ct_full + NCHUNK;           // [NCHUNK]  (unused)
-  uint64_t* xin_full = z_pad + NCHUNK;          // [2]       TMA: lrelu(x) strip landed in X[b] -> issuer, epilogue
-  uint64_t* x_free = xin_full + 2;              // [2]       last block's epilogue is done with X[b] -> producer
-  uint64_t* x_ready = x_free + 2;               // [NT]      X rows of m-tile written (ConvT epilogue / E2) -> issuer
-  uint64_t* d1_full = x_ready + NT;             // [NT]
-  uint64_t* h_full = d1_full + NT;              // [NT]      h in TMEM, D1 drained                -> issuer
-  uint64_t* d2_full = h_full + NT;              // [NT]
-  uint64_t* z_full = d2_full + NT;              // [NT]      merge accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_full + NT);
+  uint64_t* in_full = w_full + 1;               // [NSLOT]          TMA: input chunk landed          -> issuer
+  uint64_t* in_empty = in_full + NSLOT;         // [NSLOT]          ConvT MMAs have read the chunk   -> producer
+  uint64_t* ct_full = in_empty + NSLOT;         // [NCTX * NCHUNK]  ConvT accumulator complete       -> epilogue
+  uint64_t* xin_full = ct_full + NCTX * NCHUNK; // [2]              TMA: lrelu(x) strip landed in X[b] -> issuer, epilogue
+  uint64_t* x_free = xin_full + 2;              // [2]              last block's epilogue is done with X[b] -> producer
+  uint64_t* x_ready = x_free + 2;               // [NTT]  X rows of the m-tile written, its TMEM columns drained -> issuer
+  uint64_t* d1_full = x_ready + NTT;            // [NTT]
+  uint64_t* h_full = d1_full + NTT;             // [NTT]  h in TMEM, D1 drained                      -> issuer
+  uint64_t* d2_full = h_full + NTT;             // [NTT]
+  uint64_t* z_full = d2_full + NTT;             // [NTT]  merge accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_full + NTT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -167,9 +181,10 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmIn);
     mbar_init(w_full, 1);
-    for (int c = 0; c < NCHUNK; ++c) { mbar_init(&in_full[c], 1); mbar_init(&in_empty[c], 1); mbar_init(&ct_full[c], 1); }
+    for (int c = 0; c < NSLOT; ++c) { mbar_init(&in_full[c], 1); mbar_init(&in_empty[c], 1); }
+    for (int c = 0; c < NCTX * NCHUNK; ++c) mbar_init(&ct_full[c], 1);
     for (int b = 0; b < 2; ++b) { mbar_init(&xin_full[b], 1); mbar_init(&x_free[b], 16); }
-    for (int t = 0; t < NT; ++t) {
+    for (int t = 0; t < NTT; ++t) {
       mbar_init(&x_ready[t], K::XR_COUNT);
       mbar_init(&d1_full[t], 1);
       mbar_init(&h_full[t], K::XR_COUNT);
@@ -186,12 +201,14 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
   const uint32_t tmem_base = *tmem_slot;
   const int grid = gridDim.x;
 
-  // unit -> (sequence group, first strip row): a unit is one strip of one sequence (NSUB = 1) or of the num_bands
-  // sequences of one utterance (merge)
+  // unit -> (sequence group, first strip row).  A unit is one span of time of NCTX consecutive sequences (NSUB = 1) or of
+  // all num_bands sequences of one utterance (merge: NSUB iterations of NCTX bands); iteration `it` of the CTA handles
+  // sequences seq0 .. seq0 + NCTX - 1
   auto unit_geom = [&](int u, int& sg, int& s0) {
     sg = u / p.strips_per_seq;
     s0 = (u - sg * p.strips_per_seq) * p.V - p.HL;
   };
+  auto xbuf = [&](int cx, int it) { return IN_CT ? cx : (it & 1); };
 
   if (warp == 0) {
     // ============================================================== TMA producer
@@ -206,54 +223,63 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
       }
       if (OUT == SF_OUT_MERGE)
         for (int b = 0; b < K::NB; ++b) tma_load_2d(sMW + b * K::MW_TILE, &p.tmMW, w_full, 0, b * 16);
-      int bs = 0;
+      int it = 0;
       for (int u = blockIdx.x; u < p.total_units; u += grid) {
         int sg, s0;
         unit_geom(u, sg, s0);
-        for (int sub = 0; sub < NSUB; ++sub, ++bs) {
-          const int seq = sg * NSUB + sub;
+        for (int sub = 0; sub < NSUB; ++sub, ++it) {
+          const int seq0 = (sg * NSUB + sub) * NCTX;
           if (IN_CT) {
             const int m0 = (s0 + 1) / 2;          // s0 is odd: strip row 0 = output row 2*m0 - 1
-            for (int c = 0; c < NCHUNK; ++c) {
-              mbar_wait(&in_empty[c], (bs & 1) ^ 1);
-              mbar_expect_tx(&in_full[c], K::IN_CHUNK_BYTES);
-              for (int kb = 0; kb < K::CT_KB; ++kb)
-                tma_load_3d(sIn + c * K::IN_CHUNK_BYTES + kb * K::IN_KB_BYTES, &p.tmIn, &in_full[c], kb * 64,
-                            m0 - 1 + 128 * c, seq);
-            }
+            for (int cx = 0; cx < NCTX; ++cx)
+              for (int c = 0; c < NCHUNK; ++c) {
+                const int sl = cx * NCHUNK + c;
+                mbar_wait(&in_empty[sl], (it & 1) ^ 1);
+                mbar_expect_tx(&in_full[sl], K::IN_CHUNK_BYTES);
+                for (int kb = 0; kb < K::CT_KB; ++kb)
+                  tma_load_3d(sIn + sl * K::IN_CHUNK_BYTES + kb * K::IN_KB_BYTES, &p.tmIn, &in_full[sl], kb * 64,
+                              m0 - 1 + 128 * c, seq0 + cx);
+              }
           } else {
-            const int buf = bs & 1;
-            mbar_wait(&x_free[buf], ((bs >> 1) & 1) ^ 1);
+            const int buf = it & 1;
+            mbar_wait(&x_free[buf], ((it >> 1) & 1) ^ 1);
             mbar_expect_tx(&xin_full[buf], K::X_BYTES);
             for (int j = 0; j < (R + 2 * G) / K::IN_ROWS; ++j)
               tma_load_3d(sX + buf * K::X_BYTES + j * K::IN_ROWS * ROWB, &p.tmIn, &xin_full[buf], 0,
-                          s0 - G + j * K::IN_ROWS, seq);
+                          s0 - G + j * K::IN_ROWS, seq0);
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ============================================================== MMA issuer (warp-uniform control flow, one lane issues)
-    const uint32_t idesc_ct = make_idesc_f16(FMT, N1);
-    const uint32_t idesc1 = make_idesc_f16(FMT, N1);
+  } else if (warp == 1 || warp == 18) {
+    // ============================================================== MMA issuers: warp 1 runs context 0, warp 18 (NCTX = 2)
+    // context 1 -- two independent in-order programs.  (One warp issuing for both contexts was the bottleneck: its
+    // ~300 clk of scalar work per op -- barrier probe, fence, descriptors through the uniform datapath, commit -- is not
+    // hidden behind anything, 8 GEMM1 + 8 GEMM2 ops cost 8 k clk per block against 3.8 k clk of MMAs.)  Warp-uniform
+    // control flow, one elected lane issues.
+    const int cx = warp == 1 ? 0 : 1;
+    const uint32_t idesc1 = make_idesc_f16(FMT, N1);     // GEMM1 and ConvT: N = 2C
     const uint32_t idesc2 = make_idesc_f16(FMT, C);
     const uint32_t idesc_z = make_idesc_f16(FMT, 16);
     mbar_wait(w_full, 0);
-    int bs = 0;
+    int it = 0;
     for (int u = blockIdx.x; u < p.total_units; u += grid) {
-      for (int sub = 0; sub < NSUB; ++sub, ++bs) {
-        const uint32_t xbase = smem_u32(sX + (IN_CT ? 0 : (bs & 1)) * K::X_BYTES);
-        if (bs > 0) {
-          // the previous band-strip's last epilogues have left tensor memory (D2) and X
-          for (int t = 0; t < NT; ++t) mbar_wait(&x_ready[t], (bs * XPB - 1) & 1);
+      for (int sub = 0; sub < NSUB; ++sub, ++it) {
+        const int bs = it;
+        const uint32_t xbase = smem_u32(sX + xbuf(cx, it) * K::X_BYTES);
+        if (it > 0) {
+          // the previous iteration's last epilogues have left this context's tensor memory and X
+          for (int t = 0; t < NT; ++t) mbar_wait(&x_ready[cx * NT + t], (it * XPB - 1) & 1);
         }
-        SF_TRACE(0, 0);
+        if (cx == 0) SF_TRACE(0, 0);
         if (IN_CT) {
           for (int c = 0; c < NCHUNK; ++c) {
-            mbar_wait(&in_full[c], bs & 1);
-            if (c == 0) SF_TRACE(0, 1);
+            const int sl = cx * NCHUNK + c;
+            mbar_wait(&in_full[sl], it & 1);
+            if (cx == 0 && c == 0) SF_TRACE(0, 1);
             tc_fence_after();
-            const uint32_t a0 = smem_u32(sIn + c * K::IN_CHUNK_BYTES);
+            const uint32_t a0 = smem_u32(sIn + sl * K::IN_CHUNK_BYTES);
+            const uint32_t d_ct = tmem_base + (cx * NT + 2 * c) * N1;
             if (elect_one()) {
 #pragma unroll
               for (int tap = 0; tap < 2; ++tap)      // tap 0: x[m] (tile row i + 1), tap 1: x[m - 1] (tile row i)
@@ -263,33 +289,34 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
                   const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sCtW + (tap * K::CT_KB + kb) * K::CTW_TILE));
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma_f16(tmem_base + K::CT_COL + c * N1, a_desc + 2 * k, b_desc + 2 * k, idesc_ct, (tap | kb | k) != 0);
+                    umma_f16(d_ct, a_desc + 2 * k, b_desc + 2 * k, idesc1, (tap | kb | k) != 0);
                 }
-              umma_commit(&ct_full[c]);
-              umma_commit(&in_empty[c]);
+              umma_commit(&ct_full[cx * NCHUNK + c]);
+              umma_commit(&in_empty[sl]);
             }
             __syncwarp();
           }
-          SF_TRACE(0, 2);
+          if (cx == 0) SF_TRACE(0, 2);
         }
 #pragma unroll 1
         for (int blk = 0; blk < NBLK; ++blk) {
           // [GEMM1 x NT, GEMM2 x NT] in this order: the epilogue behind GEMM2(t) rewrites tile t's rows of X in place,
-          // which GEMM1(t +- 1) read -- the tensor pipe runs in issue order.  (A polling scheduler that issued
-          // whichever of the two queues was ready was SLOWER: every mbarrier probe costs ~150 clk.)
+          // which GEMM1(t +- 1) read -- the tensor pipe runs one thread's MMAs in issue order.  (A polling scheduler that
+          // issued whichever of the two queues was ready was SLOWER: every mbarrier probe costs ~150 clk.)
           const int d = p.dil[blk];
           const uint32_t w1 = smem_u32(sW + blk * K::BLK_W), w2 = w1 + 3 * K::W1_TILE;
           for (int t = 0; t < NT; ++t) {
-            // inputs of this block for tiles t-1, t, t+1
+            const int T = cx * NT + t;
+            // inputs of this block for tiles t-1, t, t+1 of the strip
             if (!IN_CT && blk == 0) {
-              if (t == 0) mbar_wait(&xin_full[bs & 1], (bs >> 1) & 1);
+              if (t == 0) mbar_wait(&xin_full[it & 1], (it >> 1) & 1);
             } else {
-              const uint32_t par = (bs * XPB + blk - (IN_CT ? 0 : 1)) & 1;
-              if (t == 0) { mbar_wait(&x_ready[0], par); if (NT > 1) mbar_wait(&x_ready[1], par); }
-              else if (t + 1 < NT) mbar_wait(&x_ready[t + 1], par);
+              const uint32_t par = (it * XPB + blk - (IN_CT ? 0 : 1)) & 1;
+              if (t == 0) { mbar_wait(&x_ready[T], par); if (NT > 1) mbar_wait(&x_ready[T + 1], par); }
+              else if (t + 1 < NT) mbar_wait(&x_ready[T + 1], par);
             }
             tc_fence_after();
-            SF_TRACE(0, 3 + blk * 8 + t);
+            if (cx == 0) SF_TRACE(0, 3 + blk * 8 + t);
             if (elect_one()) {
 #pragma unroll
               for (int tap = 0; tap < 3; ++tap) {
@@ -297,38 +324,40 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
                 const uint64_t b_desc = make_kmajor_desc<ROWB>(w1 + tap * K::W1_TILE);
 #pragma unroll
                 for (int k = 0; k < C / 16; ++k)
-                  umma_f16(tmem_base + t * N1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (tap | k) != 0);
+                  umma_f16(tmem_base + T * N1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (tap | k) != 0);
               }
-              umma_commit(&d1_full[t]);
+              umma_commit(&d1_full[T]);
             }
             __syncwarp();
           }
           for (int t = 0; t < NT; ++t) {
-            mbar_wait(&h_full[t], (bs * NBLK + blk) & 1);
+            const int T = cx * NT + t;
+            mbar_wait(&h_full[T], (it * NBLK + blk) & 1);
             tc_fence_after();
-            SF_TRACE(0, 3 + blk * 8 + 4 + t);
+            if (cx == 0) SF_TRACE(0, 3 + blk * 8 + 4 + t);
             if (elect_one()) {
               const uint64_t b_desc = make_kmajor_desc<ROWB>(w2);
 #pragma unroll
               for (int k = 0; k < C / 16; ++k)      // A = h in TMEM: k-step k sits on the value columns 16k .. 16k+7
-                umma_f16_ts(tmem_base + t * N1 + C, tmem_base + t * N1 + 16 * k, b_desc + 2 * k, idesc2, k != 0);
-              umma_commit(&d2_full[t]);
+                umma_f16_ts(tmem_base + T * N1 + C, tmem_base + T * N1 + 16 * k, b_desc + 2 * k, idesc2, k != 0);
+              umma_commit(&d2_full[T]);
             }
             __syncwarp();
           }
         }
         if (OUT == SF_OUT_MERGE) {
           for (int t = 0; t < NT; ++t) {
-            mbar_wait(&x_ready[t], (bs * XPB + NBLK) & 1);
+            const int T = cx * NT + t;
+            mbar_wait(&x_ready[T], (it * XPB + NBLK) & 1);
             tc_fence_after();
-            SF_TRACE(0, 27 + t);
+            if (cx == 0) SF_TRACE(0, 27 + t);
             if (elect_one()) {
               const uint64_t a_desc = make_kmajor_desc<ROWB>(xbase + (G + 128 * t) * ROWB);
-              const uint64_t b_desc = make_kmajor_desc<ROWB>(smem_u32(sMW + sub * K::MW_TILE));
+              const uint64_t b_desc = make_kmajor_desc<ROWB>(smem_u32(sMW + (sub * NCTX + cx) * K::MW_TILE));
 #pragma unroll
               for (int k = 0; k < C / 16; ++k)
-                umma_f16(tmem_base + K::Z_COL + t * 16, a_desc + 2 * k, b_desc + 2 * k, idesc_z, k != 0);
-              umma_commit(&z_full[t]);
+                umma_f16(tmem_base + T * N1 + C, a_desc + 2 * k, b_desc + 2 * k, idesc_z, k != 0);
+              umma_commit(&z_full[T]);
             }
             __syncwarp();
           }
@@ -339,7 +368,7 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
     // ============================================================== epilogue groups (warps 2..17)
     const int eg = (warp - 2) >> 2, q = warp & 3, ew = warp - 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int mt = C == 32 ? eg : (eg >> 1);               // m-tile of the block epilogues
+    const int mt = C == 32 ? eg : (eg >> 1);               // m-tile (within a strip) of the block epilogues
     const int c_lo = C == 32 ? 0 : 32 * (eg & 1);          // this thread's 32 channels
     // ConvT epilogue geometry: chunk, output phase r, accumulator columns, m-tile the written rows fall into
     const int ct_c = C == 32 ? (eg >> 1) : 0;
@@ -348,21 +377,21 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
     const int ct_mt = 2 * ct_c + (q >> 1);
     const int ct_sr = 256 * ct_c + 2 * (32 * q + lane) + ct_r;   // strip row this thread writes
     const int sr = 128 * mt + 32 * q + lane;                     // strip row of the block epilogues
-    float* scratch = reinterpret_cast<float*>(smem + K::OFF_FILM) + ew * NBLK * 128;
+    float* scratch = reinterpret_cast<float*>(smem + K::OFF_FILM) + ew * 128;
     auto sw_chunk = [](int row, int j) { return ROWB == 128 ? (j ^ (row & 7)) : (j ^ ((row >> 1) & 3)); };
     float y_acc = 0.f;
-    int bs = 0;
+    int it = 0;
     for (int u = blockIdx.x; u < p.total_units; u += grid) {
       int sg, s0;
       unit_geom(u, sg, s0);
-      for (int sub = 0; sub < NSUB; ++sub, ++bs) {
-        const int seq = sg * NSUB + sub;
-        const int bidx = seq / p.num_bands;                     // utterance (FiLM row)
-        uint8_t* X = sX + (IN_CT ? 0 : (bs & 1)) * K::X_BYTES;
+      for (int sub = 0; sub < NSUB; ++sub, ++it) {
+        const int bs = it;
+        const int seq0 = (sg * NSUB + sub) * NCTX;
+        const int bidx = seq0 / p.num_bands;                    // utterance (FiLM row): the same for all contexts
         const int l = s0 + sr;
         const bool in_seq = l >= 0 && l < p.L;
         const bool warp_in_seq = __all_sync(0xffffffffu, in_seq);
-        // FiLM coefficients of this warp's 32 rows (at most two frames: P >= 32) for every block of the band-strip,
+        // FiLM coefficients of this warp's 32 rows (at most two frames: P >= 32) for every block of the iteration,
         // fetched now so that the L2 latency hides behind the ConvT phase
         const int lw = s0 + 128 * mt + 32 * q;
         const int t_first = lw < 0 ? 0 : min(lw / p.P, p.T - 1);
@@ -378,164 +407,176 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
         }
         if (IN_CT) {
           // ---------------------------------------------------------- ConvT epilogue: + bias, leaky_relu -> X
-          if (bs > 0) mbar_wait(&x_ready[ct_mt], (bs * XPB - 1) & 1);     // the tile's previous owner is done with its rows
-          mbar_wait(&ct_full[ct_c], bs & 1);
-          tc_fence_after();
-          if (q == 0) SF_TRACE(1 + eg, 0);
-          uint32_t v[32];
-          tmem_ld32(lane_addr + K::CT_COL + ct_c * N1 + ct_col, v);
-          tmem_ld_wait();
-          const int cl = s0 + ct_sr;
-          const float keep = (cl >= 0 && cl < p.L) ? 1.f : 0.f;           // rows outside the sequence are the next conv's zero padding
-          const int crow = G + ct_sr;
-          uint8_t* cxrow = X + crow * ROWB;
+#pragma unroll 1
+          for (int cx = 0; cx < NCTX; ++cx) {
+            uint8_t* X = sX + xbuf(cx, it) * K::X_BYTES;
+            if (it > 0) mbar_wait(&x_ready[cx * NT + ct_mt], (it * XPB - 1) & 1);   // the tile's previous owner is done with its rows
+            mbar_wait(&ct_full[cx * NCHUNK + ct_c], it & 1);
+            tc_fence_after();
+            if (q == 0 && cx == 0) SF_TRACE(1 + eg, 0);
+            uint32_t v[32];
+            tmem_ld32(lane_addr + (cx * NT + 2 * ct_c) * N1 + ct_col, v);
+            tmem_ld_wait();
+            const int cl = s0 + ct_sr;
+            const float keep = (cl >= 0 && cl < p.L) ? 1.f : 0.f;           // rows outside the sequence are the next conv's zero padding
+            const int crow = G + ct_sr;
+            uint8_t* cxrow = X + crow * ROWB;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 B0 = *reinterpret_cast<const float4*>(sPar + c_lo + 8 * j);
-            const float4 B1 = *reinterpret_cast<const float4*>(sPar + c_lo + 8 * j + 4);
-            const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
-            uint32_t w[4];
+            for (int j = 0; j < 4; ++j) {
+              const float4 B0 = *reinterpret_cast<const float4*>(sPar + c_lo + 8 * j);
+              const float4 B1 = *reinterpret_cast<const float4*>(sPar + c_lo + 8 * j + 4);
+              const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
+              uint32_t w[4];
 #pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-              const float x0 = (__uint_as_float(v[8 * j + 2 * e2]) + bv[2 * e2]) * keep;
-              const float x1 = (__uint_as_float(v[8 * j + 2 * e2 + 1]) + bv[2 * e2 + 1]) * keep;
-              w[e2] = pack2t<FMT>(lrelu_fast(x0), lrelu_fast(x1));
+              for (int e2 = 0; e2 < 4; ++e2) {
+                const float x0 = (__uint_as_float(v[8 * j + 2 * e2]) + bv[2 * e2]) * keep;
+                const float x1 = (__uint_as_float(v[8 * j + 2 * e2 + 1]) + bv[2 * e2 + 1]) * keep;
+                w[e2] = pack2t<FMT>(lrelu_fast(x0), lrelu_fast(x1));
+              }
+              *reinterpret_cast<uint4*>(cxrow + (sw_chunk(crow, (c_lo >> 3) + j) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            *reinterpret_cast<uint4*>(cxrow + (sw_chunk(crow, (c_lo >> 3) + j) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x_ready[cx * NT + ct_mt]);
+            if (q == 0 && cx == 0) SF_TRACE(1 + eg, 1);
           }
-          tc_fence_before();
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&x_ready[ct_mt]);
-          if (q == 0) SF_TRACE(1 + eg, 1);
         } else {
-          mbar_wait(&xin_full[bs & 1], (bs >> 1) & 1);          // acquire the TMA-written strip (residual reads)
+          mbar_wait(&xin_full[it & 1], (it >> 1) & 1);          // acquire the TMA-written strip (residual reads)
         }
         const int row = G + sr;
-        uint8_t* xrow = X + row * ROWB;
-        {
-          const int f = lane >> 4, which = (lane >> 3) & 1, j = lane & 7;
-#pragma unroll
-          for (int b = 0; b < NBLK; ++b) reinterpret_cast<float4*>(scratch + b * 128)[f * 16 + which * 8 + j] = film_st[b];
-          __syncwarp();
-        }
 #pragma unroll 1
         for (int blk = 0; blk < NBLK; ++blk) {
           const float* par = sPar + C + blk * 3 * C;
-          // ---------------------------------------------------------- GLU + FiLM epilogue: D1 -> h (TMEM)
-          const float* film_b = my_film + blk * 128;
-          mbar_wait(&d1_full[mt], (bs * NBLK + blk) & 1);
-          tc_fence_after();
-          if (q == 0) SF_TRACE(1 + eg, 2 + blk * 4);
+          const float* film_b = my_film;
+          {   // this block's FiLM coefficients -> the warp's scratch (the previous block's readers are through: __syncwarp below)
+            float4 f4 = film_st[0];
 #pragma unroll
-          for (int cc = 0; cc < 32; cc += 16) {
-            uint32_t va[16], vg[16];
-            tmem_ld16(lane_addr + mt * N1 + c_lo + cc, va);
-            tmem_ld16(lane_addr + mt * N1 + C + c_lo + cc, vg);
-            tmem_ld_wait();
-            if (q == 0 && blk == 1 && cc == 0) SF_TRACE(1 + eg, 16);
-            uint32_t hw[8];
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              const float4 A = *reinterpret_cast<const float4*>(par + c_lo + cc + 4 * i4);
-              const float4 Gt = *reinterpret_cast<const float4*>(par + C + c_lo + cc + 4 * i4);
-              const float4 S = *reinterpret_cast<const float4*>(film_b + cc + 4 * i4);
-              const float4 Tt = *reinterpret_cast<const float4*>(film_b + 32 + cc + 4 * i4);
-              const float av[4] = {A.x, A.y, A.z, A.w}, gv[4] = {Gt.x, Gt.y, Gt.z, Gt.w};
-              const float sv[4] = {S.x, S.y, S.z, S.w}, tv[4] = {Tt.x, Tt.y, Tt.z, Tt.w};
-              float hv[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float a = __uint_as_float(va[4 * i4 + e]) + av[e];                 // (conv_a + b_a) / 2
-                const float th = tanh_approx(__uint_as_float(vg[4 * i4 + e]) + gv[e]);   // tanh(g / 2)
-                hv[e] = fmaf(fmaf(a, th, a), sv[e], tv[e]);                              // a sigmoid(g) (1 + scale) + shift
-              }
-              hw[2 * i4] = pack2t<FMT>(hv[0], hv[1]);
-              hw[2 * i4 + 1] = pack2t<FMT>(hv[2], hv[3]);
-            }
-            tmem_st8(lane_addr + mt * N1 + c_lo + cc, hw);     // over the value columns just read
+            for (int b = 1; b < NBLK; ++b) if (blk == b) f4 = film_st[b];
+            reinterpret_cast<float4*>(scratch)[(lane >> 4) * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)] = f4;
+            __syncwarp();
           }
-          if (q == 0 && blk == 1) SF_TRACE(1 + eg, 17);
-          tmem_st_wait();
-          if (q == 0 && blk == 1) SF_TRACE(1 + eg, 18);
-          tc_fence_before();
-          __syncwarp();                                         // (also: every lane is done with the FiLM scratch)
-          if (lane == 0) mbar_arrive(&h_full[mt]);
-          if (q == 0) SF_TRACE(1 + eg, 3 + blk * 4);
-          // ---------------------------------------------------------- epilogue 2: x + W2 h + b2
           const bool last = blk == NBLK - 1;
-          mbar_wait(&d2_full[mt], (bs * NBLK + blk) & 1);
-          tc_fence_after();
-          if (q == 0) SF_TRACE(1 + eg, 4 + blk * 4);
-          uint32_t vd[32];
-          tmem_ld32(lane_addr + mt * N1 + C + c_lo, vd);
-          uint4 xa[4];
+          // ---------------------------------------------------------- GLU + FiLM epilogue: D1 -> h (TMEM)
+#pragma unroll 1
+          for (int cx = 0; cx < NCTX; ++cx) {
+            const int T = cx * NT + mt;
+            mbar_wait(&d1_full[T], (it * NBLK + blk) & 1);
+            tc_fence_after();
+            if (q == 0 && cx == 0) SF_TRACE(1 + eg, 2 + blk * 4);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) xa[j] = *reinterpret_cast<const uint4*>(xrow + (sw_chunk(row, (c_lo >> 3) + j) << 4));
-          tmem_ld_wait();
-          if (q == 0 && blk == 1) SF_TRACE(1 + eg, 19);
-          uint4 ow[4];
-          const bool act = !last || OUT == SF_OUT_LRELU;        // store leaky_relu(y) (the next GEMM1's operand) or raw y
+            for (int cc = 0; cc < 32; cc += 16) {
+              uint32_t va[16], vg[16];
+              tmem_ld16(lane_addr + T * N1 + c_lo + cc, va);
+              tmem_ld16(lane_addr + T * N1 + C + c_lo + cc, vg);
+              tmem_ld_wait();
+              uint32_t hw[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t xw[4] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w};
-            const float4 B0 = *reinterpret_cast<const float4*>(par + 2 * C + c_lo + 8 * j);
-            const float4 B1 = *reinterpret_cast<const float4*>(par + 2 * C + c_lo + 8 * j + 4);
-            const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
-            uint32_t o[4];
+              for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 A = *reinterpret_cast<const float4*>(par + c_lo + cc + 4 * i4);
+                const float4 Gt = *reinterpret_cast<const float4*>(par + C + c_lo + cc + 4 * i4);
+                const float4 S = *reinterpret_cast<const float4*>(film_b + cc + 4 * i4);
+                const float4 Tt = *reinterpret_cast<const float4*>(film_b + 32 + cc + 4 * i4);
+                const float av[4] = {A.x, A.y, A.z, A.w}, gv[4] = {Gt.x, Gt.y, Gt.z, Gt.w};
+                const float sv[4] = {S.x, S.y, S.z, S.w}, tv[4] = {Tt.x, Tt.y, Tt.z, Tt.w};
+                float hv[4];
 #pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-              // (packed 16-bit leaky_relu / inverse here saves ~1.5 instructions per element but was measured to cost
-              // 3.5 dB of SNR (70.1 -> 66.6) for no change in the epilogue's latency: fp32 it is)
-              const float2 xs = unpack2t<FMT>(xw[e2]);
-              float y0 = (lrelu_inv_fast(xs.x) + bv[2 * e2]) + __uint_as_float(vd[8 * j + 2 * e2]);
-              float y1 = (lrelu_inv_fast(xs.y) + bv[2 * e2 + 1]) + __uint_as_float(vd[8 * j + 2 * e2 + 1]);
-              if (act) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
-              o[e2] = pack2t<FMT>(y0, y1);
+                for (int e = 0; e < 4; ++e) {
+                  const float a = __uint_as_float(va[4 * i4 + e]) + av[e];                 // (conv_a + b_a) / 2
+                  const float th = tanh_approx(__uint_as_float(vg[4 * i4 + e]) + gv[e]);   // tanh(g / 2)
+                  hv[e] = fmaf(fmaf(a, th, a), sv[e], tv[e]);                              // a sigmoid(g) (1 + scale) + shift
+                }
+                hw[2 * i4] = pack2t<FMT>(hv[0], hv[1]);
+                hw[2 * i4 + 1] = pack2t<FMT>(hv[2], hv[3]);
+              }
+              tmem_st8(lane_addr + T * N1 + c_lo + cc, hw);     // over the value columns just read
             }
-            ow[j] = make_uint4(o[0], o[1], o[2], o[3]);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_full[T]);
+            if (q == 0 && cx == 0) SF_TRACE(1 + eg, 3 + blk * 4);
           }
-          if (!warp_in_seq && !in_seq) {                        // rows outside the sequence: the next conv's zero padding
+          // ---------------------------------------------------------- epilogue 2: x + W2 h + b2
+#pragma unroll 1
+          for (int cx = 0; cx < NCTX; ++cx) {
+            const int T = cx * NT + mt;
+            uint8_t* xrow = sX + xbuf(cx, it) * K::X_BYTES + row * ROWB;
+            mbar_wait(&d2_full[T], (it * NBLK + blk) & 1);
+            tc_fence_after();
+            if (q == 0 && cx == 0) SF_TRACE(1 + eg, 4 + blk * 4);
+            uint32_t vd[32];
+            tmem_ld32(lane_addr + T * N1 + C + c_lo, vd);
+            uint4 xa[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ow[j] = make_uint4(0u, 0u, 0u, 0u);
-          }
-          if (q == 0 && blk == 1) SF_TRACE(1 + eg, 20);
-          if (!last || OUT == SF_OUT_MERGE) {
+            for (int j = 0; j < 4; ++j) xa[j] = *reinterpret_cast<const uint4*>(xrow + (sw_chunk(row, (c_lo >> 3) + j) << 4));
+            tmem_ld_wait();
+            uint4 ow[4];
+            const bool act = !last || OUT == SF_OUT_LRELU;      // store leaky_relu(y) (the next GEMM1's operand) or raw y
 #pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(xrow + (sw_chunk(row, (c_lo >> 3) + j) << 4)) = ow[j];
-            if (q == 0 && blk == 1) SF_TRACE(1 + eg, 21);
-            fence_proxy_async_smem();
-            if (q == 0 && blk == 1) SF_TRACE(1 + eg, 22);
-          } else if (in_seq && sr >= p.HL && sr < R - p.HR) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out16 + ((long long)seq * p.L + l) * C + c_lo);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t xw[4] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w};
+              const float4 B0 = *reinterpret_cast<const float4*>(par + 2 * C + c_lo + 8 * j);
+              const float4 B1 = *reinterpret_cast<const float4*>(par + 2 * C + c_lo + 8 * j + 4);
+              const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
+              uint32_t o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = ow[j];
+              for (int e2 = 0; e2 < 4; ++e2) {
+                // (packed 16-bit leaky_relu / inverse here saves ~1.5 instructions per element but was measured to cost
+                // 3.5 dB of SNR (70.1 -> 66.6) for no change in the epilogue's latency: fp32 it is)
+                const float2 xs = unpack2t<FMT>(xw[e2]);
+                float y0 = (lrelu_inv_fast(xs.x) + bv[2 * e2]) + __uint_as_float(vd[8 * j + 2 * e2]);
+                float y1 = (lrelu_inv_fast(xs.y) + bv[2 * e2 + 1]) + __uint_as_float(vd[8 * j + 2 * e2 + 1]);
+                if (act) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
+                o[e2] = pack2t<FMT>(y0, y1);
+              }
+              ow[j] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            if (!warp_in_seq && !in_seq) {                      // rows outside the sequence: the next conv's zero padding
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ow[j] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            if (!last || OUT == SF_OUT_MERGE) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(xrow + (sw_chunk(row, (c_lo >> 3) + j) << 4)) = ow[j];
+              fence_proxy_async_smem();
+            } else if (in_seq && sr >= p.HL && sr < R - p.HR) {
+              uint4* dst = reinterpret_cast<uint4*>(p.out16 + ((long long)(seq0 + cx) * p.L + l) * C + c_lo);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[j] = ow[j];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&x_ready[T]);
+              if (!IN_CT && last) mbar_arrive(&x_free[it & 1]);
+            }
+            if (q == 0 && cx == 0) SF_TRACE(1 + eg, 5 + blk * 4);
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&x_ready[mt]);
-            if (!IN_CT && last) mbar_arrive(&x_free[bs & 1]);
-          }
-          if (q == 0) SF_TRACE(1 + eg, 5 + blk * 4);
         }
         if (OUT == SF_OUT_MERGE) {
           // ---------------------------------------------------------- merge: z_k[l] = m_k . x[l]  ->  y[l] += sum_k z_k[l+k-3]
-          mbar_wait(&z_full[mt], bs & 1);
-          tc_fence_after();
-          if (q == 0) SF_TRACE(1 + eg, 14);
-          uint32_t vz[16];
-          tmem_ld16(lane_addr + K::Z_COL + mt * 16, vz);
-          tmem_ld_wait();
-          tc_fence_before();
-          named_bar_sync(1, 512);                               // the previous band's gather is complete
+#pragma unroll 1
+          for (int cx = 0; cx < NCTX; ++cx) {
+            const int T = cx * NT + mt;
+            mbar_wait(&z_full[T], it & 1);
+            tc_fence_after();
+            if (q == 0 && cx == 0) SF_TRACE(1 + eg, 14);
+            uint32_t vz[16];
+            tmem_ld16(lane_addr + T * N1 + C, vz);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x_ready[T]);              // the tile's TMEM columns are free for the next iteration
+            named_bar_sync(1, 512);                               // the previous band's gather is complete
 #pragma unroll
-          for (int k = 0; k < 7; ++k) sZ[k * R + sr] = __uint_as_float(vz[k]) + __uint_as_float(vz[8 + k]);
-          named_bar_sync(1, 512);
+            for (int k = 0; k < 7; ++k) sZ[k * R + sr] = __uint_as_float(vz[k]) + __uint_as_float(vz[8 + k]);
+            named_bar_sync(1, 512);
 #pragma unroll
-          for (int k = 0; k < 7; ++k) {
-            const int rr = sr + k - 3;
-            if (rr >= 0 && rr < R) y_acc += sZ[k * R + rr];
+            for (int k = 0; k < 7; ++k) {
+              const int rr = sr + k - 3;
+              if (rr >= 0 && rr < R) y_acc += sZ[k * R + rr];
+            }
           }
           if (sub == NSUB - 1) {
             if (in_seq && sr >= p.HL && sr < R - p.HR) {
@@ -568,9 +609,9 @@ static int sf_num_sms() {
   return n[dev & 15];
 }
 
-template <int C, bool IN_CT, int NBLK, int OUT, int FMT>
+template <int C, bool IN_CT, int NBLK, int OUT, int NCTX, int FMT>
 static int launch_stage_fused_t(const StageFusedArgs& a, cudaStream_t stream) {
-  using K = SfCfg<C, IN_CT, NBLK, OUT>;
+  using K = SfCfg<C, IN_CT, NBLK, OUT, NCTX>;
   StageFusedParams p{};
   const int L = IN_CT ? 2 * a.Lin : a.Lin;
   p.L = L; p.Lin = a.Lin; p.T = a.T; p.P = L / a.T; p.num_bands = a.num_bands; p.n_seq = a.N;
@@ -584,7 +625,8 @@ static int launch_stage_fused_t(const StageFusedArgs& a, cudaStream_t stream) {
   if (IN_CT) halo |= 1;                          // strips start at an odd output row (ConvT phase alignment)
   p.HL = halo; p.HR = halo; p.V = K::R - 2 * halo;
   p.strips_per_seq = ceil_div(L, p.V);
-  const int groups = OUT == SF_OUT_MERGE ? a.N / a.num_bands : a.N;
+  B200_CHECK_ARG(a.num_bands % NCTX == 0, "stage_fused: %d contexts need num_bands %% %d == 0", NCTX, NCTX);
+  const int groups = OUT == SF_OUT_MERGE ? a.N / a.num_bands : a.N / NCTX;
   p.total_units = p.strips_per_seq * groups;
   B200_CHECK_ARG(p.P >= 32 && L % a.T == 0, "stage_fused: L=%d T=%d", L, a.T);
   B200_CHECK_ARG(OUT != SF_OUT_MERGE || a.num_bands == K::NB, "stage_fused: merge needs %d bands", K::NB);
@@ -616,14 +658,14 @@ static int launch_stage_fused_t(const StageFusedArgs& a, cudaStream_t stream) {
   static bool configured[16] = {};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
-  auto kernel = stage_fused_kernel<C, IN_CT, NBLK, OUT, FMT>;
+  auto kernel = stage_fused_kernel<C, IN_CT, NBLK, OUT, NCTX, FMT>;
   if (!configured[dev & 15]) {
     B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
     configured[dev & 15] = true;
   }
   const int sms = sf_num_sms();
   const int grid = p.total_units < sms ? p.total_units : sms;
-  kernel<<<grid, 576, K::SMEM, stream>>>(p);
+  kernel<<<grid, 576 + 32 * (NCTX - 1), K::SMEM, stream>>>(p);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
@@ -631,13 +673,19 @@ static int launch_stage_fused_t(const StageFusedArgs& a, cudaStream_t stream) {
 int stage_fused_launch(const StageFusedArgs& a, cudaStream_t stream) {
   B200_CHECK_ARG(a.fmt == 0 || a.fmt == 1, "stage_fused: bad format");
   B200_CHECK_ARG(a.N > 0 && a.Lin > 0 && a.T > 0 && a.N % a.num_bands == 0, "stage_fused: bad shape");
-#define SF(CC, CT, NB_, O)                                                                    \
+  // B200VOC_SF_NCTX=1: one strip per CTA instead of two for the C = 32 stage (A/B runs)
+  static const bool one_ctx = [] { const char* e = getenv("B200VOC_SF_NCTX"); return e && e[0] == '1'; }();
+#define SF(CC, CT, NB_, O, NC)                                                                 \
   if (a.C == CC && (a.in_ct != 0) == CT && a.nblk == NB_ && a.out_mode == O)                   \
-    return a.fmt == 0 ? launch_stage_fused_t<CC, CT, NB_, O, 0>(a, stream) : launch_stage_fused_t<CC, CT, NB_, O, 1>(a, stream)
-  SF(32, true, 3, SF_OUT_MERGE);
-  SF(32, true, 3, SF_OUT_RAW);
-  SF(64, true, 1, SF_OUT_LRELU);
-  SF(64, false, 2, SF_OUT_RAW);
+    return a.fmt == 0 ? launch_stage_fused_t<CC, CT, NB_, O, NC, 0>(a, stream) : launch_stage_fused_t<CC, CT, NB_, O, NC, 1>(a, stream)
+  if (!one_ctx && a.num_bands % 2 == 0) {
+    SF(32, true, 3, SF_OUT_MERGE, 2);
+    SF(32, true, 3, SF_OUT_RAW, 2);
+  }
+  SF(32, true, 3, SF_OUT_MERGE, 1);
+  SF(32, true, 3, SF_OUT_RAW, 1);
+  SF(64, true, 1, SF_OUT_LRELU, 1);
+  SF(64, false, 2, SF_OUT_RAW, 1);
 #undef SF
   set_error("stage_fused: unsupported configuration (C=%d in_ct=%d nblk=%d out=%d)", a.C, a.in_ct, a.nblk, a.out_mode);
   return B200VOC_ERR_UNSUPPORTED;
