@@ -192,6 +192,21 @@ int b200voc_resblock(const void* a16, const void* w_packed, const float* b_conv,
                      const float* film, int N, int L, int C, int dilation, int T, int num_bands, int fmt,
                      int store_lrelu, void* out16, void* stream);
 
+/* One NARROW stage of Generator.forward (generator.py:85-98: `for layer in block` over ConvTranspose1d + the three
+ * ResidualBlocks of stages 2 and 3, C = 64 / 32 output channels, stride 2) as one or two kernels with the intermediate
+ * activations on chip, and -- C = 32, num_bands = 4, wav_out != NULL -- generator.py:96-98 (cat + band_merge + tanh)
+ * folded in.  x16[N, Lin, 2C] raw; convt_w_packed / res_w_packed[3] from the pack functions above; film[B, T,
+ * film_stride] fp32 with block j's (1+scale | shift) at column film_cols[j]; out16[N, 2*Lin, C] raw (or NULL when
+ * wav_out[N/4, 2*Lin] fp32 is given); scratch16[N, 2*Lin, C] is needed for C = 64 only (the stage runs as two
+ * launches).  merge_w_packed: b200voc_pack_merge_weight of band_merge.weight [1, 4*32, 7]. */
+int64_t b200voc_merge_packed_elems(int num_bands);
+int b200voc_pack_merge_weight(const float* w_ref, int num_bands, int fmt, void* w_packed, void* stream);
+int b200voc_stage_fused(const void* x16, const void* convt_w_packed, const float* convt_bias,
+                        const void* const* res_w_packed, const float* const* b_conv, const float* const* b_proj,
+                        const int* dilations, const float* film, const int* film_cols, int film_stride, int N, int Lin,
+                        int C, int T, int num_bands, int fmt, void* out16, void* scratch16, const void* merge_w_packed,
+                        const float* merge_bias, float* wav_out, void* stream);
+
 /* ----------------------------------------------------------------------------------------
  * STFT family (replaces vocoder7/stft.py:9-54 and the torchaudio MelSpectrogram call sites
  * reference_encoder/utils.py:31-36).  fp32 throughout.  frames = 1 + N / hop, bins = n_fft/2+1.

@@ -27,6 +27,22 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().b200voc_version() >= 100
 
 
+def test_product_library_has_no_experiment_exports():
+    """experiment / trace entry points live in the development build only (include/b200voc_dev.h, `make dev`)"""
+    from b200voc import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    text = open(os.path.join(ROOT, "include", "b200voc_dev.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    dev_syms = sorted(set(re.findall(r"\b(b200voc_[a-z0-9_]+)\s*\(", text)))
+    assert set(dev_syms) == set(_lib.DEV_EXPORTS)
+    for s in dev_syms:
+        assert not hasattr(lib, s), f"{s} must not be exported by the product library"
+    if os.path.exists(_lib.DEV_LIB_PATH):
+        dev = ctypes.CDLL(_lib.DEV_LIB_PATH)
+        for s in dev_syms + list(_lib.EXPORTS):
+            assert hasattr(dev, s), s
+
+
 def test_state_dict_layout_matches_oracle_and_reference():
     from b200voc import GANConfig, Generator
     from oracle import vocoder7_oracle as O

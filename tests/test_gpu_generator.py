@@ -48,7 +48,7 @@ def test_generator_matches_golden(models, golden_dir, name, kw):
     assert wav.shape == ref.shape
     assert float((wav - ref).abs().max()) <= 1e-3
     assert O.snr_db(ref, wav) >= 40.0
-    assert gen.launch_count() >= 21          # the CUDA path actually ran
+    assert gen.launch_count() >= 16          # the CUDA path actually ran (16 launches with the fused narrow stages, 22 without)
 
 
 @pytest.mark.parametrize("B,T", [(1, 1), (1, 7), (3, 33), (2, 172), (5, 61)])
@@ -307,7 +307,7 @@ def test_generator_with_attention_matches_golden(golden_dir, name, window):
     want = torch.from_numpy(gold["tap_attn"])                  # band 0, batch 0, 8 channels, 64 steps
     got = tap.view(-1, 64, wav.shape[-1] // 2).cpu()[0, :8, :64]
     assert float((got - want).abs().max()) <= 4e-3 * max(1.0, float(want.abs().max()))
-    assert gen.launch_count() == 25          # 24 + band_split im2col
+    assert gen.launch_count() in (19, 25)    # fused narrow stages: 19; layer by layer (B200VOC_FUSED=0): 24 + band_split im2col
 
 
 def test_generator_with_attention_matches_oracle_batch():

@@ -789,6 +789,46 @@ int b200voc_resblock(const void* a16, const void* w_packed, const float* b_conv,
   return resblock_launch(a16, w_packed, b_conv, b_proj, film, 2 * C, N, L, C, dilation, T, num_bands, fmt, fmt, store_lrelu,
                          out16, reinterpret_cast<cudaStream_t>(stream));
 }
+/* One narrow stage in fused form (stage_fused.cu) */
+int64_t b200voc_merge_packed_elems(int num_bands) { return (int64_t)num_bands * 16 * 32; }
+int b200voc_pack_merge_weight(const float* w_ref, int num_bands, int fmt, void* w_packed, void* stream) {
+  B200_CHECK_ARG(w_ref && w_packed && num_bands > 0, "pack_merge_weight: bad argument");
+  return pack_merge_launch(w_ref, num_bands, fmt, w_packed, reinterpret_cast<cudaStream_t>(stream));
+}
+int b200voc_stage_fused(const void* x16, const void* convt_w_packed, const float* convt_bias,
+                        const void* const* res_w_packed, const float* const* b_conv, const float* const* b_proj,
+                        const int* dilations, const float* film, const int* film_cols, int film_stride, int N, int Lin,
+                        int C, int T, int num_bands, int fmt, void* out16, void* scratch16, const void* merge_w_packed,
+                        const float* merge_bias, float* wav_out, void* stream) {
+  B200_CHECK_ARG(x16 && convt_w_packed && convt_bias && res_w_packed && b_conv && b_proj && dilations && film && film_cols,
+                 "stage_fused: null argument");
+  B200_CHECK_ARG(C == 32 || C == 64, "stage_fused: C=%d unsupported (32/64: the narrow stages)", C);
+  B200_CHECK_ARG(N > 0 && Lin > 0 && T > 0 && (2 * Lin) % T == 0 && (2 * Lin) / T >= 32,
+                 "stage_fused: Lin=%d T=%d (2*Lin must be a multiple of T, at least 32 samples per frame)", Lin, T);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  StageFusedArgs a{};
+  a.N = N; a.C = C; a.T = T; a.num_bands = num_bands; a.fmt = fmt;
+  a.ct_w = convt_w_packed; a.ct_b = convt_bias; a.film = film; a.film_stride = film_stride;
+  auto set_blk = [&](int slot, int j) {
+    a.blk_w[slot] = res_w_packed[j]; a.b_conv[slot] = b_conv[j]; a.b_proj[slot] = b_proj[j]; a.dil[slot] = dilations[j];
+    a.film_col[slot] = film_cols[j];
+  };
+  if (C == 64) {
+    B200_CHECK_ARG(out16 && scratch16 && !wav_out, "stage_fused: C=64 needs out16 and scratch16 (and has no merge)");
+    a.x_in = x16; a.Lin = Lin; a.in_ct = 1; a.nblk = 1; a.out_mode = 0; a.out16 = scratch16;
+    set_blk(0, 0);
+    B200_TRY(stage_fused_launch(a, st));
+    a.x_in = scratch16; a.Lin = 2 * Lin; a.in_ct = 0; a.nblk = 2; a.out_mode = 1; a.out16 = out16;
+    set_blk(0, 1); set_blk(1, 2);
+    return stage_fused_launch(a, st);
+  }
+  B200_CHECK_ARG((wav_out != nullptr) != (out16 != nullptr), "stage_fused: C=32 writes either out16 or wav_out");
+  B200_CHECK_ARG(!wav_out || (merge_w_packed && merge_bias && num_bands == 4), "stage_fused: merge needs packed taps, bias and 4 bands");
+  a.x_in = x16; a.Lin = Lin; a.in_ct = 1; a.nblk = 3; a.out_mode = wav_out ? 2 : 1; a.out16 = out16;
+  a.merge_w16 = merge_w_packed; a.merge_b = merge_bias; a.wav = wav_out;
+  set_blk(0, 0); set_blk(1, 1); set_blk(2, 2);
+  return stage_fused_launch(a, st);
+}
 /* GlobalStyleTokens.forward (vocoder7/gst.py:24-35) */
 int64_t b200voc_gst_scratch_bytes(int B, int T, int num_tokens) {
   return (B > 0 && T > 0 && num_tokens > 0) ? gst_scratch_floats(B, T, num_tokens) * 4 : 0;

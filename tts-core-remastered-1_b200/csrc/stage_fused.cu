@@ -85,7 +85,7 @@ struct SfCfg {
   static constexpr int NTT = NCTX * NT;               // m-tiles in flight per CTA
   static constexpr int R = NT * 128;
   static constexpr int G = 8;                         // guard rows on each side of X (>= max dilation)
-  static constexpr int NXB = IN_CT ? NCTX : 2;        // X buffers: one per context; a single TMA-loaded strip is double buffered
+  static constexpr int NXB = (IN_CT || NCTX == 2) ? NCTX : 2;   // X buffers: one per context; a single TMA-loaded strip is double buffered
   static constexpr int X_BYTES = (R + 2 * G) * ROWB;
   static constexpr int CT_KB = (2 * C) / 64;          // 64-channel k-blocks of the ConvT input
   static constexpr int NCHUNK = R / 256;              // ConvT chunks per strip: 128 GEMM rows -> 256 strip rows
@@ -130,7 +130,6 @@ struct SfCfg {
                 X_BYTES % 1024 == 0 && W1_TILE % 1024 == 0 && W2_TILE % 1024 == 0 && IN_KB_BYTES % 1024 == 0,
                 "swizzle alignment");
   static_assert(OUT != SF_OUT_MERGE || (C == 32 && IN_CT), "merge follows the last (C = 32) stage");
-  static_assert(IN_CT || NCTX == 1, "TMA-loaded strips: one context (double-buffered X)");
 };
 
 template <int C, bool IN_CT, int NBLK, int OUT, int NCTX, int FMT>
@@ -208,7 +207,10 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
     sg = u / p.strips_per_seq;
     s0 = (u - sg * p.strips_per_seq) * p.V - p.HL;
   };
-  auto xbuf = [&](int cx, int it) { return IN_CT ? cx : (it & 1); };
+  // X buffer of context cx in iteration it; TMA-loaded strips: barrier index and phase of xin_full / x_free
+  auto xbuf = [&](int cx, int it) { return (IN_CT || NCTX == 2) ? cx : (it & 1); };
+  auto xin_idx = [&](int cx, int it) { return NCTX == 2 ? cx : (it & 1); };
+  auto xin_par = [&](int it) { return (uint32_t)(NCTX == 2 ? (it & 1) : ((it >> 1) & 1)); };
 
   if (warp == 0) {
     // ============================================================== TMA producer
@@ -241,12 +243,14 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
                               m0 - 1 + 128 * c, seq0 + cx);
               }
           } else {
-            const int buf = it & 1;
-            mbar_wait(&x_free[buf], ((it >> 1) & 1) ^ 1);
-            mbar_expect_tx(&xin_full[buf], K::X_BYTES);
-            for (int j = 0; j < (R + 2 * G) / K::IN_ROWS; ++j)
-              tma_load_3d(sX + buf * K::X_BYTES + j * K::IN_ROWS * ROWB, &p.tmIn, &xin_full[buf], 0,
-                          s0 - G + j * K::IN_ROWS, seq0);
+            for (int cx = 0; cx < NCTX; ++cx) {
+              const int bi = xin_idx(cx, it);
+              mbar_wait(&x_free[bi], xin_par(it) ^ 1);
+              mbar_expect_tx(&xin_full[bi], K::X_BYTES);
+              for (int j = 0; j < (R + 2 * G) / K::IN_ROWS; ++j)
+                tma_load_3d(sX + xbuf(cx, it) * K::X_BYTES + j * K::IN_ROWS * ROWB, &p.tmIn, &xin_full[bi], 0,
+                            s0 - G + j * K::IN_ROWS, seq0 + cx);
+            }
           }
         }
       }
@@ -309,7 +313,7 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
             const int T = cx * NT + t;
             // inputs of this block for tiles t-1, t, t+1 of the strip
             if (!IN_CT && blk == 0) {
-              if (t == 0) mbar_wait(&xin_full[it & 1], (it >> 1) & 1);
+              if (t == 0) mbar_wait(&xin_full[xin_idx(cx, it)], xin_par(it));
             } else {
               const uint32_t par = (it * XPB + blk - (IN_CT ? 0 : 1)) & 1;
               if (t == 0) { mbar_wait(&x_ready[T], par); if (NT > 1) mbar_wait(&x_ready[T + 1], par); }
@@ -442,7 +446,7 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
             if (q == 0 && cx == 0) SF_TRACE(1 + eg, 1);
           }
         } else {
-          mbar_wait(&xin_full[it & 1], (it >> 1) & 1);          // acquire the TMA-written strip (residual reads)
+          for (int cx = 0; cx < NCTX; ++cx) mbar_wait(&xin_full[xin_idx(cx, it)], xin_par(it));   // acquire the TMA-written strips (residual reads)
         }
         const int row = G + sr;
 #pragma unroll 1
@@ -549,7 +553,7 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
             __syncwarp();
             if (lane == 0) {
               mbar_arrive(&x_ready[T]);
-              if (!IN_CT && last) mbar_arrive(&x_free[it & 1]);
+              if (!IN_CT && last) mbar_arrive(&x_free[xin_idx(cx, it)]);
             }
             if (q == 0 && cx == 0) SF_TRACE(1 + eg, 5 + blk * 4);
           }
@@ -685,6 +689,7 @@ int stage_fused_launch(const StageFusedArgs& a, cudaStream_t stream) {
   SF(32, true, 3, SF_OUT_MERGE, 1);
   SF(32, true, 3, SF_OUT_RAW, 1);
   SF(64, true, 1, SF_OUT_LRELU, 1);
+  if (!one_ctx && a.num_bands % 2 == 0) SF(64, false, 2, SF_OUT_RAW, 2);
   SF(64, false, 2, SF_OUT_RAW, 1);
 #undef SF
   set_error("stage_fused: unsupported configuration (C=%d in_ct=%d nblk=%d out=%d)", a.C, a.in_ct, a.nblk, a.out_mode);
