@@ -85,3 +85,42 @@ def test_pcm16_output_and_length_mask(models):
         assert torch.equal(msk[b, 0, :n], f32[b, 0, :n])
         assert not bool(msk[b, 0, n:].any())
         assert torch.equal(both[b, 0, :n], pcm[b, 0, :n]) and not bool(both[b, 0, n:].any())
+
+
+def test_weight_updates_through_data_need_invalidate_and_copies_are_independent():
+    """round-1 ADVICE: (1) in-place updates through .data (the reference trainer's EMA update, vocoder7/trainer.py:53-55)
+    do not bump the version counter the weight pack is keyed on -- Generator.invalidate() forces the re-pack;
+    (2) copy.deepcopy (the EMA / eval copy idiom) must not share the native handle."""
+    import copy
+    from b200voc import GANConfig, Generator
+    torch.manual_seed(3)
+    gen = Generator(GANConfig(use_attention=False)).eval().cuda()
+    ins = [x.cuda() for x in O.synthetic_inputs(1, 12, seed=5)]
+    with torch.no_grad():
+        a = gen(*ins).clone()
+        for p in gen.parameters():
+            p.data.mul_(0.5)
+        gen.invalidate()
+        b = gen(*ins).clone()
+        assert not torch.equal(a, b)
+        twin = copy.deepcopy(gen)
+        assert twin._handle is None and gen._handle is not None
+        c = twin(*ins).clone()
+        assert twin._handle != gen._handle
+        assert torch.equal(b, c)
+        for p in twin.parameters():
+            p.data.mul_(2.0)
+        twin.invalidate()
+        assert torch.equal(gen(*ins), b)                   # the original still runs ITS weights
+        assert torch.equal(twin(*ins), a)                  # x0.5 then x2.0 is exact in binary floating point
+    del twin
+
+
+def test_learnable_stft_is_loud_about_missing_backward():
+    import b200voc
+    m = b200voc.LearnableSTFT(1024, 256).cuda().train()
+    wav = torch.rand(1, 1, 4000, device="cuda", requires_grad=True)
+    with pytest.raises(Exception):
+        m(wav)
+    with torch.no_grad():
+        assert m(wav).shape == (1, 513, 16)

@@ -116,6 +116,60 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def _worker_long(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tts-core-remastered-1_b200"))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    synth = _oracle_synth()
+    mel, pros, sty, emo = O.synthetic_inputs(2, 50, seed=77)
+    got = S.sharded_synthesize_long(synth, mel, pros, sty, emo, chunk_frames=16, halo=6, max_batch=3, gather_to=0)
+    ok = True
+    if rank == 0:
+        single = S.synthesize_long(synth, mel, pros, sty, emo, chunk_frames=16, halo=6, max_batch=3)
+        ok = got.shape == single.shape and float((got - single).abs().max()) <= 1e-6
+        ok = ok and float((got - synth(mel, pros, sty, emo)).abs().max()) <= 1e-6     # == the un-chunked forward
+    else:
+        units, pieces = got
+        ok = len(units) == len(pieces) > 0
+    # fewer utterances than ranks: one shard is empty and still takes part in the gather
+    one = [O.synthetic_inputs(1, 7, seed=5)]
+    g1 = S.sharded_synthesize(synth, [one[0][0][0]], [one[0][1][0]], [one[0][2][0]], [one[0][3][0]], gather_to=0)
+    if rank == 0:
+        ok = ok and sorted(g1) == [0] and bool(torch.equal(g1[0], synth(*one[0])[0]))
+    else:
+        ok = ok and g1 == {}
+    # streaming shard of equally long host utterances
+    mels, pr, st, em = O.synthetic_inputs(5, 6, seed=9)
+    lo, wavs = S.sharded_synthesize_streaming(synth, torch.device("cpu"), mels, pr, st, em, max_batch=2)
+    ok = ok and lo == (0 if rank == 0 else 3) and wavs.shape[0] == (3 if rank == 0 else 2)
+    ok = ok and float((wavs - synth(mels[lo:lo + wavs.shape[0]], pr[lo:lo + wavs.shape[0]], st[lo:lo + wavs.shape[0]],
+                                    em[lo:lo + wavs.shape[0]])).abs().max()) <= 1e-6
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sharded_long_form_and_ragged_gather_gloo_world2():
+    """configs[4] host logic: chunk units spread over 2 ranks + one ragged gather == single-device synthesize_long ==
+    the un-chunked forward; a rank with an empty shard takes part in the gather; streaming shards cover the list."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_worker_long, args=(world, port, ret), nprocs=world, join=True)
+    assert ret[0] is True and ret[1] is True
+
+
+def test_long_units_cover_every_utterance():
+    units = S.long_units(3, 5167, 512, 8)
+    assert len(units) == 3 * 11
+    for b in range(3):
+        mine = [u for u in units if u[0] == b]
+        assert mine[0][3] == 0 and mine[-1][4] == 5167
+        assert all(x[4] == y[3] for x, y in zip(mine, mine[1:]))
+
+
 def test_sharded_synthesis_gloo_world2():
     world = 2
     mgr = mp.Manager()

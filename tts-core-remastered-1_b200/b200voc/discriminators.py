@@ -62,6 +62,11 @@ class _CriticBase(nn.Module):
         self.discriminators.append(seq)
         self._specs.append(specs)
 
+    def invalidate(self) -> None:
+        """Drop the cached spectral-normalised weights (needed after in-place updates made through ``.data``, which
+        do not bump the version counters the cache is keyed on)."""
+        self._wcache = {}
+
     # ---- spectral-normalised weights, cached per parameter version ------------------------------------
     def _weights(self, d: int):
         convs = [m for m in self.discriminators[d] if not isinstance(m, nn.LeakyReLU)]

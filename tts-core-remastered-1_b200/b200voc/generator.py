@@ -140,6 +140,35 @@ class Generator(nn.Module):
         self._packed_key = key
         return self._handle
 
+    def invalidate(self) -> None:
+        """Force a re-pack of the kernel-layout weights on the next forward.  The pack is keyed on every parameter's
+        (storage pointer, version counter); in-place updates made through ``.data`` (the reference trainer's EMA
+        update, vocoder7/trainer.py:53-55, some checkpoint loaders) do NOT bump the version counter, so call this
+        after such an update -- ``load_state_dict`` and ``.to()`` are detected without it."""
+        self._packed_key = None
+
+    repack = invalidate
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return out
+
+    def __getstate__(self):
+        # the native handle (a raw pointer), its pack key and the workspace belong to THIS object: a deepcopy / pickle
+        # of the module (the usual EMA / eval copy idiom) gets none of them and packs its own on first use
+        state = dict(self.__dict__)
+        state["_handle"], state["_packed_key"], state["_workspace"] = None, None, None
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
     def workspace_bytes(self, B: int, T: int) -> int:
         return int(_lib.load().b200voc_gen_workspace_bytes(self._handle, B, T))
 
@@ -150,6 +179,7 @@ class Generator(nn.Module):
         try:
             if self._handle is not None and _lib._lib is not None:
                 _lib._lib.b200voc_gen_destroy(self._handle)
+            self._handle = None
         except Exception:
             pass
 

@@ -183,17 +183,53 @@ class StreamingSynthesizer:
 
 
 # ------------------------------------------------------------------ multi-GPU (one process per GPU)
+def _dist_info(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def _comm_device(group=None) -> torch.device:
+    """Device the collective's buffers must live on: the current CUDA device under NCCL (also for a rank whose
+    shard is empty and therefore has no tensor to infer it from), the host under gloo."""
+    import torch.distributed as dist
+    if dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def gather_flat(local_flat: torch.Tensor, sizes: Sequence[int], dst: int, group=None) -> Optional[List[torch.Tensor]]:
+    """The single final collective of a sharded job, as a true gather: rank r contributes a flat fp32 buffer of
+    sizes[r] elements (sizes are known to every rank from the plan: nothing is padded, nothing is exchanged to
+    agree on them) and only `dst` receives -- point-to-point sends batched into one NCCL group (gloo: the same
+    calls).  Returns the list of per-rank buffers on dst, None elsewhere."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = _comm_device(group)
+    if int(local_flat.numel()) != int(sizes[rank]):
+        raise ValueError(f"rank {rank} contributes {local_flat.numel()} elements, the plan says {sizes[rank]}")
+    if rank == dst:
+        parts = [local_flat.to(dev) if r == dst else torch.empty(int(sizes[r]), device=dev, dtype=torch.float32)
+                 for r in range(world)]
+        ops = [dist.P2POp(dist.irecv, parts[r], r, group) for r in range(world) if r != dst and sizes[r] > 0]
+    else:
+        parts = None
+        send = local_flat.to(dev).contiguous()
+        ops = [dist.P2POp(dist.isend, send, dst, group)] if sizes[rank] > 0 else []
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return parts
+
+
 def sharded_synthesize(synth: Synth, mels: Sequence[torch.Tensor], prosodies: Sequence[torch.Tensor],
                        styles: Sequence[torch.Tensor], emotions: Sequence[torch.Tensor], max_batch: int = 16,
                        gather_to: Optional[int] = None, group=None, **kw):
     """Every rank holds the full (host) work list, synthesizes only its shard, no data-path
     collective.  Returns {index: wav} for the local shard; if `gather_to` is a rank, that rank
     additionally receives every waveform (one gather at the end: the only communication)."""
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized():
-        rank, world = dist.get_rank(group), dist.get_world_size(group)
-    else:
-        rank, world = 0, 1
+    rank, world = _dist_info(group)
     lengths = [int(m.shape[-1]) for m in mels]
     mine = plan_shards(lengths, world)[rank]
     wavs = synthesize_batch(synth, [mels[i] for i in mine], [prosodies[i] for i in mine],
@@ -205,24 +241,117 @@ def sharded_synthesize(synth: Synth, mels: Sequence[torch.Tensor], prosodies: Se
 
 
 def gather_waveforms(local: Dict[int, torch.Tensor], lengths: Sequence[int], dst: int, hop: int = 256, group=None):
-    """The single final collective: all ranks contribute their shard, `dst` gets {index: wav} for
-    every utterance (other ranks get their local dict back).  Implemented as one all_gather of a
-    padded [n_max, L_max] buffer per rank (NCCL and gloo both support it)."""
+    """The single final collective: `dst` gets {index: wav} for every utterance, other ranks get their local dict
+    back.  A gather (only dst receives), ragged (every waveform travels at its own length)."""
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     shards = plan_shards(lengths, world)
-    n_max = max(len(s) for s in shards)
-    l_max = hop * max(lengths) if lengths else 0
-    dev = next(iter(local.values())).device if local else torch.device("cpu")
-    buf = torch.zeros(max(n_max, 1), l_max, device=dev, dtype=torch.float32)
-    for k, i in enumerate(shards[rank]):
-        buf[k, :hop * lengths[i]] = local[i].reshape(-1)
-    parts = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(parts, buf, group=group)
+    sizes = [sum(hop * int(lengths[i]) for i in sh) for sh in shards]
+    dev = _comm_device(group)
+    flat = (torch.cat([local[i].reshape(-1).to(dev) for i in shards[rank]]) if shards[rank]
+            else torch.empty(0, device=dev, dtype=torch.float32))
+    parts = gather_flat(flat, sizes, dst, group=group)
     if rank != dst:
         return local
     full = {}
     for r in range(world):
-        for k, i in enumerate(shards[r]):
-            full[i] = parts[r][k, :hop * lengths[i]].reshape(1, -1).clone()
+        off = 0
+        for i in shards[r]:
+            n = hop * int(lengths[i])
+            full[i] = parts[r][off:off + n].reshape(1, -1).clone()
+            off += n
     return full
+
+
+def sharded_synthesize_streaming(synth: Synth, device, mels: torch.Tensor, prosodies: torch.Tensor, styles: torch.Tensor,
+                                 emotions: torch.Tensor, max_batch: int = 16, hop: int = 256, group=None, **kw):
+    """BASELINE configs[3]: n equally long utterances given as HOST tensors (mels[n, 80, T], ..., ideally pinned) are
+    sharded over the ranks (contiguous blocks: equal lengths need no balancing) and each rank pushes its shard through
+    the host-in / host-out StreamingSynthesizer in batches of `max_batch`.  No collective.  Returns (first index,
+    host waveforms [n_local, 1, hop * T]) of this rank's shard."""
+    rank, world = _dist_info(group)
+    n, T = int(mels.shape[0]), int(mels.shape[-1])
+    per = (n + world - 1) // world
+    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    pin = torch.device(device).type == "cuda"
+    out = torch.empty(hi - lo, 1, hop * T)
+    if pin:
+        out = out.pin_memory()
+    starts = list(range(lo, hi, max_batch))
+    # a ragged last batch has its own shape: the streamer re-allocates its slots for it (one extra allocation per job)
+    full = [s for s in starts if min(hi, s + max_batch) - s == max_batch]
+    tail = [s for s in starts if s not in full]
+    streamer = StreamingSynthesizer(synth, device, depth=2, **kw)
+    for group_starts in (full, tail):
+        if group_starts:
+            streamer.run([(mels[s:min(hi, s + max_batch)], prosodies[s:min(hi, s + max_batch)],
+                           styles[s:min(hi, s + max_batch)], emotions[s:min(hi, s + max_batch)]) for s in group_starts],
+                         [out[s - lo:min(hi, s + max_batch) - lo] for s in group_starts])
+    return lo, out
+
+
+# ------------------------------------------------------------------ long-form synthesis over several GPUs
+def long_units(B: int, T: int, chunk_frames: int, halo: int) -> List[Tuple[int, int, int, int, int]]:
+    """Work units of a long-form job: (utterance, in_start, in_end, keep_start, keep_end) in frames, utterance-major.
+    Units are independent (chunk + halo), so one utterance may be spread over several GPUs."""
+    plan = chunk_plan(T, chunk_frames, halo)
+    return [(b, a, e, ks, ke) for b in range(B) for (a, e, ks, ke) in plan]
+
+
+def synthesize_units(synth: Synth, units: Sequence[Tuple[int, int, int, int, int]], mel: torch.Tensor,
+                     prosody: torch.Tensor, style: torch.Tensor, emotion: torch.Tensor, hop: int = 256,
+                     max_batch: int = 16, **kw) -> List[torch.Tensor]:
+    """Synthesizes the given (chunk + halo) units -- batched by identical input shape and left context, like
+    synthesize_long -- and returns the KEPT piece of each, [hop * (keep_end - keep_start)] samples, in `units` order."""
+    out: List[Optional[torch.Tensor]] = [None] * len(units)
+    groups: Dict[Tuple[int, int], List[int]] = {}
+    for k, (b, a, e, ks, ke) in enumerate(units):
+        groups.setdefault((e - a, ks - a), []).append(k)
+    for (_, _), idx in groups.items():
+        for s in range(0, len(idx), max_batch):
+            part = idx[s:s + max_batch]
+            m = torch.stack([mel[units[k][0], :, units[k][1]:units[k][2]] for k in part])
+            p = torch.stack([prosody[units[k][0], units[k][1]:units[k][2]] for k in part])
+            st = torch.stack([style[units[k][0]] for k in part])
+            em = torch.stack([emotion[units[k][0]] for k in part])
+            wav = synth(m, p, st, em, **kw)
+            for j, k in enumerate(part):
+                _, a, _, ks, ke = units[k]
+                out[k] = wav[j, 0, (ks - a) * hop:(ke - a) * hop].clone()
+    return out  # type: ignore[return-value]
+
+
+def sharded_synthesize_long(synth: Synth, mel: torch.Tensor, prosody: torch.Tensor, style: torch.Tensor,
+                            emotion: torch.Tensor, chunk_frames: int = 512, halo: int = 8, hop: int = 256,
+                            max_batch: int = 16, gather_to: Optional[int] = None, group=None, **kw):
+    """BASELINE configs[4]: long-form batch mel[B, 80, T] cut into (chunk + halo) units that are spread over the ranks
+    (greedy by input frames; a 60 s utterance spans GPUs), no collective in the math.  Every rank returns
+    (units, pieces) of its shard; with `gather_to`, that rank instead returns the stitched [B, 1, hop * T] waveforms
+    (one ragged gather, then overlap-discard stitching: the kept pieces tile each utterance exactly).  The result is
+    the same samples synthesize_long produces on one device (units are batch-independent)."""
+    rank, world = _dist_info(group)
+    B, _, T = mel.shape
+    units = long_units(B, T, chunk_frames, halo)
+    shards = plan_shards([u[2] - u[1] for u in units], world)
+    mine = [units[k] for k in shards[rank]]
+    pieces = synthesize_units(synth, mine, mel, prosody, style, emotion, hop=hop, max_batch=max_batch, **kw)
+    if gather_to is None:
+        return mine, pieces
+    sizes = [sum(hop * (units[k][4] - units[k][3]) for k in sh) for sh in shards]
+    if world == 1:
+        parts = [torch.cat([x.reshape(-1) for x in pieces])] if pieces else [torch.empty(0)]
+    else:
+        dev = _comm_device(group)
+        flat = torch.cat([x.reshape(-1).to(dev) for x in pieces]) if pieces else torch.empty(0, device=dev)
+        parts = gather_flat(flat, sizes, gather_to, group=group)
+    if rank != gather_to:
+        return mine, pieces
+    out = torch.empty(B, 1, hop * T, device=parts[0].device, dtype=torch.float32)
+    for r in range(world):
+        off = 0
+        for k in shards[r]:
+            b, _, _, ks, ke = units[k]
+            n = hop * (ke - ks)
+            out[b, 0, ks * hop:ke * hop] = parts[r][off:off + n]
+            off += n
+    return out

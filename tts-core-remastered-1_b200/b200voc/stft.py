@@ -98,6 +98,11 @@ class LearnableSTFT(nn.Module):
         self.filterbank = nn.Parameter(torch.randn(n_fft // 2 + 1))
 
     def forward(self, wav: torch.Tensor) -> torch.Tensor:
+        # inference kernel: the reference module is differentiable (stft.py:22-34), this forward is not -- say so
+        # instead of silently returning a tensor without grad_fn (the differentiable consumer is STFTLoss below)
+        if torch.is_grad_enabled() and (wav.requires_grad or self.filterbank.requires_grad and self.training):
+            raise _lib.B200VocError("LearnableSTFT.forward has no backward: use STFTLoss (differentiable w.r.t. the "
+                                    "waveform and the gains), or call it under torch.no_grad() / in eval() mode")
         return stft_magnitude(wav, self.n_fft, self.hop_length, self.filterbank)
 
 
