@@ -31,6 +31,7 @@ extern "C" {
 #define B200VOC_ERR_UNSUPPORTED (-2)
 #define B200VOC_ERR_CUDA (-3)
 #define B200VOC_ERR_STATE (-4)
+#define B200VOC_ERR_OVERFLOW (-5)   /* overflow check enabled and a 16-bit activation left the storage format's range */
 
 /* 16-bit tensor-core operand / activation storage formats (tcgen05 kind::f16 runs both at the
  * same rate). */
@@ -160,6 +161,11 @@ const char* b200voc_gen_profile_name(const b200voc_gen* g, int i);
 float b200voc_gen_profile_ms(const b200voc_gen* g, int i);
 double b200voc_gen_profile_flops(const b200voc_gen* g, int i);
 double b200voc_gen_profile_bytes(const b200voc_gen* g, int i);
+/* Debug aid for the 16-bit storage plan: when enabled, every forward counts the Inf / NaN values of each layer's stored
+ * activations (fp16 saturates at 65504) and fails with B200VOC_ERR_OVERFLOW naming the first layer that overflowed
+ * (costs one pass over every activation buffer and a stream synchronisation; the last stage then runs without the fused
+ * band_merge so that its output can be inspected).  Off by default. */
+int b200voc_gen_set_overflow_check(b200voc_gen* g, int enable);
 /* how many kernels one forward(B,T) launches (bench.py's gpu_launches). */
 int b200voc_gen_launch_count(const b200voc_gen* g);
 int b200voc_gen_destroy(b200voc_gen* g);

@@ -318,3 +318,78 @@ def test_generator_with_attention_matches_oracle_batch():
         wav = gen(mel.cuda(), pros.cuda(), sty.cuda(), emo.cuda()).cpu()
     assert float((wav - ref).abs().max()) <= 1e-3
     assert O.snr_db(ref, wav) >= 40.0
+
+
+@pytest.mark.parametrize("window", [None, 4096])
+def test_generator_with_attention_long_sequence(window):
+    """round-1 VERDICT: the attention kernel was only compared with the oracle up to L = 2688.  T = 200 -> L = 25600
+    positions at stage 2 = 200 key tiles of online-softmax rescaling per query tile (global), or windows of 4096
+    positions of which the last is ragged (25600 = 6 x 4096 + 1024).  L is always 128 * T at this layer, so a
+    sequence length that is not a multiple of 128 cannot occur."""
+    ocfg, ora, gen = _attn_models(window)
+    mel, pros, sty, emo = O.synthetic_inputs(1, 200, seed=71)
+    with torch.no_grad():
+        ref = O.generator_forward(ora.state_dict(), ocfg, mel, pros, sty, emo)
+        wav = gen(mel.cuda(), pros.cuda(), sty.cuda(), emo.cuda()).cpu()
+    assert float((wav - ref).abs().max()) <= 1e-3
+    assert O.snr_db(ref, wav) >= 40.0
+
+
+# ------------------------------------------------------------------ input scale / 16-bit range (round-1 VERDICT)
+def _scaled_models(scale_keys=None, factor=1.0, plan="fp16"):
+    from b200voc import GANConfig, Generator
+    ocfg = O.OracleConfig(use_attention=False)
+    ora = O.make_generator(ocfg, seed=1234)
+    sd = {k: v.clone() for k, v in ora.state_dict().items()}
+    if scale_keys:
+        for k in sd:
+            if any(s in k for s in scale_keys) and k.endswith("weight"):
+                sd[k] *= factor
+    gen = Generator(GANConfig(use_attention=False, precision=plan)).eval()
+    gen.load_state_dict(sd)
+    gen = gen.cuda()
+    gen.set_overflow_check(True)
+    return ocfg, sd, gen
+
+
+def test_generator_log_mel_scale_inputs():
+    """mels in the log-mel range (randn * 2 - 4) instead of unit-variance noise: same gates, and the
+    overflow check (every stored 16-bit activation is inspected) stays silent"""
+    ocfg, sd, gen = _scaled_models()
+    mel, pros, sty, emo = O.synthetic_inputs(2, 64, seed=33)
+    mel = mel * 2.0 - 4.0
+    with torch.no_grad():
+        ref = O.generator_forward(sd, ocfg, mel, pros, sty, emo)
+        wav = gen(mel.cuda(), pros.cuda(), sty.cuda(), emo.cuda()).cpu()
+    assert float((wav - ref).abs().max()) <= 1e-3
+    assert O.snr_db(ref, wav) >= 40.0
+
+
+def test_generator_large_activations_stay_in_range():
+    """band_split weights x4 -> every activation of the network ~4x larger (max |x| ~ 8): still far inside the fp16
+    range, no overflow, SNR gate holds (the absolute error scales with the activations, so max-abs is checked
+    relative to the 4x signal before the tanh)"""
+    ocfg, sd, gen = _scaled_models(("band_split",), 4.0)
+    mel, pros, sty, emo = O.synthetic_inputs(2, 64, seed=34)
+    with torch.no_grad():
+        ref = O.generator_forward(sd, ocfg, mel, pros, sty, emo)
+        wav = gen(mel.cuda(), pros.cuda(), sty.cuda(), emo.cuda()).cpu()
+    assert bool(torch.isfinite(wav).all())
+    assert O.snr_db(ref, wav) >= 40.0
+    assert float((wav - ref).abs().max()) <= 4e-3
+
+
+def test_generator_fp16_overflow_is_detected_not_silent():
+    """all upsampling / residual conv weights x6: activations grow by orders of magnitude per stage and leave the fp16
+    range; with the overflow check enabled the forward fails loudly and names the layer, and the bf16 plan (8 exponent
+    bits) runs the same weights without overflow"""
+    from b200voc import _lib
+    ocfg, sd, gen = _scaled_models(("upsample_blocks",), 6.0)
+    mel, pros, sty, emo = [x.cuda() for x in O.synthetic_inputs(1, 32, seed=35)]
+    with torch.no_grad():
+        with pytest.raises(_lib.B200VocOverflowError) as ei:
+            gen(mel, pros, sty, emo)
+        assert "overflow" in str(ei.value)
+        _, _, gen_bf = _scaled_models(("upsample_blocks",), 6.0, plan="bf16")
+        wav = gen_bf(mel, pros, sty, emo)
+    assert bool(torch.isfinite(wav).all())

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb200voc.so")
 # only the debug drivers under tests/ select it, with B200VOC_LIB=dev
 DEV_LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb200voc_dev.so")
 
-OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
+OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE, ERR_OVERFLOW = 0, -1, -2, -3, -4, -5
 FMT_FP16, FMT_BF16 = 0, 1
 PLAN_FP16, PLAN_BF16, PLAN_MIXED = 0, 1, 2
 PLANS = {"fp16": PLAN_FP16, "bf16": PLAN_BF16, "mixed": PLAN_MIXED}
@@ -57,6 +57,7 @@ _SIGNATURES = {
     "b200voc_spectral_norm_weight": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "b200voc_avg_pool1d_k4s2p1": (C.c_int, [_P, _I64, _I, _P, _P]),
     "b200voc_gen_launch_count": (C.c_int, [_P]),
+    "b200voc_gen_set_overflow_check": (C.c_int, [_P, _I]),
     "b200voc_gen_profile_enable": (C.c_int, [_P, _I]),
     "b200voc_gen_profile_count": (C.c_int, [_P]),
     "b200voc_gen_profile_name": (C.c_char_p, [_P, _I]),
@@ -98,6 +99,10 @@ class B200VocError(RuntimeError):
     pass
 
 
+class B200VocOverflowError(B200VocError):
+    """a 16-bit activation overflowed its storage format (raised only when the overflow check is enabled)"""
+
+
 def load() -> C.CDLL:
     """dlopen the in-tree library and bind every symbol the header declares."""
     global _lib
@@ -125,6 +130,8 @@ def check(status: int, what: str = "") -> None:
     text = f"b200voc {what} failed ({status}): {msg}"
     if status in (ERR_BAD_ARG, ERR_UNSUPPORTED):
         raise ValueError(text)
+    if status == ERR_OVERFLOW:
+        raise B200VocOverflowError(text)
     raise B200VocError(text)
 
 

@@ -118,6 +118,8 @@ class Generator(nn.Module):
             cc = self._c_config()
             _lib.check(lib.b200voc_gen_create(C.byref(cc), C.byref(h)), "gen_create")
             self._handle = h.value
+            if getattr(self, "_overflow_check", False):
+                _lib.check(lib.b200voc_gen_set_overflow_check(self._handle, 1))
         sd = self.state_dict()
         n = lib.b200voc_gen_num_weights(self._handle)
         expected = {lib.b200voc_gen_weight_name(self._handle, i).decode(): lib.b200voc_gen_weight_numel(self._handle, i)
@@ -168,6 +170,13 @@ class Generator(nn.Module):
         for k, v in self.__getstate__().items():
             new.__dict__[k] = copy.deepcopy(v, memo)
         return new
+
+    def set_overflow_check(self, enable: bool = True) -> None:
+        """Debug aid: every forward then counts Inf / NaN values in each layer's stored 16-bit activations and raises
+        ``B200VocOverflowError`` naming the first layer that left the storage format's range (fp16: 65504)."""
+        self._overflow_check = bool(enable)
+        if self._handle is not None:
+            _lib.check(_lib.load().b200voc_gen_set_overflow_check(self._handle, int(self._overflow_check)))
 
     def workspace_bytes(self, B: int, T: int) -> int:
         return int(_lib.load().b200voc_gen_workspace_bytes(self._handle, B, T))

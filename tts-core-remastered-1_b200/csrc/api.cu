@@ -118,6 +118,7 @@ int gst_launch(const float* mel, int time_major, int B, int T, int channels, int
                const float* b0, const float* w1, const float* b1, const float* tokens, float* scratch, float* style,
                cudaStream_t st);
 int tap_extract_launch(const void*, int, int, int, int, int, float*, cudaStream_t);
+int overflow_count_launch(const void* x16, long long n, int fmt, unsigned long long* counter, cudaStream_t st);
 int copy_f32_launch(const float*, float*, long long, float add, cudaStream_t, float mul = 1.0f);
 int cvt16_launch(const float*, void*, long long, int, cudaStream_t, float mul = 1.0f);
 int attention_launch(const void* x16, const void* wqkv, const float* bqkv, const void* wo, const float* bo, int N,
@@ -189,6 +190,8 @@ struct b200voc_gen {
   float* att_stage_w;            // fp32 staging [4][C*C]
   bool finalized;
   int launches;
+  bool check_overflow;               // debug: count Inf / NaN in every stored activation (b200voc_gen_set_overflow_check)
+  unsigned long long* ovf_dev;       // [64] per-layer counters
   std::vector<void*> allocs;
   // optional per-launch CUDA-event timing of the last forward
   bool profile;
@@ -284,6 +287,8 @@ int b200voc_gen_create(const b200voc_gen_config* cfg, b200voc_gen** out) {
   g->att_stage = cfg->n_stages / 2;
   g->launches = 0;
   g->profile = false;
+  g->check_overflow = false;
+  g->ovf_dev = nullptr;
   const int nb = cfg->num_bands, bs = g->band_size, cd = cfg->cond_dim;
   int st = B200VOC_OK;
 #define A(ptr, n) if (st == B200VOC_OK) st = dev_alloc(g, &(ptr), (n))
@@ -359,6 +364,7 @@ int b200voc_gen_create(const b200voc_gen_config* cfg, b200voc_gen** out) {
   A(g->merge_w, (long long)c * nb * 7);
   A(g->merge_b, 1);
   A(g->merge_w16, (long long)nb * 16 * 32);
+  A(g->ovf_dev, 64);
   add_slot(g, "band_merge.weight", (long long)c * nb * 7, W_MERGE_W);
   add_slot(g, "band_merge.bias", 1, W_MERGE_B);
 #undef A
@@ -576,6 +582,14 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
     ++launches;                            \
   } while (0)
 
+  // debug overflow check: one counter per stored activation, read back at the end of the forward
+  std::vector<std::string> ovf_names;
+  if (g->check_overflow) B200_CUDA(cudaMemsetAsync(g->ovf_dev, 0, 64 * sizeof(unsigned long long), st));
+  auto ovf = [&](const char* name, const void* buf, long long n, int fmt) -> int {
+    if (!g->check_overflow || ovf_names.size() >= 64) return B200VOC_OK;
+    ovf_names.push_back(name);
+    return overflow_count_launch(buf, n, fmt, g->ovf_dev + (ovf_names.size() - 1), st);
+  };
   const double dBT = (double)B * T;
   // FiLM projection: split-fp16 tensor-core GEMM (fp32-level accuracy); B200VOC_FILM_SGEMM=1 selects the fp32
   // CUDA-core SGEMM it replaced (A/B runs)
@@ -610,6 +624,7 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
                                         g->stages[0].fmt, mel_time_major, ws + w.a3, act[cur], st));
   if (!split_fp32) ++launches;      // im2col + GEMM
   if (tap == "split" && tap_out) B200_TRY(tap_extract_launch(act[cur], N, T, g->H, g->stages[0].fmt, 0, tap_out, st));
+  B200_TRY(ovf("band_split", act[cur], (long long)N * T * g->H, g->stages[0].fmt));
 
   // Narrow stages (Cout = 64 / 32, stride 2): ONE or two launches per stage with the intermediate activations on
   // chip (stage_fused.cu); after the last stage band_merge + tanh are folded in as well.  B200VOC_FUSED=0 (or a tap
@@ -658,8 +673,11 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
         set_blk(0, 1); set_blk(1, 2);
         snprintf(nm, sizeof nm, "stage%d.b", (int)i);
         RUN(nm, 2 * fl_res, 2 * by_out, stage_fused_launch(a, st));
+        B200_TRY(ovf("stage.a (ConvT + block 0)", act[cur ^ 1], (long long)N * L * s.Cout, s.fmt));
+        B200_TRY(ovf(nm, act[cur], (long long)N * L * s.Cout, s.fmt));
       } else {
-        const bool merge = is_last && nb == 4 && !att_here && tap != "res3.2" && !(tap.size() > 3 && tap.compare(0, 3, "res") == 0);
+        const bool merge = is_last && nb == 4 && !att_here && !g->check_overflow && tap != "res3.2" &&
+                           !(tap.size() > 3 && tap.compare(0, 3, "res") == 0);
         a.x_in = act[cur]; a.Lin = L; a.in_ct = 1; a.nblk = 3; a.out_mode = merge ? 2 : 1; a.out16 = act[cur ^ 1];
         a.merge_w16 = g->merge_w16; a.merge_b = g->merge_b; a.valid_samples = valid_samples; a.pcm16 = pcm16; a.wav = wav_out;
         set_blk(0, 0); set_blk(1, 1); set_blk(2, 2);
@@ -669,6 +687,7 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
             by_in + (merge ? (double)B * L * 4 : by_out), stage_fused_launch(a, st));
         if (!merge) cur ^= 1;
         merged = merge;
+        if (!merge) B200_TRY(ovf(nm, act[cur], (long long)N * L * s.Cout, s.fmt));
       }
       snprintf(nm, sizeof nm, "res%d.%d", (int)i, (int)s.res.size() - 1);
       if (tap == nm && tap_out && !merged) B200_TRY(tap_extract_launch(act[cur], N, L, s.Cout, s.fmt, 0, tap_out, st));
@@ -695,6 +714,7 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
     cur ^= 1;
     L *= s.s;
     if (tap == nm && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, s.Cout, s.fmt, carry_lrelu, tap_out, st));
+    B200_TRY(ovf(nm, act[cur], (long long)N * L * s.Cout, s.fmt));
     const bool att_here = (int)i == g->att_stage && g->cfg.use_attention;
     for (size_t j = 0; j < s.res.size(); ++j) {
       const ResW& r = s.res[j];
@@ -709,6 +729,7 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
                           nb, s.fmt, out_fmt, store_lrelu, act[cur ^ 1], st));
       cur ^= 1;
       if (tap == nm && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, r.C, out_fmt, store_lrelu, tap_out, st));
+      B200_TRY(ovf(nm, act[cur], (long long)N * L * r.C, out_fmt));
     }
     if (att_here) {
       uint16_t* sc = reinterpret_cast<uint16_t*>(ws + w.att);
@@ -729,6 +750,23 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
                         st));
 #undef RUN
   g->launches = launches;
+  if (g->check_overflow && !ovf_names.empty()) {
+    unsigned long long host[64];
+    B200_CUDA(cudaMemcpyAsync(host, g->ovf_dev, ovf_names.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < ovf_names.size(); ++i)
+      if (host[i]) {
+        set_error("16-bit overflow: %llu Inf/NaN values in the stored output of layer '%s' (fp16 saturates at 65504: use "
+                  "precision='bf16' / 'mixed' or rescale the inputs)", host[i], ovf_names[i].c_str());
+        return B200VOC_ERR_OVERFLOW;
+      }
+  }
+  return B200VOC_OK;
+}
+
+int b200voc_gen_set_overflow_check(b200voc_gen* g, int enable) {
+  B200_CHECK_ARG(g, "set_overflow_check: null handle");
+  g->check_overflow = enable != 0;
   return B200VOC_OK;
 }
 

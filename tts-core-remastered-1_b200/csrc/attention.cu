@@ -73,8 +73,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, seq = blockIdx.y;
-  const int nkt = p.n_ktiles_window;
-  const int kt0 = (blockIdx.x / nkt) * nkt;        // first key tile of this query tile's window
+  const int kt0 = (blockIdx.x / p.n_ktiles_window) * p.n_ktiles_window;   // first key tile of this query tile's window
+  const int nkt = min(p.n_ktiles_window, p.L / 128 - kt0);                // (the last window of a sequence may be shorter)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -315,7 +315,7 @@ int attention_launch(const void* x16, const void* wqkv, const float* bqkv, const
   B200_CHECK_ARG(C == 64, "attention: channels %d unsupported (64)", C);
   B200_CHECK_ARG(L % 128 == 0, "attention: L=%d must be a multiple of 128", L);
   int win = (window <= 0 || window >= L) ? L : window;
-  B200_CHECK_ARG(win % 128 == 0 && L % win == 0, "attention: window %d must be a multiple of 128 dividing L=%d", win, L);
+  B200_CHECK_ARG(win % 128 == 0, "attention: window %d must be a multiple of 128", win);
   uint16_t* qkv = reinterpret_cast<uint16_t*>(scratch);
   uint16_t* vt = qkv + (long long)N * L * 192;
   // 1) fused q|k|v projection (q rows of wqkv / bqkv carry log2(e)/sqrt(C))

@@ -618,6 +618,21 @@ int band_merge_launch(const void* x16, const float* w, const float* bias, int B,
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
+// overflow check (debug): how many stored 16-bit activations are Inf / NaN (exponent field all ones)
+__global__ void overflow_count_kernel(const uint16_t* __restrict__ x, long long n, int fmt, unsigned long long* counter) {
+  const uint16_t mask = fmt == 0 ? 0x7C00 : 0x7F80;
+  unsigned int c = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    c += (x[i] & mask) == mask;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, (unsigned long long)c);
+}
+int overflow_count_launch(const void* x16, long long n, int fmt, unsigned long long* counter, cudaStream_t st) {
+  overflow_count_kernel<<<1184, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(x16), n, fmt, counter);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
 int tap_extract_launch(const void* x16, int N, int L, int C, int fmt, int stored_lrelu, float* out, cudaStream_t st) {
   tap_extract_kernel<<<grid_for((long long)N * L * C), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(x16), N, L, C,
                                                                      fmt, stored_lrelu, out);
