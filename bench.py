@@ -438,8 +438,10 @@ def multi_gpu_jobs(gen, dev, rank, world, barrier):
         pros[lo:hi].normal_(generator=g)
         sty = torch.randn(n, 128, generator=g).pin_memory()
         emo = torch.softmax(torch.randn(n, 6, generator=g), -1).pin_memory()
-        S.sharded_synthesize_streaming(gen, dev, mels[:, :, :], pros, sty, emo, max_batch=B_PER_GPU)   # warm-up (pinned buffers, slots)
-        dt, (lo2, wavs) = timed(lambda: S.sharded_synthesize_streaming(gen, dev, mels, pros, sty, emo, max_batch=B_PER_GPU))
+        host_wavs = torch.empty(hi - lo, 1, HOP * T).pin_memory()       # allocated once, as a serving loop would
+        S.sharded_synthesize_streaming(gen, dev, mels, pros, sty, emo, max_batch=B_PER_GPU, out=host_wavs)   # warm-up
+        dt, (lo2, wavs) = timed(lambda: S.sharded_synthesize_streaming(gen, dev, mels, pros, sty, emo, max_batch=B_PER_GPU,
+                                                                       out=host_wavs))
         audio = n * HOP * T / SR
         sizes = [(min(n, (r + 1) * per) - min(n, r * per)) * HOP * T for r in range(world)]
         gms = gather_ms(wavs.to(dev).reshape(-1), sizes)

@@ -264,19 +264,23 @@ def gather_waveforms(local: Dict[int, torch.Tensor], lengths: Sequence[int], dst
 
 
 def sharded_synthesize_streaming(synth: Synth, device, mels: torch.Tensor, prosodies: torch.Tensor, styles: torch.Tensor,
-                                 emotions: torch.Tensor, max_batch: int = 16, hop: int = 256, group=None, **kw):
+                                 emotions: torch.Tensor, max_batch: int = 16, hop: int = 256, group=None,
+                                 out: Optional[torch.Tensor] = None, **kw):
     """BASELINE configs[3]: n equally long utterances given as HOST tensors (mels[n, 80, T], ..., ideally pinned) are
     sharded over the ranks (contiguous blocks: equal lengths need no balancing) and each rank pushes its shard through
     the host-in / host-out StreamingSynthesizer in batches of `max_batch`.  No collective.  Returns (first index,
-    host waveforms [n_local, 1, hop * T]) of this rank's shard."""
+    host waveforms [n_local, 1, hop * T]) of this rank's shard; `out` (pinned, that shape) is reused when given -- a
+    serving loop allocates it once, pinning 100s of MB costs as much as synthesizing them."""
     rank, world = _dist_info(group)
     n, T = int(mels.shape[0]), int(mels.shape[-1])
     per = (n + world - 1) // world
     lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
-    pin = torch.device(device).type == "cuda"
-    out = torch.empty(hi - lo, 1, hop * T)
-    if pin:
-        out = out.pin_memory()
+    if out is None:
+        out = torch.empty(hi - lo, 1, hop * T)
+        if torch.device(device).type == "cuda":
+            out = out.pin_memory()
+    elif tuple(out.shape) != (hi - lo, 1, hop * T):
+        raise ValueError(f"out must have shape {(hi - lo, 1, hop * T)}, got {tuple(out.shape)}")
     starts = list(range(lo, hi, max_batch))
     # a ragged last batch has its own shape: the streamer re-allocates its slots for it (one extra allocation per job)
     full = [s for s in starts if min(hi, s + max_batch) - s == max_batch]
