@@ -217,6 +217,10 @@ int b200voc_stage_fused(const void* x16, const void* convt_w_packed, const float
  * STFT family (replaces vocoder7/stft.py:9-54 and the torchaudio MelSpectrogram call sites
  * reference_encoder/utils.py:31-36).  fp32 throughout.  frames = 1 + N / hop, bins = n_fft/2+1.
  * -------------------------------------------------------------------------------------- */
+/* Builds and caches (per device) the window / twiddle tables of n_fft and, for n_mels > 0, the sparse HTK mel
+ * filterbank, so that the calls below never allocate or copy synchronously (required before CUDA-graph capture; without
+ * it the first call of a configuration builds its tables lazily). */
+int b200voc_stft_prepare(int n_fft, int n_mels, int sample_rate);
 /* LearnableSTFT.forward (stft.py:22-34): out[B,bins,frames] = |STFT(wav[B,N])| * gain[bins]
  * (gain may be NULL = ones). */
 int b200voc_stft_mag(const float* wav, int B, int N, int n_fft, int hop, const float* gain, float* out, void* stream);

@@ -5,9 +5,9 @@ from .config import GANConfig
 from .generator import Generator, ResidualBlock, SelfAttention
 from .gst import GlobalStyleTokens
 from .discriminators import MultiPeriodDiscriminator, MultiScaleDiscriminator, MultiBandDiscriminator
-from .stft import LearnableSTFT, STFTLoss, stft, istft, mel_spectrogram, log_mel, stft_magnitude
+from .stft import LearnableSTFT, STFTLoss, stft, istft, mel_spectrogram, log_mel, stft_magnitude, stft_prepare
 from . import _lib
 
 __all__ = ["GANConfig", "Generator", "GlobalStyleTokens", "MultiPeriodDiscriminator", "MultiScaleDiscriminator",
            "MultiBandDiscriminator", "ResidualBlock", "SelfAttention", "LearnableSTFT", "STFTLoss", "stft", "istft",
-           "mel_spectrogram", "log_mel", "stft_magnitude"]
+           "mel_spectrogram", "log_mel", "stft_magnitude", "stft_prepare"]

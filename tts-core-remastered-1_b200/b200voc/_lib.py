@@ -75,6 +75,7 @@ _SIGNATURES = {
     "b200voc_merge_packed_elems": (_I64, [_I]),
     "b200voc_pack_merge_weight": (C.c_int, [_P, _I, _I, _P, _P]),
     "b200voc_stage_fused": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "b200voc_stft_prepare": (C.c_int, [_I, _I, _I]),
     "b200voc_stft_mag": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "b200voc_stft_complex": (C.c_int, [_P, _I, _I, _I, _I, _P, _P]),
     "b200voc_stft_logmel": (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

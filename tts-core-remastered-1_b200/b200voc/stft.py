@@ -31,6 +31,14 @@ def _prep(wav: torch.Tensor) -> torch.Tensor:
     return wav.detach().to(torch.float32).contiguous()
 
 
+def stft_prepare(n_fft: int, n_mels: int = 0, sample_rate: int = 22050, device=None) -> None:
+    """Build the window / twiddle (and, for ``n_mels > 0``, mel filterbank) tables of this configuration on `device`
+    now, so that the transforms never allocate or copy synchronously afterwards -- required before capturing them in a
+    CUDA graph (``b200voc_stft_prepare``)."""
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        _lib.check(_lib.load().b200voc_stft_prepare(int(n_fft), int(n_mels), int(sample_rate)), "stft_prepare")
+
+
 def stft_magnitude(wav: torch.Tensor, n_fft: int, hop_length: int, gain: Optional[torch.Tensor] = None) -> torch.Tensor:
     """|STFT(wav)| * gain[:, None] -> [B, n_fft/2+1, 1+N//hop]."""
     w = _prep(wav)

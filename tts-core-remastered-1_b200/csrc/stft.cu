@@ -642,6 +642,37 @@ istft1024_kernel(const IstftParams p) {
   __syncthreads();
   float* o = p.wav + (long long)b * p.Nout;
   const float* wv = reinterpret_cast<const float*>(win2);
+  // gather overlap-add.  Fast path (hop a power of two, every frame of this CTA's block inside the signal): thread =
+  // sample offset within a hop, no divisions, no per-contribution bounds tests; the window envelope sum_q w^2 depends
+  // only on the offset, so it is computed once per thread.  (The generic loop below spent ~150 instructions per
+  // sample on index arithmetic: the ALU pipe was this kernel's busiest unit, profiles/r01_final_stft_kernels_ncu.txt.)
+  const int hop = p.hop;
+  const bool pow2 = (hop & (hop - 1)) == 0 && hop <= (int)blockDim.x && (p.joff % hop) == 0;
+  const bool interior = f_lo >= 0 && f_lo + kISlots <= p.frames;
+  if (pow2 && interior) {
+    const int nhop = opb / hop;                          // output hops of this CTA (kISlots - ratio + 1)
+    const int lanes_per = blockDim.x / hop;              // threads that share one offset (they split the hops)
+    const int r = threadIdx.x % hop, part = threadIdx.x / hop;
+    float env = 0.f;
+    for (int q = 0; q < ratio; ++q) { const float w = wv[r + q * hop]; env = fmaf(w, w, env); }
+    const float inv_env = p.normalize ? (env > 1e-11f ? 1.0f / env : 0.f) : 1.0f;
+    // output sample n = n0 + h * hop + r: padded coordinate j = n + joff, newest frame f_hi = j / hop, contribution q
+    // comes from slot (f_hi - q - f_lo) at position r + q * hop
+    const int s_hi0 = (n0 + p.joff) / hop - f_lo;        // slot of f_hi for h = 0 (= ratio - 1)
+    for (int h = part; h < nhop; h += lanes_per) {
+      const int n = n0 + h * hop + r;
+      if (n >= p.Nout) break;
+      float acc = 0.f;
+#pragma unroll 4
+      for (int q = 0; q < ratio; ++q) {
+        const int idx = r + q * hop;
+        const float2 z = slots[(s_hi0 + h - q) * kISlotStride + pad(idx >> 1)];
+        acc += (idx & 1) ? z.y : z.x;
+      }
+      o[n] = p.normalize ? acc * inv_env : acc;
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < opb; i += blockDim.x) {
     const int n = n0 + i;
     if (n >= p.Nout) break;
@@ -747,6 +778,25 @@ __global__ void __launch_bounds__(256) stft_fold_reflect_kernel(const float* __r
 using namespace b200;
 
 extern "C" {
+
+/* Builds (and caches, per device) the tables the STFT family needs -- window, twiddles, and for n_mels > 0 the sparse
+ * HTK mel filterbank -- so that the transform calls themselves never allocate or copy synchronously: call it once per
+ * (n_fft, n_mels, sample_rate) before capturing the transforms in a CUDA graph or calling them from a latency-critical
+ * loop.  Without it the first call of each configuration builds the tables lazily (cudaMalloc + synchronous copies). */
+int b200voc_stft_prepare(int n_fft, int n_mels, int sample_rate) {
+  if (n_fft != 512 && n_fft != 1024 && n_fft != 2048) {
+    set_error("stft_prepare: n_fft=%d unsupported (512/1024/2048, vocoder7/config.py:39 stft_sizes)", n_fft);
+    return B200VOC_ERR_UNSUPPORTED;
+  }
+  FftTables t;
+  B200_TRY(get_fft_tables(n_fft, &t));
+  if (n_mels > 0) {
+    B200_CHECK_ARG(n_mels <= 512 && sample_rate > 0, "stft_prepare: bad mel arguments");
+    MelTable m;
+    B200_TRY(get_mel_table(n_fft, n_mels, sample_rate, &m));
+  }
+  return B200VOC_OK;
+}
 
 int b200voc_stft_mag(const float* wav, int B, int N, int n_fft, int hop, const float* gain, float* out, void* stream) {
   B200_TRY(check_stft_args(wav, B, N, n_fft, hop));
