@@ -117,7 +117,11 @@ struct SfCfg {
   // at 16k; GEMM2 accumulator = the gate columns [C, 2C); merge accumulator = [C, C + 16) once epilogue 2 has read them;
   // the ConvT accumulator of chunk c (2C columns) = tile 2c of its context
   static constexpr int N1 = 2 * C;
-  static constexpr int TMEM_NEED = NTT * N1;
+  // PIPE_CT (one context, room in TMEM): the ConvT accumulators get their own columns and the ConvT MMAs of strip
+  // s + 1 are issued behind the GEMM1s of strip s, so they run under its epilogues
+  static constexpr bool PIPE_CT = IN_CT && NCTX == 1 && (NTT + NCHUNK) * N1 <= 512;
+  static constexpr int CT_COL = NTT * N1;
+  static constexpr int TMEM_NEED = NTT * N1 + (PIPE_CT ? NCHUNK * N1 : 0);
   static constexpr uint32_t TMEM_COLS = TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
   static constexpr int XR_COUNT = C == 32 ? 4 : 8;    // warp arrivals that complete x_ready / h_full of one m-tile
   // x_ready completions per iteration: [ConvT epilogue], one per block, [merge epilogue]
@@ -276,14 +280,13 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
           for (int t = 0; t < NT; ++t) mbar_wait(&x_ready[cx * NT + t], (it * XPB - 1) & 1);
         }
         if (cx == 0) SF_TRACE(0, 0);
-        if (IN_CT) {
+        auto issue_ct = [&](int it_ct) {
           for (int c = 0; c < NCHUNK; ++c) {
             const int sl = cx * NCHUNK + c;
-            mbar_wait(&in_full[sl], it & 1);
-            if (cx == 0 && c == 0) SF_TRACE(0, 1);
+            mbar_wait(&in_full[sl], it_ct & 1);
             tc_fence_after();
             const uint32_t a0 = smem_u32(sIn + sl * K::IN_CHUNK_BYTES);
-            const uint32_t d_ct = tmem_base + (cx * NT + 2 * c) * N1;
+            const uint32_t d_ct = tmem_base + (K::PIPE_CT ? K::CT_COL + c * N1 : (cx * NT + 2 * c) * N1);
             if (elect_one()) {
 #pragma unroll
               for (int tap = 0; tap < 2; ++tap)      // tap 0: x[m] (tile row i + 1), tap 1: x[m - 1] (tile row i)
@@ -300,6 +303,9 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
             }
             __syncwarp();
           }
+        };
+        if (IN_CT && (!K::PIPE_CT || it == 0)) {
+          issue_ct(it);
           if (cx == 0) SF_TRACE(0, 2);
         }
 #pragma unroll 1
@@ -333,6 +339,12 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
               umma_commit(&d1_full[T]);
             }
             __syncwarp();
+          }
+          if (K::PIPE_CT && blk == NBLK - 1) {
+            // next strip's ConvT behind this strip's last GEMM1s: its accumulator columns are free (the ConvT epilogue of
+            // this strip arrived on x_ready long ago) and its input chunk was prefetched
+            const bool more = sub + 1 < NSUB || u + grid < p.total_units;
+            if (more) issue_ct(it + 1);
           }
           for (int t = 0; t < NT; ++t) {
             const int T = cx * NT + t;
@@ -419,7 +431,7 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
             tc_fence_after();
             if (q == 0 && cx == 0) SF_TRACE(1 + eg, 0);
             uint32_t v[32];
-            tmem_ld32(lane_addr + (cx * NT + 2 * ct_c) * N1 + ct_col, v);
+            tmem_ld32(lane_addr + (K::PIPE_CT ? K::CT_COL + ct_c * N1 : (cx * NT + 2 * ct_c) * N1) + ct_col, v);
             tmem_ld_wait();
             const int cl = s0 + ct_sr;
             const float keep = (cl >= 0 && cl < p.L) ? 1.f : 0.f;           // rows outside the sequence are the next conv's zero padding
