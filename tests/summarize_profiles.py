@@ -52,7 +52,9 @@ want = ["Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.
         "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
-        "launch__shared_mem_per_block_dynamic", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"]
+        "launch__shared_mem_per_block_dynamic", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]
 idx = [h.index(w) for w in want if w in h]
 seen = collections.OrderedDict()
 for r in rr[2:]:
