@@ -88,6 +88,10 @@ int64_t b200voc_gen_workspace_bytes(const b200voc_gen* g, int B, int T);
 /* Generator.forward (generator.py:50-98).
  *   mel[B,channels,T] prosody[B,T,18] style[B,style_dim] emotion[B,6]  (fp32, contiguous)
  *   wav_out[B,1,hop*T] fp32.
+ * Stream-ordered on `stream` for the caller (inputs may be released / outputs read by later work on that stream) and
+ * capturable in a CUDA graph; internally the conditioning chain (style / emotion projections, prosody MLP, FiLM GEMM)
+ * is forked onto a stream owned by the handle and joined before the first residual block, so two forwards on the SAME
+ * handle must themselves be ordered (same stream, or an event between them); use one handle per concurrent stream.
  * tap_name/tap_out (both NULL normally): copy the named intermediate ("split","up0","res0.0",..,
  * "attn", oracle tap names) as fp32 [num_bands*B? no: B*num_bands, C, L] into tap_out. */
 int b200voc_gen_forward(b200voc_gen* g, const float* mel, const float* prosody, const float* style,

@@ -190,6 +190,8 @@ struct b200voc_gen {
   float* att_stage_w;            // fp32 staging [4][C*C]
   bool finalized;
   int launches;
+  cudaStream_t side;                 // conditioning chain (style/emotion, cond MLP, FiLM GEMM) runs here, under band_split + up0
+  cudaEvent_t ev_fork, ev_join;
   bool check_overflow;               // debug: count Inf / NaN in every stored activation (b200voc_gen_set_overflow_check)
   unsigned long long* ovf_dev;       // [64] per-layer counters
   std::vector<void*> allocs;
@@ -289,6 +291,14 @@ int b200voc_gen_create(const b200voc_gen_config* cfg, b200voc_gen** out) {
   g->profile = false;
   g->check_overflow = false;
   g->ovf_dev = nullptr;
+  g->side = nullptr; g->ev_fork = nullptr; g->ev_join = nullptr;
+  if (cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("gen_create: could not create the side stream / events");
+    delete g;
+    return B200VOC_ERR_CUDA;
+  }
   const int nb = cfg->num_bands, bs = g->band_size, cd = cfg->cond_dim;
   int st = B200VOC_OK;
 #define A(ptr, n) if (st == B200VOC_OK) st = dev_alloc(g, &(ptr), (n))
@@ -601,7 +611,18 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
     B200_TRY(pack_film3_launch(g->film_w, g->film_cols, g->film_w3, st));
     g->film_packed = true;
   }
-  // conditioning (generator.py:65-73) and all FiLM projections (frame rate, fp32)
+  // conditioning (generator.py:65-73) and all FiLM projections (frame rate, fp32): three small latency-bound kernels
+  // nobody needs before the first residual block -- they run on the handle's side stream under band_split + up0 (fork /
+  // join by events, so the call stays stream-ordered for the caller and capturable in a CUDA graph).  With per-launch
+  // profiling on (or B200VOC_SIDE_STREAM=0) everything stays on the caller's stream so that each event pair brackets one kernel.
+  static const bool side_env = [] { const char* e = getenv("B200VOC_SIDE_STREAM"); return !(e && e[0] == '0'); }();
+  const bool use_side = side_env && !g->profile && tap.empty();
+  cudaStream_t main_st = st;
+  if (use_side) {
+    B200_CUDA(cudaEventRecord(g->ev_fork, main_st));
+    B200_CUDA(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
+    st = g->side;
+  }
   RUN("style_emo", 2.0 * B * cd * (g->cfg.style_dim + 6), 0,
       style_emo_launch(style, emotion, g->sty_w, g->sty_b, g->emo_w, g->emo_b, B, g->cfg.style_dim, cd, w_style, w_emo,
                        style_drop, emo_drop, sty, emo, st));
@@ -611,6 +632,10 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
   RUN("film", 2.0 * dBT * cd * g->film_cols, dBT * (cd + g->film_cols) * 4,
       film_sgemm ? film_launch(cond, g->film_w, g->film_b, B * T, g->film_cols, film, st)
                  : film_tc_launch(ws + w.cond3, g->film_w3, g->film_b, B * T, g->film_cols, film, st));
+  if (use_side) {
+    B200_CUDA(cudaEventRecord(g->ev_join, g->side));
+    st = main_st;
+  }
   if (tap == "cond" && tap_out) {  // raw [B, T, cd]; the host transposes
     B200_CUDA(cudaMemcpyAsync(tap_out, cond, (size_t)B * T * cd * 4, cudaMemcpyDeviceToDevice, st));
   }
@@ -639,7 +664,7 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
     if (tap.compare(0, strlen(b), b) == 0 && tap.back() != '0' + (char)(g->cfg.n_dilations - 1)) return true;
     return false;
   };
-  bool merged = false;
+  bool merged = false, joined = !use_side;
   int L = T;
   for (size_t i = 0; i < g->stages.size(); ++i) {
     const StageW& s = g->stages[i];
@@ -649,6 +674,7 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
                          (is_last || g->stages[i + 1].fmt == s.fmt) && !tap_inside(i) && T * (L * 2 / T) == L * 2 &&
                          s.res[0].dilation <= 8 && s.res[1].dilation <= 8 && s.res[2].dilation <= 8;
     if (fusable) {
+      if (!joined) { B200_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0)); joined = true; }   // FiLM is read from here on
       StageFusedArgs a{};
       a.N = N; a.C = s.Cout; a.T = T; a.num_bands = nb; a.fmt = s.fmt;
       a.ct_w = s.up_w; a.ct_b = s.up_b; a.film = film; a.film_stride = g->film_cols;
@@ -716,6 +742,7 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
     if (tap == nm && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, s.Cout, s.fmt, carry_lrelu, tap_out, st));
     B200_TRY(ovf(nm, act[cur], (long long)N * L * s.Cout, s.fmt));
     const bool att_here = (int)i == g->att_stage && g->cfg.use_attention;
+    if (!joined) { B200_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0)); joined = true; }     // FiLM is read from here on
     for (size_t j = 0; j < s.res.size(); ++j) {
       const ResW& r = s.res[j];
       const bool last = j + 1 == s.res.size();
@@ -743,6 +770,7 @@ int b200voc_gen_forward_ex(b200voc_gen* g, const float* mel, const float* prosod
       if (tap == "attn" && tap_out) B200_TRY(tap_extract_launch(act[cur], N, L, s.Cout, s.fmt, 0, tap_out, st));
     }
   }
+  if (!joined) { B200_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0)); joined = true; }
   const StageW& last = g->stages.back();
   if (!merged)
   RUN("band_merge", 2.0 * B * (double)L * nb * last.Cout * 7, (double)N * L * last.Cout * 2 + (double)B * L * 4,
@@ -797,6 +825,9 @@ int b200voc_gen_destroy(b200voc_gen* g) {
   if (!g) return B200VOC_OK;
   for (void* p : g->allocs) cudaFree(p);
   for (cudaEvent_t e : g->ev) cudaEventDestroy(e);
+  if (g->side) cudaStreamDestroy(g->side);
+  if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+  if (g->ev_join) cudaEventDestroy(g->ev_join);
   delete g;
   return B200VOC_OK;
 }
