@@ -70,7 +70,8 @@ def test_kernel_plan_expects_exactly_the_state_dict():
     h = ctypes.c_void_p()
     rc = lib.b200voc_gen_create(ctypes.byref(cc), ctypes.byref(h))
     if rc != 0:   # no CUDA driver in this container: create needs device memory -> loud failure
-        assert rc == _lib.ERR_CUDA and b"cudaMalloc" in lib.b200voc_last_error_string()
+        msg = lib.b200voc_last_error_string()
+        assert rc == _lib.ERR_CUDA and (b"cudaMalloc" in msg or b"stream" in msg), msg
         return
     n = lib.b200voc_gen_num_weights(h)
     names = {lib.b200voc_gen_weight_name(h, i).decode(): lib.b200voc_gen_weight_numel(h, i) for i in range(n)}
