@@ -109,8 +109,11 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    dev = os.environ.get("B200VOC_LIB", "") == "dev"
+    sel = os.environ.get("B200VOC_LIB", "")
+    dev = sel == "dev"
     path = DEV_LIB_PATH if dev else LIB_PATH
+    if sel.endswith(".so"):        # A/B runs of two builds on the same box (tests/ab_step.py); never set in production
+        path = os.path.abspath(sel)
     if not os.path.exists(path):
         raise B200VocError(
             f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -199,26 +199,33 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
         }
       };
-      int gc = 0;
-      for (int it = 0; it < n_my_tiles; ++it) {
-        for (int j = 0; j < NCH; ++j, ++gc) {
-          for (int tap = 0; tap < 3; ++tap)
-            for (int kb = 0; kb < KPT; kb += K::SUBS) {
-              uint8_t* dst = w_slot(K::SUBS);
-              if (dst)
-                for (int sub = 0; sub < K::SUBS; ++sub)
-                  load_w(dst + sub * K::W_TILE, &tmW1, tap * C + (kb + sub) * 64, j * 128);
-              ++wi;
+      // compact code on purpose (no unrolling in the producer / issuer roles): the kernel's instruction footprint
+      // exceeds the instruction caches and the issuer's fetch stalls were its largest stall reason (ncu: no_instruction)
+      const int total_chunks = n_my_tiles * NCH;
+#pragma unroll 1
+      for (int gc = 0, j = 0; gc <= total_chunks; ++gc) {
+        if (gc < total_chunks) {
+#pragma unroll 1
+          for (int s3 = 0; s3 < 3 * (KPT / K::SUBS); ++s3) {
+            const int tap = s3 / (KPT / K::SUBS), kb = (s3 - tap * (KPT / K::SUBS)) * K::SUBS;
+            uint8_t* dst = w_slot(K::SUBS);
+            if (dst) {
+#pragma unroll
+              for (int sub = 0; sub < K::SUBS; ++sub)
+                load_w(dst + sub * K::W_TILE, &tmW1, tap * C + (kb + sub) * 64, j * 128);
             }
-          if (gc >= 1) load_w2((gc - 1) % NCH);
+            ++wi;
+          }
         }
+        if (gc >= 1) load_w2((gc - 1) % NCH);
+        if (++j == NCH) j = 0;
       }
-      if (gc >= 1) load_w2((gc - 1) % NCH);
     }
   } else if (warp == 18) {
     // ------------------------------------------------------------ TMA producer of the input tiles (own warp: a
     // wait for a free input slot must not hold up the weight stream)
     if (lane == 0) {
+#pragma unroll 1
       for (int it = 0; it < n_my_tiles; ++it) {
         const int tile = tile_of(it);
         const int seq = tile / p.tiles_per_seq, l0 = (tile - seq * p.tiles_per_seq) * 128;
@@ -227,6 +234,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (RB3_DBG(16) && it >= NA) { mbar_arrive(&a_full[ab]); continue; }
         RB3_TRACE(0, it, 0);
         mbar_expect_tx(&a_full[ab], K::A_BYTES);
+#pragma unroll 1
         for (int kb = 0; kb < KPT; ++kb)
           tma_load_3d(sA + ab * K::A_BYTES + kb * K::A_KB_BYTES, &tmX, &a_full[ab], kb * 64, l0 - K::HALO, seq);
       }
@@ -315,10 +323,11 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         __syncwarp();
       };
-      int gc = 0;
-      for (int it = 0; it < n_my_tiles; ++it) {
-        const int ab = it % NA;
-        for (int j = 0; j < NCH; ++j, ++gc) {
+      const int total_chunks = n_my_tiles * NCH;
+#pragma unroll 1
+      for (int gc = 0, it = 0, j = 0; gc <= total_chunks; ++gc) {
+        if (gc < total_chunks) {
+          const int ab = it % NA;
           const int b = gc & 1;
           {
             const uint32_t pha = (it / NA) & 1, phd = ((gc >> 1) & 1) ^ 1;
@@ -330,37 +339,40 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             RB3_TRACE(1, gc, 1);
           }
           tc_fence_after();
-          for (int tap = 0; tap < 3; ++tap)
-            for (int kb = 0; kb < KPT; kb += K::SUBS) {
-              const int s = acquire_w();
-              const uint32_t a_addr = smem_u32(sA + ab * K::A_BYTES + kb * K::A_KB_BYTES) +
-                                      (K::HALO + (tap - 1) * p.dilation) * 128;
-              const uint32_t a_desc = desc_lo(a_addr);
-              const uint32_t b_desc = desc_lo(smem_u32(sW + s * K::W_SLOT));
-              if (elect_one()) {
-                if (!RB3_DBG(32))
+          const uint32_t a_tile = smem_u32(sA + ab * K::A_BYTES) + K::HALO * 128;
+#pragma unroll 1
+          for (int s3 = 0; s3 < 3 * (KPT / K::SUBS); ++s3) {
+            const int tap = s3 / (KPT / K::SUBS), kb = (s3 - tap * (KPT / K::SUBS)) * K::SUBS;
+            const int s = acquire_w();
+            const uint32_t a_desc = desc_lo(a_tile + kb * K::A_KB_BYTES + (tap - 1) * p.dilation * 128);
+            const uint32_t b_desc = desc_lo(smem_u32(sW + s * K::W_SLOT));
+            if (elect_one()) {
+              if (!RB3_DBG(32))
 #pragma unroll
-                for (int sub = 0; sub < K::SUBS; ++sub)
+              for (int sub = 0; sub < K::SUBS; ++sub)
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    mma(tmem_base + b * 128, a_desc + (sub * K::A_KB_BYTES >> 4) + 2 * k,
-                        b_desc + (sub * K::W_TILE >> 4) + 2 * k, (tap | kb | sub | k) != 0);
-                commit(&w_empty[s]);
-              }
-              __syncwarp();
-              ++wi;
+                for (int k = 0; k < 4; ++k)
+                  mma(tmem_base + b * 128, a_desc + (sub * K::A_KB_BYTES >> 4) + 2 * k,
+                      b_desc + (sub * K::W_TILE >> 4) + 2 * k, (s3 | sub | k) != 0);
+              commit(&w_empty[s]);
             }
+            __syncwarp();
+            ++wi;
+          }
           if (elect_one()) {
             commit(&d1_full[b]);
             if (!K::INPLACE && j == NCH - 1) commit(&a_empty[ab]);        // INPLACE: released by the store epilogue
           }
           __syncwarp();
           RB3_TRACE(1, gc, 2);
-          if (gc >= 1) g2((gc - 1) / NCH, (gc - 1) % NCH);
-          RB3_TRACE(1, gc, 3);
         }
+        if (gc >= 1) {
+          const int pj = j == 0 ? NCH - 1 : j - 1;
+          g2(j == 0 ? it - 1 : it, pj);
+        }
+        if (gc < total_chunks) RB3_TRACE(1, gc, 3);
+        if (++j == NCH) { j = 0; ++it; }
       }
-      if (gc >= 1) g2((gc - 1) / NCH, (gc - 1) % NCH);
     }
   } else if (warp < 10) {
     // ------------------------------------------------------------ epilogue 1 (warps 2..9): GLU + FiLM -> h
@@ -490,7 +502,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tc_fence_after();
       uint8_t* abase = sA + ab * K::A_BYTES + (row + K::HALO) * 128;
       if (!RB3_DBG(2))
-#pragma unroll 2
+#pragma unroll 1
       for (int c0 = 0; c0 < C; c0 += 16) {
         uint32_t vd[16];
         tmem_ld16(lane_addr + K::D2_COL + db * C + c0, vd);

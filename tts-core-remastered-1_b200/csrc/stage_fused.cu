@@ -36,6 +36,11 @@
 // quadrant); C = 32: group g owns m-tile g; C = 64: two groups share an m-tile (32 channels each).
 #include <stdlib.h>
 
+// this kernel keeps the inlined mbarrier wait loop (ptx.cuh): its 16 epilogue warps wait often and briefly, and the
+// out-of-line slow path costs more there than the smaller code saves (A/B on one box: stage2.a 1.09 vs 1.25 ms)
+#ifndef B200VOC_INLINE_WAIT
+#define B200VOC_INLINE_WAIT 1
+#endif
 #include "common.cuh"
 #include "ptx.cuh"
 
