@@ -319,6 +319,42 @@ def secondary_measurements(dev, dev_in, B, T):
     except Exception as e:
         out["frontend"] = {"error": str(e)[:200]}
     try:
+        # BASELINE configs[0] shape (B = 1, T = 172 = 2 s): launch-bound, so the serving form is one CUDA graph per
+        # request shape (b200voc.scheduler.GraphedSynthesizer); eager call beside it
+        from b200voc.scheduler import GraphedSynthesizer
+        torch.manual_seed(1234)
+        gen_s = Generator(GANConfig(use_attention=False)).eval().to(dev)
+        g0 = torch.Generator().manual_seed(3)
+        small = [torch.randn(1, 80, 172, generator=g0).to(dev), torch.randn(1, 172, 18, generator=g0).to(dev),
+                 torch.randn(1, 128, generator=g0).to(dev), torch.softmax(torch.randn(1, 6, generator=g0), -1).to(dev)]
+        gs = GraphedSynthesizer(gen_s)
+        o_small = torch.empty(1, 1, HOP * 172, device=dev)
+        with torch.no_grad():
+            for _ in range(3):
+                gs(*small)
+                gen_s(*small, out=o_small)
+            torch.cuda.synchronize()
+            a, b_, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            n_small = 50
+            a.record()
+            for _ in range(n_small):
+                gs(*small)
+            b_.record()
+            for _ in range(n_small):
+                gen_s(*small, out=o_small)
+            c.record()
+            torch.cuda.synchronize()
+            same = bool(torch.equal(gs(*small), gen_s(*small)))
+        g_ms, e_ms = a.elapsed_time(b_) / n_small, b_.elapsed_time(c) / n_small
+        out["small_request"] = {
+            "workload": "BASELINE configs[0] shape: 1 x T=172 (2 s), attention off", "graph_ms": g_ms, "eager_ms": e_ms,
+            "graph_audio_s_per_s": HOP * 172 / SR / (g_ms / 1e3), "eager_audio_s_per_s": HOP * 172 / SR / (e_ms / 1e3),
+            "launches_per_forward": gen_s.launch_count(), "bit_identical": same,
+            "note": "one CUDA graph per exact request shape, 4 input copies + 1 graph launch per call"}
+        del gs, gen_s
+    except Exception as e:
+        out["small_request"] = {"error": str(e)[:200]}
+    try:
         # SURVEY 8f rank 4 (forward half): the three critics the trainer runs on every waveform
         # (vocoder7/trainer.py:86-92); first correct CUDA path, fp32 direct convolution
         from b200voc import MultiPeriodDiscriminator, MultiScaleDiscriminator, MultiBandDiscriminator

@@ -179,3 +179,30 @@ def test_forward_and_stft_are_cuda_graph_capturable():
     e2.record()
     torch.cuda.synchronize()
     print(f"B=1 T=172 generator + log-mel: graph replay {e0.elapsed_time(e1) / 20:.3f} ms, eager {e1.elapsed_time(e2) / 20:.3f} ms")
+
+
+def test_graphed_synthesizer_matches_eager_across_shapes():
+    """scheduler.GraphedSynthesizer: one CUDA graph per exact request shape, replayed on static buffers -- bit-identical
+    to the eager forward, also when shapes alternate (each graph keeps its own workspace alive) and when the least
+    recently used graph is evicted and re-captured."""
+    from b200voc import GANConfig, Generator
+    from b200voc.scheduler import GraphedSynthesizer
+    ora = O.make_generator(O.OracleConfig(use_attention=False), seed=1234)
+    gen = Generator(GANConfig(use_attention=False)).eval()
+    gen.load_state_dict(ora.state_dict())
+    gen = gen.cuda()
+    gs = GraphedSynthesizer(gen, max_graphs=2)
+    shapes = [(1, 20), (2, 33), (1, 20), (3, 9), (2, 33), (1, 20)]
+    for i, (B, T) in enumerate(shapes):
+        ins = [x.cuda() for x in O.synthetic_inputs(B, T, seed=10 + i)]
+        got = gs(*ins).clone()
+        with torch.no_grad():
+            want = gen(*ins)
+        assert torch.equal(got, want), (i, B, T)
+    assert gs.captures == 5 and len(gs._graphs) == 2       # (1,20) was evicted by (3,9) and captured again
+    ins = [x.cuda() for x in O.synthetic_inputs(1, 20, seed=99)]
+    got16 = gs(*ins, out_dtype=torch.int16).clone()         # flags / formats are part of the key
+    with torch.no_grad():
+        assert torch.equal(got16, gen(*ins, out_dtype=torch.int16))
+    with pytest.raises(ValueError):
+        gs(*[x.cpu() for x in ins])

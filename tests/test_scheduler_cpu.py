@@ -177,3 +177,14 @@ def test_sharded_synthesis_gloo_world2():
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert ret[0] is True and ret[1] is True
+
+
+def test_graphed_synthesizer_refuses_cpu_and_caller_buffers():
+    """GraphedSynthesizer (one CUDA graph per request shape) has no CPU path and owns its output buffer."""
+    import pytest
+    from b200voc.scheduler import GraphedSynthesizer
+    gs = GraphedSynthesizer(lambda *a, **k: None)
+    x = [torch.zeros(1, 80, 4), torch.zeros(1, 4, 18), torch.zeros(1, 128), torch.zeros(1, 6)]
+    with pytest.raises(ValueError):
+        gs(*x)
+    assert gs.captures == 0

@@ -182,6 +182,61 @@ class StreamingSynthesizer:
         ev_out[-1].synchronize()             # ... and the host may read host_outs as soon as run() returns
 
 
+class GraphedSynthesizer:
+    """Small requests are launch bound: a B = 1, T = 172 forward (BASELINE configs[0]) is ~0.1 ms of tensor work
+    behind ~16 kernel launches and the host-side argument checks.  This wrapper captures ONE CUDA graph per exact
+    request shape (B, T, out dtype, mel layout) -- the forward never allocates or synchronises after its first call
+    -- and replays it on static device buffers: a call is 4 small device copies + one graph launch.  Shapes are
+    never padded to a bucket (zero mel frames are not the convolution's zero padding, see ``group_by_length``): a
+    serving loop sees few distinct shapes (fixed chunk + halo units of ``synthesize_long``, fixed batch sizes), and
+    the least recently used graph is dropped beyond ``max_graphs``.  The result tensor is the graph's static output
+    buffer: consume or copy it before the next call with the same shape.  Flag arguments (style_drop, ...) are part
+    of the key because they are baked into the captured launches."""
+
+    def __init__(self, gen, max_graphs: int = 16, warmup: int = 2):
+        self.gen, self.max_graphs, self.warmup = gen, int(max_graphs), int(warmup)
+        self._graphs: Dict[tuple, dict] = {}
+        self.captures = 0
+
+    def _capture(self, key, mel, prosody, style, emotion, kw) -> dict:
+        dev = mel.device
+        static = [torch.empty(t.shape, dtype=torch.float32, device=dev) for t in (mel, prosody, style, emotion)]
+        for d, t in zip(static, (mel, prosody, style, emotion)):
+            d.copy_(t)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        out = None
+        with torch.no_grad(), torch.cuda.stream(side):
+            for _ in range(max(1, self.warmup)):          # packing, function attributes, workspace: outside the capture
+                out = self.gen(*static, **kw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph):
+            self.gen(*static, out=out, **kw)
+        self.captures += 1
+        # the captured launches hold raw pointers into the generator's workspace: keep that tensor alive with the graph
+        # (a later, larger request makes the generator allocate a new one; this graph keeps using its own)
+        return dict(graph=graph, static=static, out=out, ws=getattr(self.gen, "_workspace", None))
+
+    def __call__(self, mel, prosody, style, emotion, **kw) -> torch.Tensor:
+        if not mel.is_cuda:
+            raise ValueError("GraphedSynthesizer needs CUDA tensors (there is no CPU path)")
+        if "out" in kw or "frame_lengths" in kw or "_tap" in kw:
+            raise ValueError("GraphedSynthesizer owns the output buffer; out=/frame_lengths=/_tap= are not supported")
+        key = (tuple(mel.shape), tuple(prosody.shape), mel.device.index, tuple(sorted(kw.items())))
+        g = self._graphs.pop(key, None)
+        if g is None:
+            if len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))          # least recently used
+            g = self._capture(key, mel, prosody, style, emotion, kw)
+        self._graphs[key] = g                                        # most recently used last
+        for d, t in zip(g["static"], (mel, prosody, style, emotion)):
+            d.copy_(t, non_blocking=True)
+        g["graph"].replay()
+        return g["out"]
+
+
 # ------------------------------------------------------------------ multi-GPU (one process per GPU)
 def _dist_info(group=None):
     import torch.distributed as dist

@@ -61,6 +61,10 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 // try_wait suspends the warp in hardware but gives up after a short, implementation-defined time, so a long wait is a
 // loop of failed probes; every instruction of that loop is an issue slot taken from a working warp: 8 bare probes per
 // trip (probe + branch each), the watchdog bookkeeping once per trip.
+// ROLE: kernels that re-balance registers between warp groups (setmaxnreg) need one copy per register budget -- ptxas
+// applies the smallest budget of all callers to a shared callee AND to every caller (measured: resblock3 compiled at
+// 56 registers everywhere with one shared copy).
+template <int ROLE>
 #ifndef B200VOC_INLINE_WAIT
 __device__ __noinline__
 #else
@@ -84,9 +88,10 @@ static void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+template <int ROLE = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  mbar_wait_slow(bar, parity);
+  mbar_wait_slow<ROLE>(bar, parity);
 }
 
 // pure polling wait (mbarrier.test_wait, never suspends): lowest wake-up latency, costs issue slots
