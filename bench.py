@@ -356,12 +356,13 @@ def secondary_measurements(dev, dev_in, B, T):
         out["small_request"] = {"error": str(e)[:200]}
     try:
         # SURVEY 8f rank 4 (forward half): the three critics the trainer runs on every waveform
-        # (vocoder7/trainer.py:86-92); first correct CUDA path, fp32 direct convolution
+        # (vocoder7/trainer.py:86-92)
         from b200voc import MultiPeriodDiscriminator, MultiScaleDiscriminator, MultiBandDiscriminator
         Bc, Tc = 4, SR
         wavc = torch.rand(Bc, 1, Tc, device=dev) * 2 - 1
         res = {"batch": Bc, "samples": Tc, "note": "critic forwards (vocoder7/discriminators.py) on 4 x 1 s, all "
-               "feature maps written; fp32 CUDA-core direct convolution (first correct path)"}
+               "feature maps written; MSD's stride-1 64->256 / 256->1024 layers (97 % of the FLOPs) on tcgen05 with split-bf16 "
+               "operands, the narrow / strided layers as fp32 direct convolution"}
         for name, cls in (("mpd", MultiPeriodDiscriminator), ("msd", MultiScaleDiscriminator),
                           ("mbd", MultiBandDiscriminator)):
             torch.manual_seed(1234)

@@ -148,6 +148,20 @@ int b200voc_disc_conv_out_len(int Lin, int K, int stride, int pad);
 int b200voc_disc_conv(const float* x, const float* w, const float* bias, int B, int Cin, int Cout, int Lin, int P,
                       int K, int stride, int pad, int64_t in_batch_stride, int64_t in_valid, float slope,
                       float* y_pre, float* y_act, void* stream);
+/* The same convolution on the tensor cores for the GEMM-shaped layers -- stride 1, P = 1, Cin a multiple of 64, Cout a
+ * multiple of 128, odd K <= 41: MultiScaleDiscriminator's Conv1d(64 -> 256, k) and Conv1d(256 -> 1024, k)
+ * (discriminators.py:71-92, 97 % of the critics' FLOPs).  tcgen05 implicit GEMM with split-bf16 operands
+ * (x = hi + lo, three MMAs per k-step, fp32 accumulation: fp32-level accuracy at bf16 range).  w_split comes from
+ * b200voc_disc_pack_weight_split (bf16 [2][Cout][K*Cin], b200voc_disc_split_weight_elems elements) applied to the
+ * spectral-normalised weight; workspace (b200voc_disc_conv_tc_workspace_bytes, 16-byte aligned) receives the
+ * channels-last split copy of x.  x is fp32 [B, Cin, L]; y_pre / y_act are fp32 [B, Cout, L + 2 pad - K + 1]. */
+int b200voc_disc_conv_tc_supported(int Cin, int Cout, int K, int stride, int P);
+int64_t b200voc_disc_conv_tc_workspace_bytes(int B, int Cin, int L);
+int64_t b200voc_disc_split_weight_elems(int Cout, int Cin, int K);
+int b200voc_disc_pack_weight_split(const float* w, int Cout, int Cin, int K, void* out, void* stream);
+int b200voc_disc_conv_tc(const float* x, const void* w_split, const float* bias, int B, int Cin, int Cout, int L, int K,
+                         int pad, float slope, float* y_pre, float* y_act, void* workspace, int64_t workspace_bytes,
+                         void* stream);
 /* torch.nn.utils.spectral_norm as the reference wraps every critic conv (discriminators.py:21-31, 76-89,
  * 125-138), evaluation mode (no power iteration): w_out = w_orig / sigma, sigma = u . (W v) with W = w_orig viewed
  * as [rows = Cout][cols = Cin*K(*1)].  sigma_out: one device float. */

@@ -126,3 +126,48 @@ def test_critic_errors_and_weight_cache():
         r, _ = O.critic_forward("msd", sd, O.OracleConfig(disc_kernel_sizes=[5, 5, 5]), x.cpu())
     _close(b[0], r[0], "after in-place weight update")
     assert a[0].shape == b[0].shape
+
+
+@pytest.mark.parametrize("B,Cin,Cout,L,K", [(2, 64, 256, 300, 15), (1, 256, 128, 130, 41), (3, 64, 128, 1, 15),
+                                            (1, 128, 256, 129, 41), (2, 256, 1024, 345, 41), (1, 64, 128, 127, 1)])
+def test_disc_conv_tensor_core_layer_matches_fp64(B, Cin, Cout, L, K):
+    """b200voc_disc_conv_tc (tcgen05 implicit GEMM, split-bf16 operands) through the C ABI against fp64 conv1d and against
+    the fp32 CUDA-core kernel it replaces: ragged lengths (L = 1, 127, 129, 130: tiles that end inside / just past a
+    128-row block), both kernel sizes of the reference (15, 41), the largest layer shape (256 -> 1024), large-magnitude
+    weights (a fresh spectral norm divides by sigma ~ 1e-3).  Bound: 6e-5 of the map's scale -- operands carry 16
+    significant bits (bf16 hi + lo, the lo.lo product dropped), a third of the critics' 2e-4 feature tolerance."""
+    import ctypes as C
+    from b200voc import _lib
+    lib = _lib.load()
+    assert lib.b200voc_disc_conv_tc_supported(Cin, Cout, K, 1, 1) == 1
+    assert lib.b200voc_disc_conv_tc_supported(Cin, Cout, K, 2, 1) == 0 and lib.b200voc_disc_conv_tc_supported(16, Cout, K, 1, 1) == 0
+    g = torch.Generator().manual_seed(Cin + L + K)
+    x = (torch.randn(B, Cin, L, generator=g) * 3.0)
+    w = torch.randn(Cout, Cin, K, generator=g) * 40.0 / (Cin * K) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    pad = K // 2
+    ref = torch.nn.functional.conv1d(x.double(), w.double(), b.double(), padding=pad)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    wsplit = torch.empty(int(lib.b200voc_disc_split_weight_elems(Cout, Cin, K)), device="cuda", dtype=torch.bfloat16)
+    st = _lib.current_stream()
+    _lib.check(lib.b200voc_disc_pack_weight_split(_lib.ptr(wd), Cout, Cin, K, _lib.ptr(wsplit), st))
+    ws = torch.empty(int(lib.b200voc_disc_conv_tc_workspace_bytes(B, Cin, L)), device="cuda", dtype=torch.uint8)
+    y_pre = torch.full((B, Cout, L), float("nan"), device="cuda")
+    y_act = torch.full((B, Cout, L), float("nan"), device="cuda")
+    _lib.check(lib.b200voc_disc_conv_tc(_lib.ptr(xd), _lib.ptr(wsplit), _lib.ptr(bd), B, Cin, Cout, L, K, pad, 0.2,
+                                        _lib.ptr(y_pre), _lib.ptr(y_act), _lib.ptr(ws), ws.numel(), st))
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    err = float((y_pre.cpu().double() - ref).abs().max())
+    assert err <= 6e-5 * scale, f"conv map: {err:.3e} vs scale {scale:.3e}"
+    err_a = float((y_act.cpu().double() - torch.nn.functional.leaky_relu(ref, 0.2)).abs().max())
+    assert err_a <= 6e-5 * scale
+    # the fp32 CUDA-core kernel on the same inputs (the path B200VOC_DISC_TC=0 keeps)
+    y2 = torch.empty_like(y_pre)
+    _lib.check(lib.b200voc_disc_conv(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(bd), B, Cin, Cout, L, 1, K, 1, pad, 0, 0, 0.2,
+                                     _lib.ptr(y2), None, st))
+    torch.cuda.synchronize()
+    assert float((y2 - y_pre).abs().max()) <= 6e-5 * scale
+    # argument validation: loud, not silent
+    assert lib.b200voc_disc_conv_tc(_lib.ptr(xd), _lib.ptr(wsplit), _lib.ptr(bd), B, Cin, Cout, L, K, pad, 0.2,
+                                    _lib.ptr(y_pre), _lib.ptr(y_act), _lib.ptr(ws), 16, st) == _lib.ERR_BAD_ARG

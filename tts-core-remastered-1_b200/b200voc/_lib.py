@@ -54,6 +54,11 @@ _SIGNATURES = {
     "b200voc_gst_forward": (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "b200voc_disc_conv_out_len": (C.c_int, [_I, _I, _I, _I]),
     "b200voc_disc_conv": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _F, _P, _P, _P]),
+    "b200voc_disc_conv_tc_supported": (C.c_int, [_I, _I, _I, _I, _I]),
+    "b200voc_disc_conv_tc_workspace_bytes": (C.c_int64, [_I, _I, _I]),
+    "b200voc_disc_split_weight_elems": (C.c_int64, [_I, _I, _I]),
+    "b200voc_disc_pack_weight_split": (C.c_int, [_P, _I, _I, _I, _P, _P]),
+    "b200voc_disc_conv_tc": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I64, _P]),
     "b200voc_spectral_norm_weight": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "b200voc_avg_pool1d_k4s2p1": (C.c_int, [_P, _I64, _I, _P, _P]),
     "b200voc_gen_launch_count": (C.c_int, [_P]),

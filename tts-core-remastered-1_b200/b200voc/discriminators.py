@@ -47,6 +47,12 @@ def _stack(n_hidden: int, k: int, strides: Sequence[int], two_d: bool) -> Tuple[
     return nn.Sequential(*mods), specs
 
 
+def _tc_enabled() -> bool:
+    """B200VOC_DISC_TC=0 keeps every layer on the fp32 CUDA-core kernel (A/B runs)."""
+    import os
+    return os.environ.get("B200VOC_DISC_TC", "1") != "0"
+
+
 class _CriticBase(nn.Module):
     """Parameter container + the layer walker shared by the three critics."""
 
@@ -87,7 +93,17 @@ class _CriticBase(nn.Module):
             _lib.check(lib.b200voc_spectral_norm_weight(_lib.ptr(w0), _lib.ptr(u), _lib.ptr(v), rows, cols,
                                                         _lib.ptr(w), _lib.ptr(sigma), _lib.current_stream()),
                        "spectral_norm_weight")
-            out.append((w, b))
+            # GEMM-shaped layers (stride 1, wide) run on the tensor cores with split-bf16 operands: pack [hi | lo] once
+            wsplit = None
+            cout, cin, k = int(w0.shape[0]), int(w0.shape[1]), int(w0.shape[2])
+            st = c.stride[0]
+            P1 = w0.dim() == 3
+            if (_tc_enabled() and P1 and lib.b200voc_disc_conv_tc_supported(cin, cout, k, int(st), 1)):
+                wsplit = torch.empty(int(lib.b200voc_disc_split_weight_elems(cout, cin, k)), device=w0.device,
+                                     dtype=torch.bfloat16)
+                _lib.check(lib.b200voc_disc_pack_weight_split(_lib.ptr(w), cout, cin, k, _lib.ptr(wsplit),
+                                                              _lib.current_stream()), "disc_pack_weight_split")
+            out.append((w, b, wsplit))
         self._wcache[d] = (key, out)
         return out
 
@@ -98,16 +114,23 @@ class _CriticBase(nn.Module):
         lib = _lib.load()
         maps: List[torch.Tensor] = []
         cur_ptr, cur_L, stride_b, valid = x_ptr, Lin, in_batch_stride, in_valid
-        for (cin, cout, k, st, pad, act), (w, b) in zip(self._specs[d], self._weights(d)):
+        for (cin, cout, k, st, pad, act), (w, b, wsplit) in zip(self._specs[d], self._weights(d)):
             Lout = int(lib.b200voc_disc_conv_out_len(cur_L, k, st, pad))
             if Lout <= 0:
                 raise ValueError(f"discriminator input of {cur_L} samples is shorter than the kernel ({k})")
             shape = (B, cout, Lout, P) if two_d else (B, cout, Lout)
             y_pre = torch.empty(shape, device=device, dtype=torch.float32)
             y_act = torch.empty(shape, device=device, dtype=torch.float32) if act else None
-            _lib.check(lib.b200voc_disc_conv(cur_ptr, _lib.ptr(w), _lib.ptr(b), B, cin, cout, cur_L, P, k, st, pad,
-                                             stride_b, valid, LRELU_SLOPE, _lib.ptr(y_pre), _lib.ptr(y_act),
-                                             _lib.current_stream()), "disc_conv")
+            if wsplit is not None and P == 1 and stride_b == 0:
+                ws = torch.empty(int(lib.b200voc_disc_conv_tc_workspace_bytes(B, cin, cur_L)), device=device,
+                                 dtype=torch.uint8)
+                _lib.check(lib.b200voc_disc_conv_tc(cur_ptr, _lib.ptr(wsplit), _lib.ptr(b), B, cin, cout, cur_L, k, pad,
+                                                    LRELU_SLOPE, _lib.ptr(y_pre), _lib.ptr(y_act), _lib.ptr(ws),
+                                                    ws.numel(), _lib.current_stream()), "disc_conv_tc")
+            else:
+                _lib.check(lib.b200voc_disc_conv(cur_ptr, _lib.ptr(w), _lib.ptr(b), B, cin, cout, cur_L, P, k, st, pad,
+                                                 stride_b, valid, LRELU_SLOPE, _lib.ptr(y_pre), _lib.ptr(y_act),
+                                                 _lib.current_stream()), "disc_conv")
             maps.append(y_pre)
             if act:
                 maps.append(y_act)

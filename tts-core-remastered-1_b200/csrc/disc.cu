@@ -165,6 +165,46 @@ __global__ void __launch_bounds__(kDcThreads) disc_conv_s1_kernel(const DiscConv
   }
 }
 
+// Score layer: Conv(C -> 1, k3, stride 1) at the end of every critic stack (discriminators.py:27-31, 85-89, 134-138):
+// one output channel, i.e. a reduction over Cin x K per position -- the generic kernel gives it ONE thread per position
+// (0.79 ms for MSD's 1024-channel map).  Here a CTA owns 64 positions and 16 channel groups split the
+// input channels (reads stay coalesced along time); partial sums are combined in shared memory in a fixed order
+// (deterministic).
+constexpr int kC1Pos = 64, kC1Groups = 16;
+__global__ void __launch_bounds__(kC1Pos * kC1Groups) disc_conv_cout1_kernel(const DiscConvParams p) {
+  __shared__ float part[kC1Groups][kC1Pos];
+  const int px = threadIdx.x & (kC1Pos - 1), cg = threadIdx.x / kC1Pos, b = blockIdx.z;
+  const long long pos = (long long)blockIdx.x * kC1Pos + px;          // flattened (lo, column)
+  const bool active = pos < (long long)p.Lout * p.P;
+  const int lo = active ? (int)(pos / p.P) : 0, col = active ? (int)(pos - (long long)lo * p.P) : 0;
+  const long long chan_stride = (long long)p.Lin * p.P;
+  const float* xb = p.x + (long long)b * p.in_batch_stride;
+  float acc = 0.f;
+  if (active) {
+    for (int ci = cg; ci < p.Cin; ci += kC1Groups) {
+      const float* xc = xb + (long long)ci * chan_stride;
+      const float* wr = p.w + (long long)ci * p.K;
+      for (int k = 0; k < p.K; ++k) {
+        const int li = lo - p.pad + k;
+        if (li >= 0 && li < p.Lin) {
+          const long long idx = (long long)li * p.P + col;
+          if (idx < p.in_valid) acc = fmaf(__ldg(xc + idx), __ldg(wr + k), acc);
+        }
+      }
+    }
+  }
+  part[cg][px] = acc;
+  __syncthreads();
+  if (cg == 0 && active) {
+    float y = __ldg(p.bias);
+#pragma unroll
+    for (int g = 0; g < kC1Groups; ++g) y += part[g][px];
+    const long long o = (long long)b * p.Lout * p.P + pos;
+    if (p.y_pre) p.y_pre[o] = y;
+    if (p.y_act) p.y_act[o] = y > 0.f ? y : p.slope * y;
+  }
+}
+
 template <int CO>
 static int launch_disc_conv(const DiscConvParams& p, cudaStream_t st) {
   const long long npos = (long long)p.Lout * p.P;
@@ -181,6 +221,13 @@ static bool disc_s1_enabled() {
   return on;
 }
 int disc_conv_launch(const DiscConvParams& p, cudaStream_t st) {
+  if (p.Cout == 1 && p.stride == 1 && p.Cin >= 64 && disc_s1_enabled()) {
+    const long long npos = (long long)p.Lout * p.P;
+    dim3 grid((unsigned)((npos + kC1Pos - 1) / kC1Pos), 1, (unsigned)p.B);
+    disc_conv_cout1_kernel<<<grid, kC1Pos * kC1Groups, 0, st>>>(p);
+    B200_CUDA(cudaGetLastError());
+    return B200VOC_OK;
+  }
   if (p.stride == 1 && p.P == 1 && p.Cout >= 16 && disc_s1_enabled()) {
     constexpr int CO = 16;
     const size_t smem = (size_t)kDcCi * p.K * CO * sizeof(float);
