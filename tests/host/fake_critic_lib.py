@@ -22,6 +22,9 @@ class FakeCriticLib:
     def b200voc_last_error_string(self):
         return b"fake"
 
+    def b200voc_disc_conv_tc_supported(self, Cin, Cout, K, stride, P):
+        return 0          # the stand-in has no tensor-core path: the walker must fall back to b200voc_disc_conv
+
     def b200voc_disc_conv_out_len(self, Lin, K, stride, pad):
         if Lin <= 0 or K <= 0 or stride <= 0 or pad < 0 or Lin + 2 * pad < K:
             return 0
