@@ -45,7 +45,7 @@ constexpr int kColPV = 256;    // PV[2]: 2 x 64 columns
 constexpr int kColF = 384;     // out-projection accumulator: 64 columns
 
 template <int FMT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmVt,
                  const __grid_constant__ CUtensorMap tmWo, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -167,8 +167,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       umma_commit(f_full);
     }
   } else {
-    // ------------------------------------------------------------ softmax / accumulate warps 2..5
-    const int q = warp & 3;
+    // ------------------------------------------------------------ softmax / accumulate warps 2..9: TWO groups of four
+    // warps (one thread per query row each).  Group g owns the key tiles j = g, g+2, ... -- i.e. always S / P / PV
+    // buffer g -- and keeps its own running (max, sum, output): with one group the kernel was bound by the latency of
+    // one warp per scheduler walking ~700 dependent instructions per key tile (2 k clk against 640 clk of MMAs); two
+    // groups overlap the softmax of tile j+1 with that of tile j.  The two partial results are merged once at the
+    // end (the usual rescale by 2^(m_g - m)).
+    const int q = warp & 3, g = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     float o_acc[kD];
@@ -192,8 +197,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       mbar_arrive(&o_empty[b]);
     };
 
-    for (int j = 0; j < nkt; ++j) {
-      const int b = j & 1;
+    int jprev = -1;
+    for (int j = g; j < nkt; j += 2) {
+      const int b = g;                                   // == j & 1
       const uint32_t ph = (j >> 1) & 1;
       mbar_wait(&s_full[b], ph);
       tc_fence_after();
@@ -239,11 +245,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       mbar_arrive(&s_empty[b]);
       l_run = l_run * alpha + l_tile;
       m_run = m_new;
-      // fold the previous tile's P V product into the running output (its alpha was computed last turn)
-      if (j >= 1) accumulate_pv(j - 1, alpha_prev);
+      // fold this group's previous tile's P V product into the running output (its alpha was computed last turn)
+      if (jprev >= 0) accumulate_pv(jprev, alpha_prev);
       alpha_prev = alpha;
+      jprev = j;
     }
-    accumulate_pv(nkt - 1, alpha_prev);
+    if (jprev >= 0) accumulate_pv(jprev, alpha_prev);
+
+    // ---- merge the two groups' partial results through the (now idle) K / V ring: every MMA has completed once both
+    // groups are past their last o_full
+    float* xch = reinterpret_cast<float*>(sK) + row * 67;         // [128][67]: o[64], m, l (34 KB <= the 64 KB ring)
+    named_bar_sync(2, 256);
+    if (g == 1) {
+#pragma unroll
+      for (int i = 0; i < kD; ++i) xch[i] = o_acc[i];
+      xch[64] = m_run;
+      xch[65] = l_run;
+    }
+    named_bar_sync(2, 256);
+    if (g == 0) {                                                 // group 0 finishes the tile
+    {
+      const float m1 = xch[64], l1 = xch[65];
+      const float m = fmaxf(m_run, m1);
+      const float a0 = ex2_approx(m_run - m), a1 = ex2_approx(m1 - m);   // m1 = -inf (no odd tile): a1 = 0
+      l_run = l_run * a0 + l1 * a1;
+#pragma unroll
+      for (int i = 0; i < kD; ++i) o_acc[i] = o_acc[i] * a0 + xch[i] * a1;
+    }
 
     // ---- tail: normalise, stage as the A operand of the out projection (reuses P buffer 0)
     // (o_full of the last tile was committed after every earlier MMA, so both P buffers are free here)
@@ -284,6 +312,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         }
         dst[c * 4 + i8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
+    }
     }
   }
   tc_fence_before();
@@ -343,8 +372,8 @@ int attention_launch(const void* x16, const void* wqkv, const float* bqkv, const
     configured[dev & 15] = true;
   }
   dim3 grid(L / 128, N);
-  if (fmt == 0) attention_kernel<0><<<grid, 192, kAttnSmem, st>>>(tmQKV, tmVt, tmWo, p);
-  else attention_kernel<1><<<grid, 192, kAttnSmem, st>>>(tmQKV, tmVt, tmWo, p);
+  if (fmt == 0) attention_kernel<0><<<grid, 320, kAttnSmem, st>>>(tmQKV, tmVt, tmWo, p);
+  else attention_kernel<1><<<grid, 320, kAttnSmem, st>>>(tmQKV, tmVt, tmWo, p);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
