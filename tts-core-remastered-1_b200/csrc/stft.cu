@@ -169,12 +169,19 @@ stft1024_kernel(const StftParams p) {
   constexpr int NFFT = 1024, N = 512, BINS = 513, SW = kFastWarps + 1;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int span_len = (kFastWarps - 1) * p.hop + NFFT;
+  // The staged outputs [BINS][SW] share their storage with the round's samples (dead once every warp holds its frame
+  // in registers; one more __syncthreads per round): 79 -> 68 KB per CTA, i.e. three resident CTAs per SM instead of
+  // two.  MODE_L1 reads a second span while the first pass's outputs are staged, so it keeps both.
+  constexpr bool ALIAS = MODE != MODE_L1;
+  constexpr int STAGE_BYTES = BINS * SW * (MODE == MODE_COMPLEX ? 8 : 4);
+  const int span_bytes = ((span_len + 3) & ~3) * 4;
+  const int head_bytes = ALIAS ? (((span_bytes > STAGE_BYTES ? span_bytes : STAGE_BYTES) + 15) & ~15) : span_bytes;
   float* span = reinterpret_cast<float*>(smem_raw);                              // one round's samples
-  float2* tw2 = reinterpret_cast<float2*>(span + ((span_len + 3) & ~3));         // [N + 1] (padded to N + 2)
+  float2* tw2 = reinterpret_cast<float2*>(smem_raw + head_bytes);                // [N + 1] (padded to N + 2)
   float2* win2 = tw2 + (N + 2);                                                  // [N] window pairs (w[2n], w[2n+1])
   float2* tw1 = win2 + N;                                                        // [16][32] W_512^(lane*k1)
   float2* wbuf = tw1 + 512;                                                      // [warps][576]
-  float* stage = reinterpret_cast<float*>(wbuf + kFastWarps * 576);              // [BINS][SW]
+  float* stage = ALIAS ? reinterpret_cast<float*>(smem_raw) : reinterpret_cast<float*>(wbuf + kFastWarps * 576);   // [BINS][SW]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   float2* T = wbuf + warp * 576;       // 16 x 33 transpose scratch, later Z[512] linear (padded)
@@ -224,6 +231,7 @@ stft1024_kernel(const StftParams p) {
         else wn = win2[n1 * 32 + lane];
         v[n1] = make_float2(x.x * wn.x, x.y * wn.y);
       }
+      if constexpr (ALIAS) __syncthreads();              // every warp has its frame: the span's storage becomes the stage
       if constexpr (REGTAB) warp_fft512_regtw<false>(v, T, treg, lane);
       else warp_fft512<false>(v, T, tw1, lane);
       // Z -> linear per-warp buffer (reusing the transpose scratch), then the real-FFT split
@@ -312,8 +320,9 @@ stft1024_kernel(const StftParams p) {
 template <int MODE>
 static int launch_stft1024(const StftParams& p, cudaStream_t st) {
   const int span_len = (kFastWarps - 1) * p.hop + 1024;
-  const size_t smem = (size_t)((span_len + 3) & ~3) * 4 + 514 * 8 + 512 * 8 + 512 * 8 + (size_t)kFastWarps * 576 * 8 +
-                      (size_t)513 * (kFastWarps + 1) * (MODE == MODE_COMPLEX ? 8 : 4) + 64;
+  const size_t span_bytes = (size_t)((span_len + 3) & ~3) * 4, stage_bytes = (size_t)513 * (kFastWarps + 1) * (MODE == MODE_COMPLEX ? 8 : 4);
+  const size_t head = MODE != MODE_L1 ? (((span_bytes > stage_bytes ? span_bytes : stage_bytes) + 15) & ~(size_t)15) : span_bytes + stage_bytes;
+  const size_t smem = head + 514 * 8 + 512 * 8 + 512 * 8 + (size_t)kFastWarps * 576 * 8 + 64;
   B200_CHECK_ARG(smem <= 227 * 1024, "stft: hop %d needs %zu bytes of shared memory", p.hop, smem);
   dim3 grid(ceil_div(p.frames, kFastWarps * kFastRounds), p.B);
   static const bool regtab = [] { const char* e = getenv("B200VOC_STFT_REGTAB"); return e && e[0] == '1'; }();
