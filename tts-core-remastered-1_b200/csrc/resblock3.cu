@@ -56,6 +56,9 @@ struct Resblock3Params {
 #endif
 extern long long* g_rb2_trace;
 
+#ifndef RB3_BIAS_MMA
+#define RB3_BIAS_MMA 1
+#endif
 template <int C, bool PAIR>
 struct Rb3Cfg {
   static constexpr int KPT = C / 64;                 // k-blocks per tap = GEMM1 chunks = GEMM2 k-blocks
@@ -88,8 +91,20 @@ struct Rb3Cfg {
   static constexpr int OFF_W = OFF_H + KPT * H_KB_BYTES;
   static constexpr int OFF_BAR = OFF_W + NW * W_SLOT;
   static constexpr int OFF_PAR = OFF_BAR + 512;
+  // BIAS_MMA: the three bias vectors are added on the tensor core -- one more K = 16 MMA per accumulator whose A
+  // operand is an all-ones tile and whose B operand carries (b/2)_hi, (b/2)_lo in two K columns (both K core matrices
+  // alias the same block, so the product is 2 (b/2) = b at hi + lo precision).  The epilogues' broadcast
+  // shared-memory loads of the biases were half of their LDS traffic (a broadcast LDS.128 costs four wavefronts) in
+  // a kernel whose shared-memory pipe is ~72 % busy (33 % tensor-core operand reads + 38 % LSU, ncu).
+  static constexpr bool BIAS_MMA = RB3_BIAS_MMA != 0 && PAIR;        // (the single-CTA fallback has no room for the tiles)
+  static constexpr int B_ROWS = W_ROWS;                     // bias-tile rows this CTA supplies per 128 GEMM columns
+  static constexpr int BIAS_TILE = B_ROWS * 16;             // one K core matrix column: [rows][8 x 16 bit]
+  static constexpr int N_BIAS_TILES = NCH + NH;             // GEMM1 chunks, then GEMM2 halves
+  static constexpr int OFF_ONES = OFF_PAR;                  // 128 bytes of 1.0 (BIAS_MMA: replaces the fp32 bias block)
+  static constexpr int OFF_BIAS = OFF_ONES + 128;
+  static constexpr int PAR_BYTES = BIAS_MMA ? 128 + N_BIAS_TILES * BIAS_TILE : 3 * C * 4;
   static_assert((2 * NA + 2 * NW + 4 + 2 * KPT + 2 * (C == 128 ? 2 : 1) + NA) * 8 + 8 <= 512, "barrier block");
-  static constexpr int OFF_FILM = OFF_PAR + 3 * C * 4;    // per GLU warp: (1+scale | shift) of its 32 channels of a chunk
+  static constexpr int OFF_FILM = OFF_PAR + PAR_BYTES;    // per GLU warp: (1+scale | shift) of its 32 channels of a chunk
   static constexpr int SMEM = OFF_FILM + 8 * 64 * 4 + 1024;
   static constexpr int D2_COL = 256;
   static constexpr uint32_t TMEM_COLS = 512;
@@ -133,10 +148,32 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   constexpr int kE1Warps = 8;                           // both GLU warp sets share every chunk (32 channels each)
   constexpr int kE2Warps = K::INPLACE ? 4 : 8;          // tile-parity set, or all 8 warps (C=256)
 
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    sPar[i] = 0.5f * p.b_conv[i];              // W1 is packed pre-scaled by 1/2 (see pack_resblock_kernel)
-    sPar[C + i] = 0.5f * p.b_conv[C + i];
-    sPar[2 * C + i] = p.b_proj[i];
+  if (!K::BIAS_MMA) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      sPar[i] = 0.5f * p.b_conv[i];              // W1 is packed pre-scaled by 1/2 (see pack_resblock_kernel)
+      sPar[C + i] = 0.5f * p.b_conv[C + i];
+      sPar[2 * C + i] = p.b_proj[i];
+    }
+  } else {
+    // all-ones A block and the bias B tiles (SWIZZLE_NONE K-major core matrices: 8 rows x 16 bytes, 8-row groups 128
+    // bytes apart).  Tile t < NCH: GEMM1 chunk t, GEMM column n <-> value channel 64 t + n (n < 64) or gate channel
+    // 64 t + n - 64; tile NCH + h: GEMM2 output channels 128 h + n.  A pair CTA supplies columns rank*64 .. +63.
+    uint16_t* ones = reinterpret_cast<uint16_t*>(smem + K::OFF_ONES);
+    uint32_t* bt = reinterpret_cast<uint32_t*>(smem + K::OFF_BIAS);
+    const uint32_t rank_s = PAIR ? cluster_ctarank() : 0;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) ones[i] = FMT == 0 ? 0x3C00 : 0x3F80;
+    for (int i = threadIdx.x; i < K::N_BIAS_TILES * K::B_ROWS; i += blockDim.x) {
+      const int t = i / K::B_ROWS, r = i - t * K::B_ROWS;
+      const int n = (PAIR ? (int)rank_s * 64 : 0) + r;
+      float bv;
+      if (t < K::NCH) bv = 0.25f * (n < 64 ? p.b_conv[t * 64 + n] : p.b_conv[C + t * 64 + n - 64]);   // (b / 2) / 2: W1 is pre-scaled by 1/2
+      else bv = 0.5f * p.b_proj[(t - K::NCH) * 128 + n];
+      const float lo = bv - unpack2t<FMT>(pack2t<FMT>(bv, 0.f)).x;
+      uint32_t* row = bt + (t * K::BIAS_TILE >> 2) + r * 4;
+      row[0] = pack2t<FMT>(bv, lo);
+      row[1] = 0u; row[2] = 0u; row[3] = 0u;
+    }
+    fence_proxy_async_smem();
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -265,6 +302,15 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       auto commit = [&](uint64_t* bar) {
         if (PAIR) umma_commit_2cta(bar, 0x3); else umma_commit(bar);      // PAIR: same barrier in both CTAs
       };
+      // bias MMA: D += ones[rows x 16] * bias_tile[128 x 16]^T.  SWIZZLE_NONE K-major descriptors (layout 0, version
+      // 1): the all-ones block is ONE 128-byte core matrix (LBO = SBO = 0: every core matrix of the operand aliases
+      // it); the bias tile's 8-row groups are 128 bytes apart (SBO) and both K core matrices alias (LBO = 0)
+      const uint64_t ones_desc = (uint64_t)((smem_u32(smem + K::OFF_ONES) & 0x3FFFFu) >> 4) | (1ull << 46);
+      auto bias_mma = [&](uint32_t d, int tile) {
+        const uint64_t b_desc = (uint64_t)((smem_u32(smem + K::OFF_BIAS + tile * K::BIAS_TILE) & 0x3FFFFu) >> 4) |
+                                ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+        if (PAIR) umma_f16_2cta(d, ones_desc, b_desc, idesc, 1); else umma_f16(d, ones_desc, b_desc, idesc, 1);
+      };
       auto wait_x = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };   // (barriers with remote arrivals)
       int wi = 0;
       // The weight-ring wait is software pipelined: while the MMAs of slot wi are being issued, a
@@ -319,7 +365,13 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         if (elect_one()) {
           commit(&h_empty[kb]);
-          if (kb == NCH - 1) commit(&d2_full[db]);
+          if (kb == NCH - 1) {
+            if (K::BIAS_MMA) {
+#pragma unroll
+              for (int half = 0; half < NH; ++half) bias_mma(tmem_base + K::D2_COL + db * C + half * 128, NCH + half);
+            }
+            commit(&d2_full[db]);
+          }
         }
         __syncwarp();
       };
@@ -360,6 +412,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             ++wi;
           }
           if (elect_one()) {
+            if (K::BIAS_MMA) bias_mma(tmem_base + b * 128, j);
             commit(&d1_full[b]);
             if (!K::INPLACE && j == NCH - 1) commit(&a_empty[ab]);        // INPLACE: released by the store epilogue
           }
@@ -456,7 +509,8 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
             for (int h4 = 0; h4 < 2; ++h4) {
               const int i4 = i8 * 2 + h4;
-              const float4 A = sBA[(ch >> 2) + i4], G = sNB[(ch >> 2) + i4];
+              float4 A = make_float4(0.f, 0.f, 0.f, 0.f), G = A;            // BIAS_MMA: already in the accumulator
+              if (!K::BIAS_MMA) { A = sBA[(ch >> 2) + i4]; G = sNB[(ch >> 2) + i4]; }
               const float av[4] = {A.x, A.y, A.z, A.w}, gv[4] = {G.x, G.y, G.z, G.w};
               const float sv[4] = {S[i4].x, S[i4].y, S[i4].z, S[i4].w}, tv[4] = {H[i4].x, H[i4].y, H[i4].z, H[i4].w};
 #pragma unroll
@@ -518,7 +572,8 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
         for (int i8 = 0; i8 < 2; ++i8) {
           const uint32_t xw[4] = {xa[i8].x, xa[i8].y, xa[i8].z, xa[i8].w};
-          const float4 B0 = sB2[(c0 >> 2) + i8 * 2], B1 = sB2[(c0 >> 2) + i8 * 2 + 1];
+          float4 B0 = make_float4(0.f, 0.f, 0.f, 0.f), B1 = B0;           // BIAS_MMA: already in the accumulator
+          if (!K::BIAS_MMA) { B0 = sB2[(c0 >> 2) + i8 * 2]; B1 = sB2[(c0 >> 2) + i8 * 2 + 1]; }
           const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
           uint32_t ow[4];
 #pragma unroll
@@ -584,7 +639,8 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int i8 = 0; i8 < 2; ++i8) {
             const uint4 xv = xa[((c0 - cp) >> 3) + i8];
             const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-            const float4 B0 = sB2[(c0 >> 2) + i8 * 2], B1 = sB2[(c0 >> 2) + i8 * 2 + 1];
+            float4 B0 = make_float4(0.f, 0.f, 0.f, 0.f), B1 = B0;         // BIAS_MMA: already in the accumulator
+            if (!K::BIAS_MMA) { B0 = sB2[(c0 >> 2) + i8 * 2]; B1 = sB2[(c0 >> 2) + i8 * 2 + 1]; }
             const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
             uint32_t ow[4];
 #pragma unroll
