@@ -515,8 +515,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               const float sv[4] = {S[i4].x, S[i4].y, S[i4].z, S[i4].w}, tv[4] = {H[i4].x, H[i4].y, H[i4].z, H[i4].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float a = __uint_as_float(va[i4 * 4 + e]) + av[e];                  // (conv_a + b_a) / 2
-                const float gg = __uint_as_float(vg[i4 * 4 + e]) + gv[e];
+                // (x + 0.0f is not a no-op for the compiler: -0 + 0 = +0, so the adds are selected away explicitly)
+                const float a = K::BIAS_MMA ? __uint_as_float(va[i4 * 4 + e]) : __uint_as_float(va[i4 * 4 + e]) + av[e];   // (conv_a + b_a) / 2
+                const float gg = K::BIAS_MMA ? __uint_as_float(vg[i4 * 4 + e]) : __uint_as_float(vg[i4 * 4 + e]) + gv[e];
                 const float th = RB3_DBG(64) ? gg : tanh_approx(gg);                        // tanh(g / 2)
                 hv[h4 * 4 + e] = fmaf(fmaf(a, th, a), sv[e], tv[e]);                      // a sigmoid(g) (1+scale) + shift
               }
@@ -579,8 +580,8 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
           for (int e2 = 0; e2 < 4; ++e2) {
             const float2 xs = unpack2t<FMT>(xw[e2]);
-            float y0 = (lrelu_inv_fast(xs.x) + bv[e2 * 2]) + __uint_as_float(vd[i8 * 8 + e2 * 2]);
-            float y1 = (lrelu_inv_fast(xs.y) + bv[e2 * 2 + 1]) + __uint_as_float(vd[i8 * 8 + e2 * 2 + 1]);
+            float y0 = (K::BIAS_MMA ? lrelu_inv_fast(xs.x) : lrelu_inv_fast(xs.x) + bv[e2 * 2]) + __uint_as_float(vd[i8 * 8 + e2 * 2]);
+            float y1 = (K::BIAS_MMA ? lrelu_inv_fast(xs.y) : lrelu_inv_fast(xs.y) + bv[e2 * 2 + 1]) + __uint_as_float(vd[i8 * 8 + e2 * 2 + 1]);
             if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
             ow[e2] = pack2t<OFMT>(y0, y1);
           }
@@ -646,8 +647,8 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
             for (int e2 = 0; e2 < 4; ++e2) {
               const float2 xs = unpack2t<FMT>(xw[e2]);
-              float y0 = (lrelu_inv_fast(xs.x) + bv[e2 * 2]) + __uint_as_float(vd[i8 * 8 + e2 * 2]);
-              float y1 = (lrelu_inv_fast(xs.y) + bv[e2 * 2 + 1]) + __uint_as_float(vd[i8 * 8 + e2 * 2 + 1]);
+              float y0 = (K::BIAS_MMA ? lrelu_inv_fast(xs.x) : lrelu_inv_fast(xs.x) + bv[e2 * 2]) + __uint_as_float(vd[i8 * 8 + e2 * 2]);
+              float y1 = (K::BIAS_MMA ? lrelu_inv_fast(xs.y) : lrelu_inv_fast(xs.y) + bv[e2 * 2 + 1]) + __uint_as_float(vd[i8 * 8 + e2 * 2 + 1]);
               if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
               ow[e2] = pack2t<OFMT>(y0, y1);
             }

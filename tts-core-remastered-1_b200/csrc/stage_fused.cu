@@ -83,6 +83,9 @@ extern long long* g_rb2_trace;
 
 enum { SF_OUT_LRELU = 0, SF_OUT_RAW = 1, SF_OUT_MERGE = 2 };
 
+#ifndef SF_BIAS_MMA
+#define SF_BIAS_MMA 1
+#endif
 template <int C, bool IN_CT, int NBLK, int OUT, int NCTX>
 struct SfCfg {
   static constexpr int ROWB = 2 * C;                  // bytes per X row = swizzle span (64 / 128)
@@ -115,7 +118,15 @@ struct SfCfg {
   static constexpr int OFF_Z = OFF_IN + (IN_CT ? NSLOT * IN_CHUNK_BYTES : 0);
   static constexpr int OFF_FILM = OFF_Z + (OUT == SF_OUT_MERGE ? 7 * R * 4 : 0);
   static constexpr int OFF_PAR = OFF_FILM + 16 * 512;                       // per epilogue warp: 2 frames x (S | T) x 32 ch of the current block
-  static constexpr int OFF_BAR = OFF_PAR + (C + NBLK * 3 * C) * 4;
+  // BIAS_MMA (as in resblock3.cu): biases are added on the tensor core by one more K = 16 MMA per accumulator -- A = an
+  // all-ones block (one aliased 128-byte core matrix), B = [b/2 hi, b/2 lo, 0 ...] per GEMM column (both K core
+  // matrices alias, so the sum is b) -- and leave the epilogues, which are instruction-issue bound: 3 of the 7.4
+  // instructions per element of the GLU epilogue and 1.3 of the 8.7 of epilogue 2 were bias loads / adds.
+  static constexpr bool BIAS_MMA = SF_BIAS_MMA != 0;
+  static constexpr int OFF_ONES = OFF_PAR;                                  // [128 B ones][ConvT tile 2C x 16 B][per block: GEMM1 2C x 16 B, GEMM2 C x 16 B]
+  static constexpr int BT_CT = 128, BT_BLK0 = BT_CT + 2 * C * 16, BT_BLK = 3 * C * 16;
+  static constexpr int PAR_BYTES = BIAS_MMA ? BT_BLK0 + NBLK * BT_BLK : (C + NBLK * 3 * C) * 4;
+  static constexpr int OFF_BAR = (OFF_PAR + PAR_BYTES + 15) & ~15;
   static constexpr int NBARS = 1 + 2 * NSLOT + NCTX * NCHUNK + 4 + 5 * NTT;
   static constexpr int SMEM = ((OFF_BAR + NBARS * 8 + 16 + 1023) & ~1023) + 1024;
   // TMEM: 2C columns per m-tile: GEMM1 accumulator = [0, 2C) (value | gate); h (packed 16-bit) over the value columns
@@ -176,14 +187,34 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
   // ---------------------------------------------------------------- one-time setup
   for (int i = threadIdx.x; i < K::NXB * K::X_BYTES / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(sX)[i] = make_uint4(0u, 0u, 0u, 0u);              // guard rows stay zero for good
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    sPar[i] = IN_CT ? p.b_ct[i] : 0.f;
+  if (!K::BIAS_MMA) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      sPar[i] = IN_CT ? p.b_ct[i] : 0.f;
 #pragma unroll
-    for (int b = 0; b < NBLK; ++b) {
-      float* q = sPar + C + b * 3 * C;
-      q[i] = 0.5f * p.b_conv[b][i];            // W1 is packed pre-scaled by 1/2 (pack_resblock_kernel)
-      q[C + i] = 0.5f * p.b_conv[b][C + i];
-      q[2 * C + i] = p.b_proj[b][i];
+      for (int b = 0; b < NBLK; ++b) {
+        float* q = sPar + C + b * 3 * C;
+        q[i] = 0.5f * p.b_conv[b][i];            // W1 is packed pre-scaled by 1/2 (pack_resblock_kernel)
+        q[C + i] = 0.5f * p.b_conv[b][C + i];
+        q[2 * C + i] = p.b_proj[b][i];
+      }
+    }
+  } else {
+    // bias tiles, SWIZZLE_NONE K-major core matrices: GEMM column n = 16 bytes at n * 16: (b/2)_hi, (b/2)_lo, 0 x 6
+    uint8_t* sB = smem + K::OFF_ONES;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) reinterpret_cast<uint16_t*>(sB)[i] = FMT == 0 ? 0x3C00 : 0x3F80;
+    auto put = [&](uint8_t* tile, int n, float bhalf) {
+      const float lo = bhalf - unpack2t<FMT>(pack2t<FMT>(bhalf, 0.f)).x;
+      uint32_t* row = reinterpret_cast<uint32_t*>(tile) + n * 4;
+      row[0] = pack2t<FMT>(bhalf, lo);
+      row[1] = 0u; row[2] = 0u; row[3] = 0u;
+    };
+    for (int n = threadIdx.x; n < 2 * C; n += blockDim.x) {
+      put(sB + K::BT_CT, n, IN_CT ? 0.5f * p.b_ct[n % C] : 0.f);              // ConvT column n = phase * C + channel
+#pragma unroll
+      for (int b = 0; b < NBLK; ++b) {
+        put(sB + K::BT_BLK0 + b * K::BT_BLK, n, 0.25f * p.b_conv[b][n]);      // value | gate; W1 is packed pre-scaled by 1/2
+        if (n < C) put(sB + K::BT_BLK0 + b * K::BT_BLK + 2 * C * 16, n, 0.5f * p.b_proj[b][n]);
+      }
     }
   }
   if (warp == 0 && lane == 0) {
@@ -274,6 +305,11 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
     const uint32_t idesc1 = make_idesc_f16(FMT, N1);     // GEMM1 and ConvT: N = 2C
     const uint32_t idesc2 = make_idesc_f16(FMT, C);
     const uint32_t idesc_z = make_idesc_f16(FMT, 16);
+    // bias MMA: D += ones[128 x 16] * tile[N x 16]^T, SWIZZLE_NONE descriptors (ones: LBO = SBO = 0; tile: SBO = 128, LBO = 0)
+    const uint64_t ones_desc = (uint64_t)((smem_u32(smem + K::OFF_ONES) & 0x3FFFFu) >> 4) | (1ull << 46);
+    auto bias_desc = [&](int off) {
+      return (uint64_t)((smem_u32(smem + K::OFF_ONES + off) & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+    };
     mbar_wait(w_full, 0);
     int it = 0;
     for (int u = blockIdx.x; u < p.total_units; u += grid) {
@@ -303,6 +339,7 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
                   for (int k = 0; k < 4; ++k)
                     umma_f16(d_ct, a_desc + 2 * k, b_desc + 2 * k, idesc1, (tap | kb | k) != 0);
                 }
+              if (K::BIAS_MMA) umma_f16(d_ct, ones_desc, bias_desc(K::BT_CT), idesc1, 1);
               umma_commit(&ct_full[cx * NCHUNK + c]);
               umma_commit(&in_empty[sl]);
             }
@@ -341,6 +378,7 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
                 for (int k = 0; k < C / 16; ++k)
                   umma_f16(tmem_base + T * N1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (tap | k) != 0);
               }
+              if (K::BIAS_MMA) umma_f16(tmem_base + T * N1, ones_desc, bias_desc(K::BT_BLK0 + blk * K::BT_BLK), idesc1, 1);
               umma_commit(&d1_full[T]);
             }
             __syncwarp();
@@ -361,6 +399,8 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
 #pragma unroll
               for (int k = 0; k < C / 16; ++k)      // A = h in TMEM: k-step k sits on the value columns 16k .. 16k+7
                 umma_f16_ts(tmem_base + T * N1 + C, tmem_base + T * N1 + 16 * k, b_desc + 2 * k, idesc2, k != 0);
+              if (K::BIAS_MMA)
+                umma_f16(tmem_base + T * N1 + C, ones_desc, bias_desc(K::BT_BLK0 + blk * K::BT_BLK + 2 * C * 16), idesc2, 1);
               umma_commit(&d2_full[T]);
             }
             __syncwarp();
@@ -444,14 +484,18 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
             uint8_t* cxrow = X + crow * ROWB;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 B0 = *reinterpret_cast<const float4*>(sPar + c_lo + 8 * j);
-              const float4 B1 = *reinterpret_cast<const float4*>(sPar + c_lo + 8 * j + 4);
+              float4 B0 = make_float4(0.f, 0.f, 0.f, 0.f), B1 = B0;       // BIAS_MMA: already in the accumulator
+              if (!K::BIAS_MMA) {
+                B0 = *reinterpret_cast<const float4*>(sPar + c_lo + 8 * j);
+                B1 = *reinterpret_cast<const float4*>(sPar + c_lo + 8 * j + 4);
+              }
               const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
               uint32_t w[4];
 #pragma unroll
               for (int e2 = 0; e2 < 4; ++e2) {
-                const float x0 = (__uint_as_float(v[8 * j + 2 * e2]) + bv[2 * e2]) * keep;
-                const float x1 = (__uint_as_float(v[8 * j + 2 * e2 + 1]) + bv[2 * e2 + 1]) * keep;
+                // (x + 0.0f is not a no-op for the compiler: -0 + 0 = +0, so the adds are selected away explicitly)
+                const float x0 = (K::BIAS_MMA ? __uint_as_float(v[8 * j + 2 * e2]) : __uint_as_float(v[8 * j + 2 * e2]) + bv[2 * e2]) * keep;
+                const float x1 = (K::BIAS_MMA ? __uint_as_float(v[8 * j + 2 * e2 + 1]) : __uint_as_float(v[8 * j + 2 * e2 + 1]) + bv[2 * e2 + 1]) * keep;
                 w[e2] = pack2t<FMT>(lrelu_fast(x0), lrelu_fast(x1));
               }
               *reinterpret_cast<uint4*>(cxrow + (sw_chunk(crow, (c_lo >> 3) + j) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -494,8 +538,11 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
               uint32_t hw[8];
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) {
-                const float4 A = *reinterpret_cast<const float4*>(par + c_lo + cc + 4 * i4);
-                const float4 Gt = *reinterpret_cast<const float4*>(par + C + c_lo + cc + 4 * i4);
+                float4 A = make_float4(0.f, 0.f, 0.f, 0.f), Gt = A;        // BIAS_MMA: already in the accumulator
+                if (!K::BIAS_MMA) {
+                  A = *reinterpret_cast<const float4*>(par + c_lo + cc + 4 * i4);
+                  Gt = *reinterpret_cast<const float4*>(par + C + c_lo + cc + 4 * i4);
+                }
                 const float4 S = *reinterpret_cast<const float4*>(film_b + cc + 4 * i4);
                 const float4 Tt = *reinterpret_cast<const float4*>(film_b + 32 + cc + 4 * i4);
                 const float av[4] = {A.x, A.y, A.z, A.w}, gv[4] = {Gt.x, Gt.y, Gt.z, Gt.w};
@@ -503,8 +550,8 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
                 float hv[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float a = __uint_as_float(va[4 * i4 + e]) + av[e];                 // (conv_a + b_a) / 2
-                  const float th = tanh_approx(__uint_as_float(vg[4 * i4 + e]) + gv[e]);   // tanh(g / 2)
+                  const float a = K::BIAS_MMA ? __uint_as_float(va[4 * i4 + e]) : __uint_as_float(va[4 * i4 + e]) + av[e];   // (conv_a + b_a) / 2
+                  const float th = tanh_approx(K::BIAS_MMA ? __uint_as_float(vg[4 * i4 + e]) : __uint_as_float(vg[4 * i4 + e]) + gv[e]);   // tanh(g / 2)
                   hv[e] = fmaf(fmaf(a, th, a), sv[e], tv[e]);                              // a sigmoid(g) (1 + scale) + shift
                 }
                 hw[2 * i4] = pack2t<FMT>(hv[0], hv[1]);
@@ -537,8 +584,11 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t xw[4] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w};
-              const float4 B0 = *reinterpret_cast<const float4*>(par + 2 * C + c_lo + 8 * j);
-              const float4 B1 = *reinterpret_cast<const float4*>(par + 2 * C + c_lo + 8 * j + 4);
+              float4 B0 = make_float4(0.f, 0.f, 0.f, 0.f), B1 = B0;       // BIAS_MMA: already in the accumulator
+              if (!K::BIAS_MMA) {
+                B0 = *reinterpret_cast<const float4*>(par + 2 * C + c_lo + 8 * j);
+                B1 = *reinterpret_cast<const float4*>(par + 2 * C + c_lo + 8 * j + 4);
+              }
               const float bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
               uint32_t o[4];
 #pragma unroll
@@ -546,8 +596,8 @@ stage_fused_kernel(const __grid_constant__ StageFusedParams p) {
                 // (packed 16-bit leaky_relu / inverse here saves ~1.5 instructions per element but was measured to cost
                 // 3.5 dB of SNR (70.1 -> 66.6) for no change in the epilogue's latency: fp32 it is)
                 const float2 xs = unpack2t<FMT>(xw[e2]);
-                float y0 = (lrelu_inv_fast(xs.x) + bv[2 * e2]) + __uint_as_float(vd[8 * j + 2 * e2]);
-                float y1 = (lrelu_inv_fast(xs.y) + bv[2 * e2 + 1]) + __uint_as_float(vd[8 * j + 2 * e2 + 1]);
+                float y0 = (K::BIAS_MMA ? lrelu_inv_fast(xs.x) : lrelu_inv_fast(xs.x) + bv[2 * e2]) + __uint_as_float(vd[8 * j + 2 * e2]);
+                float y1 = (K::BIAS_MMA ? lrelu_inv_fast(xs.y) : lrelu_inv_fast(xs.y) + bv[2 * e2 + 1]) + __uint_as_float(vd[8 * j + 2 * e2 + 1]);
                 if (act) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); }
                 o[e2] = pack2t<FMT>(y0, y1);
               }
