@@ -32,6 +32,7 @@ struct MelTable {      // CSR by mel bin over frequency bins
   const int* off;      // [n_mels] offset into w
   const float* w;
   int n_mels;
+  int nnz;             // number of weights (length of w)
 };
 
 struct FftTables {     // per (device, n_fft), built once on the host in double precision
@@ -194,6 +195,13 @@ stft1024_kernel(const StftParams p) {
     sincospif(-2.0f * (float)((t * k1) & 511) / 512.0f, &s, &c);
     tw1[i] = make_float2(c, s);
   }
+  // MODE_MEL: the sparse filterbank's weights live in shared memory (4 KB for 80 HTK mels): read through __ldg they
+  // were 130 of the ~550 load/store-pipe wavefronts per frame of a kernel whose LSU pipe is 76 % busy
+  constexpr int kMelSmemMax = 2048;
+  float* sMelW = reinterpret_cast<float*>(wbuf + kFastWarps * 576);
+  const bool mel_smem = MODE == MODE_MEL && p.mel.nnz <= kMelSmemMax;
+  if (mel_smem)
+    for (int i = threadIdx.x; i < p.mel.nnz; i += blockDim.x) sMelW[i] = __ldg(p.mel.w + i);
   float l1_acc = 0.f;
   constexpr int NPASS = MODE == MODE_L1 ? 2 : 1;
   float2 wreg[REGTAB ? 16 : 1], treg[REGTAB ? 16 : 1];
@@ -236,9 +244,11 @@ stft1024_kernel(const StftParams p) {
       else warp_fft512<false>(v, T, tw1, lane);
       // Z -> linear per-warp buffer (reusing the transpose scratch), then the real-FFT split
       {
-        float2* zp = T + pad((lane & 15) + 256 * (lane >> 4));
+        // linear (unpadded) Z: a half-warp stores / loads 16 consecutive float2 = all 32 banks once; the k + k/8 padding
+        // of the Stockham path made lane 15 collide with lane 0 (2 x the wavefronts of 48 accesses per frame, ncu)
+        float2* zp = T + (lane & 15) + 256 * (lane >> 4);
 #pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) zp[18 * k2] = v[k2];          // pad(k + 16*k2) = pad(k) + 18*k2
+        for (int k2 = 0; k2 < 16; ++k2) zp[16 * k2] = v[k2];
       }
       __syncwarp();
       // real-FFT split, two bins per pair of loads: with a = (Z[k] + conj Z[N-k])/2, d = (Z[k] - conj Z[N-k])/2,
@@ -262,7 +272,7 @@ stft1024_kernel(const StftParams p) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int k = lane + 32 * j;                       // 0 .. 255, partner bin N - k
-        const float2 zk = T[pad(k)], zn = T[pad((N - k) & (N - 1))], wk = tw2[k];
+        const float2 zk = T[k], zn = T[(N - k) & (N - 1)], wk = tw2[k];
         const float2 a = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
         const float2 d = make_float2(0.5f * (zk.x - zn.x), 0.5f * (zk.y + zn.y));
         const float2 wd = cmul(wk, d);
@@ -271,7 +281,7 @@ stft1024_kernel(const StftParams p) {
         emit(N - k, make_float2(a.x + t.x, -(a.y + t.y)));
       }
       if (lane == 0) {
-        const float2 zm = T[pad(N / 2)];
+        const float2 zm = T[N / 2];
         emit(N / 2, make_float2(zm.x, -zm.y));
       }
       __syncwarp();
@@ -295,10 +305,16 @@ stft1024_kernel(const StftParams p) {
       float* o = p.out + (long long)b * p.mel.n_mels * p.frames + f0 + f;
       for (int m = kk; m < p.mel.n_mels; m += 32) {
         const int lo = __ldg(p.mel.lo + m), cnt = __ldg(p.mel.cnt + m);
-        const float* wv = p.mel.w + __ldg(p.mel.off + m);
+        const int woff = __ldg(p.mel.off + m);
         const float* sp = stage + lo * SW + f;
         float acc = 0.f;
-        for (int k = 0; k < cnt; ++k) acc = fmaf(__ldg(wv + k), sp[k * SW], acc);
+        if (mel_smem) {
+          const float* wv = sMelW + woff;
+          for (int k = 0; k < cnt; ++k) acc = fmaf(wv[k], sp[k * SW], acc);
+        } else {
+          const float* wv = p.mel.w + woff;
+          for (int k = 0; k < cnt; ++k) acc = fmaf(__ldg(wv + k), sp[k * SW], acc);
+        }
         if (p.log_compress) acc = logf(fmaxf(acc, 1e-5f));
         if (fok) o[(long long)m * p.frames] = acc;
       }
@@ -322,7 +338,8 @@ static int launch_stft1024(const StftParams& p, cudaStream_t st) {
   const int span_len = (kFastWarps - 1) * p.hop + 1024;
   const size_t span_bytes = (size_t)((span_len + 3) & ~3) * 4, stage_bytes = (size_t)513 * (kFastWarps + 1) * (MODE == MODE_COMPLEX ? 8 : 4);
   const size_t head = MODE != MODE_L1 ? (((span_bytes > stage_bytes ? span_bytes : stage_bytes) + 15) & ~(size_t)15) : span_bytes + stage_bytes;
-  const size_t smem = head + 514 * 8 + 512 * 8 + 512 * 8 + (size_t)kFastWarps * 576 * 8 + 64;
+  const size_t mel_bytes = (MODE == MODE_MEL && p.mel.nnz <= 2048) ? (size_t)((p.mel.nnz + 3) & ~3) * 4 : 0;
+  const size_t smem = head + 514 * 8 + 512 * 8 + 512 * 8 + (size_t)kFastWarps * 576 * 8 + mel_bytes + 64;
   B200_CHECK_ARG(smem <= 227 * 1024, "stft: hop %d needs %zu bytes of shared memory", p.hop, smem);
   dim3 grid(ceil_div(p.frames, kFastWarps * kFastRounds), p.B);
   static const bool regtab = [] { const char* e = getenv("B200VOC_STFT_REGTAB"); return e && e[0] == '1'; }();
@@ -424,6 +441,7 @@ static int get_fft_tables(int n_fft, FftTables* out) {
 struct MelDev {
   int *lo, *cnt, *off;
   float* w;
+  int nnz;
 };
 static std::mutex g_mel_mu;
 static std::map<std::tuple<int, int, int, int>, MelDev> g_mel_cache;
@@ -473,6 +491,7 @@ static int get_mel_table(int n_fft, int n_mels, int sr, MelTable* out) {
     B200_CUDA(cudaMemcpy(d.cnt, cnt.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
     B200_CUDA(cudaMemcpy(d.off, off.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
     B200_CUDA(cudaMemcpy(d.w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    d.nnz = (int)w.size();
     it = g_mel_cache.emplace(key, d).first;
   }
   out->lo = it->second.lo;
@@ -480,6 +499,7 @@ static int get_mel_table(int n_fft, int n_mels, int sr, MelTable* out) {
   out->off = it->second.off;
   out->w = it->second.w;
   out->n_mels = n_mels;
+  out->nnz = it->second.nnz;
   return B200VOC_OK;
 }
 
