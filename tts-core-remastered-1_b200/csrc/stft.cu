@@ -638,7 +638,7 @@ istft1024_kernel(const IstftParams p) {
       for (int j = 0; j < 9; ++j) {
         const int k = k0 + 32 * (jj * 9 + j);
         if (k == 0 || k == N) v[j].y = 0.f;                // c2r ignores the imaginary part of DC / Nyquist
-        if (k < N) dst[pad(k)] = v[j];
+        if (k < N) dst[k] = v[j];            // linear slots: the Stockham k + k/8 padding 2-way conflicts here
         else if (k == N) xN[sidx] = v[j];
       }
     }
@@ -653,8 +653,8 @@ istft1024_kernel(const IstftParams p) {
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
       const int k = 32 * n1 + lane;
-      const float2 xk = X[pad(k)];
-      const float2 xnk = k == 0 ? xn : X[pad(N - k)];
+      const float2 xk = X[k];
+      const float2 xnk = k == 0 ? xn : X[N - k];
       v[n1] = irfft_pack(xk, cconj(xnk), tw2[k]);
     }
     __syncwarp();                                          // all reads of X done before it is overwritten
@@ -665,7 +665,7 @@ istft1024_kernel(const IstftParams p) {
     for (int k2 = 0; k2 < 16; ++k2) {
       const int m = mb + 16 * k2;
       const float2 w = win2[m];
-      X[pad(m)] = make_float2(v[k2].x * w.x * inv_n, v[k2].y * w.y * inv_n);
+      X[m] = make_float2(v[k2].x * w.x * inv_n, v[k2].y * w.y * inv_n);
     }
   }
   __syncthreads();
@@ -695,8 +695,7 @@ istft1024_kernel(const IstftParams p) {
 #pragma unroll 4
       for (int q = 0; q < ratio; ++q) {
         const int idx = r + q * hop;
-        const float2 z = slots[(s_hi0 + h - q) * kISlotStride + pad(idx >> 1)];
-        acc += (idx & 1) ? z.y : z.x;
+        acc += reinterpret_cast<const float*>(slots + (s_hi0 + h - q) * kISlotStride)[idx];   // sample idx of the frame: one 4-byte load
       }
       o[n] = p.normalize ? acc * inv_env : acc;
     }
@@ -713,8 +712,7 @@ istft1024_kernel(const IstftParams p) {
       const int idx = j - f * p.hop;
       if (f < 0 || f >= p.frames || idx >= NFFT) continue;
       const float w = wv[idx];
-      const float2 z = slots[(f - f_lo) * kISlotStride + pad(idx >> 1)];
-      acc += (idx & 1) ? z.y : z.x;
+      acc += reinterpret_cast<const float*>(slots + (f - f_lo) * kISlotStride)[idx];
       env = fmaf(w, w, env);
     }
     o[n] = !p.normalize ? acc : env > 1e-11f ? acc / env : 0.f;
