@@ -59,6 +59,9 @@ extern long long* g_rb2_trace;
 #ifndef RB3_BIAS_MMA
 #define RB3_BIAS_MMA 1
 #endif
+#ifndef RB3_WS
+#define RB3_WS 1
+#endif
 template <int C, bool PAIR>
 struct Rb3Cfg {
   static constexpr int KPT = C / 64;                 // k-blocks per tap = GEMM1 chunks = GEMM2 k-blocks
@@ -86,10 +89,18 @@ struct Rb3Cfg {
   static constexpr int W_SLOT = SUBS * W_TILE;
   static constexpr int NW = 5;
   static constexpr int ND2 = C == 128 ? 2 : 1;
+  // WS (C = 128 pairs): WEIGHT STATIONARY -- a pair holds all of W1 and W2 (each CTA its half of every tile: 96 + 16
+  // KB), loaded once per launch, and h goes back into TMEM over the value columns of the GEMM1 accumulator it came from
+  // (packed 16-bit pairs, tcgen05.st) to be GEMM2's A operand (TS-mode MMA), so there is no h buffer and no weight ring:
+  // the kernel is bound by the shared-memory data pipe and the ring's TMA writes (112 KB per tile), the
+  // h stores and GEMM2's operand reads were a quarter of what that pipe carried; the issuer loses its per-slot barrier
+  // wait + commit.  The accumulator buffer is handed back by GEMM2's commit (it holds h until then).
+  static constexpr bool WS = RB3_WS != 0 && C == 128 && PAIR;
+  static constexpr int N_W1_TILES = NCH * 3 * KPT, N_W_TILES = N_W1_TILES + KPT * NH;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_H = OFF_A + NA * A_BYTES;
-  static constexpr int OFF_W = OFF_H + KPT * H_KB_BYTES;
-  static constexpr int OFF_BAR = OFF_W + NW * W_SLOT;
+  static constexpr int OFF_W = OFF_H + (WS ? 0 : KPT * H_KB_BYTES);
+  static constexpr int OFF_BAR = OFF_W + (WS ? N_W_TILES * W_TILE : NW * W_SLOT);
   static constexpr int OFF_PAR = OFF_BAR + 512;
   // BIAS_MMA: the three bias vectors are added on the tensor core -- one more K = 16 MMA per accumulator whose A
   // operand is an all-ones tile and whose B operand carries (b/2)_hi, (b/2)_lo in two K columns (both K core matrices
@@ -182,7 +193,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmOut);
     for (int b = 0; b < NA; ++b) { mbar_init(&a_full[b], 1); mbar_init(&a_empty[b], 1); }
     for (int b = 0; b < NW; ++b) { mbar_init(&w_full[b], 1); mbar_init(&w_empty[b], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&d1_full[b], 1); mbar_init(&d1_empty[b], kCtas * kE1Warps); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&d1_full[b], 1); mbar_init(&d1_empty[b], K::WS ? 1 : kCtas * kE1Warps); }
     for (int b = 0; b < KPT; ++b) { mbar_init(&h_full[b], kCtas * kE1Warps); mbar_init(&h_empty[b], 1); }
     for (int b = 0; b < ND2; ++b) { mbar_init(&d2_full[b], 1); mbar_init(&d2_empty[b], kCtas * kE2Warps); }
     for (int b = 0; b < NA; ++b) mbar_init(&a_peer[b], 1);
@@ -236,6 +247,18 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
         }
       };
+      if (K::WS) {
+        // all weights once: tile (chunk j, tap, k-block kb) of W1 at index (j*3 + tap)*KPT + kb, then W2's k-blocks
+        if (rank == 0) mbar_expect_tx(&w_full[0], kCtas * K::N_W_TILES * K::W_TILE);
+#pragma unroll 1
+        for (int t = 0; t < K::N_W1_TILES; ++t) {
+          const int j = t / (3 * KPT), tap = (t / KPT) % 3, kb = t % KPT;
+          tma_load_2d_2cta(sW + t * K::W_TILE, &tmW1, &w_full[0], tap * C + kb * 64, j * 128 + rank * 64);
+        }
+#pragma unroll 1
+        for (int kb = 0; kb < KPT; ++kb)
+          tma_load_2d_2cta(sW + (K::N_W1_TILES + kb) * K::W_TILE, &tmW2, &w_full[0], kb * 64, rank * 64);
+      } else {
       // compact code on purpose (no unrolling in the producer / issuer roles): the kernel's instruction footprint
       // exceeds the instruction caches and the issuer's fetch stalls were its largest stall reason (ncu: no_instruction)
       const int total_chunks = n_my_tiles * NCH;
@@ -256,6 +279,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         if (gc >= 1) load_w2((gc - 1) % NCH);
         if (++j == NCH) j = 0;
+      }
       }
     }
   } else if (warp == 18) {
@@ -324,6 +348,30 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         w_ready = mbar_test(&w_full[wn % NW], (wn / NW) & 1);
         return s;
       };
+      // WS: GEMM2 k-block of chunk gc2 with h read from TMEM (buffer gc2 & 1, k-step k at columns 16k .. 16k+7 of the
+      // accumulator's value half); its commit hands the buffer back to GEMM1
+      auto g2_ws = [&](int gc2) {
+        const int it2 = gc2 / NCH, kb = gc2 - it2 * NCH, b2 = gc2 & 1, db = it2 % ND2;
+        const uint32_t phh = (gc2 >> 1) & 1, phd = ((it2 / ND2) & 1) ^ 1;
+        const bool rh = mbar_test(&h_full[b2], phh), rd = kb == 0 ? mbar_test(&d2_empty[db], phd) : true;
+        if (!rh) wait_x(&h_full[b2], phh);
+        RB3_TRACE(2, gc2, 0);
+        if (!rd) wait_x(&d2_empty[db], phd);
+        RB3_TRACE(2, gc2, 1);
+        tc_fence_after();
+        const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + (K::N_W1_TILES + kb) * K::W_TILE));
+        if (elect_one()) {
+          if (!RB3_DBG(8))
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_2cta_ts(tmem_base + K::D2_COL + db * C, tmem_base + b2 * 128 + 16 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          if (kb == NCH - 1) {
+            if (K::BIAS_MMA) bias_mma(tmem_base + K::D2_COL + db * C, NCH);
+            commit(&d2_full[db]);
+          }
+        }
+        __syncwarp();
+      };
       auto g2 = [&](int it2, int kb) {
         const int db = it2 % ND2;
         const uint32_t phh = it2 & 1, phd = ((it2 / ND2) & 1) ^ 1;
@@ -383,7 +431,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int b = gc & 1;
           {
             const uint32_t pha = (it / NA) & 1, phd = ((gc >> 1) & 1) ^ 1;
-            const bool ra = j == 0 ? mbar_test(&a_full[ab], pha) : true, rd = mbar_test(&d1_empty[b], phd);
+            // WS: no d1_empty -- GEMM1 of chunk gc overwrites the buffer GEMM2 of chunk gc-2 read h from, and that MMA
+            // was issued earlier by this thread (the tensor pipe runs one thread's MMAs in order)
+            const bool ra = j == 0 ? mbar_test(&a_full[ab], pha) : true, rd = K::WS ? true : mbar_test(&d1_empty[b], phd);
             if (!ra) mbar_wait(&a_full[ab], pha);
             if (PAIR && j == 0) wait_x(&a_peer[ab], pha);
             RB3_TRACE(1, gc, 0);
@@ -392,6 +442,25 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
           tc_fence_after();
           const uint32_t a_tile = smem_u32(sA + ab * K::A_BYTES) + K::HALO * 128;
+          if (K::WS) {
+            if (gc == 0) { mbar_wait(&w_full[0], 0); tc_fence_after(); }      // the resident weights have landed (both CTAs' halves)
+            const uint32_t w_base = smem_u32(sW + j * 3 * KPT * K::W_TILE);
+#pragma unroll 1
+            for (int tap = 0; tap < 3; ++tap) {
+              const uint32_t a_desc = desc_lo(a_tile + (tap - 1) * p.dilation * 128);
+              const uint32_t b_desc = desc_lo(w_base + tap * KPT * K::W_TILE);
+              if (elect_one()) {
+                if (!RB3_DBG(32))
+#pragma unroll
+                for (int kb = 0; kb < KPT; ++kb)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    mma(tmem_base + b * 128, a_desc + (kb * K::A_KB_BYTES >> 4) + 2 * k,
+                        b_desc + (kb * K::W_TILE >> 4) + 2 * k, (tap | kb | k) != 0);
+              }
+              __syncwarp();
+            }
+          } else
 #pragma unroll 1
           for (int s3 = 0; s3 < 3 * (KPT / K::SUBS); ++s3) {
             const int tap = s3 / (KPT / K::SUBS), kb = (s3 - tap * (KPT / K::SUBS)) * K::SUBS;
@@ -420,8 +489,12 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           RB3_TRACE(1, gc, 2);
         }
         if (gc >= 1) {
-          const int pj = j == 0 ? NCH - 1 : j - 1;
-          g2(j == 0 ? it - 1 : it, pj);
+          if (K::WS) {
+            g2_ws(gc - 1);
+          } else {
+            const int pj = j == 0 ? NCH - 1 : j - 1;
+            g2(j == 0 ? it - 1 : it, pj);
+          }
         }
         if (gc < total_chunks) RB3_TRACE(1, gc, 3);
         if (++j == NCH) { j = 0; ++it; }
@@ -464,7 +537,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           stage = __ldg(reinterpret_cast<const float4*>(film + (lane < 8 ? 0 : C) + ch0) + (lane & 7));
         mbar_wait(&d1_full[b], (gc >> 1) & 1);
         if (q == 0 && par == 0) RB3_TRACE(3, gc, 0);
-        mbar_wait(&h_empty[j], (it & 1) ^ 1);
+        if (!K::WS) mbar_wait(&h_empty[j], (it & 1) ^ 1);
         if (q == 0 && par == 0) RB3_TRACE(3, gc, 1);
         tc_fence_after();
         if (uniform) {
@@ -503,6 +576,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             for (int i4 = 0; i4 < 4; ++i4) { S[i4] = __ldg(fs + i4); H[i4] = __ldg(fh + i4); }
           }
           tmem_ld_wait();
+          uint32_t hw8[8];
 #pragma unroll
           for (int i8 = 0; i8 < 2; ++i8) {
             float hv[8];
@@ -522,19 +596,34 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 hv[h4 * 4 + e] = fmaf(fmaf(a, th, a), sv[e], tv[e]);                      // a sigmoid(g) (1+scale) + shift
               }
             }
+            if (K::WS) {
+              hw8[i8 * 4 + 0] = pack2t<FMT>(hv[0], hv[1]); hw8[i8 * 4 + 1] = pack2t<FMT>(hv[2], hv[3]);
+              hw8[i8 * 4 + 2] = pack2t<FMT>(hv[4], hv[5]); hw8[i8 * 4 + 3] = pack2t<FMT>(hv[6], hv[7]);
+            } else {
             const int chunk = (cl >> 3) + i8;
             if (!RB3_DBG(256) || hv[0] == 123.456f)
             *reinterpret_cast<uint4*>(hrow + ((chunk ^ (row & 7)) << 4)) =
                 make_uint4(pack2t<FMT>(hv[0], hv[1]), pack2t<FMT>(hv[2], hv[3]), pack2t<FMT>(hv[4], hv[5]),
                            pack2t<FMT>(hv[6], hv[7]));
+            }
           }
+          // WS: the 16 channels just computed, as 8 packed columns over the first 8 of the value columns they came from
+          // (k-step cl/16 of GEMM2's TMEM A operand)
+          if (K::WS) tmem_st8(lane_addr + b * 128 + cl, hw8);
         }
+        if (K::WS) {
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_leader(&h_full[b]);
+        } else {
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           arrive_leader(&h_full[j]);
           arrive_leader(&d1_empty[b]);
+        }
         }
         if (q == 0 && par == 0) RB3_TRACE(3, gc, 2);
       }
