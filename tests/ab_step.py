@@ -1,6 +1,6 @@
 """A/B driver (test infrastructure): times the Generator step (B=16 x T=861, BASELINE configs[1]) and its per-layer
 CUDA-event profile with two builds of the library on the SAME box, alternating, in fresh processes.
-    python tests/ab_step.py <libA.so> <libB.so> [rounds]          (child: python tests/ab_step.py --child)
+    python tests/ab_step.py <libA.so> <libB.so> [<libC.so> ...] [rounds]          (child: python tests/ab_step.py --child)
 Box-to-box spread under the power cap is ~5 %, larger than most kernel changes: only same-box pairs are comparable."""
 import json
 import os
@@ -47,8 +47,9 @@ def child():
 
 
 def main():
-    libs = sys.argv[1:3]
-    rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    libs = [a for a in sys.argv[1:] if a.endswith(".so")]          # two or more builds
+    rest = [a for a in sys.argv[1:] if not a.endswith(".so")]
+    rounds = int(rest[0]) if rest else 3
     res = {l: [] for l in libs}
     for r in range(rounds):
         for l in libs:
