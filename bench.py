@@ -657,7 +657,14 @@ def run_b200(args):
                      "frac": achieved / peak if peak else None, "traffic": traffic,
                      "kernel": "resblock3_kernel<128,...,PAIR> (stage-1 fused residual block on CTA pairs, tcgen05.mma.cta_group::2: conv k3 + GLU + FiLM + 1x1 + residual, 3 launches/step)",
                      "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
-                     "flops_per_launch": dom_flops, "ms_per_launch": dom_ms},
+                     "flops_per_launch": dom_flops, "ms_per_launch": dom_ms,
+                     "share_of_step": (sum(v["ms"] for v in dom) / conv_ms) if conv_ms > 0 else None,
+                     # the longest SINGLE launch is the fused last stage (instruction / shared-memory-pipe bound)
+                     "longest_single_launch": (lambda v: {"kernel": "stage_fused_kernel<32,...> (stage 3: ConvT + 3 residual blocks + band_merge + tanh)",
+                                                          "ms": v["ms"], "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12,
+                                                          "frac_of_tensor_peak": v["flops"] / (v["ms"] * 1e-3) / 1e12 / peak if peak else None,
+                                                          "bound": "shared-memory data pipe (ncu: LSU 53 % + tensor-core operand reads 46 %) and instruction issue (62 %)"})(
+                         per_layer["stage3+merge"]) if "stage3+merge" in per_layer and per_layer["stage3+merge"]["ms"] > 0 else None},
         "whole_step": {"algorithmic_tflop": total_flops / 1e12, "sum_kernel_ms": conv_ms,
                        "tflops_over_step": total_flops / (ms_total / args.steps * 1e-3) / 1e12 * 1.0,
                        "frac_of_tensor_peak": total_flops / (ms_total / args.steps * 1e-3) / 1e12 / peak},
