@@ -167,6 +167,12 @@ int b200voc_disc_conv_tc(const float* x, const void* w_split, const float* bias,
  * as [rows = Cout][cols = Cin*K(*1)].  sigma_out: one device float. */
 int b200voc_spectral_norm_weight(const float* w_orig, const float* u, const float* v, int rows, int cols,
                                  float* w_out, float* sigma_out, void* stream);
+/* The same in TRAINING mode -- what every critic forward of the reference trainer runs (vocoder7/trainer.py:86-115 on
+ * modules in .train()): one power iteration first, v <- normalize(W^T u), u <- normalize(W v) with x / max(||x||, eps)
+ * (torch's eps = 1e-12), then sigma = u . (W v) and w_out = w_orig / sigma.  u[rows] and v[cols] are UPDATED IN PLACE
+ * (the module's weight_u / weight_v buffers).  scratch: rows + cols floats. */
+int b200voc_spectral_norm_train(const float* w_orig, float* u, float* v, int rows, int cols, float eps, float* w_out,
+                                float* sigma_out, float* scratch, void* stream);
 /* F.avg_pool1d(x, 4, 2, 1) of discriminators.py:99 over `rows` rows of Lin samples -> (Lin-2)/2+1 samples. */
 int b200voc_avg_pool1d_k4s2p1(const float* x, int64_t rows, int Lin, float* y, void* stream);
 

@@ -432,12 +432,29 @@ def spectral_norm_weight(w_orig: torch.Tensor, u: torch.Tensor, v: torch.Tensor)
     return w_orig / sigma
 
 
-def _critic_stack(sd, d: int, plan, x: torch.Tensor, two_d: bool):
+def spectral_norm_power_iteration(w_orig: torch.Tensor, u: torch.Tensor, v: torch.Tensor, eps: float = 1e-12):
+    """``torch.nn.utils.spectral_norm`` in TRAINING mode (SpectralNorm.compute_weight with do_power_iteration=True,
+    n_power_iterations = 1 -- what every critic forward of the reference trainer runs, vocoder7/trainer.py:86-115 on the
+    modules built at discriminators.py:21-31, 76-89, 125-138): v <- normalize(W^T u), u <- normalize(W v), both with
+    x / max(||x||, eps); then sigma = u . (W v) and weight = weight_orig / sigma.  Returns (weight, u_new, v_new);
+    the reference updates the ``weight_u`` / ``weight_v`` buffers in place."""
+    W = w_orig.flatten(1)
+    v_new = F.normalize(torch.mv(W.t(), u), dim=0, eps=eps)
+    u_new = F.normalize(torch.mv(W, v_new), dim=0, eps=eps)
+    sigma = torch.dot(u_new, torch.mv(W, v_new))
+    return w_orig / sigma, u_new, v_new
+
+
+def _critic_stack(sd, d: int, plan, x: torch.Tensor, two_d: bool, training: bool = False):
     maps = []
     idx = 0
     for cin, cout, k, st, pad, act in plan:
         pre = f"discriminators.{d}.{idx}."
-        w = spectral_norm_weight(sd[pre + "weight_orig"], sd[pre + "weight_u"], sd[pre + "weight_v"])
+        if training:                                  # one power iteration per forward, u / v updated in place
+            w, sd[pre + "weight_u"], sd[pre + "weight_v"] = spectral_norm_power_iteration(
+                sd[pre + "weight_orig"], sd[pre + "weight_u"], sd[pre + "weight_v"])
+        else:
+            w = spectral_norm_weight(sd[pre + "weight_orig"], sd[pre + "weight_u"], sd[pre + "weight_v"])
         if two_d:
             x = F.conv2d(x, w, sd[pre + "bias"], stride=(st, 1), padding=(pad, 0))
         else:
@@ -450,25 +467,27 @@ def _critic_stack(sd, d: int, plan, x: torch.Tensor, two_d: bool):
     return maps[-1], maps[:-1]
 
 
-def critic_forward(kind: str, sd: Dict[str, torch.Tensor], cfg, x: torch.Tensor):
+def critic_forward(kind: str, sd: Dict[str, torch.Tensor], cfg, x: torch.Tensor, training: bool = False):
     """Functional restatement of the three ``forward`` methods (discriminators.py:34-60, 92-108, 141-157):
-    returns (outputs, features) exactly as the reference does."""
+    returns (outputs, features) exactly as the reference does.  ``training=True`` is the module in ``.train()`` mode:
+    every spectral norm runs one power iteration first and ``sd``'s ``weight_u`` / ``weight_v`` entries are replaced by
+    the updated vectors (the reference updates the buffers in place)."""
     plans, two_d = critic_plans(kind, cfg)
     B, _, T = x.shape
     outs, feats = [], []
     if kind == "mpd":
         for d, p in enumerate(cfg.disc_periods):
             xp = F.pad(x, (0, (p - T % p) % p))                       # discriminators.py:45-49
-            o, f = _critic_stack(sd, d, plans[d], xp.view(B, 1, xp.shape[2] // p, p), True)
+            o, f = _critic_stack(sd, d, plans[d], xp.view(B, 1, xp.shape[2] // p, p), True, training)
             outs.append(o), feats.append(f)
     elif kind == "msd":
         pooled = F.avg_pool1d(x, 4, 2, 1)
         for d, s in enumerate([x, pooled, pooled][:len(plans)]):      # discriminators.py:99: both pooled from x
-            o, f = _critic_stack(sd, d, plans[d], s, False)
+            o, f = _critic_stack(sd, d, plans[d], s, False, training)
             outs.append(o), feats.append(f)
     else:
         for d, band in enumerate(torch.chunk(x, cfg.num_bands, dim=2)):   # discriminators.py:147: chunks of TIME
-            o, f = _critic_stack(sd, d, plans[d], band, False)
+            o, f = _critic_stack(sd, d, plans[d], band, False, training)
             outs.append(o), feats.append(f)
     return outs, feats
 

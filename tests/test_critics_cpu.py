@@ -127,3 +127,48 @@ def test_entry_points_validate_arguments_before_touching_the_device():
     assert lib.b200voc_disc_conv(one, one, one, 0, 1, 4, 100, 1, 5, 3, 2, 0, 0, 0.2, one, 0, 0) == _lib.ERR_BAD_ARG
     assert lib.b200voc_spectral_norm_weight(one, one, one, 0, 5, one, one, 0) == _lib.ERR_BAD_ARG
     assert lib.b200voc_avg_pool1d_k4s2p1(one, 1, 1, one, 0) == _lib.ERR_BAD_ARG
+
+
+def test_oracle_training_mode_spectral_norm_is_pinned_to_torch():
+    """The oracle's training-mode spectral norm (one power iteration per forward, u / v updated in place) against the
+    implementation the reference calls, ``torch.nn.utils.spectral_norm`` on a module in .train() (discriminators.py:76-89
+    builds exactly this; the trainer never switches the critics to eval, vocoder7/trainer.py:86-115): weight, u and v
+    after one and after two forwards, then a whole MSD stack in training mode against the restated forward."""
+    import torch.nn as nn
+    torch.manual_seed(7)
+    conv = nn.utils.spectral_norm(nn.Conv1d(16, 64, kernel_size=41, stride=1, padding=20)).train()
+    x = torch.randn(2, 16, 50)
+    w0, u, v = conv.weight_orig.detach().clone(), conv.weight_u.detach().clone(), conv.weight_v.detach().clone()
+    for _ in range(2):
+        with torch.no_grad():
+            y = conv(x)
+        w, u, v = O.spectral_norm_power_iteration(w0, u, v)
+        assert torch.allclose(conv.weight_u, u, rtol=0, atol=1e-6) and torch.allclose(conv.weight_v, v, rtol=0, atol=1e-6)
+        ref = torch.nn.functional.conv1d(x, w, conv.bias.detach(), padding=20)
+        assert float((y - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+    # whole stack: a reference-shaped module in .train() vs critic_forward(training=True)
+    cfg = O.OracleConfig()
+    sd = O.make_critic_state("msd", cfg, seed=1234)
+    plans, _ = O.critic_plans("msd", cfg)
+    torch.manual_seed(1234)
+    discs = []
+    for plan in plans:                                        # same construction order as make_critic_state
+        mods = []
+        for cin, cout, k, st, pad, act in plan:
+            mods.append(nn.utils.spectral_norm(nn.Conv1d(cin, cout, k, stride=st, padding=pad)))
+            if act:
+                mods.append(nn.LeakyReLU(0.2))
+        discs.append(nn.Sequential(*mods).train())
+    for d, seq in enumerate(discs):
+        for j, m in enumerate(seq):
+            if not isinstance(m, nn.LeakyReLU):
+                for name in ("weight_orig", "weight_u", "weight_v", "bias"):
+                    assert torch.equal(getattr(m, name), sd[f"discriminators.{d}.{j}.{name}"]), (d, j, name)
+    xw = torch.rand(1, 1, 900) * 2 - 1
+    sd_t = {k: t.clone() for k, t in sd.items()}
+    outs, feats = O.critic_forward("msd", sd_t, cfg, xw, training=True)
+    with torch.no_grad():
+        got = discs[0](xw)
+    assert float((got - outs[0]).abs().max()) <= 2e-4 * max(1.0, float(outs[0].abs().max()))
+    assert torch.allclose(discs[0][0].weight_u, sd_t["discriminators.0.0.weight_u"], atol=1e-6)
+    assert not torch.equal(sd_t["discriminators.0.0.weight_u"], sd["discriminators.0.0.weight_u"])

@@ -171,3 +171,36 @@ def test_disc_conv_tensor_core_layer_matches_fp64(B, Cin, Cout, L, K):
     # argument validation: loud, not silent
     assert lib.b200voc_disc_conv_tc(_lib.ptr(xd), _lib.ptr(wsplit), _lib.ptr(bd), B, Cin, Cout, L, K, pad, 0.2,
                                     _lib.ptr(y_pre), _lib.ptr(y_act), _lib.ptr(ws), 16, st) == _lib.ERR_BAD_ARG
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_critic_training_mode_spectral_norm(kind):
+    """.train(): every forward first runs one power iteration per layer (b200voc_spectral_norm_train) and updates the
+    weight_u / weight_v buffers in place, as torch.nn.utils.spectral_norm does for the reference trainer
+    (vocoder7/trainer.py:86-115).  Two consecutive forwards against the oracle's training-mode forward: maps, u and v;
+    then .eval() uses the updated vectors."""
+    cfg = O.OracleConfig()
+    sd = O.make_critic_state(kind, cfg, seed=1234)
+    mod = _host(kind).train()
+    x = torch.rand(2, 1, 2403) * 2 - 1
+    sd_t = {k: t.clone() for k, t in sd.items()}
+    for step in range(2):
+        outs, feats = mod(x.cuda())
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            r_outs, r_feats = O.critic_forward(kind, sd_t, cfg, x, training=True)
+        for i in range(len(outs)):
+            _close(outs[i], r_outs[i], f"{kind} score {i} (training step {step})")
+            for j in range(len(feats[i])):
+                _close(feats[i][j], r_feats[i][j], f"{kind} feature {i}.{j} (training step {step})")
+        got = mod.state_dict()
+        for k in sd_t:
+            if k.endswith("weight_u") or k.endswith("weight_v"):
+                assert float((got[k].cpu() - sd_t[k]).abs().max()) <= 2e-5, (k, step)
+    assert not torch.equal(mod.state_dict()["discriminators.0.0.weight_u"].cpu(), sd["discriminators.0.0.weight_u"])
+    mod.eval()
+    outs, _ = mod(x.cuda())
+    with torch.no_grad():
+        r_outs, _ = O.critic_forward(kind, sd_t, cfg, x)
+    for i in range(len(outs)):
+        _close(outs[i], r_outs[i], f"{kind} score {i} (eval after training steps)")

@@ -146,3 +146,23 @@ def test_stft1024_hops_not_multiple_of_4(hop):
     assert got.shape == ref.shape
     assert torch.isfinite(torch.view_as_real(got)).all()
     assert float((got - ref).abs().max()) <= 2e-5 * 32 * 4
+
+
+def test_stft_loss_backward_applies_upstream_gradient_on_device():
+    """the upstream gradient reaches the kernels' outputs as a device scalar (no host read of grad_out): scaling the loss
+    scales every gradient"""
+    import b200voc
+    torch.manual_seed(5)
+    mod = b200voc.STFTLoss(b200voc.GANConfig()).cuda()
+    fake, real = torch.rand(2, 4096) * 2 - 1, torch.rand(2, 4096) * 2 - 1
+    grads = []
+    for s in (1.0, -2.5):
+        f = fake.cuda().requires_grad_(True)
+        for m in mod.stfts:
+            m.filterbank.grad = None
+        (mod(f, real.cuda()) * s).backward()
+        grads.append((f.grad.clone(), [m.filterbank.grad.clone() for m in mod.stfts]))
+    (g1, fb1), (g2, fb2) = grads
+    assert torch.allclose(g2, -2.5 * g1, rtol=1e-6, atol=1e-12) and float(g1.abs().max()) > 0
+    for a, b in zip(fb1, fb2):
+        assert torch.allclose(b, -2.5 * a, rtol=1e-6, atol=1e-12)

@@ -60,6 +60,7 @@ _SIGNATURES = {
     "b200voc_disc_pack_weight_split": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "b200voc_disc_conv_tc": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I64, _P]),
     "b200voc_spectral_norm_weight": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
+    "b200voc_spectral_norm_train": (C.c_int, [_P, _P, _P, _I, _I, _F, _P, _P, _P, _P]),
     "b200voc_avg_pool1d_k4s2p1": (C.c_int, [_P, _I64, _I, _P, _P]),
     "b200voc_gen_launch_count": (C.c_int, [_P]),
     "b200voc_gen_set_overflow_check": (C.c_int, [_P, _I]),

@@ -6,10 +6,12 @@ Same constructors, same ``state_dict`` keys (``discriminators.<i>.<j>.{weight_or
 from ``torch.nn.utils.spectral_norm``) and the same return value ``(outputs, features)`` -- one score map per
 sub-discriminator and the list of every intermediate conv / LeakyReLU map -- so a reference checkpoint loads
 unchanged and ``compute_gan_loss`` (vocoder7/losses.py:8-52) consumes the result as is.  ``forward`` runs the
-CUDA kernels of ``csrc/disc.cu`` through the C ABI; the torch modules below only hold parameters.  Spectral
-normalisation follows evaluation-mode semantics (sigma from the stored ``u``/``v``, no power iteration) and is
-applied on the GPU once per parameter version.  No CPU / PyTorch fallback, no autograd (the backward kernels are
-the other half of rank 4)."""
+CUDA kernels of ``csrc/disc.cu`` / ``csrc/disc_gemm.cu`` through the C ABI; the torch modules below only hold
+parameters.  Spectral normalisation follows the module's mode like ``torch.nn.utils.spectral_norm``: in ``.eval()``
+sigma comes from the stored ``u``/``v`` (applied on the GPU once per parameter version), in ``.train()`` every forward
+first runs one power iteration and updates the ``weight_u`` / ``weight_v`` buffers in place
+(``b200voc_spectral_norm_train``).  No CPU / PyTorch fallback, no autograd (the backward kernels are the other half
+of rank 4)."""
 from __future__ import annotations
 
 from typing import List, Sequence, Tuple
@@ -78,21 +80,33 @@ class _CriticBase(nn.Module):
         convs = [m for m in self.discriminators[d] if not isinstance(m, nn.LeakyReLU)]
         key = tuple((c.weight_orig.data_ptr(), c.weight_orig._version, c.weight_u._version, c.weight_v._version,
                      c.bias.data_ptr(), c.bias._version) for c in convs)
+        train = self.training            # .train(): one power iteration per forward, u / v updated in place, nothing cached
         hit = self._wcache.get(d)
-        if hit is not None and hit[0] == key:
+        if not train and hit is not None and hit[0] == key:
             return hit[1]
         lib = _lib.load()
         out = []
         for c in convs:
             w0, u, v, b = c.weight_orig.detach(), c.weight_u.detach(), c.weight_v.detach(), c.bias.detach()
             _lib.require_cuda(w0, u, v, b)           # parameters must have been moved with .to('cuda')
-            w0, u, v, b = (t.to(torch.float32).contiguous() for t in (w0, u, v, b))
+            w0, b = w0.to(torch.float32).contiguous(), b.to(torch.float32).contiguous()
             rows, cols = w0.shape[0], w0.numel() // w0.shape[0]
             w = torch.empty_like(w0)
             sigma = torch.empty(1, device=w0.device, dtype=torch.float32)
-            _lib.check(lib.b200voc_spectral_norm_weight(_lib.ptr(w0), _lib.ptr(u), _lib.ptr(v), rows, cols,
-                                                        _lib.ptr(w), _lib.ptr(sigma), _lib.current_stream()),
-                       "spectral_norm_weight")
+            if train:
+                # torch.nn.utils.spectral_norm, training mode (the reference trainer's every critic forward,
+                # vocoder7/trainer.py:86-115): the module's weight_u / weight_v buffers ARE the kernel's in/out vectors
+                if u.dtype != torch.float32 or v.dtype != torch.float32 or not (u.is_contiguous() and v.is_contiguous()):
+                    raise _lib.B200VocError("training-mode spectral norm needs contiguous fp32 weight_u / weight_v buffers")
+                scratch = torch.empty(rows + cols, device=w0.device, dtype=torch.float32)
+                _lib.check(lib.b200voc_spectral_norm_train(_lib.ptr(w0), _lib.ptr(u), _lib.ptr(v), rows, cols, 1e-12,
+                                                           _lib.ptr(w), _lib.ptr(sigma), _lib.ptr(scratch),
+                                                           _lib.current_stream()), "spectral_norm_train")
+            else:
+                u, v = u.to(torch.float32).contiguous(), v.to(torch.float32).contiguous()
+                _lib.check(lib.b200voc_spectral_norm_weight(_lib.ptr(w0), _lib.ptr(u), _lib.ptr(v), rows, cols,
+                                                            _lib.ptr(w), _lib.ptr(sigma), _lib.current_stream()),
+                           "spectral_norm_weight")
             # GEMM-shaped layers (stride 1, wide) run on the tensor cores with split-bf16 operands: pack [hi | lo] once
             wsplit = None
             cout, cin, k = int(w0.shape[0]), int(w0.shape[1]), int(w0.shape[2])
@@ -104,7 +118,10 @@ class _CriticBase(nn.Module):
                 _lib.check(lib.b200voc_disc_pack_weight_split(_lib.ptr(w), cout, cin, k, _lib.ptr(wsplit),
                                                               _lib.current_stream()), "disc_pack_weight_split")
             out.append((w, b, wsplit))
-        self._wcache[d] = (key, out)
+        if train:
+            self._wcache.pop(d, None)        # u / v changed: an eval-mode forward must recompute
+        else:
+            self._wcache[d] = (key, out)
         return out
 
     # ---- one critic: walk its conv stack --------------------------------------------------------------

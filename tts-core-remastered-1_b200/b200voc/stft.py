@@ -151,7 +151,9 @@ class _STFTLossFn(torch.autograd.Function):
         lib = _lib.load()
         grad_wav = torch.zeros_like(f)
         grad_gains = [torch.zeros(n // 2 + 1, device=f.device, dtype=torch.float32) for n in n_ffts]
-        scale = float(grad_out) * lam
+        # the kernels are linear in `scale`: run them with the constant lambda and apply the upstream gradient as a
+        # DEVICE scalar afterwards -- float(grad_out) would be a host synchronisation (and not graph-capturable)
+        scale = lam
         with torch.cuda.device(f.device):
             need = max(int(lib.b200voc_stft_l1_backward_workspace_bytes(B, N, n, hop)) for n in n_ffts)
             ws = torch.empty(need, dtype=torch.uint8, device=f.device)
@@ -160,6 +162,10 @@ class _STFTLossFn(torch.autograd.Function):
                 _lib.check(lib.b200voc_stft_l1_backward(_lib.ptr(f), _lib.ptr(r), B, N, n, hop, _lib.ptr(gs), scale,
                                                         _lib.ptr(grad_wav), _lib.ptr(gg), _lib.ptr(ws), ws.numel(),
                                                         _lib.current_stream()), "stft_l1_backward")
+        go = grad_out.detach().to(device=f.device, dtype=torch.float32)
+        grad_wav.mul_(go)
+        for gg in grad_gains:
+            gg.mul_(go)
         return (grad_wav.view(shape), None, None, None, None, *grad_gains)
 
 

@@ -286,6 +286,69 @@ int spectral_norm_launch(const float* w_orig, const float* u, const float* v, in
   return B200VOC_OK;
 }
 
+// Training-mode spectral norm (torch.nn.utils.spectral_norm with do_power_iteration, n_power_iterations = 1: what every
+// critic forward of vocoder7/trainer.py:86-115 runs):  v <- normalize(W^T u),  u <- normalize(W v)  (x / max(||x||, eps)),
+// sigma = u . (W v) = ||W v||^2 / max(||W v||, eps),  weight = W / sigma; u and v are updated in place.  This runs once per
+// layer per forward, so unlike the load-time sigma kernel it is spread over the chip: two passes over W (the largest,
+// 1024 x 10496, is 43 MB) plus two single-CTA vector normalisations.  fp32 products, fp64 accumulation.
+__global__ void __launch_bounds__(256) sn_wt_u_kernel(const float* __restrict__ w, const float* __restrict__ u, int rows,
+                                                      int cols, float* __restrict__ t) {
+  const int c = blockIdx.x * 256 + threadIdx.x;          // one column per thread: W^T u = sum_r u[r] W[r][:], coalesced
+  if (c >= cols) return;
+  double acc = 0.0;
+  for (int r = 0; r < rows; ++r) acc += (double)__ldg(u + r) * (double)__ldg(w + (long long)r * cols + c);
+  t[c] = (float)acc;
+}
+__global__ void __launch_bounds__(256) sn_w_v_kernel(const float* __restrict__ w, const float* __restrict__ v, int rows,
+                                                     int cols, float* __restrict__ s) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // one warp per row
+  if (r >= rows) return;
+  const float* wr = w + (long long)r * cols;
+  double d = 0.0;
+  for (int c = lane; c < cols; c += 32) d += (double)__ldg(wr + c) * (double)__ldg(v + c);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  if (lane == 0) s[r] = (float)d;
+}
+// out = x / max(||x||, eps); sigma_out (optional) = ||x||^2 / max(||x||, eps) = out . x.  One CTA, fixed order.
+__global__ void __launch_bounds__(1024) sn_normalize_kernel(const float* __restrict__ x, int n, float eps,
+                                                            float* __restrict__ out, float* __restrict__ sigma_out) {
+  __shared__ double part[32];
+  __shared__ double total;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) { const double xv = (double)x[i]; acc += xv * xv; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 32; ++i) s += part[i];
+    total = s;
+  }
+  __syncthreads();
+  const float norm = (float)sqrt(total);
+  const float den = fmaxf(norm, eps);
+  for (int i = threadIdx.x; i < n; i += 1024) out[i] = x[i] / den;
+  if (sigma_out && threadIdx.x == 0) *sigma_out = (float)(total / (double)den);
+}
+int spectral_norm_train_launch(const float* w_orig, float* u, float* v, int rows, int cols, float eps, float* w_out,
+                               float* sigma, float* scratch, cudaStream_t st) {
+  float* t = scratch;            // [cols]
+  float* s = scratch + cols;     // [rows]
+  sn_wt_u_kernel<<<(cols + 255) / 256, 256, 0, st>>>(w_orig, u, rows, cols, t);
+  sn_normalize_kernel<<<1, 1024, 0, st>>>(t, cols, eps, v, nullptr);
+  sn_w_v_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w_orig, v, rows, cols, s);
+  sn_normalize_kernel<<<1, 1024, 0, st>>>(s, rows, eps, u, sigma);
+  B200_CUDA(cudaGetLastError());
+  const long long n = (long long)rows * cols;
+  const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  sn_scale_kernel<<<blocks, 256, 0, st>>>(w_orig, sigma, n, w_out);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
 // F.avg_pool1d(x, kernel_size=4, stride=2, padding=1) (count_include_pad=True: the divisor is always 4).
 __global__ void __launch_bounds__(256) avg_pool_k4s2p1_kernel(const float* __restrict__ x, long long rows, int Lin,
                                                               int Lout, float* __restrict__ y) {
@@ -346,6 +409,14 @@ int b200voc_spectral_norm_weight(const float* w_orig, const float* u, const floa
   B200_CHECK_ARG(w_orig && u && v && w_out && sigma_out, "spectral_norm_weight: null argument");
   B200_CHECK_ARG(rows > 0 && cols > 0, "spectral_norm_weight: bad shape (%d x %d)", rows, cols);
   return b200::spectral_norm_launch(w_orig, u, v, rows, cols, w_out, sigma_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200voc_spectral_norm_train(const float* w_orig, float* u, float* v, int rows, int cols, float eps, float* w_out,
+                                float* sigma_out, float* scratch, void* stream) {
+  B200_CHECK_ARG(w_orig && u && v && w_out && sigma_out && scratch, "spectral_norm_train: null argument");
+  B200_CHECK_ARG(rows > 0 && cols > 0 && eps >= 0.f, "spectral_norm_train: bad shape (%d x %d)", rows, cols);
+  return b200::spectral_norm_train_launch(w_orig, u, v, rows, cols, eps, w_out, sigma_out, scratch,
+                                          reinterpret_cast<cudaStream_t>(stream));
 }
 
 int b200voc_avg_pool1d_k4s2p1(const float* x, int64_t rows, int Lin, float* y, void* stream) {
