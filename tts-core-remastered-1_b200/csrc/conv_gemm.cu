@@ -223,6 +223,238 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------- CTA-pair variant, BN = 256
+// The single-CTA kernel at BN = 256 loads 48 KB (A 16 + B 32) per 512 clk of MMAs: ~11-13 TB/s of L2 -> shared-memory
+// traffic chip-wide (ncu l1tex__m_xbar2l1tex_read_bytes), which is what bounds it (tensor pipe 51-63 %).  Here two
+// CTAs (a cluster of 2) own two neighbouring 128-row tiles of the same column tile and the leader issues ONE
+// tcgen05.mma.cta_group::2 (M = 256, N = 256) per k-step: each CTA loads its own A tile and only HALF of the weight
+// tile (32 KB per stage instead of 48, and the ring gets a fourth stage).  Both CTAs' loads signal the leader's `full`
+// barrier (cp.async.bulk.tensor ... cta_group::2), commits are multicast to both CTAs' `empty` / `acc_full` barriers,
+// the peer's epilogue warps arrive on the leader's `acc_empty` through mapa.
+template <int STAGES, int FMT, bool LRELU>
+__global__ void __launch_bounds__(192, 1)
+gemm_taps_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmOut, const GemmTapsParams p) {
+  constexpr int BN = 256;
+  constexpr int B_HALF = 128 * 128;                  // this CTA's 128 of the 256 weight rows x 64 k
+  constexpr int STAGE_BYTES = kATileBytes + B_HALF;
+  constexpr int STAGING = 128 * BN * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + STAGING);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;      // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]  (the leader's copy is the one waited on)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int kpt = p.k_per_tap >> 6;
+  const int num_k = p.n_taps * kpt;
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int total_tiles = m_pairs * p.n_tiles * p.n_seq;
+  const int pair0 = (int)(blockIdx.x >> 1), pair_stride = (int)(gridDim.x >> 1);
+  // pair tile -> (m0 of THIS CTA's row tile, n0, seq); a row tile past the end is all out of bounds (TMA zero-fills the
+  // loads and clips the stores)
+  auto decode = [&](int t, int& m0, int& n0, int& seq, bool& part_b) {
+    const int nt = t % p.n_tiles, rest = t / p.n_tiles;
+    n0 = nt * BN;
+    seq = rest / m_pairs;
+    part_b = (n0 / p.cout) < p.pad;
+    m0 = (2 * (rest - seq * m_pairs) + (int)rank) * 128 + (part_b ? 1 : 0);
+  };
+  auto arrive_leader = [&](uint64_t* bar) {
+    if (rank == 0) mbar_arrive(bar); else mbar_arrive_remote(mapa_u32(bar, 0));
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 2 * 4);          // one arrival per epilogue warp of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, 2 * BN);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0;
+      for (int t = pair0; t < total_tiles; t += pair_stride) {
+        int m0, n0, seq;
+        bool part_b;
+        decode(t, m0, n0, seq, part_b);
+        for (int kb = 0; kb < num_k; ++kb, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);      // both CTAs' bytes land on the leader's barrier
+          const int tap = kb / kpt, kk = kb - tap * kpt;
+          uint8_t* st = smem + s * STAGE_BYTES;
+          tma_load_3d_2cta(st, &tmA, &full[s], kk * 64, m0 + p.tap_shift[tap], seq);
+          tma_load_2d_2cta(st + kATileBytes, &tmB, &full[s], tap * p.k_per_tap + kk * 64, n0 + (int)rank * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_f16_m(FMT, 256, BN);
+      bool ready = false;
+      int g = 0, i = 0;
+      for (int t = pair0; t < total_tiles; t += pair_stride, ++i) {
+        const int buf = i & 1;
+        mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < num_k; ++kb, ++g) {
+          const int s = g % STAGES;
+          if (!ready) mbar_wait(&full[s], (g / STAGES) & 1);
+          tc_fence_after();
+          ready = mbar_test(&full[(g + 1) % STAGES], ((g + 1) / STAGES) & 1);
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t a_desc = make_kmajor_desc<128>(a_addr);
+          const uint64_t b_desc = make_kmajor_desc<128>(a_addr + kATileBytes);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2cta(tmem_base + buf * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            umma_commit_2cta(&empty[s], 0x3);
+            if (kb == num_k - 1) umma_commit_2cta(&acc_full[buf], 0x3);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int blk_bytes = 128 * 128;
+    const bool issuer = warp == 2 && lane == 0;
+    int i = 0;
+    for (int t = pair0; t < total_tiles; t += pair_stride, ++i) {
+      int m0, n0, seq;
+      bool part_b;
+      decode(t, m0, n0, seq, part_b);
+      const int buf = i & 1;
+      mbar_wait(&acc_full[buf], (i >> 1) & 1);
+      tc_fence_after();
+      if (i >= 1) {                                  // the staging buffer is free once its previous stores have read it
+        if (issuer) tma_store_wait_read();
+        named_bar_sync(1, 128);
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + (col0 % p.cout));
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = __ldg(b4 + j);
+          float y0 = __uint_as_float(v[4 * j + 0]) + bb.x, y1 = __uint_as_float(v[4 * j + 1]) + bb.y;
+          float y2 = __uint_as_float(v[4 * j + 2]) + bb.z, y3 = __uint_as_float(v[4 * j + 3]) + bb.w;
+          if (LRELU) { y0 = lrelu_fast(y0); y1 = lrelu_fast(y1); y2 = lrelu_fast(y2); y3 = lrelu_fast(y3); }
+          w[2 * j] = pack2t<FMT>(y0, y1);
+          w[2 * j + 1] = pack2t<FMT>(y2, y3);
+        }
+        uint8_t* dst = staging + (c >> 1) * blk_bytes + row * 128;  // block = 64 channels, this chunk = half of it
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(dst + ((((c & 1) * 4 + j) ^ (row & 7)) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive_leader(&acc_empty[buf]);   // accumulator drained: the MMAs of pair tile i+2 may start
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (issuer && !(p.dbg & 4)) {
+        for (int j = 0; j < BN / 64; ++j) {
+          const int col = n0 + j * 64;
+          const int r = col / p.cout, co0 = col % p.cout;
+          const int rr = part_b ? r - p.pad + p.stride : r - p.pad;
+          const int mm = part_b ? m0 - 1 : m0;
+          tma_store_4d(&tmOut, staging + j * blk_bytes, co0, rr, mm, seq);
+        }
+        tma_store_commit();
+      }
+    }
+    if (issuer) tma_store_wait_read();
+  }
+  tc_fence_before();
+  cluster_sync_all();                                  // the peer may still read our shared memory / TMEM until here
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, 2 * BN);
+}
+
+template <int FMT, bool LRELU>
+static int launch_gemm_taps_pair_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                                   const GemmTapsParams& p, int n_seq, cudaStream_t stream) {
+  constexpr int STAGES = 4;
+  constexpr int SMEM = STAGES * (kATileBytes + 128 * 128) + 128 * 256 * 2 + 256 + 1024;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  static bool configured[16] = {};
+  static int sms[16] = {};
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  auto kernel = gemm_taps_pair_kernel<STAGES, FMT, LRELU>;
+  if (!configured[dev & 15]) {
+    B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    B200_CUDA(cudaDeviceGetAttribute(&sms[dev & 15], cudaDevAttrMultiProcessorCount, dev));
+    configured[dev & 15] = true;
+  }
+  GemmTapsParams pp = p;
+  {
+    const char* e = getenv("B200VOC_DBG");
+    pp.dbg = e ? atoi(e) : 0;
+  }
+  pp.m_tiles = ceil_div(p.rows_per_seq, 128);
+  pp.n_tiles = p.n_total / 256;
+  pp.n_seq = n_seq;
+  const long long total = (long long)((pp.m_tiles + 1) / 2) * pp.n_tiles * n_seq;
+  const long long cap = sms[dev & 15] / 2;
+  const int pairs = (int)(total < cap ? total : cap);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmOut, pp));
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
+
+static bool gemm_taps_pair_enabled() {          // B200VOC_TAPS_PAIR=0 keeps the single-CTA kernel (A/B runs)
+  static const bool on = [] { const char* e = getenv("B200VOC_TAPS_PAIR"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+static int launch_gemm_taps_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                                 const GemmTapsParams& p, int n_seq, cudaStream_t stream) {
+  if (p.fmt == 0) {
+    if (p.store_lrelu) return launch_gemm_taps_pair_t<0, true>(tmA, tmB, tmOut, p, n_seq, stream);
+    return launch_gemm_taps_pair_t<0, false>(tmA, tmB, tmOut, p, n_seq, stream);
+  }
+  if (p.store_lrelu) return launch_gemm_taps_pair_t<1, true>(tmA, tmB, tmOut, p, n_seq, stream);
+  return launch_gemm_taps_pair_t<1, false>(tmA, tmB, tmOut, p, n_seq, stream);
+}
+
 template <int BN, int STAGES, int FMT, bool LRELU>
 static int launch_gemm_taps_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                               const GemmTapsParams& p, int n_seq, cudaStream_t stream) {
@@ -312,6 +544,10 @@ int convt1d_launch(const void* x16, const void* w_packed, const float* bias, int
   // tiles must be phase-pure w.r.t. the padding boundary: BN divides p*Cout
   const int pc = p.pad * Cout;
   if (pc % 256 == 0 && n_total % 256 == 0) {
+    if (gemm_taps_pair_enabled() && (long long)ceil_div(Lin, 128) * N >= 2) {
+      B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 128, 128));   // half weight tiles
+      return launch_gemm_taps_pair(tmA, tmB, tmOut, p, N, stream);
+    }
     B200_TRY(make_tmap_2d(&tmB, w_packed, 2 * Cin, n_total, (uint64_t)2 * Cin * 2, 64, 256, 128));
     return launch_gemm_taps<256, 3>(tmA, tmB, tmOut, p, N, stream);
   } else if (pc % 128 == 0 && n_total % 128 == 0) {
