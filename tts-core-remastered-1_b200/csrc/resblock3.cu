@@ -72,7 +72,7 @@ struct Rb3Cfg {
   static constexpr int A_KB_BYTES = A_ROWS * 128;    // 18 KB per k-block
   static constexpr int A_BYTES = KPT * A_KB_BYTES;
   static constexpr bool INPLACE = C == 128;          // stage the output over the input tile + TMA store
-  static constexpr int NA = C == 128 ? 3 : 1;            // input tiles have their own producer warp (18)
+  static constexpr int NA = C == 128 ? 3 : (RB3_WS != 0 && PAIR ? 2 : 1);   // input tiles have their own producer warp (18)
   static constexpr int H_KB_BYTES = 128 * 128;       // 16 KB per k-block
   // PAIR: two CTAs (a cluster of 2) work on two neighbouring row tiles with ONE tcgen05.mma.cta_group::2 per
   // k-step (M = 256): each CTA stages only HALF of every weight tile (64 of its 128 rows), so the same
@@ -87,7 +87,7 @@ struct Rb3Cfg {
   // (~50 dependent instructions, sharing its scheduler with 4 epilogue warps) costs about as much as 4 MMAs.
   static constexpr int SUBS = PAIR ? 2 : 1;
   static constexpr int W_SLOT = SUBS * W_TILE;
-  static constexpr int NW = 5;
+  static constexpr int NW = (RB3_WS != 0 && PAIR && C == 256) ? 4 : 5;
   static constexpr int ND2 = C == 128 ? 2 : 1;
   // WS (C = 128 pairs): WEIGHT STATIONARY -- a pair holds all of W1 and W2 (each CTA its half of every tile: 96 + 16
   // KB), loaded once per launch, and h goes back into TMEM over the value columns of the GEMM1 accumulator it came from
@@ -95,11 +95,13 @@ struct Rb3Cfg {
   // the kernel is bound by the shared-memory data pipe and the ring's TMA writes (112 KB per tile), the
   // h stores and GEMM2's operand reads were a quarter of what that pipe carried; the issuer loses its per-slot barrier
   // wait + commit.  The accumulator buffer is handed back by GEMM2's commit (it holds h until then).
-  static constexpr bool WS = RB3_WS != 0 && C == 128 && PAIR;
+  static constexpr bool TSH = RB3_WS != 0 && PAIR;          // h through TMEM (both widths).  C = 256 keeps its weight ring
+                                                           // (W1 is 768 KB) and spends the h buffer's 64 KB on a SECOND input tile
+  static constexpr bool WS = TSH && C == 128;
   static constexpr int N_W1_TILES = NCH * 3 * KPT, N_W_TILES = N_W1_TILES + KPT * NH;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_H = OFF_A + NA * A_BYTES;
-  static constexpr int OFF_W = OFF_H + (WS ? 0 : KPT * H_KB_BYTES);
+  static constexpr int OFF_W = OFF_H + (TSH ? 0 : KPT * H_KB_BYTES);
   static constexpr int OFF_BAR = OFF_W + (WS ? N_W_TILES * W_TILE : NW * W_SLOT);
   static constexpr int OFF_PAR = OFF_BAR + 512;
   // BIAS_MMA: the three bias vectors are added on the tensor core -- one more K = 16 MMA per accumulator whose A
@@ -348,9 +350,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         w_ready = mbar_test(&w_full[wn % NW], (wn / NW) & 1);
         return s;
       };
-      // WS: GEMM2 k-block of chunk gc2 with h read from TMEM (buffer gc2 & 1, k-step k at columns 16k .. 16k+7 of the
-      // accumulator's value half); its commit hands the buffer back to GEMM1
-      auto g2_ws = [&](int gc2) {
+      // TSH: GEMM2 k-block of chunk gc2 with h read from TMEM (buffer gc2 & 1, k-step k at columns 16k .. 16k+7 of the
+      // accumulator's value half); W2's k-block is resident (WS) or the next ring slot (both column halves)
+      auto g2_ts = [&](int gc2) {
         const int it2 = gc2 / NCH, kb = gc2 - it2 * NCH, b2 = gc2 & 1, db = it2 % ND2;
         const uint32_t phh = (gc2 >> 1) & 1, phd = ((it2 / ND2) & 1) ^ 1;
         const bool rh = mbar_test(&h_full[b2], phh), rd = kb == 0 ? mbar_test(&d2_empty[db], phd) : true;
@@ -359,18 +361,28 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (!rd) wait_x(&d2_empty[db], phd);
         RB3_TRACE(2, gc2, 1);
         tc_fence_after();
-        const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sW + (K::N_W1_TILES + kb) * K::W_TILE));
+        int s = 0;
+        if (!K::WS) s = acquire_w();
+        const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(K::WS ? sW + (K::N_W1_TILES + kb) * K::W_TILE : sW + s * K::W_SLOT));
         if (elect_one()) {
           if (!RB3_DBG(8))
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_2cta_ts(tmem_base + K::D2_COL + db * C, tmem_base + b2 * 128 + 16 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          for (int half = 0; half < NH; ++half)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2cta_ts(tmem_base + K::D2_COL + db * C + half * 128, tmem_base + b2 * 128 + 16 * k,
+                               b_desc + (half * K::W_TILE >> 4) + 2 * k, idesc, (kb | k) != 0);
+          if (!K::WS) commit(&w_empty[s]);
           if (kb == NCH - 1) {
-            if (K::BIAS_MMA) bias_mma(tmem_base + K::D2_COL + db * C, NCH);
+            if (K::BIAS_MMA) {
+#pragma unroll
+              for (int half = 0; half < NH; ++half) bias_mma(tmem_base + K::D2_COL + db * C + half * 128, NCH + half);
+            }
             commit(&d2_full[db]);
           }
         }
         __syncwarp();
+        if (!K::WS) ++wi;
       };
       auto g2 = [&](int it2, int kb) {
         const int db = it2 % ND2;
@@ -433,7 +445,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const uint32_t pha = (it / NA) & 1, phd = ((gc >> 1) & 1) ^ 1;
             // WS: no d1_empty -- GEMM1 of chunk gc overwrites the buffer GEMM2 of chunk gc-2 read h from, and that MMA
             // was issued earlier by this thread (the tensor pipe runs one thread's MMAs in order)
-            const bool ra = j == 0 ? mbar_test(&a_full[ab], pha) : true, rd = K::WS ? true : mbar_test(&d1_empty[b], phd);
+            const bool ra = j == 0 ? mbar_test(&a_full[ab], pha) : true, rd = K::TSH ? true : mbar_test(&d1_empty[b], phd);
             if (!ra) mbar_wait(&a_full[ab], pha);
             if (PAIR && j == 0) wait_x(&a_peer[ab], pha);
             RB3_TRACE(1, gc, 0);
@@ -489,8 +501,8 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           RB3_TRACE(1, gc, 2);
         }
         if (gc >= 1) {
-          if (K::WS) {
-            g2_ws(gc - 1);
+          if (K::TSH) {
+            g2_ts(gc - 1);
           } else {
             const int pj = j == 0 ? NCH - 1 : j - 1;
             g2(j == 0 ? it - 1 : it, pj);
@@ -537,7 +549,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           stage = __ldg(reinterpret_cast<const float4*>(film + (lane < 8 ? 0 : C) + ch0) + (lane & 7));
         mbar_wait(&d1_full[b], (gc >> 1) & 1);
         if (q == 0 && par == 0) RB3_TRACE(3, gc, 0);
-        if (!K::WS) mbar_wait(&h_empty[j], (it & 1) ^ 1);
+        if (!K::TSH) mbar_wait(&h_empty[j], (it & 1) ^ 1);
         if (q == 0 && par == 0) RB3_TRACE(3, gc, 1);
         tc_fence_after();
         if (uniform) {
@@ -596,7 +608,7 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 hv[h4 * 4 + e] = fmaf(fmaf(a, th, a), sv[e], tv[e]);                      // a sigmoid(g) (1+scale) + shift
               }
             }
-            if (K::WS) {
+            if (K::TSH) {
               hw8[i8 * 4 + 0] = pack2t<FMT>(hv[0], hv[1]); hw8[i8 * 4 + 1] = pack2t<FMT>(hv[2], hv[3]);
               hw8[i8 * 4 + 2] = pack2t<FMT>(hv[4], hv[5]); hw8[i8 * 4 + 3] = pack2t<FMT>(hv[6], hv[7]);
             } else {
@@ -609,9 +621,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
           // WS: the 16 channels just computed, as 8 packed columns over the first 8 of the value columns they came from
           // (k-step cl/16 of GEMM2's TMEM A operand)
-          if (K::WS) tmem_st8(lane_addr + b * 128 + cl, hw8);
+          if (K::TSH) tmem_st8(lane_addr + b * 128 + cl, hw8);
         }
-        if (K::WS) {
+        if (K::TSH) {
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
