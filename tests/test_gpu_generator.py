@@ -217,6 +217,53 @@ def test_resblock_layer(C, d, fmt, store_lrelu):
     assert float(((got - ref).abs() / (ref.abs() + 1.0)).max()) <= 3 * ulp
 
 
+@pytest.mark.parametrize("C,fmt", [(128, 0), (256, 0), (128, 1), (64, 0)])
+def test_resblock_layer_large_biases(C, fmt):
+    """the biases are added on the tensor core as [b/2 hi, b/2 lo] columns against an all-ones operand (resblock3.cu,
+    stage_fused.cu): biases of magnitude ~5-8 with awkward mantissas must come through (a missing or misplaced bias
+    column is an O(1) error).  With |h| ~ 5-10 the 16-bit rounding of h ahead of GEMM2 is itself several output ulps
+    at |out| ~ 1, hence 8 ulps here instead of the 3 of the unit-scale test."""
+    _l, lib = _lib()
+    dt = torch.float16 if fmt == 0 else torch.bfloat16
+    B, nb, T, P, d = 1, 4, 3, 128, 3
+    N, L = B * nb, T * P
+    g = torch.Generator().manual_seed(77 + C)
+    x = torch.randn(N, C, L, generator=g) * 0.5
+    if lib.b200voc_resblock_input_is_lrelu(C):
+        a = F.leaky_relu(x, 0.1).to(dt)
+        xr = torch.where(a.float() >= 0, a.float(), a.float() * 10.0)
+    else:
+        a = x.to(dt)
+        xr = a.float()
+    cond = torch.randn(B, 128, T, generator=g)
+    wc = torch.randn(2 * C, C, 3, generator=g) / (3 * C) ** 0.5
+    bc = torch.randn(2 * C, generator=g) * 2.0 + 1.2345678      # value biases ~ +-5, gate biases keep the gates open / shut
+    wf = torch.randn(2 * C, 128, 1, generator=g) / 128 ** 0.5
+    bf = torch.randn(2 * C, generator=g) * 0.1
+    wp_ = torch.randn(C, C, 1, generator=g) / C ** 0.5
+    bp = torch.randn(C, generator=g) * 8.0 + 0.0123456
+    xq = xr.double().view(B, nb, C, L)
+    ref = torch.stack([O.residual_block_forward(xq[:, k], cond.double(), wc.to(dt).double(), bc.double(), wf.double(),
+                                                bf.double(), wp_.to(dt).double(), bp.double(), d) for k in range(nb)], 1)
+    ref = ref.reshape(N, C, L)
+    film = F.conv1d(cond, wf, bf)
+    film[:, :C] += 1.0
+    film_cl = film.transpose(1, 2).contiguous().cuda()
+    a_cl = a.transpose(1, 2).contiguous().cuda()
+    wpk = torch.empty(lib.b200voc_resblock_packed_elems(C), dtype=dt, device="cuda")
+    st = _l.current_stream()
+    wcd, wpd, bcd, bpd = wc.cuda(), wp_.cuda(), bc.cuda(), bp.cuda()
+    _l.check(lib.b200voc_pack_resblock_weights(_l.ptr(wcd), _l.ptr(wpd), C, fmt, _l.ptr(wpk), st))
+    out = torch.full((N, L, C), float("nan"), dtype=dt, device="cuda")
+    _l.check(lib.b200voc_resblock(_l.ptr(a_cl), _l.ptr(wpk), _l.ptr(bcd), _l.ptr(bpd), _l.ptr(film_cl), N, L, C, d, T,
+                                  nb, fmt, 0, _l.ptr(out), st))
+    torch.cuda.synchronize()
+    got = out.float().cpu().transpose(1, 2).double()
+    assert not bool(torch.isnan(got).any())
+    ulp = 2.0 ** -11 if fmt == 0 else 2.0 ** -8
+    assert float(((got - ref).abs() / (ref.abs() + 1.0)).max()) <= 8 * ulp
+
+
 @pytest.mark.parametrize("C", [128, 256, 64])
 def test_resblock_layer_odd_tile_count(C):
     """an odd number of 128-row tiles: the CTA-pair kernel's peer CTA gets one all-out-of-bounds tile
