@@ -151,12 +151,23 @@ def test_disc_conv_tensor_core_layer_matches_fp64(B, Cin, Cout, L, K):
     wsplit = torch.empty(int(lib.b200voc_disc_split_weight_elems(Cout, Cin, K)), device="cuda", dtype=torch.bfloat16)
     st = _lib.current_stream()
     _lib.check(lib.b200voc_disc_pack_weight_split(_lib.ptr(wd), Cout, Cin, K, _lib.ptr(wsplit), st))
-    ws = torch.empty(int(lib.b200voc_disc_conv_tc_workspace_bytes(B, Cin, L)), device="cuda", dtype=torch.uint8)
-    y_pre = torch.full((B, Cout, L), float("nan"), device="cuda")
-    y_act = torch.full((B, Cout, L), float("nan"), device="cuda")
+    # outputs and workspace sit inside larger buffers with sentinel guards on both sides: the kernels must not write a
+    # single element outside what the ABI says they own (ragged last tiles, the all-out-of-range rows of a 128-row block)
+    G = 4096
+    ws_bytes = int(lib.b200voc_disc_conv_tc_workspace_bytes(B, Cin, L))
+    ws_big = torch.full((ws_bytes + 2 * G,), 0xA5, device="cuda", dtype=torch.uint8)
+    ws = ws_big[G:G + ws_bytes]
+    n_out = B * Cout * L
+    pre_big = torch.full((n_out + 2 * G,), -777.0, device="cuda")
+    act_big = torch.full((n_out + 2 * G,), -777.0, device="cuda")
+    y_pre, y_act = pre_big[G:G + n_out].view(B, Cout, L), act_big[G:G + n_out].view(B, Cout, L)
+    y_pre.fill_(float("nan")); y_act.fill_(float("nan"))
     _lib.check(lib.b200voc_disc_conv_tc(_lib.ptr(xd), _lib.ptr(wsplit), _lib.ptr(bd), B, Cin, Cout, L, K, pad, 0.2,
                                         _lib.ptr(y_pre), _lib.ptr(y_act), _lib.ptr(ws), ws.numel(), st))
     torch.cuda.synchronize()
+    for big in (pre_big, act_big):
+        assert bool((big[:G] == -777.0).all()) and bool((big[G + n_out:] == -777.0).all()), "write outside the output map"
+    assert bool((ws_big[:G] == 0xA5).all()) and bool((ws_big[G + ws_bytes:] == 0xA5).all()), "write outside the workspace"
     scale = float(ref.abs().max())
     err = float((y_pre.cpu().double() - ref).abs().max())
     assert err <= 6e-5 * scale, f"conv map: {err:.3e} vs scale {scale:.3e}"
