@@ -206,3 +206,25 @@ def test_graphed_synthesizer_matches_eager_across_shapes():
         assert torch.equal(got16, gen(*ins, out_dtype=torch.int16))
     with pytest.raises(ValueError):
         gs(*[x.cpu() for x in ins])
+
+
+@pytest.mark.parametrize("B,T,dtype", [(1, 9, torch.float32), (3, 23, torch.float32), (2, 16, torch.int16)])
+def test_forward_writes_nothing_outside_the_output(B, T, dtype):
+    """the waveform is written by the fused last-stage kernel strip by strip (halo rows are recomputed, never stored):
+    sentinel guards on both sides of ``out=`` must survive, for float and PCM16 outputs and ragged strip counts"""
+    from b200voc import GANConfig, Generator
+    ora = O.make_generator(O.OracleConfig(use_attention=False), seed=1234)
+    gen = Generator(GANConfig(use_attention=False)).eval()
+    gen.load_state_dict(ora.state_dict())
+    gen = gen.cuda()
+    ins = [x.cuda() for x in O.synthetic_inputs(B, T, seed=3)]
+    n, G = B * 256 * T, 8192
+    sentinel = 12345 if dtype == torch.int16 else -777.0
+    big = torch.full((n + 2 * G,), sentinel, device="cuda", dtype=dtype)
+    out = big[G:G + n].view(B, 1, 256 * T)
+    with torch.no_grad():
+        got = gen(*ins, out=out, out_dtype=dtype)
+        want = gen(*ins, out_dtype=dtype)
+    torch.cuda.synchronize()
+    assert bool((big[:G] == sentinel).all()) and bool((big[G + n:] == sentinel).all())
+    assert torch.equal(got, want)
