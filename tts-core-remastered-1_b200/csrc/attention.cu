@@ -223,11 +223,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     };
 
     int jprev = -1;
+    // j % 3 and j / 3 advance by rule (j grows by 2): no divisions in the loop
+    int sb = g, q3 = 0;                                  // S / P buffer j % 3 and j / 3 of the current tile
     for (int j = g; j < nkt; j += 2) {
-      const int b = g;                                   // == j & 1: P / PV buffer
+      const int b = g;                                   // == j & 1: PV buffer
       const uint32_t ph = (j >> 1) & 1;
-      const int sb = j % 3;                              // S buffer
-      mbar_wait(&s_full[sb], (j / 3) & 1);
+      mbar_wait(&s_full[sb], q3 & 1);
       tc_fence_after();
       // pass 1: maximum of this thread's 64 columns (scores are already in the log2 domain), then of the row
       float m_half = -INFINITY;
@@ -245,7 +246,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       const float m_new = fmaxf(m_run, fmaxf(m_half, sMax[(h ^ 1) * 128 + row]));
       const float alpha = ex2_approx(m_run - m_new);     // exp2(-inf) = 0 on the first tile
       // pass 2: p = exp2(s - m), partial row sum, 16-bit P into k-block h of the swizzled K-major operand tile
-      mbar_wait(&p_empty[sb], ((j / 3) & 1) ^ 1);        // P buffer = j % 3 as well
+      mbar_wait(&p_empty[sb], (q3 & 1) ^ 1);             // P buffer = j % 3 as well
       float l_tile = 0.f;
       uint8_t* prow = sP + sb * kP_BYTES + h * 128 * 128 + row * 128;
 #pragma unroll 1
@@ -280,6 +281,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       if (jprev >= 0) accumulate_pv(jprev, alpha_prev);
       alpha_prev = alpha;
       jprev = j;
+      if (sb >= 1) { sb -= 1; q3 += 1; } else sb += 2;   // (j + 2) % 3, (j + 2) / 3
     }
     if (jprev >= 0) accumulate_pv(jprev, alpha_prev);
 
