@@ -33,6 +33,13 @@ struct MelTable {      // CSR by mel bin over frequency bins
   const float* w;
   int n_mels;
   int nnz;             // number of weights (length of w)
+  // the same filters as 4-aligned, zero-padded runs (stft1024's mel stage reads bins and weights as float4):
+  // filter m covers bins lo4[m] .. lo4[m] + 4*n4[m] - 1 with weights w4[off4[m] ...] (off4 a multiple of 4)
+  const int* lo4;
+  const int* n4;
+  const int* off4;
+  const float* w4;
+  int nnz4;
 };
 
 struct FftTables {     // per (device, n_fft), built once on the host in double precision
@@ -197,11 +204,15 @@ stft1024_kernel(const StftParams p) {
   }
   // MODE_MEL: the sparse filterbank's weights live in shared memory (4 KB for 80 HTK mels): read through __ldg they
   // were 130 of the ~550 load/store-pipe wavefronts per frame of a kernel whose LSU pipe is 76 % busy
-  constexpr int kMelSmemMax = 2048;
+  // The mel stage reads FOUR bins and four weights per load (float4): the staged power spectrum is frame-major there
+  // ([8 frames][516]: 516 = 4 mod 32, so the 8 frames of a quarter warp cover all 32 banks) and the filters are
+  // 4-aligned zero-padded runs -- with one 4-byte load per bin and per weight the stage was 30 % of the kernel's
+  // shared-memory wavefronts (2.2 per bin load: the four filters a warp evaluates conflicted).
+  constexpr int kMelSmemMax = 2560, MSW = 516;
   float* sMelW = reinterpret_cast<float*>(wbuf + kFastWarps * 576);
-  const bool mel_smem = MODE == MODE_MEL && p.mel.nnz <= kMelSmemMax;
+  const bool mel_smem = MODE == MODE_MEL && p.mel.nnz4 <= kMelSmemMax;
   if (mel_smem)
-    for (int i = threadIdx.x; i < p.mel.nnz; i += blockDim.x) sMelW[i] = __ldg(p.mel.w + i);
+    for (int i = threadIdx.x; i < p.mel.nnz4; i += blockDim.x) sMelW[i] = __ldg(p.mel.w4 + i);
   float l1_acc = 0.f;
   constexpr int NPASS = MODE == MODE_L1 ? 2 : 1;
   float2 wreg[REGTAB ? 16 : 1], treg[REGTAB ? 16 : 1];
@@ -257,7 +268,7 @@ stft1024_kernel(const StftParams p) {
         if (MODE == MODE_COMPLEX) {
           reinterpret_cast<float2*>(stage)[k * SW + warp] = X;
         } else if (MODE == MODE_MEL) {
-          stage[k * SW + warp] = X.x * X.x + X.y * X.y;
+          stage[warp * MSW + k] = X.x * X.x + X.y * X.y;       // frame-major (see the mel stage)
         } else {
           float mag = sqrtf(X.x * X.x + X.y * X.y);
           if (p.gain) mag *= __ldg(p.gain + k);
@@ -284,6 +295,7 @@ stft1024_kernel(const StftParams p) {
         const float2 zm = T[N / 2];
         emit(N / 2, make_float2(zm.x, -zm.y));
       }
+      if (MODE == MODE_MEL && lane >= 1 && lane <= 3) stage[warp * MSW + BINS - 1 + lane] = 0.f;   // zero-weight padding bins 513..515
       __syncwarp();
     }
     __syncthreads();
@@ -304,16 +316,17 @@ stft1024_kernel(const StftParams p) {
     } else if (MODE == MODE_MEL) {
       float* o = p.out + (long long)b * p.mel.n_mels * p.frames + f0 + f;
       for (int m = kk; m < p.mel.n_mels; m += 32) {
-        const int lo = __ldg(p.mel.lo + m), cnt = __ldg(p.mel.cnt + m);
-        const int woff = __ldg(p.mel.off + m);
-        const float* sp = stage + lo * SW + f;
+        const int lo4 = __ldg(p.mel.lo4 + m), n4 = __ldg(p.mel.n4 + m), woff = __ldg(p.mel.off4 + m);
+        const float4* sp = reinterpret_cast<const float4*>(stage + f * MSW + lo4);
+        const float4* wv = reinterpret_cast<const float4*>((mel_smem ? sMelW : p.mel.w4) + woff);
         float acc = 0.f;
-        if (mel_smem) {
-          const float* wv = sMelW + woff;
-          for (int k = 0; k < cnt; ++k) acc = fmaf(wv[k], sp[k * SW], acc);
-        } else {
-          const float* wv = p.mel.w + woff;
-          for (int k = 0; k < cnt; ++k) acc = fmaf(__ldg(wv + k), sp[k * SW], acc);
+        for (int i = 0; i < n4; ++i) {
+          const float4 w4 = mel_smem ? wv[i] : __ldg(wv + i);
+          const float4 p4 = sp[i];
+          acc = fmaf(w4.x, p4.x, acc);                    // bins in ascending order, as the 4-byte loop summed them
+          acc = fmaf(w4.y, p4.y, acc);
+          acc = fmaf(w4.z, p4.z, acc);
+          acc = fmaf(w4.w, p4.w, acc);
         }
         if (p.log_compress) acc = logf(fmaxf(acc, 1e-5f));
         if (fok) o[(long long)m * p.frames] = acc;
@@ -338,7 +351,7 @@ static int launch_stft1024(const StftParams& p, cudaStream_t st) {
   const int span_len = (kFastWarps - 1) * p.hop + 1024;
   const size_t span_bytes = (size_t)((span_len + 3) & ~3) * 4, stage_bytes = (size_t)513 * (kFastWarps + 1) * (MODE == MODE_COMPLEX ? 8 : 4);
   const size_t head = MODE != MODE_L1 ? (((span_bytes > stage_bytes ? span_bytes : stage_bytes) + 15) & ~(size_t)15) : span_bytes + stage_bytes;
-  const size_t mel_bytes = (MODE == MODE_MEL && p.mel.nnz <= 2048) ? (size_t)((p.mel.nnz + 3) & ~3) * 4 : 0;
+  const size_t mel_bytes = (MODE == MODE_MEL && p.mel.nnz4 <= 2560) ? (size_t)p.mel.nnz4 * 4 : 0;
   const size_t smem = head + 514 * 8 + 512 * 8 + 512 * 8 + (size_t)kFastWarps * 576 * 8 + mel_bytes + 64;
   B200_CHECK_ARG(smem <= 227 * 1024, "stft: hop %d needs %zu bytes of shared memory", p.hop, smem);
   dim3 grid(ceil_div(p.frames, kFastWarps * kFastRounds), p.B);
@@ -442,6 +455,9 @@ struct MelDev {
   int *lo, *cnt, *off;
   float* w;
   int nnz;
+  int *lo4, *n4, *off4;
+  float* w4;
+  int nnz4;
 };
 static std::mutex g_mel_mu;
 static std::map<std::tuple<int, int, int, int>, MelDev> g_mel_cache;
@@ -492,6 +508,30 @@ static int get_mel_table(int n_fft, int n_mels, int sr, MelTable* out) {
     B200_CUDA(cudaMemcpy(d.off, off.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
     B200_CUDA(cudaMemcpy(d.w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
     d.nnz = (int)w.size();
+    {
+      std::vector<int> lo4(n_mels), n4(n_mels), off4(n_mels);
+      std::vector<float> w4;
+      for (int m = 0; m < n_mels; ++m) {
+        lo4[m] = lo[m] & ~3;
+        const int end = lo[m] + cnt[m];
+        n4[m] = cnt[m] > 0 ? (end - lo4[m] + 3) / 4 : 0;
+        off4[m] = (int)w4.size();
+        for (int i = 0; i < 4 * n4[m]; ++i) {
+          const int k = lo4[m] + i;
+          w4.push_back(k >= lo[m] && k < end ? w[off[m] + (k - lo[m])] : 0.f);
+        }
+      }
+      if (w4.empty()) w4.resize(4, 0.f);
+      B200_CUDA(cudaMalloc(&d.lo4, n_mels * sizeof(int)));
+      B200_CUDA(cudaMalloc(&d.n4, n_mels * sizeof(int)));
+      B200_CUDA(cudaMalloc(&d.off4, n_mels * sizeof(int)));
+      B200_CUDA(cudaMalloc(&d.w4, w4.size() * sizeof(float)));
+      B200_CUDA(cudaMemcpy(d.lo4, lo4.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+      B200_CUDA(cudaMemcpy(d.n4, n4.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+      B200_CUDA(cudaMemcpy(d.off4, off4.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+      B200_CUDA(cudaMemcpy(d.w4, w4.data(), w4.size() * sizeof(float), cudaMemcpyHostToDevice));
+      d.nnz4 = (int)w4.size();
+    }
     it = g_mel_cache.emplace(key, d).first;
   }
   out->lo = it->second.lo;
@@ -500,6 +540,11 @@ static int get_mel_table(int n_fft, int n_mels, int sr, MelTable* out) {
   out->w = it->second.w;
   out->n_mels = n_mels;
   out->nnz = it->second.nnz;
+  out->lo4 = it->second.lo4;
+  out->n4 = it->second.n4;
+  out->off4 = it->second.off4;
+  out->w4 = it->second.w4;
+  out->nnz4 = it->second.nnz4;
   return B200VOC_OK;
 }
 
