@@ -224,6 +224,16 @@ stft1024_kernel(const StftParams p) {
       treg[n1] = tw1[n1 * 32 + lane];
     }
   }
+  // The NEXT round's samples are requested into registers (up to PF float4 per thread: hop <= 292) as soon as this
+  // round's frames sit in registers, and stored to shared memory at the top of the next round: the span fill was a
+  // phase in which every warp of the CTA waited for HBM (long_scoreboard 18 % of the stall samples).
+  constexpr int PF = 3;
+  float4 pf[PF];
+  bool have_pf = false;
+  auto interior = [&](int f0r) {
+    const int s0r = f0r * p.hop - N;
+    return s0r >= 0 && s0r + span_len <= p.Nsamp && ((s0r | p.Nsamp | span_len) & 3) == 0;   // (hop % 4 == 2: span_len % 4 == 2)
+  };
 #pragma unroll 1
   for (int round = 0; round < kFastRounds; ++round) {
     const int f0 = (blockIdx.x * kFastRounds + round) * kFastWarps;
@@ -233,7 +243,14 @@ stft1024_kernel(const StftParams p) {
       const float* w = (pass == 0 ? p.wav : p.wav2) + (long long)b * p.Nsamp;
       __syncthreads();                                   // previous users of span / stage are done
       const int s0 = f0 * p.hop - N;                     // first sample of the span (may be < 0: reflect)
-      if (s0 >= 0 && s0 + span_len <= p.Nsamp && ((s0 | p.Nsamp | span_len) & 3) == 0) {   // (hop % 4 == 2: span_len % 4 == 2)
+      if (have_pf) {
+#pragma unroll
+        for (int t = 0; t < PF; ++t) {
+          const int i = threadIdx.x + t * (kFastWarps * 32);
+          if (i < (span_len >> 2)) reinterpret_cast<float4*>(span)[i] = pf[t];
+        }
+        have_pf = false;
+      } else if (interior(f0)) {
         const float4* src = reinterpret_cast<const float4*>(w + s0);     // interior: plain vector loads
         for (int i = threadIdx.x; i < (span_len >> 2); i += blockDim.x) reinterpret_cast<float4*>(span)[i] = __ldg(src + i);
       } else {
@@ -251,6 +268,18 @@ stft1024_kernel(const StftParams p) {
         v[n1] = make_float2(x.x * wn.x, x.y * wn.y);
       }
       if constexpr (ALIAS) __syncthreads();              // every warp has its frame: the span's storage becomes the stage
+      if (NPASS == 1 && round + 1 < kFastRounds && (span_len >> 2) <= PF * kFastWarps * 32) {
+        const int f0n = f0 + kFastWarps;
+        if (f0n < p.frames && interior(f0n)) {
+          const float4* src = reinterpret_cast<const float4*>(w + f0n * p.hop - N);
+#pragma unroll
+          for (int t = 0; t < PF; ++t) {
+            const int i = threadIdx.x + t * (kFastWarps * 32);
+            if (i < (span_len >> 2)) pf[t] = __ldg(src + i);
+          }
+          have_pf = true;
+        }
+      }
       if constexpr (REGTAB) warp_fft512_regtw<false>(v, T, treg, lane);
       else warp_fft512<false>(v, T, tw1, lane);
       // Z -> linear per-warp buffer (reusing the transpose scratch), then the real-FFT split
