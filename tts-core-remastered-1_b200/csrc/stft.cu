@@ -165,7 +165,10 @@ stft_kernel(const StftParams p) {
 // ------------------------------------------------------------------ fast path, n_fft = 1024
 // One warp per frame (fft_warp.cuh), 8 warps = 8 consecutive frames per round, kRounds rounds per
 // CTA.  Window samples and the per-lane twiddles live in registers for the whole CTA.
-constexpr int kFastWarps = 8, kFastRounds = 4;
+constexpr int kFastWarps = 8;
+// rounds (of 8 frames) per CTA: the fused log-mel gains from amortising the table set-up and the one cold span load over 8
+// rounds (0.766 -> 0.744 ms), the store-heavy magnitude / complex modes are better with more, shorter CTAs (measured)
+template <int MODE> struct FastRounds { static constexpr int value = MODE == 2 ? 8 : 4; };
 
 // REGTAB (opt-in, B200VOC_STFT_REGTAB=1): the 16 window pairs and 15 stage-1 twiddles a lane needs are the same for
 // every frame, so they are read from shared memory once per CTA and kept in registers -- 31 of the ~119 64-bit
@@ -234,6 +237,7 @@ stft1024_kernel(const StftParams p) {
     const int s0r = f0r * p.hop - N;
     return s0r >= 0 && s0r + span_len <= p.Nsamp && ((s0r | p.Nsamp | span_len) & 3) == 0;   // (hop % 4 == 2: span_len % 4 == 2)
   };
+  constexpr int kFastRounds = FastRounds<MODE>::value;
 #pragma unroll 1
   for (int round = 0; round < kFastRounds; ++round) {
     const int f0 = (blockIdx.x * kFastRounds + round) * kFastWarps;
@@ -383,7 +387,7 @@ static int launch_stft1024(const StftParams& p, cudaStream_t st) {
   const size_t mel_bytes = (MODE == MODE_MEL && p.mel.nnz4 <= 2560) ? (size_t)p.mel.nnz4 * 4 : 0;
   const size_t smem = head + 514 * 8 + 512 * 8 + 512 * 8 + (size_t)kFastWarps * 576 * 8 + mel_bytes + 64;
   B200_CHECK_ARG(smem <= 227 * 1024, "stft: hop %d needs %zu bytes of shared memory", p.hop, smem);
-  dim3 grid(ceil_div(p.frames, kFastWarps * kFastRounds), p.B);
+  dim3 grid(ceil_div(p.frames, kFastWarps * FastRounds<MODE>::value), p.B);
   static const bool regtab = [] { const char* e = getenv("B200VOC_STFT_REGTAB"); return e && e[0] == '1'; }();
   if (regtab) {   // opt-in A/B variant (written after the round's GPU budget was spent: not yet measured)
     B200_CUDA(cudaFuncSetAttribute(stft1024_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
