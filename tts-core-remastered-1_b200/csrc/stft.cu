@@ -766,6 +766,23 @@ istft1024_kernel(const IstftParams p) {
     // output sample n = n0 + h * hop + r: padded coordinate j = n + joff, newest frame f_hi = j / hop, contribution q
     // comes from slot (f_hi - q - f_lo) at position r + q * hop
     const int s_hi0 = (n0 + p.joff) / hop - f_lo;        // slot of f_hi for h = 0 (= ratio - 1)
+    const float* flat = reinterpret_cast<const float*>(slots);
+    constexpr int S2 = 2 * kISlotStride;                 // floats per slot
+    if (ratio == 4) {
+      // hop = n_fft / 4 (the reference's setting): the four contributions of a sample sit at fixed offsets from one
+      // running pointer -- 4 loads, 3 adds, 1 multiply, 1 store per sample (the generic loop below spent ~50
+      // instructions per sample on index arithmetic: 17 % of the kernel's instructions)
+      const float* pq = flat + (s_hi0 + part) * S2 + r;
+      float* on = o + n0 + part * hop + r;
+      const int step = lanes_per * S2, ostep = lanes_per * hop;
+      int n = n0 + part * hop + r;
+#pragma unroll 2
+      for (int h = part; h < nhop && n < p.Nout; h += lanes_per, pq += step, on += ostep, n += ostep) {
+        const float acc = ((pq[0] + pq[hop - S2]) + pq[2 * hop - 2 * S2]) + pq[3 * hop - 3 * S2];
+        *on = p.normalize ? acc * inv_env : acc;
+      }
+      return;
+    }
     for (int h = part; h < nhop; h += lanes_per) {
       const int n = n0 + h * hop + r;
       if (n >= p.Nout) break;
@@ -773,7 +790,7 @@ istft1024_kernel(const IstftParams p) {
 #pragma unroll 4
       for (int q = 0; q < ratio; ++q) {
         const int idx = r + q * hop;
-        acc += reinterpret_cast<const float*>(slots + (s_hi0 + h - q) * kISlotStride)[idx];   // sample idx of the frame: one 4-byte load
+        acc += flat[(s_hi0 + h - q) * S2 + idx];          // sample idx of the frame: one 4-byte load
       }
       o[n] = p.normalize ? acc * inv_env : acc;
     }
