@@ -46,6 +46,7 @@ struct FftTables {     // per (device, n_fft), built once on the host in double 
   const float* win;    // [n_fft] periodic Hann
   const float2* tw;    // [<= n_fft/2] per-pass Stockham twiddle tables (fft_core.cuh)
   const float2* tw2;   // [n_fft/2+1] exp(-pi i k / (n_fft/2))
+  const float2* tw1;   // [16][32] exp(-2 pi i lane k1 / 512): stage-1 twiddles of the warp-per-frame FFT (n_fft = 1024)
 };
 
 static int get_fft_tables(int n_fft, FftTables* out);
@@ -200,10 +201,7 @@ stft1024_kernel(const StftParams p) {
   for (int i = threadIdx.x; i <= N; i += blockDim.x) tw2[i] = __ldg(p.tab.tw2 + i);
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     win2[i] = __ldg(reinterpret_cast<const float2*>(p.tab.win) + i);
-    const int k1 = i >> 5, t = i & 31;
-    float s, c;
-    sincospif(-2.0f * (float)((t * k1) & 511) / 512.0f, &s, &c);
-    tw1[i] = make_float2(c, s);
+    tw1[i] = __ldg(p.tab.tw1 + i);
   }
   // MODE_MEL: the sparse filterbank's weights live in shared memory (4 KB for 80 HTK mels): read through __ldg they
   // were 130 of the ~550 load/store-pipe wavefronts per frame of a kernel whose LSU pipe is 76 % busy
@@ -473,8 +471,18 @@ static int get_fft_tables(int n_fft, FftTables* out) {
     B200_CUDA(cudaMemcpy(dwin, win.data(), n_fft * sizeof(float), cudaMemcpyHostToDevice));
     B200_CUDA(cudaMemcpy(dtw, tw.data(), N * sizeof(float2), cudaMemcpyHostToDevice));
     B200_CUDA(cudaMemcpy(dtw2, tw2.data(), (N + 1) * sizeof(float2), cudaMemcpyHostToDevice));
+    // stage-1 twiddles of the warp FFT (fft_warp.cuh): the kernels used to evaluate 512 sincospif per CTA for them
+    std::vector<float2> tw1(512);
+    for (int i = 0; i < 512; ++i) {
+      const int k1 = i >> 5, tl = i & 31;
+      const double a = -2.0 * M_PI * (double)((tl * k1) & 511) / 512.0;
+      tw1[i] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    float2* dtw1;
+    B200_CUDA(cudaMalloc(&dtw1, 512 * sizeof(float2)));
+    B200_CUDA(cudaMemcpy(dtw1, tw1.data(), 512 * sizeof(float2), cudaMemcpyHostToDevice));
     FftTables t{};
-    t.win = dwin; t.tw = dtw; t.tw2 = dtw2;
+    t.win = dwin; t.tw = dtw; t.tw2 = dtw2; t.tw1 = dtw1;
     it = g_tab_cache.emplace(key, t).first;
   }
   *out = it->second;
@@ -691,10 +699,7 @@ istft1024_kernel(const IstftParams p) {
   for (int i = threadIdx.x; i <= N; i += blockDim.x) tw2[i] = __ldg(p.tab.tw2 + i);
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     win2[i] = __ldg(reinterpret_cast<const float2*>(p.tab.win) + i);
-    const int k1 = i >> 5, t = i & 31;
-    float s, c;
-    sincospif(-2.0f * (float)((t * k1) & 511) / 512.0f, &s, &c);
-    tw1[i] = make_float2(c, s);
+    tw1[i] = __ldg(p.tab.tw1 + i);
   }
   {
     // thread = (frame slot s = tid & 15, bin k = tid >> 4 + 32*j): 16 slots of one bin are one 128-byte
