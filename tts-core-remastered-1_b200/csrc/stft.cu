@@ -677,9 +677,9 @@ istft_kernel(const IstftParams p) {
 // half spectrum into the 512-point complex input on the fly, runs the inverse FFT in registers and
 // writes the windowed, scaled samples back over its slot; then every thread gathers n_fft/hop
 // contributions per output sample and divides by the window envelope.
-constexpr int kISlots = 16, kISlotStride = 577;     // float2 per slot (odd stride: conflict-free block load)
+constexpr int kISlotsLog = 5, kISlots = 1 << kISlotsLog, kISlotStride = 577;     // float2 per slot (odd stride: conflict-free block load)
 
-__global__ void __launch_bounds__(kISlots * 32, 2)
+__global__ void __launch_bounds__(kISlots * 32, kISlots == 16 ? 2 : 1)
 istft1024_kernel(const IstftParams p) {
   constexpr int NFFT = 1024, N = 512;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -704,7 +704,7 @@ istft1024_kernel(const IstftParams p) {
   {
     // thread = (frame slot s = tid & 15, bin k = tid >> 4 + 32*j): 16 slots of one bin are one 128-byte
     // line of spec[b, k, f_lo ..]; loads are issued 9 at a time so their latencies overlap
-    const int sidx = threadIdx.x & (kISlots - 1), k0 = threadIdx.x >> 4;
+    const int sidx = threadIdx.x & (kISlots - 1), k0 = threadIdx.x >> kISlotsLog;
     const int f = f_lo + sidx;
     const bool fok = f >= 0 && f < p.frames;
     const float2* sp = p.spec + (long long)b * bins * p.frames + (fok ? f : 0);
