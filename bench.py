@@ -367,17 +367,42 @@ def secondary_measurements(dev, dev_in, B, T):
                           ("mbd", MultiBandDiscriminator)):
             torch.manual_seed(1234)
             crit = cls(GANConfig()).eval().to(dev)
-            crit(wavc)
+            with torch.no_grad():
+                crit(wavc)
             torch.cuda.synchronize()
             a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            for _ in range(3):
-                crit(wavc)
+            with torch.no_grad():
+                for _ in range(3):
+                    crit(wavc)
             b_.record()
             torch.cuda.synchronize()
             ms = a.elapsed_time(b_) / 3
             fl = crit.forward_flops(Bc, Tc)
             res[name] = {"ms": ms, "gflop": fl / 1e9, "tflops": fl / (ms * 1e-3) / 1e12}
+            # the critic half of a training step (vocoder7/trainer.py:86-115): .train() forward (power iteration) +
+            # backward of a loss over every score and feature map down to the weights and the waveform
+            try:
+                crit.train()
+                wg = wavc.clone().requires_grad_(True)
+
+                def d_step():
+                    crit.zero_grad(set_to_none=True)
+                    o, f = crit(wg)
+                    loss = sum((s_ ** 2).mean() for s_ in o) + sum(m.abs().mean() for fs in f for m in fs)
+                    loss.backward()
+                d_step()
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(3):
+                    d_step()
+                b_.record()
+                torch.cuda.synchronize()
+                ms_t = a.elapsed_time(b_) / 3
+                res[name]["train_fwd_bwd_ms"] = ms_t
+                res[name]["train_fwd_bwd_tflops"] = 3 * fl / (ms_t * 1e-3) / 1e12
+            except Exception as e:
+                res[name]["train_fwd_bwd_error"] = str(e)[:200]
             del crit
         out["critics"] = res
     except Exception as e:

@@ -176,6 +176,53 @@ int b200voc_spectral_norm_train(const float* w_orig, float* u, float* v, int row
 /* F.avg_pool1d(x, 4, 2, 1) of discriminators.py:99 over `rows` rows of Lin samples -> (Lin-2)/2+1 samples. */
 int b200voc_avg_pool1d_k4s2p1(const float* x, int64_t rows, int Lin, float* y, void* stream);
 
+/* ---- Discriminator backward (the critic half of the training step) --------------------
+ * Replaces what autograd runs for `d_loss.backward()` / `g_loss.backward()` through the critics
+ * (vocoder7/trainer.py:86-115 over vocoder7/discriminators.py:8-157).  The host module chains these per layer, last
+ * layer first (b200voc/discriminators.py, _CriticStackFn.backward).  Shapes and the in_batch_stride / in_valid
+ * conventions are those of b200voc_disc_conv; every reduction runs in a fixed order (deterministic).
+ *
+ * b200voc_disc_lrelu_bwd: g = gy_pre + (gy_act + g_next) * (y_pre > 0 ? 1 : slope) -- the gradient of a conv map that
+ *   is itself a returned feature (gy_pre), whose LeakyReLU is a returned feature (gy_act) and the next layer's input
+ *   (g_next = that layer's dgrad).  Any of the three may be NULL; y_pre may be NULL only if gy_act and g_next are.
+ * b200voc_disc_bias_grad: db[co] = sum over batch and the per_channel = Lout*P positions of g[B, Cout, per_channel].
+ * b200voc_disc_conv_dgrad: dx[b,ci,li,c] = sum_{co,k} w[co,ci,k] g[b,co,lo,c] with lo*stride - pad + k = li, written
+ *   in the layer input's layout (positions past in_valid are F.pad's zeros and receive nothing); accumulate != 0 adds
+ *   to dx.  w is the spectral-normalised weight the forward used.
+ * b200voc_disc_conv_wgrad: dw[co,ci,k] = sum_{b,lo,c} g[b,co,lo,c] x[b,ci,lo*stride - pad + k,c]; scratch
+ *   (b200voc_disc_conv_wgrad_scratch_bytes, may be 0 -> NULL) holds per-slice partial sums.
+ * b200voc_avg_pool1d_k4s2p1_bwd: gradient of F.avg_pool1d(x, 4, 2, 1) (discriminators.py:99): dx[rows, Lin].
+ * b200voc_spectral_norm_bwd: dw_orig = (dw - <dw, w> u v^T) / sigma for w = w_orig / sigma, sigma = u . (W_orig v) with
+ *   u, v constants (torch computes the power iteration under no_grad); u, v, sigma are the ones the forward used;
+ *   scratch: b200voc_spectral_norm_bwd_scratch_bytes bytes, 8-byte aligned. */
+int b200voc_disc_lrelu_bwd(const float* y_pre, const float* gy_pre, const float* gy_act, const float* g_next, float slope,
+                           int64_t n, float* g_out, void* stream);
+int b200voc_disc_bias_grad(const float* g, int B, int Cout, int64_t per_channel, float* db, void* stream);
+int b200voc_disc_conv_dgrad(const float* g, const float* w, int B, int Cin, int Cout, int Lin, int P, int K, int stride,
+                            int pad, int64_t in_batch_stride, int64_t in_valid, int accumulate, float* dx, void* stream);
+int64_t b200voc_disc_conv_wgrad_scratch_bytes(int B, int Cin, int Cout, int Lin, int P, int K, int stride, int pad);
+int b200voc_disc_conv_wgrad(const float* x, const float* g, int B, int Cin, int Cout, int Lin, int P, int K, int stride,
+                            int pad, int64_t in_batch_stride, int64_t in_valid, float* dw, float* scratch, void* stream);
+int b200voc_avg_pool1d_k4s2p1_bwd(const float* gy, int64_t rows, int Lin, float* dx, void* stream);
+int64_t b200voc_spectral_norm_bwd_scratch_bytes(void);
+int b200voc_spectral_norm_bwd(const float* dw, const float* w, const float* u, const float* v, const float* sigma, int rows,
+                              int cols, float* dw_orig, void* scratch, void* stream);
+/* Tensor-core forms for the GEMM-shaped layers (stride 1, P = 1: MSD's Conv1d(64 -> 256, k) and Conv1d(256 -> 1024, k),
+ * discriminators.py:71-92).
+ *   dgrad: a stride-1 convolution of g with the transposed, tap-flipped weight -- b200voc_disc_flip_weight
+ *     (wt[ci][co][k] = w[co][ci][K-1-k]) -> b200voc_disc_pack_weight_split(wt, Cin, Cout, K) -> b200voc_disc_conv_tc(g,
+ *     ..., B, Cout, Cin, Lout, K, pad' = K-1-pad, ...) with a zero bias; b200voc_disc_conv_dgrad_tc_supported says
+ *     whether the shape qualifies (Cout % 64 == 0, Cin % 128 == 0).
+ *   wgrad: one split-bf16 tcgen05 GEMM over positions, M = Cout, N = Cin*K, operands [g_hi|g_lo|g_hi] and the im2col
+ *     [x_hi|x_hi|x_lo] packed into `workspace` (b200voc_disc_conv_wgrad_tc_workspace_bytes, 1024-byte aligned; the batch
+ *     is processed in chunks that keep the packed operands under 1 GiB).  x [B, Cin, Lin], g [B, Cout, Lin+2pad-K+1]. */
+int b200voc_disc_conv_dgrad_tc_supported(int Cin, int Cout, int K, int stride, int P, int pad);
+int b200voc_disc_flip_weight(const float* w, int Cout, int Cin, int K, float* wt, void* stream);
+int b200voc_disc_conv_wgrad_tc_supported(int B, int Cin, int Cout, int Lin, int K, int stride, int P, int pad);
+int64_t b200voc_disc_conv_wgrad_tc_workspace_bytes(int B, int Cin, int Cout, int Lin, int K, int pad);
+int b200voc_disc_conv_wgrad_tc(const float* x, const float* g, int B, int Cin, int Cout, int Lin, int K, int pad, float* dw,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Per-launch CUDA-event timing of the LAST forward (bench.py's roofline numbers).  Enable, run a
  * forward, synchronise the stream, then read entry i: layer name (oracle tap names), elapsed ms,
  * algorithmic FLOPs and algorithmic HBM bytes (DESIGN.md states the per-unit figures). */

@@ -439,8 +439,9 @@ def spectral_norm_power_iteration(w_orig: torch.Tensor, u: torch.Tensor, v: torc
     x / max(||x||, eps); then sigma = u . (W v) and weight = weight_orig / sigma.  Returns (weight, u_new, v_new);
     the reference updates the ``weight_u`` / ``weight_v`` buffers in place."""
     W = w_orig.flatten(1)
-    v_new = F.normalize(torch.mv(W.t(), u), dim=0, eps=eps)
-    u_new = F.normalize(torch.mv(W, v_new), dim=0, eps=eps)
+    with torch.no_grad():            # torch runs the power iteration under no_grad: u, v are constants of the graph
+        v_new = F.normalize(torch.mv(W.t(), u), dim=0, eps=eps)
+        u_new = F.normalize(torch.mv(W, v_new), dim=0, eps=eps)
     sigma = torch.dot(u_new, torch.mv(W, v_new))
     return w_orig / sigma, u_new, v_new
 

@@ -73,3 +73,88 @@ class FakeCriticLib:
         out = sum(xv[:, k:k + 2 * Lout:2] for k in range(4)) * np.float32(0.25)
         _arr(y, rows * Lout)[:] = out.astype(np.float32).reshape(-1)
         return 0
+
+    # ------------------------------------------------------------------ backward (csrc/disc_bwd.cu conventions)
+    def b200voc_disc_conv_dgrad_tc_supported(self, cin, cout, k, stride, P, pad):
+        return 0
+
+    def b200voc_disc_conv_wgrad_tc_supported(self, B, cin, cout, Lin, k, stride, P, pad):
+        return 0
+
+    def b200voc_disc_conv_wgrad_scratch_bytes(self, B, cin, cout, Lin, P, K, stride, pad):
+        return 0
+
+    def b200voc_spectral_norm_bwd_scratch_bytes(self):
+        return 2048
+
+    def b200voc_disc_lrelu_bwd(self, y, gy, ga, gn, slope, n, g_out, stream):
+        a = np.zeros(n, np.float32)
+        if ga:
+            a += _arr(ga, n)
+        if gn:
+            a += _arr(gn, n)
+        r = a * np.where(_arr(y, n) > 0, np.float32(1), np.float32(slope)) if (ga or gn) else np.zeros(n, np.float32)
+        if gy:
+            r = r + _arr(gy, n)
+        _arr(g_out, n)[:] = r
+        return 0
+
+    def b200voc_disc_bias_grad(self, g, B, cout, per_c, db, stream):
+        _arr(db, cout)[:] = _arr(g, B * cout * per_c).reshape(B, cout, per_c).sum(axis=(0, 2))
+        return 0
+
+    def _gather_index(self, Lin, P, K, stride, pad, Lout):
+        li = np.arange(Lout)[:, None] * stride - pad + np.arange(K)[None, :]                 # [Lout, K]
+        idx = li[:, :, None] * P + np.arange(P)[None, None, :]                                # [Lout, K, P]
+        return li, idx
+
+    def b200voc_disc_conv_dgrad(self, g, w, B, cin, cout, Lin, P, K, stride, pad, in_batch_stride, in_valid, accumulate,
+                                dx, stream):
+        Lout = self.b200voc_disc_conv_out_len(Lin, K, stride, pad)
+        sb = in_batch_stride or cin * Lin * P
+        valid = in_valid or Lin * P
+        gv = _arr(g, B * cout * Lout * P).reshape(B, cout, Lout, P)
+        wv = _arr(w, cout * cin * K).reshape(cout, cin, K)
+        li, idx = self._gather_index(Lin, P, K, stride, pad, Lout)
+        ok = (li[:, :, None] >= 0) & (li[:, :, None] < Lin) & (idx < valid)
+        contrib = np.einsum("bolp,oik->bilkp", gv, wv)                                        # [B, cin, Lout, K, P]
+        for b in range(B):
+            for ci in range(cin):
+                row_len = min(valid, Lin * P)
+                row = _arr(dx + 4 * (b * sb + ci * Lin * P), row_len)
+                acc = np.zeros(Lin * P, np.float32)
+                np.add.at(acc, np.where(ok, idx, 0).ravel(), np.where(ok, contrib[b, ci], 0).ravel().astype(np.float32))
+                row[:] = (row if accumulate else 0) + acc[:row_len]
+        return 0
+
+    def b200voc_disc_conv_wgrad(self, x, g, B, cin, cout, Lin, P, K, stride, pad, in_batch_stride, in_valid, dw, scratch,
+                                stream):
+        Lout = self.b200voc_disc_conv_out_len(Lin, K, stride, pad)
+        sb = in_batch_stride or cin * Lin * P
+        valid = in_valid or Lin * P
+        gv = _arr(g, B * cout * Lout * P).reshape(B, cout, Lout, P)
+        li, idx = self._gather_index(Lin, P, K, stride, pad, Lout)
+        ok = (li[:, :, None] >= 0) & (li[:, :, None] < Lin) & (idx < valid)
+        cols = np.zeros((B, cin, Lout, K, P), np.float32)
+        for b in range(B):
+            for ci in range(cin):
+                row = _arr(x + 4 * (b * sb + ci * Lin * P), min(valid, Lin * P))
+                cols[b, ci] = np.where(ok, row[np.where(ok, idx, 0)], 0)
+        _arr(dw, cout * cin * K).reshape(cout, cin, K)[:] = np.einsum("bolp,bilkp->oik", gv, cols)
+        return 0
+
+    def b200voc_avg_pool1d_k4s2p1_bwd(self, gy, rows, Lin, dx, stream):
+        Lout = (Lin - 2) // 2 + 1
+        g = _arr(gy, rows * Lout).reshape(rows, Lout)
+        pad = np.zeros((rows, Lin + 4), np.float32)
+        for k in range(4):
+            pad[:, k:k + 2 * Lout:2] += 0.25 * g
+        _arr(dx, rows * Lin).reshape(rows, Lin)[:] = pad[:, 1:1 + Lin]
+        return 0
+
+    def b200voc_spectral_norm_bwd(self, dw, w, u, v, sigma, rows, cols, out, scratch, stream):
+        dwv, wv = _arr(dw, rows * cols).reshape(rows, cols), _arr(w, rows * cols).reshape(rows, cols)
+        dot = float((dwv.astype(np.float64) * wv).sum())
+        _arr(out, rows * cols).reshape(rows, cols)[:] = (dwv - np.float32(dot) * np.outer(_arr(u, rows), _arr(v, cols))) \
+            / _arr(sigma, 1)[0]
+        return 0

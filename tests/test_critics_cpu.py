@@ -90,11 +90,11 @@ def test_host_layer_walker_against_oracle(monkeypatch, kind, B, T):
     assert len(outs) == len(r_outs) and [len(f) for f in feats] == [len(f) for f in r_feats]
     for a, b in zip(outs, r_outs):
         assert a.shape == b.shape
-        assert float((a - b).abs().max()) <= 1e-4 * max(1.0, float(b.abs().max()))
+        assert float((a.detach() - b).abs().max()) <= 1e-4 * max(1.0, float(b.abs().max()))
     for fa, fb in zip(feats, r_feats):
         for a, b in zip(fa, fb):
             assert a.shape == b.shape
-            assert float((a - b).abs().max()) <= 1e-4 * max(1.0, float(b.abs().max()))
+            assert float((a.detach() - b).abs().max()) <= 1e-4 * max(1.0, float(b.abs().max()))
     # the spectral-normalised weights are cached per parameter version: a second call launches no new sigma pass
     n_calls = len(fake.conv_calls)
     mod(x)
@@ -102,6 +102,68 @@ def test_host_layer_walker_against_oracle(monkeypatch, kind, B, T):
     if kind == "mbd":      # chunks are read in place: batch stride = T, valid = chunk length
         first = [c for c in fake.conv_calls[:n_calls] if c[1] == 1]
         assert all(c[8] == T for c in first) and {c[9] for c in first} <= {-(-T // 4), T - 3 * (-(-T // 4))}
+
+
+def _gan_like_loss(outs, feats):
+    """A scalar that touches every returned map, the way compute_gan_loss (vocoder7/losses.py:8-52) does: squared
+    scores (least-squares GAN terms) and mean-abs features (feature matching)."""
+    loss = 0.0
+    for o in outs:
+        loss = loss + ((o - 1.0) ** 2).mean()
+    for fs in feats:
+        for j, f in enumerate(fs):
+            loss = loss + (0.5 + 0.1 * j) * f.abs().mean()
+    return loss
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_host_autograd_node_against_oracle(monkeypatch, kind):
+    """The backward chain of b200voc/discriminators.py (_CriticStackFn: feature-gradient merge, bias / weight gradients,
+    spectral-norm backward, dgrad down to the waveform through the period view / pooled scales / time chunks) driven
+    through the numpy stand-in, against torch autograd over the oracle: d loss / d weight_orig, d bias, d waveform."""
+    from fake_critic_lib import FakeCriticLib
+    from b200voc import GANConfig, _lib
+    cfg = GANConfig(disc_kernel_sizes=[5, 9, 9])
+    ocfg = O.OracleConfig(disc_kernel_sizes=[5, 9, 9])
+    torch.manual_seed(11)
+    mod = _host_cls(kind)(cfg).eval()
+    fake = FakeCriticLib()
+    monkeypatch.setattr(_lib, "load", lambda: fake)
+    monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(_lib, "current_stream", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    B, T = 2, 203
+    x = torch.randn(B, 1, T, generator=torch.Generator().manual_seed(5)).requires_grad_(True)
+    outs, feats = mod(x)
+    assert outs[0].requires_grad
+    _gan_like_loss(outs, feats).backward()
+    # oracle: the same scalar under torch autograd
+    sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    for k in sd:
+        if k.endswith("weight_orig") or k.endswith("bias"):
+            sd[k].requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+    r_outs, r_feats = O.critic_forward(kind, sd, ocfg, xr)
+    _gan_like_loss(r_outs, r_feats).backward()
+
+    def close(a, b, what):
+        assert a is not None, what
+        assert a.shape == b.shape, what
+        err, scale = float((a - b).abs().max()), float(b.abs().max())
+        assert err <= 2e-4 * scale + 1e-7, f"{what}: {err:.3e} vs scale {scale:.3e}"
+    close(x.grad, xr.grad, "d loss / d waveform")
+    for name, p in mod.named_parameters():
+        close(p.grad, sd[name].grad, name)
+    # a loss that touches only the scores (the critics' own adversarial terms): feature gradients arrive as None
+    mod.zero_grad()
+    outs, _ = mod(x.detach())
+    sum((o ** 2).mean() for o in outs).backward()
+    for k in sd:
+        sd[k].grad = None
+    r_outs, _ = O.critic_forward(kind, sd, ocfg, x.detach())
+    sum((o ** 2).mean() for o in r_outs).backward()
+    for name, p in mod.named_parameters():
+        close(p.grad, sd[name].grad, name + " (scores only)")
 
 
 def test_short_waveforms_raise():
@@ -172,3 +234,19 @@ def test_oracle_training_mode_spectral_norm_is_pinned_to_torch():
     assert float((got - outs[0]).abs().max()) <= 2e-4 * max(1.0, float(outs[0].abs().max()))
     assert torch.allclose(discs[0][0].weight_u, sd_t["discriminators.0.0.weight_u"], atol=1e-6)
     assert not torch.equal(sd_t["discriminators.0.0.weight_u"], sd["discriminators.0.0.weight_u"])
+
+
+def test_oracle_training_mode_gradient_is_pinned_to_torch():
+    """Backward of the oracle's training-mode spectral norm == autograd through ``torch.nn.utils.spectral_norm`` on a
+    module in .train() (u, v from the power iteration are constants of the graph): the reference the critic backward
+    kernels are tested against (tests/test_gpu_critics_bwd.py)."""
+    import torch.nn as nn
+    torch.manual_seed(3)
+    conv = nn.utils.spectral_norm(nn.Conv1d(8, 16, 5, padding=2)).train()
+    x = torch.randn(2, 8, 30)
+    w0 = conv.weight_orig.detach().clone().requires_grad_(True)
+    u, v = conv.weight_u.clone(), conv.weight_v.clone()
+    (conv(x) ** 2).mean().backward()
+    w, _, _ = O.spectral_norm_power_iteration(w0, u, v)
+    (torch.nn.functional.conv1d(x, w, conv.bias.detach(), padding=2) ** 2).mean().backward()
+    assert float((w0.grad - conv.weight_orig.grad).abs().max()) <= 1e-6 * float(w0.grad.abs().max())

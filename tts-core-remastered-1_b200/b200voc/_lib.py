@@ -62,6 +62,19 @@ _SIGNATURES = {
     "b200voc_spectral_norm_weight": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "b200voc_spectral_norm_train": (C.c_int, [_P, _P, _P, _I, _I, _F, _P, _P, _P, _P]),
     "b200voc_avg_pool1d_k4s2p1": (C.c_int, [_P, _I64, _I, _P, _P]),
+    "b200voc_disc_lrelu_bwd": (C.c_int, [_P, _P, _P, _P, _F, _I64, _P, _P]),
+    "b200voc_disc_bias_grad": (C.c_int, [_P, _I, _I, _I64, _P, _P]),
+    "b200voc_disc_conv_dgrad": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _I, _P, _P]),
+    "b200voc_disc_conv_wgrad_scratch_bytes": (C.c_int64, [_I, _I, _I, _I, _I, _I, _I, _I]),
+    "b200voc_disc_conv_wgrad": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _P, _P, _P]),
+    "b200voc_avg_pool1d_k4s2p1_bwd": (C.c_int, [_P, _I64, _I, _P, _P]),
+    "b200voc_spectral_norm_bwd_scratch_bytes": (C.c_int64, []),
+    "b200voc_spectral_norm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "b200voc_disc_conv_dgrad_tc_supported": (C.c_int, [_I, _I, _I, _I, _I, _I]),
+    "b200voc_disc_flip_weight": (C.c_int, [_P, _I, _I, _I, _P, _P]),
+    "b200voc_disc_conv_wgrad_tc_supported": (C.c_int, [_I, _I, _I, _I, _I, _I, _I, _I]),
+    "b200voc_disc_conv_wgrad_tc_workspace_bytes": (C.c_int64, [_I, _I, _I, _I, _I, _I]),
+    "b200voc_disc_conv_wgrad_tc": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I64, _P]),
     "b200voc_gen_launch_count": (C.c_int, [_P]),
     "b200voc_gen_set_overflow_check": (C.c_int, [_P, _I]),
     "b200voc_gen_profile_enable": (C.c_int, [_P, _I]),

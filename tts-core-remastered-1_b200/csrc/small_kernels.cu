@@ -212,7 +212,7 @@ splitgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_f16(0, 128);
+    const uint32_t idesc = make_idesc_f16(OUT16 ? 0 : p.fmt, 128)   /* fp32-output form: fmt 0 = fp16 operands, 1 = bf16 */;
     for (int kb = 0; kb < p.KB; ++kb) {
       const int s = kb % kSgStages;
       mbar_wait(&full[s], (kb / kSgStages) & 1);
@@ -292,7 +292,7 @@ splitgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && n0 + c * 32 < p.ncols) {                           // boxes past the last column: nothing to store
             tma_store_3d(&tmO, stg + c * 4096, 2 * (n0 + c * 32), row0, 0);   // the map counts 16-bit units
             tma_store_commit();
           }
@@ -330,6 +330,24 @@ int film_tc_launch(const void* cond3, const void* w3, const float* b_all, int M,
   SplitGemmParams p{};
   p.M = M; p.KB = 6; p.ncols = ncols; p.bias = b_all; p.out = out;
   return launch_splitgemm<false>(tmA, tmW, tmO, p, dim3(ceil_div(M, 128), ncols / 128, 1), st);
+}
+
+// General form of the same kernel: out[M][N] (fp32, row pitch N, N % 4 == 0) = A[M][Kdim] . W[N][Kdim]^T + bias, both
+// operands 16-bit K-major (fmt 0 = fp16, 1 = bf16), Kdim a multiple of 64; rows past M / N are zero-filled on load and
+// clipped on store by the tensor maps.  `bias` must hold N rounded up to 128 floats.  The critics' wgrad (disc_bwd.cu)
+// runs through this with split-bf16 operands.
+int splitgemm_f32_launch(const void* A, const void* W, const float* bias, int M, int N, long long Kdim, int fmt,
+                         float* out, cudaStream_t st) {
+  B200_CHECK_ARG(A && W && bias && out, "splitgemm: null argument");
+  B200_CHECK_ARG(M > 0 && N > 0 && N % 4 == 0 && Kdim > 0 && Kdim % 64 == 0 && Kdim / 64 < (1ll << 30),
+                 "splitgemm: bad shape (M=%d N=%d K=%lld)", M, N, Kdim);
+  CUtensorMap tmA, tmW, tmO;
+  B200_TRY(make_tmap_3d(&tmA, A, (uint64_t)Kdim, M, 1, (uint64_t)Kdim * 2, (uint64_t)M * Kdim * 2, 64, 128, 128));
+  B200_TRY(make_tmap_3d(&tmW, W, (uint64_t)Kdim, N, 1, (uint64_t)Kdim * 2, (uint64_t)N * Kdim * 2, 64, 128, 128));
+  B200_TRY(make_tmap_3d(&tmO, out, 2ull * N, M, 1, (uint64_t)N * 4, (uint64_t)M * N * 4, 64, 32, 128));
+  SplitGemmParams p{};
+  p.M = M; p.KB = (int)(Kdim / 64); p.ncols = N; p.bias = bias; p.out = out; p.fmt = fmt;
+  return launch_splitgemm<false>(tmA, tmW, tmO, p, dim3(ceil_div(M, 128), ceil_div(N, 128), 1), st);
 }
 
 // ------------------------------------------------------------------ K3 on the tensor cores: band_split as 4 GEMMs
