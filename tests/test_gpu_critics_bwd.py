@@ -280,7 +280,7 @@ def test_critic_backward_matches_oracle_autograd(kind, training):
     cfg, ocfg = b200voc.GANConfig(), O.OracleConfig()
     mod = _host(kind, cfg, seed=1234)
     mod.train(training)
-    sd = {k: v.detach().cpu().clone() for k, v in mod.state_dict().items()}
+    sd = {k: v.detach().cpu().double() for k, v in mod.state_dict().items()}      # fp64 reference: no noise of its own
     x = (torch.rand(2, 1, 2403, generator=torch.Generator().manual_seed(8)) * 2 - 1)
     xg = x.cuda().requires_grad_(True)
     outs, feats = mod(xg)
@@ -291,7 +291,7 @@ def test_critic_backward_matches_oracle_autograd(kind, training):
     for k in sd:
         if k.endswith("weight_orig") or k.endswith("bias"):
             sd[k].requires_grad_(True)
-    xr = x.clone().requires_grad_(True)
+    xr = x.double().requires_grad_(True)
     r_outs, r_feats = O.critic_forward(kind, sd, ocfg, xr, training=training)
     _loss(r_outs, r_feats).backward()
     _close(xg.grad, xr.grad, f"{kind}: d loss / d waveform")
