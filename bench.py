@@ -388,9 +388,10 @@ def secondary_measurements(dev, dev_in, B, T):
 
                 def d_step():
                     crit.zero_grad(set_to_none=True)
-                    o, f = crit(wg)
-                    loss = sum((s_ ** 2).mean() for s_ in o) + sum(m.abs().mean() for fs in f for m in fs)
-                    loss.backward()
+                    with torch.enable_grad():
+                        o, f = crit(wg)
+                        loss = sum((s_ ** 2).mean() for s_ in o) + sum(m.abs().mean() for fs in f for m in fs)
+                        loss.backward()
                 d_step()
                 torch.cuda.synchronize()
                 a.record()

