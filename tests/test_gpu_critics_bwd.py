@@ -284,10 +284,8 @@ def test_critic_backward_matches_oracle_autograd(kind, training):
     cfg, ocfg = b200voc.GANConfig(), O.OracleConfig()
     mod = _host(kind, cfg, seed=1234)
     # Let the power iteration converge first (sigma -> the spectral norm, what a critic looks like a few steps into
-    # training).  With the FRESH u, v of the initialiser sigma = u . (W v) is a nearly cancelling sum of order 1e-3, the
-    # weights W / sigma are huge and every map of the deep MSD stacks amplifies the forward's 1e-5 round-off: measured
-    # (tests/diag_critic_bwd.py) 2e-3 on some MSD gradients and 2e-2 on the score bias -- a cancelling mean -- with
-    # tensor-core AND with all-fp32 forwards, while MPD / MBD agree to 1e-6: conditioning of the problem, not the kernels.
+    # training).  With the FRESH u, v of the initialiser sigma = u . (W v) is a nearly cancelling sum of order 1e-3 and the
+    # weights W / sigma are huge: the score bias gradient of MSD (a cancelling mean) is then off by 2e-2 whichever kernels run.
     mod.train()
     with torch.no_grad():
         for _ in range(6):
@@ -307,10 +305,17 @@ def test_critic_backward_matches_oracle_autograd(kind, training):
     xr = x.double().requires_grad_(True)
     r_outs, r_feats = O.critic_forward(kind, sd, ocfg, xr, training=training)
     _loss(r_outs, r_feats).backward()
-    _close(xg.grad, xr.grad, f"{kind}: d loss / d waveform")
+    # MPD / MBD run fp32 end to end and agree with fp64 autograd to 6e-7 (measured): bound 1e-5.  MSD's wide layers run on
+    # the tensor cores with split-bf16 operands: its feature maps carry 4e-5 of round-off (bound 2e-4, test_gpu_critics.py)
+    # and the deep stack's gradients -- cancelling sums over 1e4..1e5 positions -- amplify that ~60x whichever kernels
+    # compute the backward (measured worst 2.8e-3 with tensor-core forwards, 8e-4 with all-fp32 forwards:
+    # tests/diag_critic_bwd.py); the MSD backward kernels themselves are held to 1e-4 per layer against fp64 above and to
+    # 2e-4 against the fp32 path on the same forward below.
+    tol = 5e-3 if kind == "msd" else 1e-5
+    _close(xg.grad, xr.grad, f"{kind}: d loss / d waveform", tol=tol)
     for name, p in mod.named_parameters():
         assert p.grad is not None, name
-        _close(p.grad, sd[name].grad, f"{kind}: {name}")
+        _close(p.grad, sd[name].grad, f"{kind}: {name}", tol=tol)
 
 
 def test_critic_backward_cuda_core_path_and_partial_losses(monkeypatch):
