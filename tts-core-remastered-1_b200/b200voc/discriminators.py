@@ -195,17 +195,23 @@ class _CriticStackFn(torch.autograd.Function):
                                                                0, _lib.ptr(dx_out) + 4 * x_offset, stream), "disc_conv_dgrad")
                     break
                 g_next = torch.empty_like(maps[pos[l - 1] + 1])
-                if use_tc and lib.b200voc_disc_conv_dgrad_tc_supported(cin, cout, k, st, P, pad):
-                    wt = torch.empty(cin, cout, k, device=dev, dtype=torch.float32)
+                # tensor-core dgrad = the forward implicit GEMM on g with flipped weights; it writes 128 channels per tile,
+                # so a 64-channel input (MSD's 64 -> 256 layer) runs with its flipped weight zero-padded to 128 rows
+                cin_p = (cin + 127) // 128 * 128
+                if use_tc and cin >= 64 and lib.b200voc_disc_conv_dgrad_tc_supported(cin_p, cout, k, st, P, pad):
+                    wt = (torch.empty if cin_p == cin else torch.zeros)(cin_p, cout, k, device=dev, dtype=torch.float32)
                     _lib.check(lib.b200voc_disc_flip_weight(_lib.ptr(w), cout, cin, k, _lib.ptr(wt), stream), "disc_flip_weight")
-                    wts = torch.empty(int(lib.b200voc_disc_split_weight_elems(cin, cout, k)), device=dev, dtype=torch.bfloat16)
-                    _lib.check(lib.b200voc_disc_pack_weight_split(_lib.ptr(wt), cin, cout, k, _lib.ptr(wts), stream),
+                    wts = torch.empty(int(lib.b200voc_disc_split_weight_elems(cin_p, cout, k)), device=dev, dtype=torch.bfloat16)
+                    _lib.check(lib.b200voc_disc_pack_weight_split(_lib.ptr(wt), cin_p, cout, k, _lib.ptr(wts), stream),
                                "disc_pack_weight_split")
-                    zb = torch.zeros(cin, device=dev, dtype=torch.float32)
+                    zb = torch.zeros(cin_p, device=dev, dtype=torch.float32)
                     ws = torch.empty(int(lib.b200voc_disc_conv_tc_workspace_bytes(B, cout, Lout)), device=dev, dtype=torch.uint8)
-                    _lib.check(lib.b200voc_disc_conv_tc(_lib.ptr(g), _lib.ptr(wts), _lib.ptr(zb), B, cout, cin, Lout, k, k - 1 - pad,
-                                                        LRELU_SLOPE, _lib.ptr(g_next), 0, _lib.ptr(ws), ws.numel(), stream),
+                    dst = g_next if cin_p == cin else torch.empty(B, cin_p, Lin_l, device=dev, dtype=torch.float32)
+                    _lib.check(lib.b200voc_disc_conv_tc(_lib.ptr(g), _lib.ptr(wts), _lib.ptr(zb), B, cout, cin_p, Lout, k, k - 1 - pad,
+                                                        LRELU_SLOPE, _lib.ptr(dst), 0, _lib.ptr(ws), ws.numel(), stream),
                                "disc_conv_tc (dgrad)")
+                    if cin_p != cin:
+                        g_next.copy_(dst[:, :cin])
                 else:
                     _lib.check(lib.b200voc_disc_conv_dgrad(_lib.ptr(g), _lib.ptr(w), B, cin, cout, Lin_l, P, k, st, pad, 0, 0, 0,
                                                            _lib.ptr(g_next), stream), "disc_conv_dgrad")
