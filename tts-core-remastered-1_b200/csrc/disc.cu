@@ -293,11 +293,23 @@ int spectral_norm_launch(const float* w_orig, const float* u, const float* v, in
 // 1024 x 10496, is 43 MB) plus two single-CTA vector normalisations.  fp32 products, fp64 accumulation.
 __global__ void __launch_bounds__(256) sn_wt_u_kernel(const float* __restrict__ w, const float* __restrict__ u, int rows,
                                                       int cols, float* __restrict__ t) {
-  const int c = blockIdx.x * 256 + threadIdx.x;          // one column per thread: W^T u = sum_r u[r] W[r][:], coalesced
-  if (c >= cols) return;
+  // W^T u = sum_r u[r] W[r][:].  CTA = 32 columns x 8 row phases (a warp reads 128 contiguous bytes of a row); the
+  // phases are combined through shared memory in a fixed order.  One column per thread over all rows (the first
+  // version) left the 1024 x 10496 matrix of MSD's widest layer to 41 latency-bound CTAs: 240 us.
+  __shared__ double part[8][32];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   double acc = 0.0;
-  for (int r = 0; r < rows; ++r) acc += (double)__ldg(u + r) * (double)__ldg(w + (long long)r * cols + c);
-  t[c] = (float)acc;
+  if (c < cols)
+    for (int r = ry; r < rows; r += 8) acc += (double)__ldg(u + r) * (double)__ldg(w + (long long)r * cols + c);
+  part[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += part[i][cx];
+    t[c] = (float)s;
+  }
 }
 __global__ void __launch_bounds__(256) sn_w_v_kernel(const float* __restrict__ w, const float* __restrict__ v, int rows,
                                                      int cols, float* __restrict__ s) {
@@ -337,7 +349,7 @@ int spectral_norm_train_launch(const float* w_orig, float* u, float* v, int rows
                                float* sigma, float* scratch, cudaStream_t st) {
   float* t = scratch;            // [cols]
   float* s = scratch + cols;     // [rows]
-  sn_wt_u_kernel<<<(cols + 255) / 256, 256, 0, st>>>(w_orig, u, rows, cols, t);
+  sn_wt_u_kernel<<<(cols + 31) / 32, 256, 0, st>>>(w_orig, u, rows, cols, t);
   sn_normalize_kernel<<<1, 1024, 0, st>>>(t, cols, eps, v, nullptr);
   sn_w_v_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w_orig, v, rows, cols, s);
   sn_normalize_kernel<<<1, 1024, 0, st>>>(s, rows, eps, u, sigma);

@@ -113,8 +113,12 @@ static int launch_dgrad(const DiscBwdParams& p, cudaStream_t st) {
   return B200VOC_OK;
 }
 int disc_dgrad_launch(const DiscBwdParams& p, cudaStream_t st) {
-  if (p.Cin >= 16) return launch_dgrad<16>(p, st);
-  if (p.Cin >= 4) return launch_dgrad<4>(p, st);
+  // 16 input channels per thread reuse every g load 16 times, but a 16-channel map of a few thousand positions is then
+  // under 100 CTAs: take fewer channels per thread until the grid fills the chip (g stays in L1 / L2)
+  const long long blocks = (((long long)p.Lin * p.P + kDbThreads - 1) / kDbThreads) * p.B;
+  if (p.Cin >= 16 && blocks * ceil_div(p.Cin, 16) >= 296) return launch_dgrad<16>(p, st);
+  if (p.Cin >= 4 && blocks * ceil_div(p.Cin, 4) >= 296) return launch_dgrad<4>(p, st);
+  if (p.Cin >= 16 && blocks * p.Cin < 296) return launch_dgrad<4>(p, st);   // tiny map: grid size does not matter
   return launch_dgrad<1>(p, st);
 }
 
@@ -136,21 +140,34 @@ __global__ void __launch_bounds__(kDwThreads) disc_wgrad_kernel(const DiscBwdPar
   float acc[kDbCo];
 #pragma unroll
   for (int c = 0; c < kDbCo; ++c) acc[c] = 0.f;
-  if (phase < nph) {
-    for (long long r = r_begin + phase; r < r_end; r += nph) {
-      const int b = (int)(r / per_b);
-      const long long q = r - (long long)b * per_b;
-      const int lo = (int)(q / p.P), col = (int)(q - (long long)lo * p.P);
-      const int li = lo * p.stride - p.pad + k;
-      float xv = 0.f;
-      if (li >= 0 && li < p.Lin) {
-        const long long idx = (long long)li * p.P + col;
-        if (idx < p.in_valid) xv = __ldg(p.x + (long long)b * p.in_batch_stride + (long long)ci * p.Lin * p.P + idx);
-      }
-      const float* gp = p.g + ((long long)b * p.Cout + co0) * per_b + q;
+  if (phase < nph && r_begin < r_end) {
+    // the slice [r_begin, r_end) of the flattened (b, lo, column) positions, batch item by batch item: 32-bit index
+    // arithmetic inside an item (per_b < 2^31 is checked by the launcher), this thread takes every nph-th position
+    const int b_first = (int)(r_begin / per_b), b_last = (int)((r_end - 1) / per_b);
+    const int per_b32 = (int)per_b;
+    long long r = r_begin + phase;                       // this thread's next position (global)
+    for (int b = b_first; b <= b_last; ++b) {
+      const long long base = (long long)b * per_b;
+      const int q_end = (int)min((long long)per_b32, r_end - base);
+      if (r >= base + q_end) continue;
+      int q = (int)(r - base);
+      const float* xb = p.x + (long long)b * p.in_batch_stride + (long long)ci * p.Lin * p.P;
+      const float* gb = p.g + ((long long)b * p.Cout + co0) * per_b;
+      const int valid = (int)min(p.in_valid, (long long)p.Lin * p.P);
+      for (; q < q_end; q += nph) {
+        int lo = q, col = 0;
+        if (p.P != 1) { lo = q / p.P; col = q - lo * p.P; }
+        const int li = lo * p.stride - p.pad + k;
+        float xv = 0.f;
+        if (li >= 0 && li < p.Lin) {
+          const int idx = li * p.P + col;
+          if (idx < valid) xv = __ldg(xb + idx);
+        }
 #pragma unroll
-      for (int c = 0; c < kDbCo; ++c)
-        if (co0 + c < p.Cout) acc[c] = fmaf(xv, __ldg(gp + (long long)c * per_b), acc[c]);
+        for (int c = 0; c < kDbCo; ++c)
+          if (co0 + c < p.Cout) acc[c] = fmaf(xv, __ldg(gb + (long long)c * per_b + q), acc[c]);
+      }
+      r = base + q;
     }
   }
 #pragma unroll
@@ -186,6 +203,7 @@ static int wgrad_slices(int B, int Cin, int Cout, int Lout, int P) {
 }
 int disc_wgrad_launch(DiscBwdParams p, float* dw, float* scratch, cudaStream_t st) {
   B200_CHECK_ARG(p.K <= kDwThreads, "disc_conv_wgrad: kernel size %d not supported (max %d)", p.K, kDwThreads);
+  B200_CHECK_ARG((long long)p.Lin * p.P < (1ll << 31) && (long long)p.Lout * p.P < (1ll << 31), "disc_conv_wgrad: map too long");
   const int Z = wgrad_slices(p.B, p.Cin, p.Cout, p.Lout, p.P);
   const long long R = (long long)p.B * p.Lout * p.P, n = (long long)p.Cout * p.Cin * p.K;
   p.r_per_z = (R + Z - 1) / Z;
@@ -329,24 +347,38 @@ __global__ void __launch_bounds__(256) disc_pack_g3_kernel(const float* __restri
     row[2 * Pp] = hi;
   }
 }
-// B operand: w3[ci * K + k][s * Pp + b * Lp + lo] = x[b, ci, lo - pad + k], segments (x_hi, x_hi, x_lo).
+// B operand: w3[ci * K + k][s * Pp + b * Lp + lo] = x[b, ci, lo - pad + k], segments (x_hi, x_hi, x_lo).  A thread packs 8
+// consecutive positions of one row (Lp is a multiple of 64, so they share b) and writes three 16-byte vectors.
 __global__ void __launch_bounds__(256) disc_pack_im2col3_kernel(const float* __restrict__ x, int Bc, int Cin, int Lin,
                                                                 int Lout, int Lp, int K, int pad, long long x_batch_stride,
                                                                 uint16_t* __restrict__ w3) {
-  const long long Pp = (long long)Bc * Lp, Kdim = 3 * Pp, total = (long long)Cin * K * Pp;
+  const long long Pp = (long long)Bc * Lp, Kdim = 3 * Pp;
+  const int groups = (int)(Pp >> 3);                                  // 8-position groups per row
+  const long long total = (long long)Cin * K * groups;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long rowi = i / Pp;                // ci * K + k
-    const long long col = i - rowi * Pp;
-    const int ci = (int)(rowi / K), k = (int)(rowi - (long long)ci * K);
-    const int b = (int)(col / Lp), lo = (int)(col - (long long)b * Lp);
-    const int li = lo - pad + k;
-    const float v = (lo < Lout && li >= 0 && li < Lin) ? __ldg(x + (long long)b * x_batch_stride + (long long)ci * Lin + li) : 0.f;
-    uint16_t hi, l;
-    split_bf16(v, hi, l);
-    uint16_t* row = w3 + rowi * Kdim + col;
-    row[0] = hi;
-    row[Pp] = hi;
-    row[2 * Pp] = l;
+    const int rowi = (int)(i / groups);                               // ci * K + k
+    const int col = (int)(i - (long long)rowi * groups) << 3;
+    const int ci = rowi / K, k = rowi - ci * K;
+    const int b = col / Lp, lo0 = col - b * Lp;
+    const float* xr = x + (long long)b * x_batch_stride + (long long)ci * Lin;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      uint16_t hh[2], ll[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int lo = lo0 + j + e, li = lo - pad + k;
+        const float v = (lo < Lout && li >= 0 && li < Lin) ? __ldg(xr + li) : 0.f;
+        split_bf16(v, hh[e], ll[e]);
+      }
+      h[j >> 1] = (uint32_t)hh[0] | ((uint32_t)hh[1] << 16);
+      l[j >> 1] = (uint32_t)ll[0] | ((uint32_t)ll[1] << 16);
+    }
+    uint16_t* row = w3 + (long long)rowi * Kdim + col;
+    const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(row) = hv;
+    *reinterpret_cast<uint4*>(row + Pp) = hv;
+    *reinterpret_cast<uint4*>(row + 2 * Pp) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 __global__ void __launch_bounds__(256) disc_add_kernel(const float* __restrict__ a, long long n, float* __restrict__ out) {
@@ -398,7 +430,7 @@ int disc_wgrad_tc_launch(const float* x, const float* g, int B, int Cin, int Cou
     disc_pack_g3_kernel<<<ew_blocks((long long)Cout * Pp), 256, 0, st>>>(g + (long long)b0 * Cout * Lout, bc, Cout, Lout, pl.Lp,
                                                                           (long long)Cout * Lout, a3);
     B200_CUDA(cudaGetLastError());
-    disc_pack_im2col3_kernel<<<ew_blocks((long long)Cin * K * Pp, 65536), 256, 0, st>>>(
+    disc_pack_im2col3_kernel<<<ew_blocks((long long)Cin * K * (Pp >> 3), 65536), 256, 0, st>>>(
         x + (long long)b0 * Cin * Lin, bc, Cin, Lin, Lout, pl.Lp, K, pad, (long long)Cin * Lin, w3);
     B200_CUDA(cudaGetLastError());
     float* out = b0 == 0 ? dw : tmp;
