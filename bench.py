@@ -362,7 +362,9 @@ def secondary_measurements(dev, dev_in, B, T):
         wavc = torch.rand(Bc, 1, Tc, device=dev) * 2 - 1
         res = {"batch": Bc, "samples": Tc, "note": "critic forwards (vocoder7/discriminators.py) on 4 x 1 s, all "
                "feature maps written; MSD's stride-1 64->256 / 256->1024 layers (97 % of the FLOPs) on tcgen05 with split-bf16 "
-               "operands, the narrow / strided layers as fp32 direct convolution"}
+               "operands, the narrow / strided layers as fp32 direct convolution; train_fwd_bwd_ms = .train() forward (one power iteration per layer) "
+               "+ backward of a loss over every score and feature map down to every weight and the waveform (csrc/disc_bwd.cu: wide "
+               "layers' dgrad / wgrad on tcgen05), host-side launch overhead included"}
         for name, cls in (("mpd", MultiPeriodDiscriminator), ("msd", MultiScaleDiscriminator),
                           ("mbd", MultiBandDiscriminator)):
             torch.manual_seed(1234)
@@ -392,14 +394,15 @@ def secondary_measurements(dev, dev_in, B, T):
                         o, f = crit(wg)
                         loss = sum((s_ ** 2).mean() for s_ in o) + sum(m.abs().mean() for fs in f for m in fs)
                         loss.backward()
-                d_step()
+                for _ in range(3):
+                    d_step()
                 torch.cuda.synchronize()
                 a.record()
-                for _ in range(3):
+                for _ in range(5):
                     d_step()
                 b_.record()
                 torch.cuda.synchronize()
-                ms_t = a.elapsed_time(b_) / 3
+                ms_t = a.elapsed_time(b_) / 5
                 res[name]["train_fwd_bwd_ms"] = ms_t
                 res[name]["train_fwd_bwd_tflops"] = 3 * fl / (ms_t * 1e-3) / 1e12
             except Exception as e:

@@ -313,6 +313,15 @@ int64_t b200voc_stft_l1_backward_workspace_bytes(int B, int N, int n_fft, int ho
 int b200voc_stft_l1_backward(const float* wav_fake, const float* wav_real, int B, int N, int n_fft, int hop,
                              const float* gain, float scale, float* grad_wav, float* grad_gain, void* workspace,
                              int64_t workspace_bytes, void* stream);
+/* Backward of LearnableSTFT.forward (vocoder7/stft.py:22-34: out = |STFT(wav)| * filterbank[:, None], differentiable in
+ * the reference through torch.stft's autograd) for an ARBITRARY upstream gradient grad_out[B, n_fft/2+1, frames]:
+ * grad_wav[B, N] += d/dwav (accumulates: zero it first), grad_gain[n_fft/2+1] += sum_{b,t} grad_out * |X| (may be NULL;
+ * gain may be NULL = all ones).  Same construction as the L1 form above (complex STFT -> spectral gradient in place ->
+ * adjoint overlap-add -> reflect fold); hop must divide n_fft/2.  workspace: b200voc_stft_mag_backward_workspace_bytes
+ * bytes, 16-byte aligned. */
+int64_t b200voc_stft_mag_backward_workspace_bytes(int B, int N, int n_fft, int hop);
+int b200voc_stft_mag_backward(const float* wav, int B, int N, int n_fft, int hop, const float* gain, const float* grad_out,
+                              float* grad_wav, float* grad_gain, void* workspace, int64_t workspace_bytes, void* stream);
 /* STFTLoss.forward (stft.py:48-54) partial sums: out_sum[0] += sum |mag(fake)-mag(real)|*|gain|
  * for one resolution (host divides by numel and multiplies lambda). */
 int b200voc_stft_l1(const float* wav_fake, const float* wav_real, int B, int N, int n_fft, int hop,

@@ -134,6 +134,40 @@ def test_stft_loss_backward_matches_autograd(B, N):
         assert float((gg - gg_ref).abs().max()) <= 1e-4 * max(1.0, float(gg_ref.abs().max()))
 
 
+@pytest.mark.parametrize("n_fft,B,N", [(512, 2, 4000), (1024, 1, 8192), (2048, 3, 2817), (1024, 2, 700)])
+def test_learnable_stft_backward_matches_autograd(n_fft, B, N):
+    """LearnableSTFT.forward is differentiable like the reference module (vocoder7/stft.py:22-34): an arbitrary upstream
+    gradient through b200voc_stft_mag_backward against fp64 autograd of the oracle -- d/d waveform (incl. the reflect
+    padding: N = 700 is shorter than two frames) and d/d filterbank."""
+    import b200voc
+    torch.manual_seed(n_fft + N)
+    mod = b200voc.LearnableSTFT(n_fft, 256).cuda()
+    g = torch.Generator().manual_seed(N)
+    wav = torch.rand(B, 1, N, generator=g) * 2 - 1
+    wd = wav.cuda().requires_grad_(True)
+    out = mod(wd)
+    assert out.requires_grad
+    up = torch.randn(out.shape, generator=g)
+    (out * up.cuda()).sum().backward()
+    fb = mod.filterbank.detach().cpu().double().requires_grad_(True)
+    w64 = wav.double().requires_grad_(True)
+    ref = O.learnable_stft_forward(w64, fb, n_fft, 256)
+    assert float((out.detach().cpu().double() - ref.detach()).abs().max()) <= 2e-5 * float(ref.detach().abs().max())
+    (ref * up.double()).sum().backward()
+    gw, gw_ref = wd.grad.cpu().double(), w64.grad
+    assert gw.shape == gw_ref.shape
+    assert float((gw - gw_ref).abs().max()) <= 1e-4 * float(gw_ref.abs().max())
+    gg, gg_ref = mod.filterbank.grad.cpu().double(), fb.grad
+    assert float((gg - gg_ref).abs().max()) <= 1e-4 * float(gg_ref.abs().max())
+    # a frozen gain: only the waveform gradient is produced; no_grad still takes the plain kernel
+    mod.filterbank.requires_grad_(False)
+    wd2 = wav.cuda().requires_grad_(True)
+    (mod(wd2) * up.cuda()).sum().backward()
+    assert torch.equal(wd2.grad, wd.grad)
+    with torch.no_grad():
+        assert not mod(wd2).requires_grad
+
+
 @pytest.mark.parametrize("hop", [110, 250, 128, 200])
 def test_stft1024_hops_not_multiple_of_4(hop):
     """n_fft=1024 fast kernel with hops where 7*hop+1024 is not a multiple of 4 (hop % 4 == 2): the

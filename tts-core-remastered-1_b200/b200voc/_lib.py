@@ -102,6 +102,8 @@ _SIGNATURES = {
     "b200voc_stft_l1": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "b200voc_stft_l1_backward_workspace_bytes": (_I64, [_I, _I, _I, _I]),
     "b200voc_stft_l1_backward": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _F, _P, _P, _P, _I64, _P]),
+    "b200voc_stft_mag_backward_workspace_bytes": (C.c_int64, [_I, _I, _I, _I]),
+    "b200voc_stft_mag_backward": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I64, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 _DEV_SIGNATURES = {

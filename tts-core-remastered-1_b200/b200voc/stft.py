@@ -106,12 +106,40 @@ class LearnableSTFT(nn.Module):
         self.filterbank = nn.Parameter(torch.randn(n_fft // 2 + 1))
 
     def forward(self, wav: torch.Tensor) -> torch.Tensor:
-        # inference kernel: the reference module is differentiable (stft.py:22-34), this forward is not -- say so
-        # instead of silently returning a tensor without grad_fn (the differentiable consumer is STFTLoss below)
-        if torch.is_grad_enabled() and (wav.requires_grad or self.filterbank.requires_grad and self.training):
-            raise _lib.B200VocError("LearnableSTFT.forward has no backward: use STFTLoss (differentiable w.r.t. the "
-                                    "waveform and the gains), or call it under torch.no_grad() / in eval() mode")
+        # differentiable like the reference module (stft.py:22-34) w.r.t. the waveform and the per-bin gains
+        if torch.is_grad_enabled() and (wav.requires_grad or self.filterbank.requires_grad):
+            return _LearnableSTFTFn.apply(wav, self.filterbank, self.n_fft, self.hop_length)
         return stft_magnitude(wav, self.n_fft, self.hop_length, self.filterbank)
+
+
+class _LearnableSTFTFn(torch.autograd.Function):
+    """out = |STFT(wav)| * gain[:, None]; backward = b200voc_stft_mag_backward (complex STFT -> G * gain * X / |X| ->
+    adjoint overlap-add -> reflect fold; gain gradient = sum G * |X|)."""
+
+    @staticmethod
+    def forward(ctx, wav, gain, n_fft, hop):
+        w = _prep(wav)
+        ctx.save_for_backward(w, gain.detach())
+        ctx.meta = (int(n_fft), int(hop), tuple(wav.shape))
+        return stft_magnitude(w, n_fft, hop, gain.detach())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        w, gain = ctx.saved_tensors
+        n_fft, hop, shape = ctx.meta
+        B, N = w.shape
+        lib = _lib.load()
+        go = grad_out.detach().to(torch.float32).contiguous()
+        gs = gain.to(torch.float32).contiguous()
+        grad_wav = torch.zeros_like(w)
+        grad_gain = torch.zeros(n_fft // 2 + 1, device=w.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(w.device):
+            ws = torch.empty(int(lib.b200voc_stft_mag_backward_workspace_bytes(B, N, n_fft, hop)), dtype=torch.uint8,
+                             device=w.device)
+            _lib.check(lib.b200voc_stft_mag_backward(_lib.ptr(w), B, N, n_fft, hop, _lib.ptr(gs), _lib.ptr(go),
+                                                     _lib.ptr(grad_wav), _lib.ptr(grad_gain), _lib.ptr(ws), ws.numel(),
+                                                     _lib.current_stream()), "stft_mag_backward")
+        return grad_wav.view(shape), grad_gain, None, None
 
 
 def _stft_loss_values(f: torch.Tensor, r: torch.Tensor, gains, n_ffts, hop: int) -> torch.Tensor:

@@ -886,6 +886,39 @@ __global__ void __launch_bounds__(256) stft_l1_grad_spec_kernel(float2* __restri
   }
 }
 
+// General form for LearnableSTFT.forward (stft.py:22-34), out = |X| * gain with an arbitrary upstream gradient G:
+//   dL/dX = G * gain * X / |X|  (same irfft weights as above),  dL/dgain[k] = sum_{b,t} G * |X|.
+__global__ void __launch_bounds__(256) stft_mag_grad_spec_kernel(float2* __restrict__ xf, const float* __restrict__ gout,
+                                                                  const float* __restrict__ gain, int bins, int frames,
+                                                                  long long total, int n_fft, float* __restrict__ grad_gain) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float contrib = 0.f;
+  int k = -1;
+  if (i < total) {
+    k = (int)((i / frames) % bins);
+    const float2 x = xf[i];
+    const float a = sqrtf(x.x * x.x + x.y * x.y);
+    const float go = gout[i];
+    const float g = gain ? __ldg(gain + k) : 1.f;
+    const bool edge = k == 0 || k == bins - 1;
+    const float coef = (edge ? (float)n_fft : 0.5f * n_fft) * g * go;
+    const float inv = a > 0.f ? coef / a : 0.f;
+    xf[i] = make_float2(x.x * inv, edge ? 0.f : x.y * inv);
+    contrib = go * a;
+  }
+  if (grad_gain != nullptr) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int k0 = __shfl_sync(full, k, 0);
+    if (__all_sync(full, k == k0)) {
+      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(full, contrib, o);
+      if (lane == 0 && k0 >= 0) atomicAdd(grad_gain + k0, contrib);
+    } else if (k >= 0) {
+      atomicAdd(grad_gain + k, contrib);
+    }
+  }
+}
+
 // grad_wav[b, n] += P[b, pad + n] + reflected contributions of the two padded ends (P is the overlap-add on
 // the padded signal of length N + 2 pad):  x_pad[j] = x[pad - j] (j < pad),  x_pad[pad + N + i] = x[N - 2 - i].
 __global__ void __launch_bounds__(256) stft_fold_reflect_kernel(const float* __restrict__ P, int B, int N, int pad,
@@ -903,6 +936,27 @@ __global__ void __launch_bounds__(256) stft_fold_reflect_kernel(const float* __r
 }  // namespace b200
 
 using namespace b200;
+
+// Adjoint of the framed, windowed forward transform applied to a prepared spectral gradient (irfft weights undone by the
+// caller): plain overlap-add on the padded signal (the iSTFT kernels without the envelope division), then the reflect
+// padding folded back; ACCUMULATES into grad_wav.
+static int stft_adjoint_fold(float2* xf, float* P, int B, int N, int n_fft, int hop, float* grad_wav, cudaStream_t st) {
+  const int frames = 1 + N / hop, pad = n_fft / 2;
+  IstftParams p{};
+  p.spec = xf; p.wav = P; p.B = B; p.frames = frames; p.hop = hop; p.Nout = N + n_fft; p.joff = 0; p.normalize = 0;
+  B200_TRY(get_fft_tables(n_fft, &p.tab));
+  int rc;
+  switch (n_fft) {
+    case 512: rc = launch_istft<512>(p, st); break;
+    case 1024: rc = (n_fft / hop <= kISlots / 2) ? launch_istft1024(p, st) : launch_istft<1024>(p, st); break;
+    case 2048: rc = launch_istft<2048>(p, st); break;
+    default: set_error("stft backward: n_fft=%d unsupported (512/1024/2048)", n_fft); return B200VOC_ERR_UNSUPPORTED;
+  }
+  B200_TRY(rc);
+  stft_fold_reflect_kernel<<<(unsigned)(((long long)B * N + 255) / 256), 256, 0, st>>>(P, B, N, pad, grad_wav);
+  B200_CUDA(cudaGetLastError());
+  return B200VOC_OK;
+}
 
 extern "C" {
 
@@ -1002,7 +1056,7 @@ int b200voc_stft_l1_backward(const float* wav_fake, const float* wav_real, int B
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "stft_l1_backward: workspace must be 16B aligned");
   B200_CHECK_ARG((n_fft / 2) % hop == 0 && n_fft / hop <= 2 * kFPB, "stft_l1_backward: hop %d must divide n_fft/2", hop);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int bins = n_fft / 2 + 1, frames = 1 + N / hop, pad = n_fft / 2;
+  const int bins = n_fft / 2 + 1, frames = 1 + N / hop;
   const long long e = (long long)B * bins * frames;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   float2* xf = reinterpret_cast<float2*>(ws);
@@ -1020,22 +1074,35 @@ int b200voc_stft_l1_backward(const float* wav_fake, const float* wav_real, int B
   stft_l1_grad_spec_kernel<<<(unsigned)((e + 255) / 256), 256, 0, st>>>(xf, magr, gain, bins, frames, e, w_elem, n_fft,
                                                                         grad_gain);
   B200_CUDA(cudaGetLastError());
-  {  // adjoint: plain overlap-add on the padded signal
-    IstftParams p{};
-    p.spec = xf; p.wav = P; p.B = B; p.frames = frames; p.hop = hop; p.Nout = N + n_fft; p.joff = 0; p.normalize = 0;
-    B200_TRY(get_fft_tables(n_fft, &p.tab));
-    int rc;
-    switch (n_fft) {
-      case 512: rc = launch_istft<512>(p, st); break;
-      case 1024: rc = (n_fft / hop <= kISlots / 2) ? launch_istft1024(p, st) : launch_istft<1024>(p, st); break;
-      case 2048: rc = launch_istft<2048>(p, st); break;
-      default: set_error("stft_l1_backward: n_fft=%d unsupported (512/1024/2048)", n_fft); return B200VOC_ERR_UNSUPPORTED;
-    }
-    B200_TRY(rc);
-  }
-  stft_fold_reflect_kernel<<<(unsigned)(((long long)B * N + 255) / 256), 256, 0, st>>>(P, B, N, pad, grad_wav);
+  return stft_adjoint_fold(xf, P, B, N, n_fft, hop, grad_wav, st);
+}
+
+int64_t b200voc_stft_mag_backward_workspace_bytes(int B, int N, int n_fft, int hop) {
+  if (B <= 0 || N <= 0 || n_fft <= 0 || hop <= 0) return 0;
+  const long long bins = n_fft / 2 + 1, frames = 1 + N / hop;
+  const long long e = (long long)B * bins * frames;
+  return e * 8 + (long long)B * (N + n_fft) * 4 + 1024;
+}
+int b200voc_stft_mag_backward(const float* wav, int B, int N, int n_fft, int hop, const float* gain, const float* grad_out,
+                              float* grad_wav, float* grad_gain, void* workspace, int64_t workspace_bytes, void* stream) {
+  B200_TRY(check_stft_args(wav, B, N, n_fft, hop));
+  B200_CHECK_ARG(grad_out && grad_wav && workspace, "stft_mag_backward: null argument");
+  B200_CHECK_ARG(workspace_bytes >= b200voc_stft_mag_backward_workspace_bytes(B, N, n_fft, hop),
+                 "stft_mag_backward: workspace too small");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "stft_mag_backward: workspace must be 16B aligned");
+  B200_CHECK_ARG((n_fft / 2) % hop == 0 && n_fft / hop <= 2 * kFPB, "stft_mag_backward: hop %d must divide n_fft/2", hop);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int bins = n_fft / 2 + 1, frames = 1 + N / hop;
+  const long long e = (long long)B * bins * frames;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float2* xf = reinterpret_cast<float2*>(ws);
+  float* P = reinterpret_cast<float*>(ws + ((e * 8 + 15) & ~15ll));
+  StftParams p{};
+  p.wav = wav; p.B = B; p.Nsamp = N; p.hop = hop; p.frames = frames; p.out = reinterpret_cast<float*>(xf);
+  B200_TRY(dispatch_stft<MODE_COMPLEX>(n_fft, p, st));
+  stft_mag_grad_spec_kernel<<<(unsigned)((e + 255) / 256), 256, 0, st>>>(xf, grad_out, gain, bins, frames, e, n_fft, grad_gain);
   B200_CUDA(cudaGetLastError());
-  return B200VOC_OK;
+  return stft_adjoint_fold(xf, P, B, N, n_fft, hop, grad_wav, st);
 }
 
 }  // extern "C"
