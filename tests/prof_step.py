@@ -34,10 +34,15 @@ else:
     ins = [torch.randn(a.B, 80, a.T, generator=g).cuda(), torch.randn(a.B, a.T, 18, generator=g).cuda(),
            torch.randn(a.B, 128, generator=g).cuda(), torch.softmax(torch.randn(a.B, 6, generator=g), -1).cuda()]
     with torch.no_grad():
+        w = gen(*ins)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         for _ in range(a.iters):
             w = gen(*ins)
+        e1.record()
     torch.cuda.synchronize()
-    print("gen ok", tuple(w.shape), float(w.abs().max()))
+    print("gen ok", tuple(w.shape), float(w.abs().max()), f"{e0.elapsed_time(e1) / a.iters:.3f} ms per forward", flush=True)
     if a.critics:
         msd = b200voc.MultiScaleDiscriminator(b200voc.GANConfig()).eval().cuda()
         outs, _ = msd(torch.rand(4, 1, 22050, device="cuda") * 2 - 1)

@@ -12,6 +12,8 @@
 // One CTA owns 128 queries of one sequence and walks the key tiles of its attention window
 // (global: all of L).  K and V^T tiles stream through a 2-deep TMA ring; S and the PV product are
 // double buffered in TMEM so the MMAs of key tile j+1 overlap the softmax of tile j.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -43,9 +45,24 @@ constexpr int kOffXm = kOffBar + 256;     // row-maximum exchange between the tw
 constexpr int kAttnSmem = kOffXm + 2 * 2 * 2 * 128 * 4 + 1024;
 constexpr int kColS = 0;       // S[3]: 3 x 128 columns (tile j in buffer j % 3)
 constexpr int kColPV = 384;    // PV[2]: 2 x 64 columns
+constexpr int kAttnPolyDefault = 0;   // set from the A/B runs (profiles/r02c_attention_poly.txt)
 constexpr int kColF = 0;       // out-projection accumulator: 64 columns over S[0] (all scores consumed by then)
 
-template <int FMT>
+// exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max relative error 7.5e-5 -- P is
+// rounded to 16 bits (4.9e-4) right after): the MUFU unit (16 exp2 per clock and SM) is what bounds this kernel at d = 64
+// (128 x 128 exponentials per 4.2 MFLOP tile = 1024 clk against 524 clk of MMAs), so every POLY-th exponential of a row
+// is evaluated here instead (8 FMA-pipe / ALU instructions for 1 MUFU instruction that holds its unit for 8 clocks).
+__device__ __forceinline__ float ex2_poly3(float x) {
+  x = fmaxf(x, -126.0f);                        // masked keys (-inf): 2^-126, which the 16-bit P rounds to zero
+  const float t = x + 12582912.0f;              // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);        // [-0.5, 0.5]
+  float q = fmaf(0.05517167f, f, 0.24261113f);
+  q = fmaf(q, f, 0.69326097f);
+  q = fmaf(q, f, 0.99992806f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));   // * 2^round(x): add to the exponent field
+}
+
+template <int FMT, int POLY>
 __global__ void __launch_bounds__(608, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmVt,
                  const __grid_constant__ CUtensorMap tmWo, const AttnParams p) {
@@ -257,7 +274,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         float pv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          pv[i] = ex2_approx(__uint_as_float(v[i]) - m_new);
+          const float xs = __uint_as_float(v[i]) - m_new;
+          pv[i] = (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == POLY - 1) ? ex2_poly3(xs) : ex2_approx(xs);
           l_tile += pv[i];
         }
 #pragma unroll
@@ -390,17 +408,30 @@ int attention_launch(const void* x16, const void* wqkv, const float* bqkv, const
   p.x16 = reinterpret_cast<const uint16_t*>(x16);
   p.bo = bo;
   p.out = reinterpret_cast<uint16_t*>(out16);
-  static bool configured[16] = {};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
-  if (!configured[dev & 15]) {
-    B200_CUDA(cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    B200_CUDA(cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    configured[dev & 15] = true;
-  }
+  // B200VOC_ATTN_POLY = n: every n-th exponential of a row on the FMA pipe (0 = all on the MUFU unit; A/B switch)
+  static const int poly = [] { const char* e = getenv("B200VOC_ATTN_POLY"); return e ? atoi(e) : kAttnPolyDefault; }();
   dim3 grid(L / 128, N);
-  if (fmt == 0) attention_kernel<0><<<grid, 608, kAttnSmem, st>>>(tmQKV, tmVt, tmWo, p);
-  else attention_kernel<1><<<grid, 608, kAttnSmem, st>>>(tmQKV, tmVt, tmWo, p);
+  auto launch = [&](auto kern) -> int {          // one (format, poly) variant per process and device in practice
+    static bool configured[16][2] = {};
+    if (!configured[dev & 15][fmt & 1]) {
+      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+      configured[dev & 15][fmt & 1] = true;
+    }
+    kern<<<grid, 608, kAttnSmem, st>>>(tmQKV, tmVt, tmWo, p);
+    return B200VOC_OK;
+  };
+  int rc;
+  switch (poly) {
+    case 2: rc = fmt == 0 ? launch(attention_kernel<0, 2>) : launch(attention_kernel<1, 2>); break;
+    case 3: rc = fmt == 0 ? launch(attention_kernel<0, 3>) : launch(attention_kernel<1, 3>); break;
+    case 4: rc = fmt == 0 ? launch(attention_kernel<0, 4>) : launch(attention_kernel<1, 4>); break;
+    case 5: rc = fmt == 0 ? launch(attention_kernel<0, 5>) : launch(attention_kernel<1, 5>); break;
+    case 6: rc = fmt == 0 ? launch(attention_kernel<0, 6>) : launch(attention_kernel<1, 6>); break;
+    default: rc = fmt == 0 ? launch(attention_kernel<0, 0>) : launch(attention_kernel<1, 0>); break;
+  }
+  B200_TRY(rc);
   B200_CUDA(cudaGetLastError());
   return B200VOC_OK;
 }
