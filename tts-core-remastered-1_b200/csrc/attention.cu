@@ -45,7 +45,7 @@ constexpr int kOffXm = kOffBar + 256;     // row-maximum exchange between the tw
 constexpr int kAttnSmem = kOffXm + 2 * 2 * 2 * 128 * 4 + 1024;
 constexpr int kColS = 0;       // S[3]: 3 x 128 columns (tile j in buffer j % 3)
 constexpr int kColPV = 384;    // PV[2]: 2 x 64 columns
-constexpr int kAttnPolyDefault = 0;   // set from the A/B runs (profiles/r02c_attention_poly.txt)
+constexpr int kAttnPolyDefault = 6;   // every 6th exponential on the FMA pipe: best of the A/B runs (profiles/r02c_attention_poly.txt)
 constexpr int kColF = 0;       // out-projection accumulator: 64 columns over S[0] (all scores consumed by then)
 
 // exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max relative error 7.5e-5 -- P is
@@ -429,6 +429,9 @@ int attention_launch(const void* x16, const void* wqkv, const float* bqkv, const
     case 4: rc = fmt == 0 ? launch(attention_kernel<0, 4>) : launch(attention_kernel<1, 4>); break;
     case 5: rc = fmt == 0 ? launch(attention_kernel<0, 5>) : launch(attention_kernel<1, 5>); break;
     case 6: rc = fmt == 0 ? launch(attention_kernel<0, 6>) : launch(attention_kernel<1, 6>); break;
+    case 7: rc = fmt == 0 ? launch(attention_kernel<0, 7>) : launch(attention_kernel<1, 7>); break;
+    case 8: rc = fmt == 0 ? launch(attention_kernel<0, 8>) : launch(attention_kernel<1, 8>); break;
+    case 10: rc = fmt == 0 ? launch(attention_kernel<0, 10>) : launch(attention_kernel<1, 10>); break;
     default: rc = fmt == 0 ? launch(attention_kernel<0, 0>) : launch(attention_kernel<1, 0>); break;
   }
   B200_TRY(rc);
