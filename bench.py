@@ -213,19 +213,22 @@ def secondary_measurements(dev, dev_in, B, T):
             torch.cuda.synchronize()
             lib.b200voc_gen_profile_enable(gen_a._handle, 1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_att = 3
             e0.record()
-            gen_a(*dev_in)
+            for _ in range(n_att):
+                gen_a(*dev_in)
             e1.record()
             torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms = e0.elapsed_time(e1) / n_att
         att = None
         for i in range(lib.b200voc_gen_profile_count(gen_a._handle)):
             if lib.b200voc_gen_profile_name(gen_a._handle, i).decode() == "attn":
                 att = dict(ms=float(lib.b200voc_gen_profile_ms(gen_a._handle, i)),
                            flops=float(lib.b200voc_gen_profile_flops(gen_a._handle, i)))
         out["with_attention"] = {
-            "value": B * HOP * T / SR / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": 1,
-            "note": "global single-head attention over L=128*T=110208 positions (97 % of all FLOPs)",
+            "value": B * HOP * T / SR / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": n_att,
+            "note": "global single-head attention over L=128*T=110208 positions (97 % of all FLOPs); every 6th exponential on the "
+                    "FMA pipe (B200VOC_ATTN_POLY); attn_* = the attention kernels of the last step",
             "attn_kernels_ms": att["ms"] if att else None,
             "attn_tflops": att["flops"] / (att["ms"] * 1e-3) / 1e12 if att else None}
         del gen_a

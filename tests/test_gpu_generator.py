@@ -97,10 +97,11 @@ def test_generator_batch_independence_and_determinism(models):
     assert torch.equal(full, rows)
 
 
-@pytest.mark.parametrize("plan,maxabs,snr", [("fp16", 1e-3, 40.0), ("mixed", 1.5e-3, 40.0), ("bf16", 2e-2, 40.0)])
+@pytest.mark.parametrize("plan,maxabs,snr", [("fp16", 1e-3, 40.0), ("mixed", 1.5e-3, 40.0), ("bf16", 7e-3, 45.0)])
 def test_precision_plans(plan, maxabs, snr):
     """fp16 (default) meets both gates; bf16 meets the SNR gate only (plain bf16 operands
-    cannot reach max-abs 1e-3 on this network, measured 5e-3)."""
+    cannot reach max-abs 1e-3 on this network, measured 4.3e-3 .. 5e-3 / 49 dB: the bound sits just above so that a
+    regression of the bf16 path shows)."""
     from b200voc import GANConfig, Generator
     ocfg = O.OracleConfig(use_attention=False)
     ora = O.make_generator(ocfg, seed=1234)
