@@ -62,53 +62,6 @@ __device__ __forceinline__ float ex2_poly3(float x) {
   return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));   // * 2^round(x): add to the exponent field
 }
 
-// Packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2: one issue slot for two lanes of a 64-bit register pair) and the
-// 3-input maximum (FMNMX3): the softmax loop is bound by issue slots next to the MUFU unit, so the subtraction of the row
-// maximum, the row sum and the polynomial run two elements per instruction.
-__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-// two exponentials by the polynomial of ex2_poly3; x2 = (s - m) for two neighbouring keys
-__device__ __forceinline__ void ex2_poly3_x2(uint64_t x2, float& p0, float& p1) {
-  float a, b;
-  f2_unpack(x2, a, b);
-  x2 = f2_pack(fmaxf(a, -126.0f), fmaxf(b, -126.0f));
-  const uint64_t magic = f2_pack(12582912.0f, 12582912.0f);
-  const uint64_t t2 = f2_add(x2, magic);
-  const uint64_t f2 = f2_sub(x2, f2_sub(t2, magic));
-  uint64_t q2 = f2_fma(f2_pack(0.05517167f, 0.05517167f), f2, f2_pack(0.24261113f, 0.24261113f));
-  q2 = f2_fma(q2, f2, f2_pack(0.69326097f, 0.69326097f));
-  q2 = f2_fma(q2, f2, f2_pack(0.99992806f, 0.99992806f));
-  float q0, q1, t0, t1;
-  f2_unpack(q2, q0, q1);
-  f2_unpack(t2, t0, t1);
-  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
-  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
-}
-
 template <int FMT, int POLY>
 __global__ void __launch_bounds__(608, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmVt,
@@ -302,7 +255,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         tmem_ld32(lane_addr + kColS + sb * 128 + h * 64 + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) m_half = fmax3(m_half, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+        for (int i = 0; i < 32; ++i) m_half = fmaxf(m_half, __uint_as_float(v[i]));
       }
       float* sMax = sMaxG + (ph & 1) * 2 * 128;          // double buffered: the partner may still be reading the previous tile's
       sMax[h * 128 + row] = m_half;
@@ -311,8 +264,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       const float alpha = ex2_approx(m_run - m_new);     // exp2(-inf) = 0 on the first tile
       // pass 2: p = exp2(s - m), partial row sum, 16-bit P into k-block h of the swizzled K-major operand tile
       mbar_wait(&p_empty[sb], (q3 & 1) ^ 1);             // P buffer = j % 3 as well
-      uint64_t l2 = f2_pack(0.f, 0.f);                   // row sum of this tile, even / odd keys
-      const uint64_t m2 = f2_pack(m_new, m_new);
+      float l_tile = 0.f;
       uint8_t* prow = sP + sb * kP_BYTES + h * 128 * 128 + row * 128;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
@@ -321,17 +273,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         tmem_ld_wait();
         float pv[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const uint64_t x2 = f2_sub(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), m2);
-          if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) {      // every POLY-th PAIR on the FMA pipe
-            ex2_poly3_x2(x2, pv[i], pv[i + 1]);
-          } else {
-            float a, b;
-            f2_unpack(x2, a, b);
-            pv[i] = ex2_approx(a);
-            pv[i + 1] = ex2_approx(b);
-          }
-          l2 = f2_add(l2, f2_pack(pv[i], pv[i + 1]));
+        for (int i = 0; i < 32; ++i) {
+          const float xs = __uint_as_float(v[i]) - m_new;
+          pv[i] = (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == POLY - 1) ? ex2_poly3(xs) : ex2_approx(xs);
+          l_tile += pv[i];
         }
 #pragma unroll
         for (int i8 = 0; i8 < 4; ++i8) {
@@ -348,9 +293,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         mbar_arrive(&p_full[sb]);
         mbar_arrive(&s_empty[sb]);
       }
-      float l_even, l_odd;
-      f2_unpack(l2, l_even, l_odd);
-      l_run = l_run * alpha + (l_even + l_odd);
+      l_run = l_run * alpha + l_tile;
       m_run = m_new;
       // fold this group's previous tile's P V product into the running output (its alpha was computed last turn)
       if (jprev >= 0) accumulate_pv(jprev, alpha_prev);
