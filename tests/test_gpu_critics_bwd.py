@@ -45,6 +45,8 @@ def _close(got, ref, what, tol=TOL):
     (1, 64, 256, 130, 1, 15, 1, 7),    # stride 1 (CUDA-core form of a tensor-core layer)
     (2, 256, 1, 33, 1, 3, 1, 1),       # score layer
     (1, 4, 16, 2, 7, 5, 3, 2),         # single output row
+    (2, 64, 4, 50, 3, 5, 3, 2),        # few output channels, many input channels (small-output wgrad kernel, columns)
+    (3, 128, 1, 7, 1, 1, 1, 0),        # pointwise score layer
 ])
 def test_dgrad_wgrad_bias_layer_matches_fp64_autograd(B, Cin, Cout, L, P, K, st, pad):
     L_, lib = _lib()

@@ -183,6 +183,64 @@ __global__ void __launch_bounds__(kDwThreads) disc_wgrad_kernel(const DiscBwdPar
     }
   }
 }
+// Score layers (Conv(C -> 1, k3), the last layer of every stack) and other layers with a handful of output channels and
+// taps: the general kernel gives such a layer one useful lane in eight and two dependent loads per FMA (190 us for MSD's
+// 1024-channel map).  Here CTA = one input channel, thread = positions tid, tid + 256, ... (coalesced along time), CO x KK
+// accumulators per thread, then a fixed-order block reduction.
+template <int CO, int KK>
+__global__ void __launch_bounds__(kDwThreads) disc_wgrad_small_kernel(const DiscBwdParams p) {
+  __shared__ float red[kDwThreads / 32][CO * KK];
+  const int ci = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_b = p.Lout * p.P;
+  const int valid = (int)min(p.in_valid, (long long)p.Lin * p.P);
+  float acc[CO][KK];
+#pragma unroll
+  for (int c = 0; c < CO; ++c)
+#pragma unroll
+    for (int k = 0; k < KK; ++k) acc[c][k] = 0.f;
+  for (int b = 0; b < p.B; ++b) {
+    const float* xb = p.x + (long long)b * p.in_batch_stride + (long long)ci * p.Lin * p.P;
+    const float* gb = p.g + (long long)b * p.Cout * per_b;
+    for (int q = threadIdx.x; q < per_b; q += kDwThreads) {
+      int lo = q, col = 0;
+      if (p.P != 1) { lo = q / p.P; col = q - lo * p.P; }
+      float xv[KK];
+#pragma unroll
+      for (int k = 0; k < KK; ++k) {
+        const int li = lo * p.stride - p.pad + k;
+        const int idx = li * p.P + col;
+        xv[k] = (k < p.K && li >= 0 && li < p.Lin && idx < valid) ? __ldg(xb + idx) : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        if (c < p.Cout) {
+          const float gv = __ldg(gb + (long long)c * per_b + q);
+#pragma unroll
+          for (int k = 0; k < KK; ++k) acc[c][k] = fmaf(gv, xv[k], acc[c][k]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CO; ++c)
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+      float v = acc[c][k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][c * KK + k] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < CO * KK) {
+    const int c = threadIdx.x / KK, k = threadIdx.x - c * KK;
+    if (c < p.Cout && k < p.K) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kDwThreads / 32; ++w) sum += red[w][threadIdx.x];
+      p.dw[((long long)c * p.Cin + ci) * p.K + k] = sum;
+    }
+  }
+}
 __global__ void __launch_bounds__(256) disc_sum_slices_kernel(const float* __restrict__ part, long long n, int Z,
                                                               float* __restrict__ out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -204,6 +262,13 @@ static int wgrad_slices(int B, int Cin, int Cout, int Lout, int P) {
 int disc_wgrad_launch(DiscBwdParams p, float* dw, float* scratch, cudaStream_t st) {
   B200_CHECK_ARG(p.K <= kDwThreads, "disc_conv_wgrad: kernel size %d not supported (max %d)", p.K, kDwThreads);
   B200_CHECK_ARG((long long)p.Lin * p.P < (1ll << 31) && (long long)p.Lout * p.P < (1ll << 31), "disc_conv_wgrad: map too long");
+  if (p.Cout <= 4 && p.K <= 5 && p.Cin >= 64) {          // few outputs per input channel, many input channels
+    p.dw = dw;
+    if (p.Cout == 1 && p.K <= 3) disc_wgrad_small_kernel<1, 3><<<p.Cin, kDwThreads, 0, st>>>(p);
+    else disc_wgrad_small_kernel<4, 5><<<p.Cin, kDwThreads, 0, st>>>(p);
+    B200_CUDA(cudaGetLastError());
+    return B200VOC_OK;
+  }
   const int Z = wgrad_slices(p.B, p.Cin, p.Cout, p.Lout, p.P);
   const long long R = (long long)p.B * p.Lout * p.P, n = (long long)p.Cout * p.Cin * p.K;
   p.r_per_z = (R + Z - 1) / Z;
