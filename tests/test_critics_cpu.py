@@ -250,3 +250,41 @@ def test_oracle_training_mode_gradient_is_pinned_to_torch():
     w, _, _ = O.spectral_norm_power_iteration(w0, u, v)
     (torch.nn.functional.conv1d(x, w, conv.bias.detach(), padding=2) ** 2).mean().backward()
     assert float((w0.grad - conv.weight_orig.grad).abs().max()) <= 1e-6 * float(w0.grad.abs().max())
+
+
+def test_backward_entry_points_validate_arguments_before_touching_the_device():
+    """The backward half of the critic ABI rejects bad arguments with ERR_BAD_ARG and a message, without a CUDA call, and
+    its capability / size queries are pure host functions (works on a CPU-only host)."""
+    from b200voc import _lib
+    lib = _lib.load()
+    one = 16
+    assert lib.b200voc_disc_conv_dgrad(0, one, 1, 4, 16, 100, 1, 5, 3, 2, 0, 0, 0, one, 0) == _lib.ERR_BAD_ARG
+    assert b"null" in lib.b200voc_last_error_string()
+    assert lib.b200voc_disc_conv_dgrad(one, one, 1, 4, 16, 2, 1, 15, 2, 3, 0, 0, 0, one, 0) == _lib.ERR_BAD_ARG
+    assert b"shorter than the kernel" in lib.b200voc_last_error_string()
+    assert lib.b200voc_disc_conv_wgrad(one, one, 0, 4, 16, 100, 1, 5, 3, 2, 0, 0, one, 0, 0) == _lib.ERR_BAD_ARG
+    assert lib.b200voc_disc_conv_wgrad(one, 0, 1, 4, 16, 100, 1, 5, 3, 2, 0, 0, one, 0, 0) == _lib.ERR_BAD_ARG
+    assert lib.b200voc_disc_bias_grad(one, 1, 0, 10, one, 0) == _lib.ERR_BAD_ARG
+    assert lib.b200voc_disc_lrelu_bwd(0, 0, one, 0, 0.2, 10, one, 0) == _lib.ERR_BAD_ARG          # ga without y
+    assert lib.b200voc_avg_pool1d_k4s2p1_bwd(one, 1, 1, one, 0) == _lib.ERR_BAD_ARG
+    assert lib.b200voc_spectral_norm_bwd(one, one, one, one, one, 0, 5, one, one, 0) == _lib.ERR_BAD_ARG
+    assert lib.b200voc_spectral_norm_bwd(one, one, one, one, one, 4, 5, one, 4, 0) == _lib.ERR_BAD_ARG   # unaligned scratch
+    assert lib.b200voc_spectral_norm_bwd_scratch_bytes() >= 8
+    # tensor-core forms: shapes that qualify / do not
+    assert lib.b200voc_disc_conv_wgrad_tc_supported(4, 256, 1024, 1379, 41, 1, 1, 20) == 1
+    assert lib.b200voc_disc_conv_wgrad_tc_supported(4, 64, 256, 2757, 15, 1, 1, 7) == 1
+    assert lib.b200voc_disc_conv_wgrad_tc_supported(4, 16, 64, 2757, 15, 2, 1, 7) == 0            # strided
+    assert lib.b200voc_disc_conv_wgrad_tc_supported(4, 256, 1, 1379, 3, 1, 1, 1) == 0             # score layer
+    assert lib.b200voc_disc_conv_wgrad_tc_supported(4, 64, 256, 100, 5, 1, 3, 2) == 0             # period columns
+    assert lib.b200voc_disc_conv_dgrad_tc_supported(256, 1024, 41, 1, 1, 20) == 1
+    assert lib.b200voc_disc_conv_dgrad_tc_supported(64, 256, 15, 1, 1, 7) == 0                    # needs the padded weight
+    assert lib.b200voc_disc_conv_dgrad_tc_supported(128, 256, 15, 1, 1, 7) == 1
+    nb = lib.b200voc_disc_conv_wgrad_tc_workspace_bytes(4, 256, 1024, 1379, 41, 20)
+    kdim = 3 * 4 * 1408                                                                           # positions padded to 64 per item
+    assert nb >= (256 * 41 + 1024) * kdim * 2 and nb % 1024 == 0
+    assert lib.b200voc_disc_conv_wgrad_tc(one, one, 4, 16, 64, 100, 15, 7, one, 1024, 1 << 30, 0) == _lib.ERR_BAD_ARG
+    # a batch whose packed operands exceed the 1 GiB cap is processed in chunks: the workspace stays bounded
+    big = lib.b200voc_disc_conv_wgrad_tc_workspace_bytes(64, 256, 1024, 1379, 41, 20)
+    assert 0 < big < (5 << 28)
+    assert lib.b200voc_disc_conv_wgrad_scratch_bytes(4, 1, 4, 22050, 1, 15, 2, 7) > 0             # sliced first layer
+    assert lib.b200voc_disc_conv_wgrad_scratch_bytes(4, 256, 1024, 1379, 1, 41, 1, 20) == 0

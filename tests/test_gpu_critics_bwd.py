@@ -177,6 +177,34 @@ def test_wgrad_tensor_core_matches_fp64(B, Cin, Cout, L, K):
     assert lib.b200voc_disc_conv_wgrad_tc(L_.ptr(xd), L_.ptr(gd), B, Cin, Cout, L, K, pad, L_.ptr(dw), base, 16, s) == L_.ERR_BAD_ARG
 
 
+def test_wgrad_tensor_core_batch_chunks(monkeypatch):
+    """A batch whose packed operands exceed the cap is processed in chunks of batch items whose partial dW are added: the
+    cap lowered to 1 MB makes B = 5 run as five chunks; the result must equal the single-pass one to fp32 rounding."""
+    L_, lib = _lib()
+    s = L_.current_stream()
+    B, Cin, Cout, L, K, pad = 5, 64, 128, 200, 15, 7
+    g_ = torch.Generator().manual_seed(1)
+    xd = (torch.randn(B, Cin, L, generator=g_) * 2.0).cuda()
+    gd = (torch.randn(B, Cout, L, generator=g_) * 1e-2).cuda()
+
+    def run():
+        nb = int(lib.b200voc_disc_conv_wgrad_tc_workspace_bytes(B, Cin, Cout, L, K, pad))
+        ws = torch.empty(nb + 1024, device="cuda", dtype=torch.uint8)
+        base = (ws.data_ptr() + 1023) & ~1023
+        dw = torch.full((Cout, Cin, K), float("nan"), device="cuda")
+        L_.check(lib.b200voc_disc_conv_wgrad_tc(L_.ptr(xd), L_.ptr(gd), B, Cin, Cout, L, K, pad, L_.ptr(dw), base, nb, s))
+        torch.cuda.synchronize()
+        return dw, nb
+    one, nb_one = run()
+    monkeypatch.setenv("B200VOC_WGRAD_TC_CAP_MB", "1")
+    many, nb_many = run()
+    assert nb_many < nb_one
+    w = torch.zeros(Cout, Cin, K, dtype=torch.float64, requires_grad=True)
+    F.conv1d(xd.cpu().double(), w, None, padding=pad).backward(gd.cpu().double())
+    _close(one, w.grad, "single pass", tol=1e-4)
+    _close(many, w.grad, "five chunks", tol=1e-4)
+
+
 @pytest.mark.parametrize("B,Cin,Cout,L,K", [(2, 128, 256, 300, 15), (1, 256, 1024, 130, 41), (2, 256, 64, 129, 15)])
 def test_dgrad_tensor_core_matches_fp64(B, Cin, Cout, L, K):
     """dgrad of a stride-1 layer = the forward tcgen05 implicit GEMM on g with flipped weights (b200voc_disc_flip_weight ->

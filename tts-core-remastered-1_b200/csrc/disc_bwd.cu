@@ -456,7 +456,12 @@ static inline int ew_blocks(long long n, int cap = 8192) {
   return (int)(b < 1 ? 1 : (b < cap ? b : cap));
 }
 
-constexpr long long kWgTcOperandCap = 1ll << 30;   // bytes of packed operands per batch chunk
+// bytes of packed operands per batch chunk (B200VOC_WGRAD_TC_CAP_MB overrides it: tests force the chunked path with it)
+static long long wgrad_tc_cap() {
+  const char* e = getenv("B200VOC_WGRAD_TC_CAP_MB");
+  const long long mb = e ? atoll(e) : 0;
+  return mb > 0 ? mb << 20 : 1ll << 30;
+}
 static inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
 struct WgTcPlan {
   int Lp, Bc;                  // padded positions per batch item, batch items per chunk
@@ -465,8 +470,9 @@ struct WgTcPlan {
 static bool wgrad_tc_plan(int B, int Cin, int Cout, int Lout, int K, WgTcPlan* pl) {
   pl->Lp = (Lout + 63) & ~63;
   const long long per_b = ((long long)Cin * K + Cout) * 3 * pl->Lp * 2;
-  if (per_b > kWgTcOperandCap) return false;
-  long long bc = kWgTcOperandCap / per_b;
+  const long long cap = wgrad_tc_cap();
+  if (per_b > cap) return false;
+  long long bc = cap / per_b;
   pl->Bc = (int)(bc < B ? bc : B);
   const long long Kdim = 3ll * pl->Bc * pl->Lp;
   pl->a3_bytes = align_up((long long)Cout * Kdim * 2, 1024);
