@@ -345,8 +345,70 @@ __global__ void __launch_bounds__(1024) sn_normalize_kernel(const float* __restr
   for (int i = threadIdx.x; i < n; i += 1024) out[i] = x[i] / den;
   if (sigma_out && threadIdx.x == 0) *sigma_out = (float)(total / (double)den);
 }
+// The same five steps in ONE single-CTA launch for the small layers (rows * cols <= 128 k: every MPD / MBD layer, the
+// narrow MSD ones): a critic forward in .train() mode runs this for every layer, and for the small ones the five launches
+// cost more than their arithmetic (MPD: 25 layers).  fp32 products, fp64 accumulation, fixed order, as above.
+constexpr int kSnSmallMax = 128 * 1024;
+__device__ __forceinline__ double sn_block_sum(double v, double* sh) {   // 1024 threads; every thread gets the total
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();                                   // sh may still be read from the previous use
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int i = 0; i < 32; ++i) s += sh[i];
+  return s;
+}
+__global__ void __launch_bounds__(1024) sn_train_small_kernel(const float* __restrict__ w, float* __restrict__ u,
+                                                              float* __restrict__ v, int rows, int cols, float eps,
+                                                              float* __restrict__ w_out, float* __restrict__ sigma,
+                                                              float* __restrict__ scratch) {
+  __shared__ double sh[32];
+  float* t = scratch;            // [cols]
+  float* sv = scratch + cols;    // [rows]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // v <- normalize(W^T u)
+  double sq = 0.0;
+  for (int c = threadIdx.x; c < cols; c += 1024) {
+    double acc = 0.0;
+    for (int r = 0; r < rows; ++r) acc += (double)u[r] * (double)__ldg(w + (long long)r * cols + c);
+    const float tf = (float)acc;
+    t[c] = tf;
+    sq += (double)tf * (double)tf;
+  }
+  double tot = sn_block_sum(sq, sh);
+  float den = fmaxf((float)sqrt(tot), eps);
+  for (int c = threadIdx.x; c < cols; c += 1024) v[c] = t[c] / den;
+  __syncthreads();
+  // u <- normalize(W v)
+  for (int r = warp; r < rows; r += 32) {
+    const float* wr = w + (long long)r * cols;
+    double d = 0.0;
+    for (int c = lane; c < cols; c += 32) d += (double)__ldg(wr + c) * (double)v[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == 0) sv[r] = (float)d;
+  }
+  __syncthreads();
+  sq = 0.0;
+  for (int r = threadIdx.x; r < rows; r += 1024) { const double x = (double)sv[r]; sq += x * x; }
+  tot = sn_block_sum(sq, sh);
+  den = fmaxf((float)sqrt(tot), eps);
+  for (int r = threadIdx.x; r < rows; r += 1024) u[r] = sv[r] / den;
+  const float sg = (float)(tot / (double)den);
+  if (threadIdx.x == 0) *sigma = sg;
+  // weight = W / sigma
+  const int n = rows * cols;
+  for (int i = threadIdx.x; i < n; i += 1024) w_out[i] = __ldg(w + i) / sg;
+}
 int spectral_norm_train_launch(const float* w_orig, float* u, float* v, int rows, int cols, float eps, float* w_out,
                                float* sigma, float* scratch, cudaStream_t st) {
+  if ((long long)rows * cols <= kSnSmallMax) {
+    sn_train_small_kernel<<<1, 1024, 0, st>>>(w_orig, u, v, rows, cols, eps, w_out, sigma, scratch);
+    B200_CUDA(cudaGetLastError());
+    return B200VOC_OK;
+  }
   float* t = scratch;            // [cols]
   float* s = scratch + cols;     // [rows]
   sn_wt_u_kernel<<<(cols + 31) / 32, 256, 0, st>>>(w_orig, u, rows, cols, t);
