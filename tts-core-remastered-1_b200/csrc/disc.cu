@@ -345,10 +345,10 @@ __global__ void __launch_bounds__(1024) sn_normalize_kernel(const float* __restr
   for (int i = threadIdx.x; i < n; i += 1024) out[i] = x[i] / den;
   if (sigma_out && threadIdx.x == 0) *sigma_out = (float)(total / (double)den);
 }
-// The same five steps in ONE single-CTA launch for the small layers (rows * cols <= 128 k: every MPD / MBD layer, the
+// The same five steps in ONE single-CTA launch for the small layers (rows * cols <= 32 k: most MPD / MBD layers, the
 // narrow MSD ones): a critic forward in .train() mode runs this for every layer, and for the small ones the five launches
 // cost more than their arithmetic (MPD: 25 layers).  fp32 products, fp64 accumulation, fixed order, as above.
-constexpr int kSnSmallMax = 128 * 1024;
+constexpr int kSnSmallMax = 32 * 1024;
 __device__ __forceinline__ double sn_block_sum(double v, double* sh) {   // 1024 threads; every thread gets the total
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
