@@ -410,6 +410,35 @@ def secondary_measurements(dev, dev_in, B, T):
                 res[name]["train_fwd_bwd_tflops"] = 3 * fl / (ms_t * 1e-3) / 1e12
             except Exception as e:
                 res[name]["train_fwd_bwd_error"] = str(e)[:200]
+            # the same step captured in ONE CUDA graph (forward, loss, backward; static input): what the narrow critics need,
+            # their eager step is bound by ~600 launches from the host
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        d_step()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                crit.zero_grad(set_to_none=True)
+                wg.grad = None
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph):
+                    with torch.enable_grad():
+                        o, f = crit(wg)
+                        loss = sum((s_ ** 2).mean() for s_ in o) + sum(m.abs().mean() for fs in f for m in fs)
+                        loss.backward()
+                gph.replay()
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(5):
+                    gph.replay()
+                b_.record()
+                torch.cuda.synchronize()
+                res[name]["train_fwd_bwd_graph_ms"] = a.elapsed_time(b_) / 5
+                del gph
+            except Exception as e:
+                res[name]["train_fwd_bwd_graph_error"] = str(e)[:200]
             del crit
         out["critics"] = res
     except Exception as e:

@@ -366,3 +366,45 @@ def test_critic_backward_cuda_core_path_and_partial_losses(monkeypatch):
     sum((o ** 2).mean() for o in outs).backward()
     for n, p in mod.named_parameters():
         _close(p.grad, tc[n], n, tol=2e-4)
+
+
+def test_critic_forward_backward_is_cuda_graph_capturable():
+    """Forward + loss + backward of a critic in ONE CUDA graph (PyTorch's whole-network capture recipe): nothing in the
+    autograd node synchronises or allocates outside the capture pool, every launch goes to the capturing stream.  The
+    replayed gradients on NEW input values equal the eager ones (the kernels are deterministic: bit for bit)."""
+    import b200voc
+    mod = _host("mbd", b200voc.GANConfig(), seed=3).eval()
+    static_x = (torch.rand(2, 1, 4096, device="cuda") * 2 - 1).requires_grad_(True)
+
+    def step():
+        outs, feats = mod(static_x)
+        _loss(outs, feats).backward()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            mod.zero_grad(set_to_none=True)
+            static_x.grad = None
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    mod.zero_grad(set_to_none=True)
+    static_x.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    new_x = torch.rand(2, 1, 4096, device="cuda") * 2 - 1
+    with torch.no_grad():
+        static_x.copy_(new_x)
+    graph.replay()
+    torch.cuda.synchronize()
+    got = {n: p.grad.clone() for n, p in mod.named_parameters()}
+    got_x = static_x.grad.clone()
+    mod.zero_grad(set_to_none=True)
+    xe = new_x.clone().requires_grad_(True)
+    outs, feats = mod(xe)
+    _loss(outs, feats).backward()
+    torch.cuda.synchronize()
+    assert torch.equal(got_x, xe.grad)
+    for n, p in mod.named_parameters():
+        assert torch.equal(got[n], p.grad), n
