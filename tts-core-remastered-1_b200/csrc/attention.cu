@@ -410,7 +410,8 @@ int attention_launch(const void* x16, const void* wqkv, const float* bqkv, const
   p.out = reinterpret_cast<uint16_t*>(out16);
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
-  // B200VOC_ATTN_POLY = n: every n-th exponential of a row on the FMA pipe (0 = all on the MUFU unit; A/B switch)
+  // B200VOC_ATTN_POLY = n: every n-th exponential of a row on the FMA pipe (built: 3, 4, 6, 8; anything else = all on the
+  // MUFU unit; A/B switch)
   static const int poly = [] { const char* e = getenv("B200VOC_ATTN_POLY"); return e ? atoi(e) : kAttnPolyDefault; }();
   dim3 grid(L / 128, N);
   auto launch = [&](auto kern) -> int {          // one (format, poly) variant per process and device in practice
@@ -424,14 +425,10 @@ int attention_launch(const void* x16, const void* wqkv, const float* bqkv, const
   };
   int rc;
   switch (poly) {
-    case 2: rc = fmt == 0 ? launch(attention_kernel<0, 2>) : launch(attention_kernel<1, 2>); break;
     case 3: rc = fmt == 0 ? launch(attention_kernel<0, 3>) : launch(attention_kernel<1, 3>); break;
     case 4: rc = fmt == 0 ? launch(attention_kernel<0, 4>) : launch(attention_kernel<1, 4>); break;
-    case 5: rc = fmt == 0 ? launch(attention_kernel<0, 5>) : launch(attention_kernel<1, 5>); break;
     case 6: rc = fmt == 0 ? launch(attention_kernel<0, 6>) : launch(attention_kernel<1, 6>); break;
-    case 7: rc = fmt == 0 ? launch(attention_kernel<0, 7>) : launch(attention_kernel<1, 7>); break;
     case 8: rc = fmt == 0 ? launch(attention_kernel<0, 8>) : launch(attention_kernel<1, 8>); break;
-    case 10: rc = fmt == 0 ? launch(attention_kernel<0, 10>) : launch(attention_kernel<1, 10>); break;
     default: rc = fmt == 0 ? launch(attention_kernel<0, 0>) : launch(attention_kernel<1, 0>); break;
   }
   B200_TRY(rc);
