@@ -67,6 +67,21 @@ class FakeCriticLib:
         _arr(w_out, rows * cols)[:] = (W / sigma).reshape(-1)
         return 0
 
+    def b200voc_spectral_norm_train(self, w_orig, u, v, rows, cols, eps, w_out, sigma_out, scratch, stream):
+        """one power iteration, u / v updated IN PLACE (csrc/disc.cu spectral_norm_train_launch)"""
+        W = _arr(w_orig, rows * cols).reshape(rows, cols).astype(np.float64)
+        uu, vv = _arr(u, rows), _arr(v, cols)
+        t = (W.T @ uu.astype(np.float64)).astype(np.float32)
+        vv[:] = t / max(float(np.sqrt((t.astype(np.float64) ** 2).sum())), eps)
+        s = (W @ vv.astype(np.float64)).astype(np.float32)
+        tot = float((s.astype(np.float64) ** 2).sum())
+        den = max(float(np.float32(np.sqrt(tot))), eps)
+        uu[:] = s / np.float32(den)
+        sigma = np.float32(tot / den)
+        _arr(sigma_out, 1)[0] = sigma
+        _arr(w_out, rows * cols)[:] = (_arr(w_orig, rows * cols) / sigma)
+        return 0
+
     def b200voc_avg_pool1d_k4s2p1(self, x, rows, Lin, y, stream):
         Lout = (Lin + 2 - 4) // 2 + 1
         xv = np.pad(_arr(x, rows * Lin).reshape(rows, Lin), ((0, 0), (1, 2 * Lout + 2 - Lin)))

@@ -166,6 +166,40 @@ def test_host_autograd_node_against_oracle(monkeypatch, kind):
         close(p.grad, sd[name].grad, name + " (scores only)")
 
 
+def test_host_autograd_node_training_mode_keeps_its_own_u_v(monkeypatch):
+    """.train(): the forward runs the power iteration and updates weight_u / weight_v in place; the reference trainer runs
+    D(fake) AND D(real) before any backward (vocoder7/trainer.py:86-115), so the node must keep the u, v of ITS forward --
+    the gradients of the first forward, taken after a second forward has moved the buffers, equal torch autograd over the
+    oracle's training-mode forward of the first call."""
+    from fake_critic_lib import FakeCriticLib
+    from b200voc import GANConfig, _lib
+    cfg = GANConfig(disc_kernel_sizes=[5, 9, 9])
+    ocfg = O.OracleConfig(disc_kernel_sizes=[5, 9, 9])
+    torch.manual_seed(13)
+    mod = _host_cls("mbd")(cfg).train()
+    fake = FakeCriticLib()
+    monkeypatch.setattr(_lib, "load", lambda: fake)
+    monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(_lib, "current_stream", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    x = torch.randn(2, 1, 211, generator=torch.Generator().manual_seed(6))
+    outs, feats = mod(x)                                     # D(fake)
+    u_after_first = mod.state_dict()["discriminators.0.0.weight_u"].clone()
+    mod(torch.randn(2, 1, 211))                              # D(real): moves u / v again
+    assert not torch.equal(mod.state_dict()["discriminators.0.0.weight_u"], u_after_first)
+    _gan_like_loss(outs, feats).backward()
+    for k in sd:
+        if k.endswith("weight_orig") or k.endswith("bias"):
+            sd[k].requires_grad_(True)
+    r_outs, r_feats = O.critic_forward("mbd", sd, ocfg, x, training=True)
+    assert torch.allclose(sd["discriminators.0.0.weight_u"], u_after_first, atol=1e-6)
+    _gan_like_loss(r_outs, r_feats).backward()
+    for name, p in mod.named_parameters():
+        g, r = p.grad, sd[name].grad
+        assert float((g - r).abs().max()) <= 5e-4 * float(r.abs().max()) + 1e-7, name
+
+
 def test_short_waveforms_raise():
     from fake_critic_lib import FakeCriticLib  # noqa: F401  (only the out_len rule is needed)
     from b200voc import _lib
