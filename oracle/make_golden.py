@@ -226,6 +226,49 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "critics_b2_t2403.npz"), **save)
     print(f"  critics_b2_t2403.npz: {os.path.getsize(os.path.join(GOLD, 'critics_b2_t2403.npz')) / 1024:.1f} KiB")
 
+    # ---- critics, backward (the critic half of the training step, vocoder7/trainer.py:86-115): autograd
+    # through the REFERENCE classes vs autograd through the restatement, in .eval() (stored u, v) and in .train() (power
+    # iteration first, u / v constants of the graph); golden gradients for tests/test_critics_cpu.py ---------------------
+    def gan_like_loss(outs, feats):
+        loss = 0.0
+        for o in outs:
+            loss = loss + ((o - 1.0) ** 2).mean()
+        for fs in feats:
+            for j, f in enumerate(fs):
+                loss = loss + (0.5 + 0.1 * j) * f.abs().mean()
+        return loss
+
+    gsave = {"x": x.numpy()}
+    for kind, cls in (("mpd", rdisc.MultiPeriodDiscriminator), ("msd", rdisc.MultiScaleDiscriminator),
+                      ("mbd", rdisc.MultiBandDiscriminator)):
+        for mode in ("eval", "train"):
+            torch.manual_seed(1234)
+            ref = cls(cfg_ref).train(mode == "train")
+            xr = x.clone().requires_grad_(True)
+            gan_like_loss(*ref(xr)).backward()
+            sd_ora = O.make_critic_state(kind, cfg_ref, seed=1234)
+            for k in sd_ora:
+                if k.endswith("weight_orig") or k.endswith("bias"):
+                    sd_ora[k].requires_grad_(True)
+            xo = x.clone().requires_grad_(True)
+            gan_like_loss(*O.critic_forward(kind, sd_ora, cfg_ref, xo, training=(mode == "train"))).backward()
+            worst = float((xr.grad - xo.grad).abs().max() / xr.grad.abs().max())
+            grads = {"x": xr.grad}
+            for name, prm in ref.named_parameters():
+                worst = max(worst, float((prm.grad - sd_ora[name].grad).abs().max() / prm.grad.abs().max()))
+                grads[name] = prm.grad
+            print(f"{kind} backward ({mode}): |reference autograd - restatement autograd|max / scale = {worst:.3e}")
+            assert worst <= 1e-5
+            for name, gr in grads.items():
+                flat = gr.detach().reshape(-1)
+                pick = torch.linspace(0, flat.numel() - 1, min(64, flat.numel())).long()
+                gsave[f"{kind}.{mode}.{name}.idx"] = pick.numpy()
+                gsave[f"{kind}.{mode}.{name}.val"] = flat[pick].numpy()
+                gsave[f"{kind}.{mode}.{name}.sum"] = np.array([float(flat.double().sum()), float(flat.double().abs().sum()),
+                                                              float(flat.abs().max())])
+    np.savez_compressed(os.path.join(GOLD, "critics_grad_b2_t2403.npz"), **gsave)
+    print(f"  critics_grad_b2_t2403.npz: {os.path.getsize(os.path.join(GOLD, 'critics_grad_b2_t2403.npz')) / 1024:.1f} KiB")
+
 
 if __name__ == "__main__":
     main()

@@ -200,6 +200,32 @@ def test_host_autograd_node_training_mode_keeps_its_own_u_v(monkeypatch):
         assert float((g - r).abs().max()) <= 5e-4 * float(r.abs().max()) + 1e-7, name
 
 
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_oracle_backward_matches_reference_golden(golden_dir, kind, mode):
+    """tests/golden/critics_grad_b2_t2403.npz holds gradients that autograd produced through the REFERENCE classes
+    (oracle/make_golden.py: .eval() and .train(), a loss over every score and feature map); autograd through the
+    restatement on seed-regenerated weights must reproduce them -- this is what pins the reference the critic backward
+    kernels are tested against (tests/test_gpu_critics_bwd.py) to the reference's own code."""
+    gold = np.load(os.path.join(golden_dir, "critics_grad_b2_t2403.npz"))
+    cfg = O.OracleConfig()
+    sd = O.make_critic_state(kind, cfg, seed=1234)
+    for k in sd:
+        if k.endswith("weight_orig") or k.endswith("bias"):
+            sd[k].requires_grad_(True)
+    x = torch.from_numpy(gold["x"]).clone().requires_grad_(True)
+    outs, feats = O.critic_forward(kind, sd, cfg, x, training=(mode == "train"))
+    _gan_like_loss(outs, feats).backward()
+    names = [k for k in sd if sd[k].requires_grad]
+    assert len(names) == {"mpd": 50, "msd": 36, "mbd": 40}[kind]
+    for name, g in [("x", x.grad)] + [(n, sd[n].grad) for n in names]:
+        flat = g.reshape(-1)
+        s_ref, a_ref, m_ref = gold[f"{kind}.{mode}.{name}.sum"]
+        got = flat[torch.from_numpy(gold[f"{kind}.{mode}.{name}.idx"])].numpy()
+        assert float(np.abs(got - gold[f"{kind}.{mode}.{name}.val"]).max()) <= 1e-5 * m_ref, name
+        assert abs(float(flat.double().abs().sum()) - a_ref) <= 1e-5 * a_ref, name
+
+
 def test_short_waveforms_raise():
     from fake_critic_lib import FakeCriticLib  # noqa: F401  (only the out_len rule is needed)
     from b200voc import _lib
